@@ -1,0 +1,141 @@
+/*
+ * scatter_b200.h -- C ABI of libscatter_b200.so: the B200 (sm_100a) implementation of SCATTER's hot path.
+ *
+ * The reference (PlatypusBytes/scatter) is pure Python and has no FFI of its own; its seams for this path are
+ * plain Python call sites.  Every entry point below names the reference call it replaces
+ * (file:line relative to the reference tree).  The Python shims in scatter_b200/ (GenerateMatrix, the solver
+ * classes, scatter.scatter) bind these symbols with ctypes -- see INTEGRATION.md for the binding.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; the caller owns every host buffer, the library owns all device memory
+ *   - one opaque context per GPU / rank; a context is not thread-safe; calls are synchronous at return
+ *   - every function returns 0 on success or a negative sc_status; sc_last_error() gives the message
+ *   - there is no CPU fallback: sc_create fails if no CUDA device is usable
+ */
+#ifndef SCATTER_B200_H
+#define SCATTER_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct sc_ctx sc_ctx;
+
+enum sc_status {
+    SC_OK = 0,
+    SC_ERR_CUDA = -1,      /* CUDA runtime error (message has the call site) */
+    SC_ERR_ARG = -2,       /* invalid argument / call order */
+    SC_ERR_STATE = -3,     /* required earlier step missing (mesh, pattern, assembly ...) */
+    SC_ERR_UNSUPPORTED = -4,
+    SC_ERR_NOCONV = -5,    /* PCG did not reach the requested tolerance */
+    SC_ERR_NCCL = -6
+};
+
+/* element types, order as in SURVEY.md 8a; gmsh node ordering (scatter/element_types.py) */
+enum sc_elem_type {
+    SC_TRI3 = 0, SC_TRI6 = 1, SC_QUAD4 = 2, SC_QUAD8 = 3, SC_TETRA4 = 4, SC_TETRA10 = 5, SC_HEXA8 = 6, SC_HEXA20 = 7
+};
+
+enum sc_matrix { SC_MAT_K = 0, SC_MAT_M = 1, SC_MAT_C = 2, SC_MAT_KHAT = 3 };
+
+/* flags for sc_assemble */
+enum sc_assemble_flags {
+    SC_ASM_K = 1,            /* stiffness values on the structural pattern */
+    SC_ASM_M_FULL = 2,       /* consistent mass on the same pattern (explicit zeros kept, system_matrix.py:98-103) */
+    SC_ASM_M_LUMPED = 4      /* row sums of the consistent mass (central-difference path) */
+};
+
+typedef struct sc_stats {
+    double  seconds_total;       /* wall time inside the call (host clock) */
+    double  seconds_device;      /* CUDA-event time of the stepping loop */
+    double  seconds_halo;        /* CUDA-event time spent in halo exchange (multi-GPU) */
+    int64_t steps;               /* time steps taken */
+    int64_t pcg_iterations;      /* total PCG iterations (Newmark) */
+    int64_t kernel_launches;     /* kernels of this library launched inside the call */
+    double  last_residual;       /* last relative PCG residual */
+    double  reserved[4];
+} sc_stats;
+
+/* ---- life cycle ------------------------------------------------------------------------------------------- */
+int         sc_create(int device, sc_ctx** out);
+void        sc_destroy(sc_ctx* ctx);
+const char* sc_last_error(sc_ctx* ctx);          /* ctx may be NULL: error of a failed sc_create */
+int         sc_version(void);
+int         sc_device_info(sc_ctx* ctx, int* sm_count, int64_t* total_mem, int64_t* free_mem, char* name, int name_len);
+int64_t     sc_kernel_launches(sc_ctx* ctx);     /* running count of kernels launched by this context */
+
+/* integration tables of one (element type, Gauss order): N[ngp*nne], dN[ngp*nne*dim], w[ngp]; runs on the host
+ * (no GPU needed).  element_types.py:52-802 + discretisation.py:436-497.  Buffers may be NULL to query sizes. */
+int         sc_shape_table(int elem_type, int order, int* nne, int* dim, int* ngp, double* N, double* dN, double* w);
+
+/* ---- mesh / numbering (replaces the ReadMesh attributes consumed at system_matrix.py:35-103:
+ *      model.nodes, model.elem, model.eq_nb_dof, model.number_eq, model.element_type) ---------------------------
+ *  xyz   [n_nodes*3] row-major (2-D elements ignore z, discretisation.py:329)
+ *  conn  [n_elem*nne] 0-based node rows, gmsh node order
+ *  eq    [n_nodes*dim] equation number or -1 for a fixed dof (mesher.py:276-310 uses NaN); must increase with
+ *        (node row, dof) exactly as the reference numbers them
+ *  active[n_nodes] or NULL: 1 = rows of this node are assembled/integrated on this rank, 0 = ghost node whose
+ *        values arrive through the halo exchange (domain decomposition; NULL = all active)                      */
+int sc_set_mesh(sc_ctx* ctx, int elem_type, int64_t n_nodes, const double* xyz, int64_t n_elem, const int32_t* conn,
+                const int64_t* eq, int64_t n_eq, const uint8_t* active);
+
+/* per-element Young's modulus, Poisson ratio, density (system_matrix.py:64-71; random_fields.py:46-57) */
+int sc_set_materials(sc_ctx* ctx, const double* young, const double* poisson, const double* density);
+
+/* ---- structural CSR pattern (the key set of k_dict, system_matrix.py:98-121): sorted rows, sorted columns ----- */
+int sc_build_pattern(sc_ctx* ctx, int64_t* nnz_out);
+int sc_get_pattern(sc_ctx* ctx, int64_t* rowptr /*[n_eq+1]*/, int32_t* col /*[nnz]*/);
+
+/* ---- element integration + deterministic assembly (GenerateMatrix.generate_stiffness_and_mass,
+ *      system_matrix.py:35-121 over discretisation.py:83-222,290-417) -------------------------------------------- */
+int sc_assemble(sc_ctx* ctx, int gauss_order, int flags, double* seconds_device /*may be NULL*/);
+
+/* add pre-summed COO entries (must lie inside the pattern): absorbing dashpots -> which = SC_MAT_C (kept as the
+ * separate term C_abs), absorbing springs -> which = SC_MAT_K (system_matrix.py:360-376) */
+int sc_add_entries(sc_ctx* ctx, int which, int64_t n, const int64_t* rows, const int64_t* cols, const double* vals);
+
+/* Rayleigh damping C = C_abs + c0 M + c1 K (system_matrix.py:198); never materialised in the time loop */
+int sc_set_rayleigh(sc_ctx* ctx, double c0, double c1);
+
+int sc_get_values(sc_ctx* ctx, int which, double* vals /*[nnz]*/);
+int sc_get_lumped_mass(sc_ctx* ctx, double* diag /*[n_eq]*/);
+/* y = A x with the device SpMV kernel (test hook; A = K, M, C or KHAT) */
+int sc_spmv(sc_ctx* ctx, int which, const double* x, double* y);
+
+/* ---- loads (replaces the per-step callback Force.update_load_at_t, force_external.py:55-74, scatter.py:151):
+ *      total external force of step t = entries step_ptr[t]..step_ptr[t+1] of (dof, val); other dofs zero -------- */
+int sc_set_load_schedule(sc_ctx* ctx, int64_t n_steps, const int64_t* step_ptr, const int64_t* dof, const double* val);
+
+/* ---- state (solver.update(t_start) restart hook, scatter.py:158) -------------------------------------------- */
+int sc_set_state(sc_ctx* ctx, const double* u, const double* v /*each [n_eq] or NULL = zeros*/);
+int sc_get_state(sc_ctx* ctx, double* u, double* v, double* a /*each [n_eq] or NULL*/);
+
+/* ---- time integration (replaces solvers.NewmarkExplicit.calculate(M, C, K, F, t0, t1), scatter.py:159) -------
+ *  Integrates load-schedule steps t_start+1 .. t_start+n_steps.  Output row r (r = 0 .. n_out-1) receives the
+ *  state at step t_start + r*out_interval ... only steps with (t % out_interval == 0) are stored, the first stored
+ *  row is the state at t_start itself when t_start % out_interval == 0.  u_out/v_out/a_out are host buffers of
+ *  n_out*n_eq doubles or NULL.  The implicit solve uses Jacobi-preconditioned CG to relative residual pcg_rtol.   */
+int sc_run_newmark(sc_ctx* ctx, double dt, int64_t t_start, int64_t n_steps, int64_t out_interval, double beta,
+                   double gamma, double pcg_rtol, int pcg_maxit, int64_t n_out, double* u_out, double* v_out,
+                   double* a_out, sc_stats* stats);
+
+/* explicit central difference with row-sum lumped M and C (solvers.CentralDifferenceSolver; scheme documented in
+ * DESIGN.md -- the reference ships no fixture for it) */
+int sc_run_central_difference(sc_ctx* ctx, double dt, int64_t t_start, int64_t n_steps, int64_t out_interval,
+                              int64_t n_out, double* u_out, double* v_out, double* a_out, sc_stats* stats);
+
+/* ---- multi-GPU (domain decomposition; one context per rank) --------------------------------------------------- */
+int sc_nccl_unique_id(void* out128 /*128 bytes*/);
+int sc_dist_init(sc_ctx* ctx, int rank, int world, const void* nccl_unique_id128);
+/* neighbour r sends dofs send_idx[send_ptr[r]..send_ptr[r+1]) of the local vector and receives into
+ * recv_idx[recv_ptr[r]..recv_ptr[r+1]) (local equation numbers) */
+int sc_set_halo(sc_ctx* ctx, int n_neighbors, const int32_t* neighbor_rank, const int64_t* send_ptr,
+                const int64_t* send_idx, const int64_t* recv_ptr, const int64_t* recv_idx);
+int sc_halo_exchange(sc_ctx* ctx, double* x_host /*[n_eq] in/out, test hook*/);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SCATTER_B200_H */

@@ -1,0 +1,111 @@
+"""Synthetic structured soil boxes (hexa8 / hexa20) -- the benchmark inputs of BASELINE.json configs 4 and 5.
+
+Node id = 1 + i + (nx+1) (j + (ny+1) k) with x fastest; hexa8 connectivity in gmsh order
+(`scatter/element_types.py:10-21`), hexa20 mid-edge nodes appended after the corner lattice in gmsh edge order
+(`element_types.py:119-131`).  y is the vertical axis as in the reference (`scatter/scatter.py:41-44`).
+
+`box_model` returns a `ReadMesh`-shaped object built from arrays (no file); `write_box_msh` emits the same mesh as
+gmsh 2.2 ASCII for small sizes so that the file reader sees the identical model.  `z_range` restricts the box to a slab
+of element layers [k0, k1) -- used by the domain decomposition so that no rank ever materialises the global mesh.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import gmsh_io
+from .mesher import ReadMesh
+
+_HEX20_EDGES = [(0, 1), (0, 3), (0, 4), (1, 2), (1, 5), (2, 3), (2, 6), (3, 7), (4, 5), (4, 7), (5, 6), (6, 7)]
+_CORNER_OFF = np.array([[0, 0, 0], [1, 0, 0], [1, 1, 0], [0, 1, 0], [0, 0, 1], [1, 0, 1], [1, 1, 1], [0, 1, 1]])
+
+
+def box_arrays(nx: int, ny: int, nz: int, h: float = 0.5, element_type: str = "hexa8", z_range=None):
+    """-> nodes (Nn,4) [id,x,y,z], elem (Ne,nne) 1-based ids, with ids local to the slab `z_range` = (k0, k1)."""
+    k0, k1 = (0, nz) if z_range is None else z_range
+    nzl = k1 - k0
+    NX, NY, NZ = nx + 1, ny + 1, nzl + 1
+    ii, jj, kk = np.meshgrid(np.arange(NX), np.arange(NY), np.arange(NZ), indexing="ij")
+    # x fastest: flatten in (k, j, i) order
+    order = (kk * NY + jj) * NX + ii
+    n_corner = NX * NY * NZ
+    xyz = np.empty((n_corner, 3))
+    xyz[order.ravel(), 0] = ii.ravel() * h
+    xyz[order.ravel(), 1] = jj.ravel() * h
+    xyz[order.ravel(), 2] = (kk.ravel() + k0) * h
+    ei, ej, ek = np.meshgrid(np.arange(nx), np.arange(ny), np.arange(nzl), indexing="ij")
+    eorder = ((ek * ny + ej) * nx + ei).ravel()
+    ne = nx * ny * nzl
+    corner = np.empty((ne, 8), dtype=np.int64)
+    for a, (di, dj, dk) in enumerate(_CORNER_OFF):
+        corner[eorder, a] = (((ek + dk) * NY + (ej + dj)) * NX + (ei + di)).ravel()
+    if element_type == "hexa8":
+        ids = np.arange(1, n_corner + 1, dtype=float)
+        return np.column_stack([ids, xyz]), corner + 1
+    if element_type != "hexa20":
+        raise ValueError("box meshes are hexa8 or hexa20")
+    # mid-edge nodes: x-edges, then y-edges, then z-edges, each group x fastest
+    nxe, nye = nx * NY * NZ, NX * ny * NZ
+    base = {0: n_corner, 1: n_corner + nxe, 2: n_corner + nxe + nye}
+
+    def edge_id(axis, i, j, k):
+        if axis == 0:
+            return base[0] + (k * NY + j) * nx + i
+        if axis == 1:
+            return base[1] + (k * ny + j) * NX + i
+        return base[2] + (k * NY + j) * NX + i
+
+    n_total = n_corner + nxe + nye + NX * NY * nzl
+    xyz_all = np.empty((n_total, 3))
+    xyz_all[:n_corner] = xyz
+    for axis, (ni, nj, nk) in enumerate([(nx, NY, NZ), (NX, ny, NZ), (NX, NY, nzl)]):
+        a, b, c = np.meshgrid(np.arange(ni), np.arange(nj), np.arange(nk), indexing="ij")
+        idx = edge_id(axis, a, b, c).ravel()
+        p = np.stack([a.ravel() * h, b.ravel() * h, (c.ravel() + k0) * h], axis=1).astype(float)
+        p[:, axis] += 0.5 * h
+        xyz_all[idx] = p
+    elem = np.empty((ne, 20), dtype=np.int64)
+    elem[:, :8] = corner
+    for m, (ca, cb) in enumerate(_HEX20_EDGES):
+        oa, ob = _CORNER_OFF[ca], _CORNER_OFF[cb]
+        axis = int(np.nonzero(ob - oa)[0][0])
+        lo = np.minimum(oa, ob)
+        elem[eorder, 8 + m] = edge_id(axis, ei + lo[0], ej + lo[1], ek + lo[2]).ravel()
+    ids = np.arange(1, n_total + 1, dtype=float)
+    return np.column_stack([ids, xyz_all]), elem + 1
+
+
+def box_boundaries(nx: int, ny: int, nz: int, h: float = 0.5, bottom: str = "111") -> dict:
+    """Bottom (y=0) `bottom`, x-sides roller "100", z-sides roller "001", top free (integration_test.py:513-518)."""
+    X, Y, Z = nx * h, ny * h, nz * h
+    return {"bottom": [bottom, [[0, 0, 0], [X, 0, 0], [0, 0, Z], [X, 0, Z]]],
+            "left": ["100", [[0, 0, 0], [0, 0, Z], [0, Y, 0], [0, Y, Z]]],
+            "right": ["100", [[X, 0, 0], [X, 0, Z], [X, Y, 0], [X, Y, Z]]],
+            "front": ["001", [[0, 0, 0], [X, 0, 0], [0, Y, 0], [X, Y, 0]]],
+            "back": ["001", [[0, 0, Z], [X, 0, Z], [0, Y, Z], [X, Y, Z]]]}
+
+
+def box_model(nx: int, ny: int, nz: int, h: float = 0.5, element_type: str = "hexa8", bottom: str = "111",
+              z_range=None) -> ReadMesh:
+    nodes, elem = box_arrays(nx, ny, nz, h, element_type, z_range)
+    m = ReadMesh.from_arrays(nodes, elem, np.ones(len(elem), dtype=np.int64), [[3.0, 1, "solid"]], element_type)
+    m.read_bc(box_boundaries(nx, ny, nz, h, bottom))
+    m.mapping()
+    return m
+
+
+def top_centre_node(nx: int, ny: int, nz: int) -> int:
+    """1-based id of the corner-lattice node at the centre of the free top surface (y = ny*h)."""
+    return 1 + nx // 2 + (nx + 1) * (ny + (ny + 1) * (nz // 2))
+
+
+def lognormal_young(n_elem: int, mean: float = 30e6, std: float = 1e6, seed: int = 26021981) -> np.ndarray:
+    """Per-element Young's modulus, lognormal with the given mean / standard deviation (random_fields.py:73-75)."""
+    rng = np.random.default_rng(seed)
+    sig2 = np.log(1.0 + (std / mean) ** 2)
+    mu = np.log(mean) - 0.5 * sig2
+    return np.exp(mu + np.sqrt(sig2) * rng.standard_normal(n_elem))
+
+
+def write_box_msh(path: str, nx: int, ny: int, nz: int, h: float = 0.5, element_type: str = "hexa8"):
+    nodes, elem = box_arrays(nx, ny, nz, h, element_type)
+    gmsh_io.write_msh(path, nodes, elem, np.ones(len(elem), dtype=int), [[3, 1, "solid"]], element_type)

@@ -1,0 +1,449 @@
+// C ABI glue of libscatter_b200.so (see include/scatter_b200.h for the contract of every entry point).
+#include <algorithm>
+#include <cstdarg>
+#include <cstring>
+#include <numeric>
+#include "common.h"
+
+namespace {
+std::string g_error;
+
+__global__ void k_find_slots(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col, const int64_t* __restrict__ rows,
+                             const int32_t* __restrict__ cols, int64_t n, int64_t* __restrict__ slot, int* __restrict__ missing) {
+    int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    const int64_t r = rows[t];
+    const int c = cols[t];
+    int64_t lo = rowptr[r], hi = rowptr[r + 1], found = -1;
+    while (lo < hi) {
+        int64_t mid = (lo + hi) >> 1;
+        int cm = col[mid];
+        if (cm == c) { found = mid; break; }
+        if (cm < c) lo = mid + 1; else hi = mid;
+    }
+    slot[t] = found;
+    if (found < 0) atomicExch(missing, 1);
+}
+__global__ void k_add_at(double* __restrict__ vals, const int64_t* __restrict__ slot, const double* __restrict__ v, int64_t n) {
+    int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (t < n && slot[t] >= 0) vals[slot[t]] += v[t];
+}
+
+template <typename T>
+int upload(sc_ctx* ctx, T** dst, const T* src, size_t n) {
+    SC_TRY(sc_alloc(ctx, dst, n));
+    if (n) SC_CUDA(ctx, cudaMemcpy(*dst, src, n * sizeof(T), cudaMemcpyHostToDevice));
+    return SC_OK;
+}
+
+void free_pattern(sc_ctx* c) {
+    sc_free(&c->d_n2e_ptr); sc_free(&c->d_n2e); sc_free(&c->d_nbr_ptr); sc_free(&c->d_nbr); sc_free(&c->d_nbr_off);
+    sc_free(&c->d_node_rl); sc_free(&c->d_node_row0); sc_free(&c->d_rowptr); sc_free(&c->d_col);
+    sc_free(&c->d_K); sc_free(&c->d_M); sc_free(&c->d_Ml); sc_free(&c->d_Khat);
+    sc_free(&c->d_cabs_rowid); sc_free(&c->d_cabs_rptr); sc_free(&c->d_cabs_col); sc_free(&c->d_cabs_slot); sc_free(&c->d_cabs_val);
+    c->cabs_n = c->cabs_rows = 0;
+    c->have_pattern = c->have_K = c->have_M = c->have_Ml = false;
+    c->nnz = 0;
+}
+void free_vectors(sc_ctx* c) {
+    sc_free(&c->d_u); sc_free(&c->d_v); sc_free(&c->d_a);
+    for (auto& w : c->work) sc_free(&w);
+    c->work.clear();
+    sc_free(&c->d_partial);
+    c->cd_resume_valid = false;
+}
+
+// values of C = C_abs + c0 M + c1 K into a fresh device buffer
+int build_C(sc_ctx* ctx, double** out) {
+    if (!ctx->have_K || !ctx->have_M) return sc_fail(ctx, SC_ERR_STATE, "C needs assembled K and full M");
+    double* tmp = nullptr;
+    SC_TRY(sc_alloc(ctx, &tmp, (size_t)ctx->nnz));
+    int rc = la_axpby_vals(ctx, tmp, ctx->c0, ctx->d_M, ctx->c1, ctx->d_K, ctx->nnz);
+    if (rc == SC_OK) rc = la_cabs_add_values(ctx, tmp, 1.0);
+    if (rc != SC_OK) { sc_free(&tmp); return rc; }
+    *out = tmp;
+    return SC_OK;
+}
+}  // namespace
+
+void sc_set_global_error(const char* msg) { g_error = msg ? msg : ""; }
+
+int sc_fail(sc_ctx* ctx, int code, const char* fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    if (ctx) ctx->err = buf;
+    g_error = buf;
+    return code;
+}
+
+extern "C" {
+
+int sc_version(void) { return 100; }
+
+const char* sc_last_error(sc_ctx* ctx) { return ctx ? ctx->err.c_str() : g_error.c_str(); }
+
+int sc_create(int device, sc_ctx** out) {
+    if (!out) return SC_ERR_ARG;
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        return sc_fail(nullptr, SC_ERR_CUDA, "no usable CUDA device (%s); this library has no CPU fallback",
+                       e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+    if (device < 0 || device >= count) return sc_fail(nullptr, SC_ERR_ARG, "device %d out of range (%d devices)", device, count);
+    sc_ctx* ctx = new sc_ctx();
+    ctx->device = device;
+    if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) != cudaSuccess) {
+        sc_fail(nullptr, SC_ERR_CUDA, "cannot initialise device %d: %s", device, cudaGetErrorString(cudaGetLastError()));
+        delete ctx;
+        return SC_ERR_CUDA;
+    }
+    cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
+    *out = ctx;
+    return SC_OK;
+}
+
+void sc_destroy(sc_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    dist_destroy(ctx);
+    free_pattern(ctx);
+    free_vectors(ctx);
+    sc_free(&ctx->d_xyz); sc_free(&ctx->d_conn); sc_free(&ctx->d_eq); sc_free(&ctx->d_active);
+    sc_free(&ctx->d_E); sc_free(&ctx->d_nu); sc_free(&ctx->d_rho);
+    sc_free(&ctx->d_load_dof); sc_free(&ctx->d_load_val); sc_free(&ctx->d_scal);
+    sc_free(&ctx->d_send_idx); sc_free(&ctx->d_recv_idx); sc_free(&ctx->d_send_buf); sc_free(&ctx->d_recv_buf);
+    if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+    delete ctx;
+}
+
+int sc_device_info(sc_ctx* ctx, int* sm_count, int64_t* total_mem, int64_t* free_mem, char* name, int name_len) {
+    if (!ctx) return SC_ERR_ARG;
+    SC_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaDeviceProp prop;
+    SC_CUDA(ctx, cudaGetDeviceProperties(&prop, ctx->device));
+    size_t f = 0, t = 0;
+    SC_CUDA(ctx, cudaMemGetInfo(&f, &t));
+    if (sm_count) *sm_count = prop.multiProcessorCount;
+    if (total_mem) *total_mem = (int64_t)t;
+    if (free_mem) *free_mem = (int64_t)f;
+    if (name && name_len > 0) { std::strncpy(name, prop.name, name_len - 1); name[name_len - 1] = 0; }
+    return SC_OK;
+}
+
+int64_t sc_kernel_launches(sc_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int sc_shape_table(int elem_type, int order, int* nne, int* dim, int* ngp, double* N, double* dN, double* w) {
+    ShapeTable t;
+    std::string err;
+    if (!sc_make_shape_table(elem_type, order, t, err)) return sc_fail(nullptr, SC_ERR_ARG, "%s", err.c_str());
+    if (nne) *nne = t.nne;
+    if (dim) *dim = t.dim;
+    if (ngp) *ngp = t.ngp;
+    if (N) std::memcpy(N, t.N.data(), t.N.size() * sizeof(double));
+    if (dN) std::memcpy(dN, t.dN.data(), t.dN.size() * sizeof(double));
+    if (w) std::memcpy(w, t.w.data(), t.w.size() * sizeof(double));
+    return SC_OK;
+}
+
+int sc_set_mesh(sc_ctx* ctx, int elem_type, int64_t n_nodes, const double* xyz, int64_t n_elem, const int32_t* conn,
+                const int64_t* eq, int64_t n_eq, const uint8_t* active) {
+    if (!ctx) return SC_ERR_ARG;
+    const int nne = sc_elem_nne(elem_type), dim = sc_elem_dim(elem_type);
+    if (nne == 0) return sc_fail(ctx, SC_ERR_ARG, "ERROR: Element type not supported");
+    if (n_nodes <= 0 || n_elem <= 0 || !xyz || !conn || !eq) return sc_fail(ctx, SC_ERR_ARG, "empty mesh");
+    if (n_nodes >= (int64_t)1 << 31 || n_eq >= (int64_t)1 << 31) return sc_fail(ctx, SC_ERR_UNSUPPORTED, "more than 2^31 nodes/equations per rank");
+    SC_CUDA(ctx, cudaSetDevice(ctx->device));
+    // equation numbers must increase with (node, dof): the pattern builder relies on it for sorted columns
+    std::vector<int32_t> eq32((size_t)n_nodes * dim);
+    int64_t next = 0;
+    for (int64_t i = 0; i < n_nodes * dim; ++i) {
+        const int64_t v = eq[i];
+        if (v < 0) { eq32[i] = -1; continue; }
+        if (v != next) return sc_fail(ctx, SC_ERR_ARG, "equation numbers must be consecutive in (node, dof) order (entry %lld is %lld, expected %lld)",
+                                      (long long)i, (long long)v, (long long)next);
+        eq32[i] = (int32_t)v;
+        ++next;
+    }
+    if (next != n_eq) return sc_fail(ctx, SC_ERR_ARG, "eq table holds %lld equations, n_eq = %lld", (long long)next, (long long)n_eq);
+    for (int64_t i = 0; i < n_elem * nne; ++i)
+        if (conn[i] < 0 || conn[i] >= n_nodes) return sc_fail(ctx, SC_ERR_ARG, "connectivity entry %lld out of range", (long long)i);
+    free_pattern(ctx);
+    free_vectors(ctx);
+    ctx->elem_type = elem_type; ctx->nne = nne; ctx->dim = dim;
+    ctx->n_nodes = n_nodes; ctx->n_elem = n_elem; ctx->n_eq = n_eq;
+    SC_TRY(upload(ctx, &ctx->d_xyz, xyz, (size_t)n_nodes * 3));
+    SC_TRY(upload(ctx, &ctx->d_conn, conn, (size_t)n_elem * nne));
+    SC_TRY(upload(ctx, &ctx->d_eq, eq32.data(), eq32.size()));
+    if (active) SC_TRY(upload(ctx, &ctx->d_active, active, (size_t)n_nodes));
+    else sc_free(&ctx->d_active);
+    ctx->have_mesh = true;
+    ctx->have_mat = false;
+    return SC_OK;
+}
+
+int sc_set_materials(sc_ctx* ctx, const double* young, const double* poisson, const double* density) {
+    if (!ctx || !ctx->have_mesh) return sc_fail(ctx, SC_ERR_STATE, "sc_set_mesh must be called first");
+    if (!young || !poisson || !density) return sc_fail(ctx, SC_ERR_ARG, "null material array");
+    SC_CUDA(ctx, cudaSetDevice(ctx->device));
+    SC_TRY(upload(ctx, &ctx->d_E, young, (size_t)ctx->n_elem));
+    SC_TRY(upload(ctx, &ctx->d_nu, poisson, (size_t)ctx->n_elem));
+    SC_TRY(upload(ctx, &ctx->d_rho, density, (size_t)ctx->n_elem));
+    ctx->have_mat = true;
+    return SC_OK;
+}
+
+int sc_build_pattern(sc_ctx* ctx, int64_t* nnz_out) {
+    if (!ctx || !ctx->have_mesh) return sc_fail(ctx, SC_ERR_STATE, "sc_set_mesh must be called first");
+    SC_CUDA(ctx, cudaSetDevice(ctx->device));
+    free_pattern(ctx);
+    SC_TRY(sc_pattern_build(ctx));
+    if (nnz_out) *nnz_out = ctx->nnz;
+    return SC_OK;
+}
+
+int sc_get_pattern(sc_ctx* ctx, int64_t* rowptr, int32_t* col) {
+    if (!ctx || !ctx->have_pattern) return sc_fail(ctx, SC_ERR_STATE, "sc_build_pattern must be called first");
+    SC_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (rowptr) SC_CUDA(ctx, cudaMemcpy(rowptr, ctx->d_rowptr, sizeof(int64_t) * (ctx->n_eq + 1), cudaMemcpyDeviceToHost));
+    if (col) SC_CUDA(ctx, cudaMemcpy(col, ctx->d_col, sizeof(int32_t) * ctx->nnz, cudaMemcpyDeviceToHost));
+    return SC_OK;
+}
+
+int sc_assemble(sc_ctx* ctx, int gauss_order, int flags, double* seconds_device) {
+    if (!ctx || !ctx->have_pattern) return sc_fail(ctx, SC_ERR_STATE, "sc_build_pattern must be called first");
+    if (!ctx->have_mat) return sc_fail(ctx, SC_ERR_STATE, "sc_set_materials must be called first");
+    if (!(flags & (SC_ASM_K | SC_ASM_M_FULL | SC_ASM_M_LUMPED))) return sc_fail(ctx, SC_ERR_ARG, "nothing to assemble");
+    SC_CUDA(ctx, cudaSetDevice(ctx->device));
+    ctx->cd_resume_valid = false;
+    return sc_assemble_run(ctx, gauss_order, flags, seconds_device);
+}
+
+int sc_add_entries(sc_ctx* ctx, int which, int64_t n, const int64_t* rows, const int64_t* cols, const double* vals) {
+    if (!ctx || !ctx->have_pattern) return sc_fail(ctx, SC_ERR_STATE, "sc_build_pattern must be called first");
+    if (which != SC_MAT_K && which != SC_MAT_C) return sc_fail(ctx, SC_ERR_ARG, "entries can be added to K or C only");
+    if (n == 0) return SC_OK;
+    SC_CUDA(ctx, cudaSetDevice(ctx->device));
+    // sort by (row, col); duplicates are a contract violation (the caller pre-sums them in a fixed order)
+    std::vector<int64_t> order((size_t)n);
+    std::iota(order.begin(), order.end(), (int64_t)0);
+    std::sort(order.begin(), order.end(), [&](int64_t a, int64_t b) { return rows[a] != rows[b] ? rows[a] < rows[b] : cols[a] < cols[b]; });
+    std::vector<int64_t> r((size_t)n);
+    std::vector<int32_t> c((size_t)n);
+    std::vector<double> v((size_t)n);
+    for (int64_t i = 0; i < n; ++i) {
+        const int64_t o = order[i];
+        if (rows[o] < 0 || rows[o] >= ctx->n_eq || cols[o] < 0 || cols[o] >= ctx->n_eq) return sc_fail(ctx, SC_ERR_ARG, "entry %lld out of range", (long long)o);
+        r[i] = rows[o]; c[i] = (int32_t)cols[o]; v[i] = vals[o];
+        if (i > 0 && r[i] == r[i - 1] && c[i] == c[i - 1]) return sc_fail(ctx, SC_ERR_ARG, "duplicate entry (%lld, %lld)", (long long)r[i], (long long)c[i]);
+    }
+    int64_t *d_r = nullptr, *d_slot = nullptr;
+    int32_t* d_c = nullptr;
+    double* d_v = nullptr;
+    int* d_flag = nullptr;
+    SC_TRY(upload(ctx, &d_r, r.data(), (size_t)n));
+    SC_TRY(upload(ctx, &d_c, c.data(), (size_t)n));
+    SC_TRY(upload(ctx, &d_v, v.data(), (size_t)n));
+    SC_TRY(sc_alloc(ctx, &d_slot, (size_t)n));
+    SC_TRY(sc_alloc(ctx, &d_flag, 1));
+    SC_CUDA(ctx, cudaMemsetAsync(d_flag, 0, sizeof(int), ctx->stream));
+    k_find_slots<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(ctx->d_rowptr, ctx->d_col, d_r, d_c, n, d_slot, d_flag);
+    SC_CHECK_LAUNCH(ctx);
+    int flag = 0;
+    SC_CUDA(ctx, cudaMemcpyAsync(&flag, d_flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    SC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    int rc = SC_OK;
+    if (flag) rc = sc_fail(ctx, SC_ERR_ARG, "an added entry lies outside the structural pattern");
+    else if (which == SC_MAT_K) {
+        if (!ctx->have_K) rc = sc_fail(ctx, SC_ERR_STATE, "K is not assembled");
+        else {
+            k_add_at<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(ctx->d_K, d_slot, d_v, n);
+            ctx->launches++;
+            if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) rc = sc_fail(ctx, SC_ERR_CUDA, "add entries failed");
+        }
+    } else {
+        // C_abs replaces any previous list: row-compressed form
+        std::vector<int64_t> rowid, rptr;
+        for (int64_t i = 0; i < n; ++i) {
+            if (i == 0 || r[i] != r[i - 1]) { rowid.push_back(r[i]); rptr.push_back(i); }
+        }
+        rptr.push_back(n);
+        sc_free(&ctx->d_cabs_rowid); sc_free(&ctx->d_cabs_rptr); sc_free(&ctx->d_cabs_col); sc_free(&ctx->d_cabs_slot); sc_free(&ctx->d_cabs_val);
+        rc = upload(ctx, &ctx->d_cabs_rowid, rowid.data(), rowid.size());
+        if (rc == SC_OK) rc = upload(ctx, &ctx->d_cabs_rptr, rptr.data(), rptr.size());
+        if (rc == SC_OK) {
+            ctx->d_cabs_col = d_c; d_c = nullptr;
+            ctx->d_cabs_slot = d_slot; d_slot = nullptr;
+            ctx->d_cabs_val = d_v; d_v = nullptr;
+            ctx->cabs_n = n;
+            ctx->cabs_rows = (int64_t)rowid.size();
+        }
+    }
+    sc_free(&d_r); sc_free(&d_c); sc_free(&d_v); sc_free(&d_slot); sc_free(&d_flag);
+    ctx->cd_resume_valid = false;
+    return rc;
+}
+
+int sc_set_rayleigh(sc_ctx* ctx, double c0, double c1) {
+    if (!ctx) return SC_ERR_ARG;
+    ctx->c0 = c0; ctx->c1 = c1;
+    ctx->cd_resume_valid = false;
+    return SC_OK;
+}
+
+int sc_get_values(sc_ctx* ctx, int which, double* vals) {
+    if (!ctx || !vals) return sc_fail(ctx, SC_ERR_ARG, "null argument");
+    SC_CUDA(ctx, cudaSetDevice(ctx->device));
+    const double* src = nullptr;
+    double* tmp = nullptr;
+    switch (which) {
+        case SC_MAT_K: if (!ctx->have_K) return sc_fail(ctx, SC_ERR_STATE, "K is not assembled"); src = ctx->d_K; break;
+        case SC_MAT_M: if (!ctx->have_M) return sc_fail(ctx, SC_ERR_STATE, "full M is not assembled"); src = ctx->d_M; break;
+        case SC_MAT_C: SC_TRY(build_C(ctx, &tmp)); src = tmp; break;
+        case SC_MAT_KHAT: if (!ctx->d_Khat) return sc_fail(ctx, SC_ERR_STATE, "no effective matrix yet"); src = ctx->d_Khat; break;
+        default: return sc_fail(ctx, SC_ERR_ARG, "unknown matrix id %d", which);
+    }
+    cudaError_t e = cudaStreamSynchronize(ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpy(vals, src, sizeof(double) * ctx->nnz, cudaMemcpyDeviceToHost);
+    sc_free(&tmp);
+    if (e != cudaSuccess) return sc_fail(ctx, SC_ERR_CUDA, "copy of matrix values failed: %s", cudaGetErrorString(e));
+    return SC_OK;
+}
+
+int sc_get_lumped_mass(sc_ctx* ctx, double* diag) {
+    if (!ctx || !ctx->have_Ml) return sc_fail(ctx, SC_ERR_STATE, "lumped mass is not assembled");
+    SC_CUDA(ctx, cudaSetDevice(ctx->device));
+    SC_CUDA(ctx, cudaMemcpy(diag, ctx->d_Ml, sizeof(double) * ctx->n_eq, cudaMemcpyDeviceToHost));
+    return SC_OK;
+}
+
+int sc_spmv(sc_ctx* ctx, int which, const double* x, double* y) {
+    if (!ctx || !ctx->have_pattern) return sc_fail(ctx, SC_ERR_STATE, "no pattern");
+    SC_CUDA(ctx, cudaSetDevice(ctx->device));
+    double *dx = nullptr, *dy = nullptr, *tmp = nullptr;
+    const double* vals = nullptr;
+    switch (which) {
+        case SC_MAT_K: if (!ctx->have_K) return sc_fail(ctx, SC_ERR_STATE, "K is not assembled"); vals = ctx->d_K; break;
+        case SC_MAT_M: if (!ctx->have_M) return sc_fail(ctx, SC_ERR_STATE, "full M is not assembled"); vals = ctx->d_M; break;
+        case SC_MAT_C: SC_TRY(build_C(ctx, &tmp)); vals = tmp; break;
+        case SC_MAT_KHAT: if (!ctx->d_Khat) return sc_fail(ctx, SC_ERR_STATE, "no effective matrix yet"); vals = ctx->d_Khat; break;
+        default: return sc_fail(ctx, SC_ERR_ARG, "unknown matrix id %d", which);
+    }
+    int rc = sc_alloc(ctx, &dx, (size_t)ctx->n_eq);
+    if (rc == SC_OK) rc = sc_alloc(ctx, &dy, (size_t)ctx->n_eq);
+    if (rc == SC_OK && cudaMemcpy(dx, x, sizeof(double) * ctx->n_eq, cudaMemcpyHostToDevice) != cudaSuccess) rc = sc_fail(ctx, SC_ERR_CUDA, "H2D failed");
+    if (rc == SC_OK) rc = la_spmv(ctx, vals, dx, dy);
+    if (rc == SC_OK && cudaStreamSynchronize(ctx->stream) != cudaSuccess) rc = sc_fail(ctx, SC_ERR_CUDA, "spmv failed: %s", cudaGetErrorString(cudaGetLastError()));
+    if (rc == SC_OK && cudaMemcpy(y, dy, sizeof(double) * ctx->n_eq, cudaMemcpyDeviceToHost) != cudaSuccess) rc = sc_fail(ctx, SC_ERR_CUDA, "D2H failed");
+    sc_free(&dx); sc_free(&dy); sc_free(&tmp);
+    return rc;
+}
+
+int sc_set_load_schedule(sc_ctx* ctx, int64_t n_steps, const int64_t* step_ptr, const int64_t* dof, const double* val) {
+    if (!ctx || !ctx->have_mesh) return sc_fail(ctx, SC_ERR_STATE, "sc_set_mesh must be called first");
+    if (n_steps < 0 || (n_steps > 0 && !step_ptr)) return sc_fail(ctx, SC_ERR_ARG, "bad load schedule");
+    SC_CUDA(ctx, cudaSetDevice(ctx->device));
+    ctx->load_steps = n_steps;
+    ctx->h_load_ptr.assign(step_ptr, step_ptr + n_steps + 1);
+    const int64_t n = n_steps > 0 ? step_ptr[n_steps] : 0;
+    std::vector<int32_t> d32((size_t)n);
+    for (int64_t i = 0; i < n; ++i) {
+        if (dof[i] < 0 || dof[i] >= ctx->n_eq) return sc_fail(ctx, SC_ERR_ARG, "load dof %lld out of range", (long long)dof[i]);
+        d32[i] = (int32_t)dof[i];
+    }
+    SC_TRY(upload(ctx, &ctx->d_load_dof, d32.data(), (size_t)n));
+    SC_TRY(upload(ctx, &ctx->d_load_val, val, (size_t)n));
+    return SC_OK;
+}
+
+int sc_set_state(sc_ctx* ctx, const double* u, const double* v) {
+    if (!ctx || !ctx->have_mesh) return sc_fail(ctx, SC_ERR_STATE, "sc_set_mesh must be called first");
+    SC_CUDA(ctx, cudaSetDevice(ctx->device));
+    const size_t n = (size_t)ctx->n_eq;
+    for (int k = 0; k < 3; ++k) {
+        double** d = k == 0 ? &ctx->d_u : k == 1 ? &ctx->d_v : &ctx->d_a;
+        const double* h = k == 0 ? u : k == 1 ? v : nullptr;
+        if (!*d) SC_TRY(sc_alloc(ctx, d, n));
+        if (h) SC_CUDA(ctx, cudaMemcpy(*d, h, n * sizeof(double), cudaMemcpyHostToDevice));
+        else SC_CUDA(ctx, cudaMemset(*d, 0, n * sizeof(double)));
+    }
+    ctx->cd_resume_valid = false;
+    return SC_OK;
+}
+
+int sc_get_state(sc_ctx* ctx, double* u, double* v, double* a) {
+    if (!ctx || !ctx->d_u) return sc_fail(ctx, SC_ERR_STATE, "no state yet");
+    SC_CUDA(ctx, cudaSetDevice(ctx->device));
+    SC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    const size_t b = sizeof(double) * ctx->n_eq;
+    if (u) SC_CUDA(ctx, cudaMemcpy(u, ctx->d_u, b, cudaMemcpyDeviceToHost));
+    if (v) SC_CUDA(ctx, cudaMemcpy(v, ctx->d_v, b, cudaMemcpyDeviceToHost));
+    if (a) SC_CUDA(ctx, cudaMemcpy(a, ctx->d_a, b, cudaMemcpyDeviceToHost));
+    return SC_OK;
+}
+
+int sc_run_newmark(sc_ctx* ctx, double dt, int64_t t_start, int64_t n_steps, int64_t out_interval, double beta, double gamma,
+                   double pcg_rtol, int pcg_maxit, int64_t n_out, double* u_out, double* v_out, double* a_out, sc_stats* stats) {
+    if (!ctx || !ctx->have_K || !ctx->have_M) return sc_fail(ctx, SC_ERR_STATE, "Newmark needs assembled K and full M");
+    if (dt <= 0 || n_steps < 0 || out_interval < 1 || beta <= 0) return sc_fail(ctx, SC_ERR_ARG, "bad time-integration arguments");
+    SC_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (stats) std::memset(stats, 0, sizeof(*stats));
+    ctx->cd_resume_valid = false;
+    return tl_newmark(ctx, dt, t_start, n_steps, out_interval, beta, gamma, pcg_rtol, pcg_maxit, n_out, u_out, v_out, a_out, stats);
+}
+
+int sc_run_central_difference(sc_ctx* ctx, double dt, int64_t t_start, int64_t n_steps, int64_t out_interval, int64_t n_out,
+                              double* u_out, double* v_out, double* a_out, sc_stats* stats) {
+    if (!ctx || !ctx->have_K || !ctx->have_Ml) return sc_fail(ctx, SC_ERR_STATE, "central difference needs assembled K and lumped M");
+    if (dt <= 0 || n_steps < 0 || out_interval < 1) return sc_fail(ctx, SC_ERR_ARG, "bad time-integration arguments");
+    SC_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (stats) std::memset(stats, 0, sizeof(*stats));
+    return tl_central_difference(ctx, dt, t_start, n_steps, out_interval, n_out, u_out, v_out, a_out, stats);
+}
+
+int sc_nccl_unique_id(void* out128) { return out128 ? dist_unique_id(out128) : SC_ERR_ARG; }
+
+int sc_dist_init(sc_ctx* ctx, int rank, int world, const void* id) {
+    if (!ctx || (world > 1 && !id) || rank < 0 || rank >= world) return sc_fail(ctx, SC_ERR_ARG, "bad rank/world");
+    return dist_init(ctx, rank, world, id);
+}
+
+int sc_set_halo(sc_ctx* ctx, int n_neighbors, const int32_t* neighbor_rank, const int64_t* send_ptr, const int64_t* send_idx,
+                const int64_t* recv_ptr, const int64_t* recv_idx) {
+    if (!ctx || !ctx->have_mesh) return sc_fail(ctx, SC_ERR_STATE, "sc_set_mesh must be called first");
+    SC_CUDA(ctx, cudaSetDevice(ctx->device));
+    ctx->n_nbr_ranks = n_neighbors;
+    ctx->nbr_rank.assign(neighbor_rank, neighbor_rank + n_neighbors);
+    ctx->send_ptr.assign(send_ptr, send_ptr + n_neighbors + 1);
+    ctx->recv_ptr.assign(recv_ptr, recv_ptr + n_neighbors + 1);
+    const int64_t ns = ctx->send_ptr.back(), nr = ctx->recv_ptr.back();
+    for (int64_t i = 0; i < ns; ++i) if (send_idx[i] < 0 || send_idx[i] >= ctx->n_eq) return sc_fail(ctx, SC_ERR_ARG, "send index out of range");
+    for (int64_t i = 0; i < nr; ++i) if (recv_idx[i] < 0 || recv_idx[i] >= ctx->n_eq) return sc_fail(ctx, SC_ERR_ARG, "recv index out of range");
+    SC_TRY(upload(ctx, &ctx->d_send_idx, send_idx, (size_t)ns));
+    SC_TRY(upload(ctx, &ctx->d_recv_idx, recv_idx, (size_t)nr));
+    SC_TRY(sc_alloc(ctx, &ctx->d_send_buf, (size_t)ns));
+    SC_TRY(sc_alloc(ctx, &ctx->d_recv_buf, (size_t)nr));
+    return SC_OK;
+}
+
+int sc_halo_exchange(sc_ctx* ctx, double* x_host) {
+    if (!ctx || !ctx->have_mesh || !x_host) return sc_fail(ctx, SC_ERR_ARG, "bad argument");
+    SC_CUDA(ctx, cudaSetDevice(ctx->device));
+    double* d = nullptr;
+    SC_TRY(sc_alloc(ctx, &d, (size_t)ctx->n_eq));
+    int rc = SC_OK;
+    if (cudaMemcpy(d, x_host, sizeof(double) * ctx->n_eq, cudaMemcpyHostToDevice) != cudaSuccess) rc = sc_fail(ctx, SC_ERR_CUDA, "H2D failed");
+    if (rc == SC_OK) rc = dist_halo(ctx, d, ctx->stream);
+    if (rc == SC_OK && cudaStreamSynchronize(ctx->stream) != cudaSuccess) rc = sc_fail(ctx, SC_ERR_CUDA, "halo exchange failed");
+    if (rc == SC_OK && cudaMemcpy(x_host, d, sizeof(double) * ctx->n_eq, cudaMemcpyDeviceToHost) != cudaSuccess) rc = sc_fail(ctx, SC_ERR_CUDA, "D2H failed");
+    sc_free(&d);
+    return rc;
+}
+
+}  // extern "C"

@@ -1,0 +1,307 @@
+// Element integration + deterministic assembly in one kernel (no element-matrix scratch, no float atomics).
+//
+// Replaces GenerateMatrix.generate_stiffness_and_mass (scatter/system_matrix.py:35-121):
+//   per element   VolumeElement/SurfaceElement.generate + compute_stiffness + compute_mass
+//                 (scatter/discretisation.py:83-222, :290-417), D from material_models.py:5-43
+//   scatter       k_dict[i,k] += Ke[j,l]; mass_dict[i,k] += Me[j,l] in element order (system_matrix.py:98-103)
+//
+// Formulation ("row gather"): one warp owns one node = DIM consecutive matrix rows.  It walks the elements touching
+// the node in ascending element id -- the same order in which the reference adds them to a slot -- and for each
+// element evaluates only the DIM x (NNE*DIM) row block of Ke that belongs to its node, accumulating into a shared
+// memory image of its CSR rows.  Nobody else writes those rows, so the sum order is fixed and the result is
+// reproducible bit for bit; the block then streams its contiguous CSR segment to HBM with coalesced stores.
+//
+// Isotropic elasticity lets the row block be formed without B or D:
+//   K[(a,i),(b,j)] = sum_g w_g detJ_g ( lam dNa_i dNb_j + mu dNa_j dNb_i + delta_ij mu dNa.dNb )
+//   M[(a,i),(b,j)] = delta_ij rho sum_g w_g detJ_g Na Nb          (consistent mass; zeros kept in the pattern)
+// which equals B^T D B with the reference's Voigt ordering; detJ is used signed (discretisation.py:126).
+#include <algorithm>
+#include "common.h"
+
+namespace {
+
+struct AsmParams {
+    const double* xyz; const int32_t* conn; const int32_t* eq;
+    const double *E, *nu, *rho;
+    const int64_t* n2e_ptr; const int32_t* n2e;
+    const int64_t* nbr_ptr; const int32_t* nbr; const uint16_t* nbr_off;
+    const int32_t* node_rl; const int64_t* node_row0; const int64_t* rowptr;
+    const double *tabN, *tabdN, *tabw;
+    double *K, *M, *Ml;
+    int64_t n_nodes;
+    int max_rl, max_nbr;
+};
+
+template <int DIM>
+__device__ __forceinline__ void invert(const double* J, double* inv, double& det);
+
+template <>
+__device__ __forceinline__ void invert<2>(const double* J, double* inv, double& det) {
+    det = J[0] * J[3] - J[1] * J[2];
+    double r = 1.0 / det;
+    inv[0] = J[3] * r; inv[1] = -J[1] * r; inv[2] = -J[2] * r; inv[3] = J[0] * r;
+}
+template <>
+__device__ __forceinline__ void invert<3>(const double* J, double* inv, double& det) {
+    double a = J[0], b = J[1], c = J[2], d = J[3], e = J[4], f = J[5], g = J[6], h = J[7], i = J[8];
+    double c0 = e * i - f * h, c1 = f * g - d * i, c2 = d * h - e * g;
+    det = a * c0 + b * c1 + c * c2;
+    double r = 1.0 / det;
+    inv[0] = c0 * r; inv[1] = (c * h - b * i) * r; inv[2] = (b * f - c * e) * r;
+    inv[3] = c1 * r; inv[4] = (a * i - c * g) * r; inv[5] = (c * d - a * f) * r;
+    inv[6] = c2 * r; inv[7] = (b * g - a * h) * r; inv[8] = (a * e - b * d) * r;
+}
+
+template <int NNE, int DIM, int NGP>
+__global__ void k_assemble(AsmParams p, int warps) {
+    constexpr int DD = DIM * DIM;
+    constexpr int JS = DD + 1;                 // inverse Jacobian + detJ*w per Gauss point
+    extern __shared__ double smem[];
+    double* sN = smem;                          // [NGP*NNE]
+    double* sdN = sN + NGP * NNE;               // [NGP*NNE*DIM]
+    double* sw = sdN + NGP * NNE * DIM;         // [NGP]
+    const int per_warp = NNE * DIM + NGP * JS + NGP * NNE * DIM + p.max_nbr + (NNE + 1) / 2;
+    double* wbase = sw + NGP;
+    double* Kst = wbase + (size_t)warps * per_warp;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    double* xs = wbase + (size_t)warp * per_warp;       // [NNE*DIM]
+    double* sJ = xs + NNE * DIM;                         // [NGP*JS]
+    double* dNg = sJ + NGP * JS;                         // [NGP*NNE*DIM]
+    double* mnode = dNg + NGP * NNE * DIM;               // [max_nbr]
+    int* cb = reinterpret_cast<int*>(mnode + p.max_nbr); // [NNE]
+
+    for (int t = threadIdx.x; t < NGP * NNE; t += blockDim.x) sN[t] = p.tabN[t];
+    for (int t = threadIdx.x; t < NGP * NNE * DIM; t += blockDim.x) sdN[t] = p.tabdN[t];
+    for (int t = threadIdx.x; t < NGP; t += blockDim.x) sw[t] = p.tabw[t];
+
+    const int64_t a0 = (int64_t)blockIdx.x * warps;
+    const int64_t a1 = min(a0 + warps, p.n_nodes);
+    const int64_t R0 = p.node_row0[a0], R1 = p.node_row0[a1];
+    const int64_t base = p.rowptr[R0];
+    const int span = (int)(p.rowptr[R1] - base);
+    for (int t = threadIdx.x; t < span; t += blockDim.x) Kst[t] = 0.0;
+    __syncthreads();
+
+    const int64_t a = a0 + warp;
+    const bool live = (a < p.n_nodes) && (p.node_rl[a] > 0);
+    int64_t nb0 = 0;
+    int nn_a = 0;
+    int rowoff[DIM];
+    if (live) {
+        nb0 = p.nbr_ptr[a];
+        nn_a = (int)(p.nbr_ptr[a + 1] - nb0);
+#pragma unroll
+        for (int i = 0; i < DIM; ++i) {
+            int r = p.eq[a * DIM + i];
+            rowoff[i] = r >= 0 ? (int)(p.rowptr[r] - base) : -1;
+        }
+        for (int t = lane; t < nn_a; t += 32) mnode[t] = 0.0;
+        __syncwarp();
+
+        for (int64_t k = p.n2e_ptr[a]; k < p.n2e_ptr[a + 1]; ++k) {
+            const int e = p.n2e[k];
+            if (lane < NNE) {
+                int c = p.conn[(int64_t)e * NNE + lane];
+                cb[lane] = c;
+#pragma unroll
+                for (int d = 0; d < DIM; ++d) xs[lane * DIM + d] = p.xyz[(int64_t)c * 3 + d];
+            }
+            __syncwarp();
+            int al = 0;
+#pragma unroll
+            for (int b = 0; b < NNE; ++b) if (cb[b] == (int)a) al = b;
+            const double E = p.E[e], nu = p.nu[e], rho = p.rho[e];
+            const double lam = E * nu / ((1.0 + nu) * (1.0 - 2.0 * nu));
+            const double mu = E / (2.0 * (1.0 + nu));
+
+            // Jacobian J[g][d][k] = sum_b dN[g][b][d] x[b][k]   (discretisation.py:113-116)
+            for (int it = lane; it < NGP * DD; it += 32) {
+                const int g = it / DD, r = it % DD, d = r / DIM, kk = r % DIM;
+                double s = 0.0;
+#pragma unroll
+                for (int b = 0; b < NNE; ++b) s += sdN[(g * NNE + b) * DIM + d] * xs[b * DIM + kk];
+                sJ[g * JS + r] = s;
+            }
+            __syncwarp();
+            for (int g = lane; g < NGP; g += 32) {
+                double J[DD], inv[DD], det;
+#pragma unroll
+                for (int r = 0; r < DD; ++r) J[r] = sJ[g * JS + r];
+                invert<DIM>(J, inv, det);
+#pragma unroll
+                for (int r = 0; r < DD; ++r) sJ[g * JS + r] = inv[r];
+                sJ[g * JS + DD] = det * sw[g];
+            }
+            __syncwarp();
+            // global derivatives dNg[g][b][k] = sum_d dN[g][b][d] Jinv[k][d]    (dN . inv(J^T), discretisation.py:128)
+            for (int it = lane; it < NGP * NNE * DIM; it += 32) {
+                const int g = it / (NNE * DIM), kk = it % DIM;
+                const int gb = it / DIM;   // g*NNE + b
+                double s = 0.0;
+#pragma unroll
+                for (int d = 0; d < DIM; ++d) s += sdN[gb * DIM + d] * sJ[g * JS + kk * DIM + d];
+                dNg[it] = s;
+            }
+            __syncwarp();
+            // row block of node `al`: item = (b, i) -> DIM entries (j)
+            for (int it = lane; it < NNE * DIM; it += 32) {
+                const int b = it / DIM, i = it % DIM;
+                double acc[DIM];
+#pragma unroll
+                for (int j = 0; j < DIM; ++j) acc[j] = 0.0;
+                double macc = 0.0;
+#pragma unroll 4
+                for (int g = 0; g < NGP; ++g) {
+                    const double wj = sJ[g * JS + DD];
+                    const double* ga = dNg + (g * NNE + al) * DIM;
+                    const double* gbv = dNg + (g * NNE + b) * DIM;
+                    double s = 0.0;
+#pragma unroll
+                    for (int d = 0; d < DIM; ++d) s += ga[d] * gbv[d];
+                    const double lga = lam * ga[i], mgb = mu * gbv[i];
+#pragma unroll
+                    for (int j = 0; j < DIM; ++j) {
+                        double t = lga * gbv[j] + mgb * ga[j];
+                        if (j == i) t += mu * s;
+                        acc[j] += wj * t;
+                    }
+                    if (i == 0) macc += wj * sN[g * NNE + al] * sN[g * NNE + b];
+                }
+                // slot lookup: position of node cb[b] in the (ascending) neighbour list of a
+                const int nodeb = cb[b];
+                int lo = 0, hi = nn_a;
+                while (lo < hi) {
+                    int mid = (lo + hi) >> 1;
+                    if (p.nbr[nb0 + mid] < nodeb) lo = mid + 1; else hi = mid;
+                }
+                if (rowoff[i] >= 0) {
+                    int o = rowoff[i] + p.nbr_off[nb0 + lo];
+#pragma unroll
+                    for (int j = 0; j < DIM; ++j)
+                        if (p.eq[(int64_t)nodeb * DIM + j] >= 0) Kst[o++] += acc[j];
+                }
+                if (i == 0) mnode[lo] += rho * macc;
+            }
+            __syncwarp();
+        }
+    }
+    __syncthreads();
+    if (p.K)
+        for (int t = threadIdx.x; t < span; t += blockDim.x) p.K[base + t] = Kst[t];
+    if (live) {
+        if (p.M) {
+            for (int q = lane; q < nn_a; q += 32) {
+                const int nodeb = p.nbr[nb0 + q];
+                const double m = mnode[q];
+                const int off = p.nbr_off[nb0 + q];
+#pragma unroll
+                for (int i = 0; i < DIM; ++i) {
+                    if (rowoff[i] < 0) continue;
+                    int64_t o = base + rowoff[i] + off;
+#pragma unroll
+                    for (int j = 0; j < DIM; ++j)
+                        if (p.eq[(int64_t)nodeb * DIM + j] >= 0) p.M[o++] = (i == j) ? m : 0.0;
+                }
+            }
+        }
+        if (p.Ml) {
+            // row sum of the consistent mass: columns (b,i) that exist, neighbour order, fixed-shape reduction
+#pragma unroll
+            for (int i = 0; i < DIM; ++i) {
+                if (rowoff[i] < 0) continue;
+                double s = 0.0;
+                for (int q = lane; q < nn_a; q += 32)
+                    if (p.eq[(int64_t)p.nbr[nb0 + q] * DIM + i] >= 0) s += mnode[q];
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+                if (lane == 0) p.Ml[p.eq[a * DIM + i]] = s;
+            }
+        }
+    }
+}
+
+template <int NNE, int DIM, int NGP>
+int launch(sc_ctx* ctx, const AsmParams& p) {
+    constexpr int JS = DIM * DIM + 1;
+    const size_t tables = (size_t)NGP * NNE + (size_t)NGP * NNE * DIM + NGP;
+    const size_t per_warp = (size_t)NNE * DIM + (size_t)NGP * JS + (size_t)NGP * NNE * DIM + p.max_nbr + (NNE + 1) / 2;
+    int warps = 8;
+    size_t bytes = 0;
+    for (; warps >= 1; warps >>= 1) {
+        bytes = (tables + warps * per_warp + (size_t)warps * DIM * p.max_rl) * sizeof(double);
+        if (bytes <= 200 * 1024) break;
+    }
+    if (warps < 1) return sc_fail(ctx, SC_ERR_UNSUPPORTED, "assembly staging does not fit in shared memory (max row length %d)", p.max_rl);
+    auto kern = k_assemble<NNE, DIM, NGP>;
+    SC_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    const unsigned grid = (unsigned)((p.n_nodes + warps - 1) / warps);
+    kern<<<grid, warps * 32, bytes, ctx->stream>>>(p, warps);
+    SC_CHECK_LAUNCH(ctx);
+    return SC_OK;
+}
+
+}  // namespace
+
+int sc_assemble_run(sc_ctx* ctx, int order, int flags, double* seconds) {
+    ShapeTable t;
+    std::string err;
+    if (!sc_make_shape_table(ctx->elem_type, order, t, err)) return sc_fail(ctx, SC_ERR_ARG, "%s", err.c_str());
+    double *dN = nullptr, *ddN = nullptr, *dw = nullptr;
+    SC_TRY(sc_alloc(ctx, &dN, t.N.size()));
+    SC_TRY(sc_alloc(ctx, &ddN, t.dN.size()));
+    SC_TRY(sc_alloc(ctx, &dw, t.w.size()));
+    SC_CUDA(ctx, cudaMemcpy(dN, t.N.data(), t.N.size() * sizeof(double), cudaMemcpyHostToDevice));
+    SC_CUDA(ctx, cudaMemcpy(ddN, t.dN.data(), t.dN.size() * sizeof(double), cudaMemcpyHostToDevice));
+    SC_CUDA(ctx, cudaMemcpy(dw, t.w.data(), t.w.size() * sizeof(double), cudaMemcpyHostToDevice));
+
+    if (flags & SC_ASM_K) SC_TRY(sc_alloc(ctx, &ctx->d_K, (size_t)ctx->nnz));
+    if (flags & SC_ASM_M_FULL) SC_TRY(sc_alloc(ctx, &ctx->d_M, (size_t)ctx->nnz));
+    if (flags & SC_ASM_M_LUMPED) {
+        SC_TRY(sc_alloc(ctx, &ctx->d_Ml, (size_t)ctx->n_eq));
+        SC_CUDA(ctx, cudaMemsetAsync(ctx->d_Ml, 0, sizeof(double) * ctx->n_eq, ctx->stream));
+    }
+    AsmParams p;
+    p.xyz = ctx->d_xyz; p.conn = ctx->d_conn; p.eq = ctx->d_eq;
+    p.E = ctx->d_E; p.nu = ctx->d_nu; p.rho = ctx->d_rho;
+    p.n2e_ptr = ctx->d_n2e_ptr; p.n2e = ctx->d_n2e;
+    p.nbr_ptr = ctx->d_nbr_ptr; p.nbr = ctx->d_nbr; p.nbr_off = ctx->d_nbr_off;
+    p.node_rl = ctx->d_node_rl; p.node_row0 = ctx->d_node_row0; p.rowptr = ctx->d_rowptr;
+    p.tabN = dN; p.tabdN = ddN; p.tabw = dw;
+    p.K = (flags & SC_ASM_K) ? ctx->d_K : nullptr;
+    p.M = (flags & SC_ASM_M_FULL) ? ctx->d_M : nullptr;
+    p.Ml = (flags & SC_ASM_M_LUMPED) ? ctx->d_Ml : nullptr;
+    p.n_nodes = ctx->n_nodes; p.max_rl = ctx->max_rl; p.max_nbr = ctx->max_nbr;
+
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    cudaEventRecord(e0, ctx->stream);
+    int rc = SC_ERR_UNSUPPORTED;
+    const int key = t.nne * 10000 + t.dim * 1000 + t.ngp;
+    switch (key) {
+#define SC_CASE(NNE, DIM, NGP) case NNE * 10000 + DIM * 1000 + NGP: rc = launch<NNE, DIM, NGP>(ctx, p); break;
+        SC_CASE(3, 2, 1) SC_CASE(3, 2, 3) SC_CASE(3, 2, 4)
+        SC_CASE(6, 2, 1) SC_CASE(6, 2, 3) SC_CASE(6, 2, 4)
+        SC_CASE(4, 2, 1) SC_CASE(4, 2, 4) SC_CASE(4, 2, 9)
+        SC_CASE(8, 2, 1) SC_CASE(8, 2, 4) SC_CASE(8, 2, 9)
+        SC_CASE(4, 3, 1) SC_CASE(4, 3, 4)
+        SC_CASE(10, 3, 1) SC_CASE(10, 3, 4)
+        SC_CASE(8, 3, 1) SC_CASE(8, 3, 8) SC_CASE(8, 3, 27)
+        SC_CASE(20, 3, 1) SC_CASE(20, 3, 8) SC_CASE(20, 3, 27)
+#undef SC_CASE
+        default: rc = sc_fail(ctx, SC_ERR_UNSUPPORTED, "no assembly kernel for nne=%d dim=%d ngp=%d", t.nne, t.dim, t.ngp);
+    }
+    cudaEventRecord(e1, ctx->stream);
+    cudaError_t se = cudaStreamSynchronize(ctx->stream);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    sc_free(&dN); sc_free(&ddN); sc_free(&dw);
+    if (rc != SC_OK) return rc;
+    if (se != cudaSuccess) return sc_fail(ctx, SC_ERR_CUDA, "assembly kernel failed: %s", cudaGetErrorString(se));
+    if (seconds) *seconds = ms * 1e-3;
+    if (flags & SC_ASM_K) ctx->have_K = true;
+    if (flags & SC_ASM_M_FULL) ctx->have_M = true;
+    if (flags & SC_ASM_M_LUMPED) ctx->have_Ml = true;
+    return SC_OK;
+}

@@ -1,0 +1,179 @@
+// Internal declarations shared by the translation units of libscatter_b200.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <string>
+#include <vector>
+#include "../../include/scatter_b200.h"
+
+#define SC_MAX_NNE 20
+#define SC_MAX_GP 27
+
+// element-independent integration tables, evaluated on the host once per (element type, order)
+struct ShapeTable {
+    int nne = 0, dim = 0, ngp = 0;
+    std::vector<double> N;    // [ngp][nne]
+    std::vector<double> dN;   // [ngp][nne][dim]
+    std::vector<double> w;    // [ngp]
+};
+// shape_tables.cpp
+int sc_elem_nne(int elem_type);
+int sc_elem_dim(int elem_type);
+bool sc_make_shape_table(int elem_type, int order, ShapeTable& out, std::string& err);
+
+template <typename T>
+struct DevBuf {
+    T* p = nullptr;
+    size_t n = 0;
+};
+
+struct NcclApi;   // dist.cu
+
+struct sc_ctx {
+    int device = 0;
+    int sm_count = 0;
+    cudaStream_t stream = nullptr;
+    cudaStream_t copy_stream = nullptr;
+    std::string err;
+    int64_t launches = 0;
+
+    // mesh
+    int elem_type = -1, nne = 0, dim = 0;
+    int64_t n_nodes = 0, n_elem = 0, n_eq = 0;
+    double* d_xyz = nullptr;        // [n_nodes*3]
+    int32_t* d_conn = nullptr;      // [n_elem*nne]
+    int32_t* d_eq = nullptr;        // [n_nodes*dim], -1 fixed
+    uint8_t* d_active = nullptr;    // [n_nodes] or null
+    double *d_E = nullptr, *d_nu = nullptr, *d_rho = nullptr;   // [n_elem]
+    bool have_mesh = false, have_mat = false;
+
+    // node-level structure (pattern.cu)
+    int64_t* d_n2e_ptr = nullptr;   // [n_nodes+1]
+    int32_t* d_n2e = nullptr;       // element ids, ascending per node
+    int64_t* d_nbr_ptr = nullptr;   // [n_nodes+1]
+    int32_t* d_nbr = nullptr;       // neighbour node rows (incl. self), ascending
+    uint16_t* d_nbr_off = nullptr;  // dof offset of neighbour inside a row of the node
+    int32_t* d_node_rl = nullptr;   // [n_nodes] row length of the node's rows (0 if inactive)
+    int64_t* d_node_row0 = nullptr; // [n_nodes+1] number of free dofs before the node (= first row of the node)
+    int max_nbr = 0, max_rl = 0;
+
+    // dof-level CSR
+    int64_t nnz = 0;
+    int64_t* d_rowptr = nullptr;    // [n_eq+1]
+    int32_t* d_col = nullptr;       // [nnz]
+    bool have_pattern = false;
+
+    // values
+    double* d_K = nullptr;          // [nnz]
+    double* d_M = nullptr;          // [nnz] (optional)
+    double* d_Ml = nullptr;         // [n_eq] lumped mass (optional)
+    double* d_Khat = nullptr;       // [nnz] effective matrix (Newmark)
+    bool have_K = false, have_M = false, have_Ml = false;
+    double c0 = 0.0, c1 = 0.0;
+
+    // C_abs (absorbing dashpots) kept as a small row-compressed list
+    int64_t cabs_n = 0, cabs_rows = 0;
+    int64_t* d_cabs_rowid = nullptr;   // [cabs_rows] row index
+    int64_t* d_cabs_rptr = nullptr;    // [cabs_rows+1]
+    int32_t* d_cabs_col = nullptr;     // [cabs_n]
+    int64_t* d_cabs_slot = nullptr;    // [cabs_n] position in the main CSR
+    double* d_cabs_val = nullptr;      // [cabs_n]
+
+    // loads
+    int64_t load_steps = 0;
+    std::vector<int64_t> h_load_ptr;
+    int32_t* d_load_dof = nullptr;
+    double* d_load_val = nullptr;
+
+    // state
+    double *d_u = nullptr, *d_v = nullptr, *d_a = nullptr;   // [n_eq]
+    std::vector<double*> work;      // work vectors [n_eq], allocated on demand
+    double* d_scal = nullptr;       // small device scalar block
+    double* d_partial = nullptr;    // reduction partials
+    double* h_pinned = nullptr;     // pinned host scalars
+    bool cd_resume_valid = false;   // work[0] holds u(t - dt) of the central-difference state at step cd_resume_t
+    int64_t cd_resume_t = 0;
+    double cd_resume_dt = 0.0;
+
+    // multi-GPU
+    int rank = 0, world = 1;
+    NcclApi* nccl = nullptr;
+    void* comm = nullptr;
+    int n_nbr_ranks = 0;
+    std::vector<int> nbr_rank;
+    std::vector<int64_t> send_ptr, recv_ptr;
+    int64_t* d_send_idx = nullptr;
+    int64_t* d_recv_idx = nullptr;
+    double* d_send_buf = nullptr;
+    double* d_recv_buf = nullptr;
+};
+
+int sc_fail(sc_ctx* ctx, int code, const char* fmt, ...);
+void sc_set_global_error(const char* msg);
+
+#define SC_CUDA(ctx, call)                                                                           \
+    do {                                                                                             \
+        cudaError_t _e = (call);                                                                     \
+        if (_e != cudaSuccess)                                                                       \
+            return sc_fail((ctx), SC_ERR_CUDA, "%s failed at %s:%d: %s", #call, __FILE__, __LINE__,  \
+                           cudaGetErrorString(_e));                                                  \
+    } while (0)
+
+#define SC_TRY(expr)              \
+    do {                          \
+        int _r = (expr);          \
+        if (_r != SC_OK) return _r; \
+    } while (0)
+
+#define SC_CHECK_LAUNCH(ctx)                                   \
+    do {                                                       \
+        (ctx)->launches++;                                     \
+        SC_CUDA((ctx), cudaGetLastError());                    \
+    } while (0)
+
+template <typename T>
+int sc_alloc(sc_ctx* ctx, T** p, size_t n) {
+    if (*p) { cudaFree(*p); *p = nullptr; }
+    if (n == 0) n = 1;
+    cudaError_t e = cudaMalloc((void**)p, n * sizeof(T));
+    if (e != cudaSuccess) {
+        *p = nullptr;
+        return sc_fail(ctx, SC_ERR_CUDA, "cudaMalloc of %zu bytes failed: %s", n * sizeof(T), cudaGetErrorString(e));
+    }
+    return SC_OK;
+}
+template <typename T>
+void sc_free(T** p) {
+    if (*p) { cudaFree(*p); *p = nullptr; }
+}
+
+// pattern.cu
+int sc_pattern_build(sc_ctx* ctx);
+// assemble.cu
+int sc_assemble_run(sc_ctx* ctx, int order, int flags, double* seconds);
+// linalg.cu
+enum { SC_SPMV_PLAIN = 0 };
+int sc_work(sc_ctx* ctx, int idx, double** out);                       // work vector idx
+int la_spmv(sc_ctx* ctx, const double* vals, const double* x, double* y);                 // y = A x
+int la_spmv2(sc_ctx* ctx, const double* va, const double* xa, const double* vb, const double* xb, double* y); // y = A xa + B xb
+int la_cabs_spmv_add(sc_ctx* ctx, const double* x, double* y, double scale);   // y += scale * C_abs x
+int la_cabs_add_values(sc_ctx* ctx, double* vals, double scale);               // vals[slot] += scale * C_abs
+int la_axpby_vals(sc_ctx* ctx, double* out, double a, const double* x, double b, const double* y, int64_t n);
+int la_extract_diag(sc_ctx* ctx, const double* vals, double* diag, bool invert);
+int la_fill(sc_ctx* ctx, double* x, double v, int64_t n);
+int la_dot(sc_ctx* ctx, const double* x, const double* y, double* d_out);     // deterministic 2-stage, result on device
+int la_scratch(sc_ctx* ctx);
+int la_cd_step(sc_ctx* ctx, const double* K, const double* u, double* uprev_next, const double* inv_d, const double* alpha);
+int la_spmv_dot(sc_ctx* ctx, const double* vals, const double* p, double* q, double* d_out);
+// timeloop.cu
+int tl_newmark(sc_ctx* ctx, double dt, int64_t t0, int64_t n_steps, int64_t oi, double beta, double gamma, double rtol,
+               int maxit, int64_t n_out, double* u_out, double* v_out, double* a_out, sc_stats* st);
+int tl_central_difference(sc_ctx* ctx, double dt, int64_t t0, int64_t n_steps, int64_t oi, int64_t n_out, double* u_out,
+                          double* v_out, double* a_out, sc_stats* st);
+// dist.cu
+int dist_init(sc_ctx* ctx, int rank, int world, const void* id);
+int dist_unique_id(void* out);
+int dist_halo(sc_ctx* ctx, double* d_x, cudaStream_t s);      // exchange ghost values of device vector x (in place)
+int dist_allreduce_sum(sc_ctx* ctx, double* d_vals, int n, cudaStream_t s);
+void dist_destroy(sc_ctx* ctx);

@@ -1,0 +1,414 @@
+// Time integration on the device.
+//
+// Replaces the external solver the reference calls at scatter/scatter.py:156-159
+// (PuggleSolvers 1.0.1: NewmarkExplicit / CentralDifferenceSolver .calculate(M, C, K, F, t0, t1)); protocol and
+// recurrence as written out in SURVEY.md 3.3 (validated against every golden history of the reference).
+//
+//   Newmark (beta, gamma), incremental form, one Jacobi-PCG solve with the fixed effective matrix per step:
+//       Khat = K + a4 C + a1 M,  a1 = 1/(beta dt^2), a4 = gamma/(beta dt),  C = C_abs + c0 M + c1 K (never stored)
+//       rhs  = dF + M (v/(beta dt) + a/(2 beta)) + C ((gamma/beta) v + dt (gamma/(2 beta) - 1) a)
+//            = dF + M x1 + K x2 + C_abs q,   x1 = p + c0 q, x2 = c1 q            (one fused two-matrix SpMV)
+//   Central difference with row-sum lumped M and C (diagonal system, one fused SpMV+update kernel per step):
+//       u+ = inv_d (F - K u) + alpha u - (alpha - 1) u-,  inv_d = 1/(m/dt^2 + c/(2dt)),  alpha = 2 m inv_d / dt^2
+#include <chrono>
+#include <cmath>
+#include "common.h"
+
+namespace {
+
+inline unsigned nblk(int64_t n, int t) { return (unsigned)((n + t - 1) / t); }
+
+// scalars on the device: [0] rz  [1] pq  [2] rz_new  [3] rr  [4] bb
+__global__ void k_pcg_init(const double* __restrict__ b, const double* __restrict__ dinv, double* __restrict__ x, double* __restrict__ r,
+                           double* __restrict__ p, int64_t n, double* __restrict__ partial, int nb) {
+    // x = 0, r = b, p = z = dinv*r ; partials of r.z and r.r
+    __shared__ double sh[2][8];
+    const int64_t chunk = (n + nb - 1) / nb;
+    const int64_t s = blockIdx.x * chunk, e = min(s + chunk, n);
+    double rz = 0.0, rr = 0.0;
+    for (int64_t i = s + threadIdx.x; i < e; i += blockDim.x) {
+        const double bi = b[i], z = dinv[i] * bi;
+        x[i] = 0.0; r[i] = bi; p[i] = z;
+        rz += bi * z; rr += bi * bi;
+    }
+    for (int o = 16; o > 0; o >>= 1) { rz += __shfl_down_sync(0xffffffffu, rz, o); rr += __shfl_down_sync(0xffffffffu, rr, o); }
+    if ((threadIdx.x & 31) == 0) { sh[0][threadIdx.x >> 5] = rz; sh[1][threadIdx.x >> 5] = rr; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double a = 0.0, c = 0.0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) { a += sh[0][w]; c += sh[1][w]; }
+        partial[blockIdx.x] = a; partial[nb + blockIdx.x] = c;
+    }
+}
+
+// x += alpha p ; r -= alpha q ; partials of r.(dinv r) and r.r          alpha = scal[0]/scal[1]
+__global__ void k_pcg_update(const double* __restrict__ scal, const double* __restrict__ p, const double* __restrict__ q,
+                             const double* __restrict__ dinv, double* __restrict__ x, double* __restrict__ r, int64_t n,
+                             double* __restrict__ partial, int nb) {
+    __shared__ double sh[2][8];
+    const double alpha = scal[0] / scal[1];
+    const int64_t chunk = (n + nb - 1) / nb;
+    const int64_t s = blockIdx.x * chunk, e = min(s + chunk, n);
+    double rz = 0.0, rr = 0.0;
+    for (int64_t i = s + threadIdx.x; i < e; i += blockDim.x) {
+        x[i] += alpha * p[i];
+        const double ri = r[i] - alpha * q[i];
+        r[i] = ri;
+        rz += ri * (dinv[i] * ri); rr += ri * ri;
+    }
+    for (int o = 16; o > 0; o >>= 1) { rz += __shfl_down_sync(0xffffffffu, rz, o); rr += __shfl_down_sync(0xffffffffu, rr, o); }
+    if ((threadIdx.x & 31) == 0) { sh[0][threadIdx.x >> 5] = rz; sh[1][threadIdx.x >> 5] = rr; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double a = 0.0, c = 0.0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) { a += sh[0][w]; c += sh[1][w]; }
+        partial[blockIdx.x] = a; partial[nb + blockIdx.x] = c;
+    }
+}
+
+// out[j] = sum partial[j*nb + k]  (one block, fixed order)
+__global__ void k_reduce2(const double* __restrict__ partial, int nb, double* __restrict__ out0, double* __restrict__ out1) {
+    __shared__ double sh[8];
+    for (int j = 0; j < 2; ++j) {
+        double s = 0.0;
+        for (int i = threadIdx.x; i < nb; i += blockDim.x) s += partial[j * nb + i];
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+        if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double t = 0.0;
+            for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += sh[w];
+            *(j == 0 ? out0 : out1) = t;
+        }
+        __syncthreads();
+    }
+}
+
+// p = dinv r + beta p, beta = scal[2]/scal[0]; then rz <- rz_new is done by k_shift
+__global__ void k_pcg_p(const double* __restrict__ scal, const double* __restrict__ r, const double* __restrict__ dinv,
+                        double* __restrict__ p, int64_t n) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double beta = scal[2] / scal[0];
+    p[i] = dinv[i] * r[i] + beta * p[i];
+}
+__global__ void k_shift(double* scal) { scal[0] = scal[2]; }
+
+// Newmark helper vectors
+__global__ void k_nm_inputs(const double* __restrict__ v, const double* __restrict__ a, double* __restrict__ x1, double* __restrict__ x2,
+                            double* __restrict__ q, double pv, double pa, double qv, double qa, double c0, double c1, int64_t n) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double vi = v[i], ai = a[i];
+    const double pp = pv * vi + pa * ai, qq = qv * vi + qa * ai;
+    x1[i] = pp + c0 * qq;
+    x2[i] = c1 * qq;
+    if (q) q[i] = qq;
+}
+__global__ void k_nm_update(const double* __restrict__ du, double* __restrict__ u, double* __restrict__ v, double* __restrict__ a,
+                            double a4, double gb, double dvc, double a1, double ivb, double i2b, int64_t n) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double d = du[i], vi = v[i], ai = a[i];
+    const double dv = a4 * d - gb * vi + dvc * ai;
+    const double da = a1 * d - ivb * vi - i2b * ai;
+    u[i] += d; v[i] = vi + dv; a[i] = ai + da;
+}
+// sparse load entries: y[dof] += scale * val   (dofs are unique within a step)
+__global__ void k_load_add(const int32_t* __restrict__ dof, const double* __restrict__ val, int64_t n, double scale,
+                           const double* __restrict__ mult, double* __restrict__ y) {
+    int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    const int d = dof[t];
+    y[d] += scale * val[t] * (mult ? mult[d] : 1.0);
+}
+__global__ void k_cd_coeffs(const double* __restrict__ m, const double* __restrict__ c, double a0, double a1, double* __restrict__ inv_d,
+                            double* __restrict__ alpha, int64_t n) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double d = a0 * m[i] + a1 * c[i];
+    const double id = d != 0.0 ? 1.0 / d : 0.0;
+    inv_d[i] = id;
+    alpha[i] = 2.0 * a0 * m[i] * id;
+}
+// lumped damping c = c0 m + c1 rowsum(K) (+ rowsum(C_abs) added separately)
+__global__ void k_cd_lumped_c(const double* __restrict__ m, const double* __restrict__ ksum, double c0, double c1, double* __restrict__ c, int64_t n) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < n) c[i] = c0 * m[i] + c1 * ksum[i];
+}
+// start-up: u_prev = u - dt v + dt^2/2 * (f - Ku - c v)/m       (rhs holds f - Ku on entry)
+__global__ void k_cd_start(const double* __restrict__ u, const double* __restrict__ v, const double* __restrict__ rhs,
+                           const double* __restrict__ m, const double* __restrict__ c, double dt, double* __restrict__ uprev, int64_t n) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double mi = m[i];
+    const double acc = mi != 0.0 ? (rhs[i] - c[i] * v[i]) / mi : 0.0;
+    uprev[i] = u[i] - dt * v[i] + 0.5 * dt * dt * acc;
+}
+__global__ void k_cd_va(const double* __restrict__ unext, const double* __restrict__ u, const double* __restrict__ uprev, double a0, double a1,
+                        double* __restrict__ v, double* __restrict__ a, int64_t n) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    v[i] = a1 * (unext[i] - uprev[i]);
+    a[i] = a0 * (unext[i] - 2.0 * u[i] + uprev[i]);
+}
+__global__ void k_neg_add(double* __restrict__ y, int64_t n) {   // y = -y
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < n) y[i] = -y[i];
+}
+
+constexpr int PCG_NB = 1024;
+
+// Jacobi-preconditioned CG for A x = b, x0 = 0.  Returns iterations and the relative residual.
+int pcg(sc_ctx* ctx, const double* vals, const double* dinv, const double* b, double* x, double* r, double* p, double* q,
+        double rtol, int maxit, int* iters, double* relres) {
+    const int64_t n = ctx->n_eq;
+    cudaStream_t st = ctx->stream;
+    double* sc = ctx->d_scal;
+    k_pcg_init<<<PCG_NB, 256, 0, st>>>(b, dinv, x, r, p, n, ctx->d_partial, PCG_NB);
+    SC_CHECK_LAUNCH(ctx);
+    k_reduce2<<<1, 256, 0, st>>>(ctx->d_partial, PCG_NB, sc + 0, sc + 4);
+    SC_CHECK_LAUNCH(ctx);
+    if (ctx->world > 1) { SC_TRY(dist_allreduce_sum(ctx, sc + 0, 1, st)); SC_TRY(dist_allreduce_sum(ctx, sc + 4, 1, st)); }
+    SC_CUDA(ctx, cudaMemcpyAsync(ctx->h_pinned, sc, 5 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    SC_CUDA(ctx, cudaStreamSynchronize(st));
+    const double bb = ctx->h_pinned[4];
+    *iters = 0;
+    *relres = 0.0;
+    if (!(bb > 0.0)) return SC_OK;   // zero right-hand side: x = 0
+    const double target = rtol * rtol * bb;
+    for (int it = 1; it <= maxit; ++it) {
+        if (ctx->world > 1) SC_TRY(dist_halo(ctx, p, st));
+        SC_TRY(la_spmv_dot(ctx, vals, p, q, sc + 1));
+        k_pcg_update<<<PCG_NB, 256, 0, st>>>(sc, p, q, dinv, x, r, n, ctx->d_partial, PCG_NB);
+        SC_CHECK_LAUNCH(ctx);
+        k_reduce2<<<1, 256, 0, st>>>(ctx->d_partial, PCG_NB, sc + 2, sc + 3);
+        SC_CHECK_LAUNCH(ctx);
+        if (ctx->world > 1) SC_TRY(dist_allreduce_sum(ctx, sc + 2, 2, st));
+        SC_CUDA(ctx, cudaMemcpyAsync(ctx->h_pinned, sc, 5 * sizeof(double), cudaMemcpyDeviceToHost, st));
+        k_pcg_p<<<nblk(n, 256), 256, 0, st>>>(sc, r, dinv, p, n);
+        SC_CHECK_LAUNCH(ctx);
+        k_shift<<<1, 1, 0, st>>>(sc);
+        SC_CHECK_LAUNCH(ctx);
+        SC_CUDA(ctx, cudaStreamSynchronize(st));
+        const double rr = ctx->h_pinned[3];
+        *iters = it;
+        *relres = std::sqrt(rr / bb);
+        if (!(rr == rr)) return sc_fail(ctx, SC_ERR_NOCONV, "PCG produced NaN at iteration %d", it);
+        if (rr <= target) return SC_OK;
+    }
+    return sc_fail(ctx, SC_ERR_NOCONV, "PCG did not converge in %d iterations (relative residual %.3e, target %.3e)", maxit, *relres, rtol);
+}
+
+int apply_load(sc_ctx* ctx, int64_t t, double scale, const double* mult, double* y) {
+    if (t < 0 || t >= ctx->load_steps) return SC_OK;   // outside the schedule: zero force
+    const int64_t s = ctx->h_load_ptr[t], e = ctx->h_load_ptr[t + 1];
+    if (e == s) return SC_OK;
+    k_load_add<<<nblk(e - s, 128), 128, 0, ctx->stream>>>(ctx->d_load_dof + s, ctx->d_load_val + s, e - s, scale, mult, y);
+    SC_CHECK_LAUNCH(ctx);
+    return SC_OK;
+}
+
+int store_row(sc_ctx* ctx, double* host, int64_t row, const double* dev) {
+    if (!host) return SC_OK;
+    SC_CUDA(ctx, cudaMemcpyAsync(host + row * ctx->n_eq, dev, sizeof(double) * ctx->n_eq, cudaMemcpyDeviceToHost, ctx->stream));
+    return SC_OK;
+}
+
+int ensure_state(sc_ctx* ctx) {
+    const int64_t n = ctx->n_eq;
+    for (double** v : {&ctx->d_u, &ctx->d_v, &ctx->d_a}) {
+        if (!*v) {
+            SC_TRY(sc_alloc(ctx, v, (size_t)n));
+            SC_CUDA(ctx, cudaMemsetAsync(*v, 0, sizeof(double) * n, ctx->stream));
+        }
+    }
+    return SC_OK;
+}
+
+}  // namespace
+
+int tl_newmark(sc_ctx* ctx, double dt, int64_t t0, int64_t n_steps, int64_t oi, double beta, double gamma, double rtol,
+               int maxit, int64_t n_out, double* u_out, double* v_out, double* a_out, sc_stats* stats) {
+    auto wall0 = std::chrono::steady_clock::now();
+    const int64_t n = ctx->n_eq;
+    cudaStream_t st = ctx->stream;
+    const int64_t launches0 = ctx->launches;
+    SC_TRY(la_scratch(ctx));
+    SC_TRY(ensure_state(ctx));
+    double *x1, *x2, *qv, *rhs, *du, *r, *p, *q, *dinv, *dinvM;
+    SC_TRY(sc_work(ctx, 0, &x1)); SC_TRY(sc_work(ctx, 1, &x2)); SC_TRY(sc_work(ctx, 2, &qv)); SC_TRY(sc_work(ctx, 3, &rhs));
+    SC_TRY(sc_work(ctx, 4, &du)); SC_TRY(sc_work(ctx, 5, &r)); SC_TRY(sc_work(ctx, 6, &p)); SC_TRY(sc_work(ctx, 7, &q));
+    SC_TRY(sc_work(ctx, 8, &dinv)); SC_TRY(sc_work(ctx, 9, &dinvM));
+    const double a1 = 1.0 / (beta * dt * dt), a4 = gamma / (beta * dt);
+    const double c0 = ctx->c0, c1 = ctx->c1;
+    const bool cabs = ctx->cabs_n > 0;
+
+    // effective matrix Khat = (1 + a4 c1) K + (a1 + a4 c0) M + a4 C_abs
+    SC_TRY(sc_alloc(ctx, &ctx->d_Khat, (size_t)ctx->nnz));
+    SC_TRY(la_axpby_vals(ctx, ctx->d_Khat, 1.0 + a4 * c1, ctx->d_K, a1 + a4 * c0, ctx->d_M, ctx->nnz));
+    SC_TRY(la_cabs_add_values(ctx, ctx->d_Khat, a4));
+    SC_TRY(la_extract_diag(ctx, ctx->d_Khat, dinv, true));
+    SC_TRY(la_extract_diag(ctx, ctx->d_M, dinvM, true));
+
+    int64_t pcg_total = 0;
+    int iters = 0;
+    double relres = 0.0;
+    int64_t row = 0;
+
+    // initial acceleration a = M^-1 (F(t0) - C v - K u) = M^-1 (F - M (c0 v) - K (c1 v + u) - C_abs v)
+    SC_TRY(la_axpby_vals(ctx, x1, c0, ctx->d_v, 0.0, nullptr, n));
+    SC_TRY(la_axpby_vals(ctx, x2, c1, ctx->d_v, 1.0, ctx->d_u, n));
+    if (ctx->world > 1) { SC_TRY(dist_halo(ctx, x1, st)); SC_TRY(dist_halo(ctx, x2, st)); }
+    SC_TRY(la_spmv2(ctx, ctx->d_M, x1, ctx->d_K, x2, rhs));
+    SC_TRY(la_cabs_spmv_add(ctx, ctx->d_v, rhs, 1.0));
+    k_neg_add<<<nblk(n, 256), 256, 0, st>>>(rhs, n);
+    SC_CHECK_LAUNCH(ctx);
+    SC_TRY(apply_load(ctx, t0, 1.0, nullptr, rhs));
+    SC_TRY(pcg(ctx, ctx->d_M, dinvM, rhs, ctx->d_a, r, p, q, rtol, maxit, &iters, &relres));
+    pcg_total += iters;
+    if (ctx->world > 1) SC_TRY(dist_halo(ctx, ctx->d_a, st));
+
+    if (t0 % oi == 0 && row < n_out) {
+        SC_TRY(store_row(ctx, u_out, row, ctx->d_u)); SC_TRY(store_row(ctx, v_out, row, ctx->d_v)); SC_TRY(store_row(ctx, a_out, row, ctx->d_a));
+        ++row;
+    }
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    cudaEventRecord(e0, st);
+    const double pv = 1.0 / (beta * dt), pa = 1.0 / (2.0 * beta);
+    const double qvv = gamma / beta, qa = dt * (gamma / (2.0 * beta) - 1.0);
+    for (int64_t t = t0 + 1; t <= t0 + n_steps; ++t) {
+        k_nm_inputs<<<nblk(n, 256), 256, 0, st>>>(ctx->d_v, ctx->d_a, x1, x2, cabs ? qv : nullptr, pv, pa, qvv, qa, c0, c1, n);
+        SC_CHECK_LAUNCH(ctx);
+        SC_TRY(la_spmv2(ctx, ctx->d_M, x1, ctx->d_K, x2, rhs));
+        if (cabs) SC_TRY(la_cabs_spmv_add(ctx, qv, rhs, 1.0));
+        SC_TRY(apply_load(ctx, t, 1.0, nullptr, rhs));
+        SC_TRY(apply_load(ctx, t - 1, -1.0, nullptr, rhs));
+        SC_TRY(pcg(ctx, ctx->d_Khat, dinv, rhs, du, r, p, q, rtol, maxit, &iters, &relres));
+        pcg_total += iters;
+        if (ctx->world > 1) SC_TRY(dist_halo(ctx, du, st));
+        k_nm_update<<<nblk(n, 256), 256, 0, st>>>(du, ctx->d_u, ctx->d_v, ctx->d_a, a4, gamma / beta, dt * (1.0 - gamma / (2.0 * beta)), a1,
+                                                   1.0 / (beta * dt), 1.0 / (2.0 * beta), n);
+        SC_CHECK_LAUNCH(ctx);
+        if (t % oi == 0 && row < n_out) {
+            SC_TRY(store_row(ctx, u_out, row, ctx->d_u)); SC_TRY(store_row(ctx, v_out, row, ctx->d_v)); SC_TRY(store_row(ctx, a_out, row, ctx->d_a));
+            ++row;
+        }
+    }
+    cudaEventRecord(e1, st);
+    SC_CUDA(ctx, cudaStreamSynchronize(st));
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    if (stats) {
+        stats->seconds_device = ms * 1e-3;
+        stats->seconds_total = std::chrono::duration<double>(std::chrono::steady_clock::now() - wall0).count();
+        stats->steps = n_steps;
+        stats->pcg_iterations = pcg_total;
+        stats->kernel_launches = ctx->launches - launches0;
+        stats->last_residual = relres;
+        stats->seconds_halo = 0.0;
+    }
+    return SC_OK;
+}
+
+int tl_central_difference(sc_ctx* ctx, double dt, int64_t t0, int64_t n_steps, int64_t oi, int64_t n_out, double* u_out,
+                          double* v_out, double* a_out, sc_stats* stats) {
+    auto wall0 = std::chrono::steady_clock::now();
+    const int64_t n = ctx->n_eq;
+    cudaStream_t st = ctx->stream;
+    const int64_t launches0 = ctx->launches;
+    SC_TRY(la_scratch(ctx));
+    SC_TRY(ensure_state(ctx));
+    double *ub, *uc, *inv_d, *alpha, *cl, *tmp, *vv, *aa;
+    SC_TRY(sc_work(ctx, 0, &ub)); SC_TRY(sc_work(ctx, 1, &uc)); SC_TRY(sc_work(ctx, 2, &inv_d)); SC_TRY(sc_work(ctx, 3, &alpha));
+    SC_TRY(sc_work(ctx, 4, &cl)); SC_TRY(sc_work(ctx, 5, &tmp));
+    const double a0 = 1.0 / (dt * dt), a1 = 1.0 / (2.0 * dt);
+
+    // lumped damping: c = c0 m + c1 rowsum(K) + rowsum(C_abs)
+    SC_TRY(la_fill(ctx, ub, 1.0, n));
+    SC_TRY(la_spmv(ctx, ctx->d_K, ub, tmp));
+    k_cd_lumped_c<<<nblk(n, 256), 256, 0, st>>>(ctx->d_Ml, tmp, ctx->c0, ctx->c1, cl, n);
+    SC_CHECK_LAUNCH(ctx);
+    SC_TRY(la_cabs_spmv_add(ctx, ub, cl, 1.0));
+    k_cd_coeffs<<<nblk(n, 256), 256, 0, st>>>(ctx->d_Ml, cl, a0, a1, inv_d, alpha, n);
+    SC_CHECK_LAUNCH(ctx);
+
+    // rotating buffers: cur = u(t), prev = u(t-dt) (overwritten by u(t+dt) each step)
+    double* cur = ctx->d_u;
+    double* prev = ub;
+    const bool resume = ctx->cd_resume_valid && ctx->cd_resume_t == t0 && ctx->cd_resume_dt == dt;
+    if (!resume) {
+        // start-up value u(t0 - dt) = u - dt v + dt^2/2 a(t0),  a(t0) = (F - K u - c v)/m
+        if (ctx->world > 1) SC_TRY(dist_halo(ctx, cur, st));
+        SC_TRY(la_spmv(ctx, ctx->d_K, cur, tmp));
+        k_neg_add<<<nblk(n, 256), 256, 0, st>>>(tmp, n);
+        SC_CHECK_LAUNCH(ctx);
+        SC_TRY(apply_load(ctx, t0, 1.0, nullptr, tmp));
+        k_cd_start<<<nblk(n, 256), 256, 0, st>>>(cur, ctx->d_v, tmp, ctx->d_Ml, cl, dt, prev, n);
+        SC_CHECK_LAUNCH(ctx);
+        if (ctx->world > 1) SC_TRY(dist_halo(ctx, prev, st));
+    }
+    ctx->cd_resume_valid = false;
+
+    const bool want_out = (u_out || v_out || a_out) && n_out > 0;
+    if (want_out) { SC_TRY(sc_work(ctx, 6, &vv)); SC_TRY(sc_work(ctx, 7, &aa)); }
+    int64_t row = 0;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    cudaEventRecord(e0, st);
+    int64_t steps_done = 0;
+    const int64_t t_end = t0 + n_steps;
+    for (int64_t t = t0; t <= t_end; ++t) {
+        const bool out_now = want_out && (t % oi == 0) && row < n_out;
+        if (t == t_end && !out_now) break;       // the extra half step is only needed for v/a of an output row
+        if (out_now) {
+            // keep u(t-dt): the step overwrites it
+            SC_CUDA(ctx, cudaMemcpyAsync(uc, prev, sizeof(double) * n, cudaMemcpyDeviceToDevice, st));
+        }
+        // prev <- u(t+dt)
+        SC_TRY(la_cd_step(ctx, ctx->d_K, cur, prev, inv_d, alpha));
+        SC_TRY(apply_load(ctx, t, 1.0, inv_d, prev));
+        if (ctx->world > 1) SC_TRY(dist_halo(ctx, prev, st));
+        if (out_now) {
+            k_cd_va<<<nblk(n, 256), 256, 0, st>>>(prev, cur, uc, a0, a1, vv, aa, n);
+            SC_CHECK_LAUNCH(ctx);
+            SC_TRY(store_row(ctx, u_out, row, cur)); SC_TRY(store_row(ctx, v_out, row, vv)); SC_TRY(store_row(ctx, a_out, row, aa));
+            ++row;
+        }
+        if (t == t_end) {
+            // state stays at t_end: put u(t_end - dt) back so that a following stage continues seamlessly
+            SC_CUDA(ctx, cudaMemcpyAsync(prev, uc, sizeof(double) * n, cudaMemcpyDeviceToDevice, st));
+            SC_CUDA(ctx, cudaMemcpyAsync(ctx->d_v, vv, sizeof(double) * n, cudaMemcpyDeviceToDevice, st));
+            SC_CUDA(ctx, cudaMemcpyAsync(ctx->d_a, aa, sizeof(double) * n, cudaMemcpyDeviceToDevice, st));
+            break;
+        }
+        double* t_ = cur; cur = prev; prev = t_;
+        ++steps_done;
+    }
+    cudaEventRecord(e1, st);
+    // normalise the buffers: d_u = u(t_end), work[0] = u(t_end - dt)
+    if (cur != ctx->d_u) {
+        SC_CUDA(ctx, cudaMemcpyAsync(uc, prev, sizeof(double) * n, cudaMemcpyDeviceToDevice, st));     // prev lives in d_u
+        SC_CUDA(ctx, cudaMemcpyAsync(ctx->d_u, cur, sizeof(double) * n, cudaMemcpyDeviceToDevice, st));
+        SC_CUDA(ctx, cudaMemcpyAsync(ub, uc, sizeof(double) * n, cudaMemcpyDeviceToDevice, st));
+    }
+    ctx->cd_resume_valid = true;
+    ctx->cd_resume_t = t_end;
+    ctx->cd_resume_dt = dt;
+    SC_CUDA(ctx, cudaStreamSynchronize(st));
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    if (stats) {
+        stats->seconds_device = ms * 1e-3;
+        stats->seconds_total = std::chrono::duration<double>(std::chrono::steady_clock::now() - wall0).count();
+        stats->steps = steps_done;
+        stats->pcg_iterations = 0;
+        stats->kernel_launches = ctx->launches - launches0;
+        stats->last_residual = 0.0;
+        stats->seconds_halo = 0.0;
+    }
+    return SC_OK;
+}
