@@ -66,6 +66,10 @@ int         sc_version(void);
 int         sc_device_info(sc_ctx* ctx, int* sm_count, int64_t* total_mem, int64_t* free_mem, char* name, int name_len);
 int64_t     sc_kernel_launches(sc_ctx* ctx);     /* running count of kernels launched by this context */
 
+/* page-locked host buffers for result rows / initial states (faster, asynchronous host<->device copies) */
+int         sc_host_alloc(void** out, int64_t bytes);
+int         sc_host_free(void* p);
+
 /* integration tables of one (element type, Gauss order): N[ngp*nne], dN[ngp*nne*dim], w[ngp]; runs on the host
  * (no GPU needed).  element_types.py:52-802 + discretisation.py:436-497.  Buffers may be NULL to query sizes. */
 int         sc_shape_table(int elem_type, int order, int* nne, int* dim, int* ngp, double* N, double* dN, double* w);

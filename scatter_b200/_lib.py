@@ -23,6 +23,7 @@ ASM_K, ASM_M_FULL, ASM_M_LUMPED = 1, 2, 4
 # every symbol include/scatter_b200.h declares (checked by tests/test_cabi_symbols.py)
 SYMBOLS = [
     "sc_create", "sc_destroy", "sc_last_error", "sc_version", "sc_device_info", "sc_kernel_launches", "sc_shape_table",
+    "sc_host_alloc", "sc_host_free",
     "sc_set_mesh", "sc_set_materials", "sc_build_pattern", "sc_get_pattern", "sc_assemble", "sc_add_entries",
     "sc_set_rayleigh", "sc_get_values", "sc_get_lumped_mass", "sc_spmv", "sc_set_load_schedule", "sc_set_state",
     "sc_get_state", "sc_run_newmark", "sc_run_central_difference", "sc_nccl_unique_id", "sc_dist_init", "sc_set_halo",
@@ -69,6 +70,8 @@ def load_library():
     lib.sc_kernel_launches.argtypes = [vp]
     lib.sc_kernel_launches.restype = i64
     lib.sc_shape_table.argtypes = [i32, i32, P(i32), P(i32), P(i32), vp, vp, vp]
+    lib.sc_host_alloc.argtypes = [P(vp), i64]
+    lib.sc_host_free.argtypes = [vp]
     lib.sc_set_mesh.argtypes = [vp, i32, i64, vp, i64, vp, vp, i64, vp]
     lib.sc_set_materials.argtypes = [vp, vp, vp, vp]
     lib.sc_build_pattern.argtypes = [vp, P(i64)]
@@ -116,6 +119,36 @@ def shape_table(elem_type: str, order: int):
     if rc != 0:
         raise ScatterB200Error(rc, lib.sc_last_error(None).decode())
     return N, dN, w
+
+
+class _PinnedOwner:
+    def __init__(self, lib, ptr):
+        self.lib, self.ptr = lib, ptr
+
+    def __del__(self):
+        try:
+            self.lib.sc_host_free(self.ptr)
+        except Exception:
+            pass
+
+
+def pinned_zeros(shape, dtype=np.float64) -> np.ndarray:
+    """numpy array backed by page-locked host memory (cudaMallocHost) -- needs a CUDA device."""
+    lib = load_library()
+    shape = tuple(int(s) for s in (shape if isinstance(shape, (tuple, list)) else (shape,)))
+    nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
+    p = C.c_void_p()
+    rc = lib.sc_host_alloc(C.byref(p), nbytes)
+    if rc != 0:
+        raise ScatterB200Error(rc, lib.sc_last_error(None).decode())
+    buf = (C.c_char * max(nbytes, 1)).from_address(p.value)
+    arr = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+    arr[...] = 0
+    _PINNED[id(buf)] = (_PinnedOwner(lib, p), buf)
+    return arr
+
+
+_PINNED = {}
 
 
 def nccl_unique_id() -> bytes:
@@ -246,7 +279,7 @@ class Context:
         last = t_start + n_steps
         return 0 if first > last else (last - first) // out_interval + 1
 
-    def run_newmark(self, dt, t_start, n_steps, out_interval=1, beta=0.25, gamma=0.5, rtol=1e-12, maxit=10000,
+    def run_newmark(self, dt, t_start, n_steps, out_interval=1, beta=0.25, gamma=0.5, rtol=1e-14, maxit=20000,
                     u_out=None, v_out=None, a_out=None, store=True):
         n_out = self.n_output_rows(t_start, n_steps, out_interval) if store else 0
         if store:

@@ -139,6 +139,18 @@ int sc_device_info(sc_ctx* ctx, int* sm_count, int64_t* total_mem, int64_t* free
 
 int64_t sc_kernel_launches(sc_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
+int sc_host_alloc(void** out, int64_t bytes) {
+    if (!out || bytes < 0) return SC_ERR_ARG;
+    cudaError_t e = cudaMallocHost(out, (size_t)(bytes > 0 ? bytes : 1));
+    if (e != cudaSuccess) return sc_fail(nullptr, SC_ERR_CUDA, "cudaMallocHost(%lld) failed: %s", (long long)bytes, cudaGetErrorString(e));
+    return SC_OK;
+}
+
+int sc_host_free(void* p) {
+    if (p && cudaFreeHost(p) != cudaSuccess) return sc_fail(nullptr, SC_ERR_CUDA, "cudaFreeHost failed");
+    return SC_OK;
+}
+
 int sc_shape_table(int elem_type, int order, int* nne, int* dim, int* ngp, double* N, double* dN, double* w) {
     ShapeTable t;
     std::string err;

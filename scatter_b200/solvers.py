@@ -45,8 +45,12 @@ class _DeviceSolver:
 
     def update(self, t_start_idx):
         row = int(t_start_idx) // self.output_interval
-        self.u0 = np.array(self.u[row])
-        self.v0 = np.array(self.v[row])
+        if self.u0 is not None and self.u0.shape == self.u[row].shape:
+            self.u0[...] = self.u[row]          # keeps (possibly page-locked) staging buffers
+            self.v0[...] = self.v[row]
+        else:
+            self.u0 = np.array(self.u[row])
+            self.v0 = np.array(self.v[row])
         self._state_dirty = True
 
     def bind(self, matrix):
@@ -95,7 +99,7 @@ class NewmarkExplicit(_DeviceSolver):
 
     def __init__(self):
         super().__init__()
-        self.pcg_rtol = 1e-12
+        self.pcg_rtol = 1e-14
         self.pcg_maxit = 20000
 
     def calculate(self, M, C, K, F, t_start_idx, t_end_idx):

@@ -1,0 +1,208 @@
+"""Host-side logic of the product (no GPU): mesh reader, numbering, absorbing faces, loads, exporter, C-ABI surface."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+import cases
+from conftest import ROOT, rel_l2
+
+
+def test_library_exports_every_declared_symbol():
+    from scatter_b200 import _lib
+    header = open(os.path.join(ROOT, "include", "scatter_b200.h")).read()
+    declared = sorted(set(re.findall(r"\b(sc_[a-z0-9_]+)\s*\(", header)))
+    assert declared, "no declarations found"
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in include/scatter_b200.h but not exported"
+    assert sorted(_lib.SYMBOLS) == declared
+    assert _lib.load_library().sc_version() >= 100
+
+
+def test_no_cpu_fallback_without_gpu():
+    """Without a CUDA device the product must fail loudly, not compute on the CPU."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from scatter_b200 import _lib
+    with pytest.raises(_lib.ScatterB200Error, match="no usable CUDA device"):
+        _lib.Context(0)
+
+
+def test_shape_tables_match_reference(golden_elements):
+    from scatter_b200 import _lib
+    G = golden_elements
+    for key in sorted({k.rsplit("__", 1)[0] for k in G.files}):
+        et, o = key.split("__")
+        N, dN, w = _lib.shape_table(et, int(o[1:]))
+        assert np.abs(N - G[key + "__N"]).max() <= 1e-14
+        assert np.abs(dN - G[key + "__dN"]).max() <= 1e-14
+        assert np.abs(w - G[key + "__W"]).max() <= 1e-15
+    with pytest.raises(_lib.ScatterB200Error, match="integration order not supported"):
+        _lib.shape_table("tetra4", 3)          # discretisation.py:491-492
+
+
+@pytest.mark.parametrize("case", list(cases.MATRIX_CASES))
+def test_mesher_numbering_is_bit_exact(case, golden_meshes, golden_matrices, oracle):
+    from scatter_b200 import mesher
+    fn, bc = cases.MATRIX_CASES[case]
+    G = golden_matrices
+    m = mesher.ReadMesh(golden_meshes[fn])
+    m.read_gmsh(); m.read_bc(bc); m.mapping(); m.connectivities(); m.get_mesh_edges()
+    assert m.number_eq == int(G[case + "__n_eq"])
+    assert np.array_equal(m.equation_table_int(), G[case + "__eq_nb_dof"])
+    assert np.array_equal(m.BC, G[case + "__BC"]) and np.array_equal(m.BC_dir, G[case + "__BC_dir"])
+    om = oracle.build_model(golden_meshes[fn], bc)
+    assert np.array_equal(np.nan_to_num(m.eq_nb_elem, nan=-1), np.nan_to_num(om.eq_nb_elem, nan=-1))
+    assert np.array_equal(m.type_BC, om.type_BC)
+    assert m.element_type == om.element_type and m.dimension == om.dimension
+    assert m.lower_element_type == om.lower_element_type and m.nb_nodes_lower_elem == om.nb_nodes_lower_elem
+
+
+def test_mesher_errors(tmp_path):
+    from scatter_b200 import mesher
+    with pytest.raises(SystemExit, match="Mesh file does not exit"):
+        mesher.ReadMesh(os.path.join(tmp_path, "missing.msh"))
+    p = os.path.join(tmp_path, "a.txt")
+    open(p, "w").write("x")
+    with pytest.raises(SystemExit, match="not a valid file"):
+        mesher.ReadMesh(p)
+
+
+def test_cube_boundary_faces_and_top_surface(golden_meshes):
+    from scatter_b200 import mesher
+    m = mesher.ReadMesh(golden_meshes["cube.msh"])
+    m.read_gmsh(); m.read_bc(cases.BC_CUBE); m.mapping(); m.connectivities(); m.get_mesh_edges()
+    assert m.boundary_elem.shape == (600, 4)           # 6 faces x 10 x 10
+    top = m.get_top_surface()
+    ys = m.nodes[top - 1, 2]
+    assert len(top) > 0 and np.allclose(ys, ys.max())
+
+
+@pytest.mark.parametrize("case", ["column_abs", "column_high_order_abs", "cube_abs"])
+def test_absorbing_entries_match_oracle(case, golden_meshes, oracle):
+    from scatter_b200 import mesher, system_matrix
+    fn, bc = cases.MATRIX_CASES[case]
+    m = mesher.ReadMesh(golden_meshes[fn])
+    m.read_gmsh(); m.read_bc(bc); m.mapping(); m.connectivities()
+    E, nu, rho = system_matrix.resolve_element_properties(m, cases.materials())
+    cd, kd = system_matrix.absorbing_entries(m, E, nu, rho, 2, [1, 1], 1e3)
+    om = oracle.build_model(golden_meshes[fn], bc)
+    Co, Ko = oracle.absorbing_matrices(om, E, nu, rho, 2, [1, 1], 1e3)
+    k = np.array(list(cd.keys()))
+    n = m.number_eq
+    C = sp.csr_matrix((list(cd.values()), (k[:, 0], k[:, 1])), shape=(n, n))
+    K = sp.csr_matrix((list(kd.values()), (k[:, 0], k[:, 1])), shape=(n, n))
+    assert abs(C - Co).max() <= 1e-13 * abs(Co).max()
+    assert abs(K - Ko).max() <= 1e-13 * abs(Ko).max()
+
+
+def test_rayleigh_coefficients_closed_form():
+    """unit_test/test_gen_matrix.py:13-60 of the reference: c0, c1 against the closed form."""
+    from scatter_b200 import system_matrix
+    f1, d1, f2, d2 = 1.0, 0.01, 30.0, 0.02
+    c0, c1 = system_matrix.rayleigh_coefficients([f1, d1, f2, d2])
+    w1, w2 = 2 * np.pi * f1, 2 * np.pi * f2
+    a0 = 2 * w1 * w2 * (d1 * w2 - d2 * w1) / (w2 ** 2 - w1 ** 2)
+    a1 = 2 * (d2 * w2 - d1 * w1) / (w2 ** 2 - w1 ** 2)
+    np.testing.assert_array_almost_equal([c0, c1], [a0, a1], decimal=12)
+    with pytest.raises(SystemExit, match="Frequencies for the Rayleigh damping are the same"):
+        system_matrix.rayleigh_coefficients([1, 0.1, 1, 0.1])
+
+
+@pytest.mark.parametrize("kind", ["pulse", "heaviside", "moving"])
+def test_load_schedule_matches_oracle(kind, golden_meshes, oracle):
+    from scatter_b200 import force_external, mesher
+    m = mesher.ReadMesh(golden_meshes["cube.msh"])
+    m.read_gmsh(); m.read_bc(cases.BC_CUBE); m.mapping(); m.connectivities()
+    om = oracle.build_model(golden_meshes["cube.msh"], cases.BC_CUBE)
+    time = np.linspace(0, 1, 201)
+    load = {"force": [10.0, -1000.0, 3.0], "node": [8] if kind == "moving" else [3, 4, 8, 700], "time": 1, "type": kind,
+            "speed": 10, "ini_steps": 50 if kind == "moving" else 7}
+    if kind == "moving":
+        load["node"] = 8
+    F = force_external.Force()
+    F.initialise_load(load, time, m, None)
+    ref = oracle.LoadSchedule(om, load, time)
+    ptr, dof, val = F.compile_schedule()
+    assert len(ptr) == len(time) + 1
+    for t in (0, 1, 3, 5, 6, 7, 49, 50, 51, 100, 150, 200):
+        dense = np.zeros(m.number_eq)
+        dense[dof[ptr[t]:ptr[t + 1]]] = val[ptr[t]:ptr[t + 1]]
+        expect = ref(t)
+        assert np.array_equal(dense, expect), (kind, t)
+        assert np.array_equal(F.update_load_at_t(t), expect)
+
+
+def test_validator():
+    from scatter_b200 import validator
+    load = {"type": "pulse"}
+    validator.ValidateLoad.validate(load)
+    assert load["ini_steps"] == 5
+    with pytest.raises(Exception, match="not supported"):
+        validator.ValidateLoad.validate({"type": "earthquake"})
+
+
+def test_exporter_reproduces_reference_vtk_and_pickle_layout(golden_meshes, golden_histories, oracle, tmp_path):
+    """Feed oracle results through the product's exporter and compare with the reference's golden VTK file."""
+    from scatter_b200 import export_results, mesher
+    H = golden_histories
+    c = cases.history_case("hexa8_pulse")
+    load = dict(c["loading"], time=0.005)       # 11 steps are enough for file data_7
+    model, _, (U, V, A, tt) = oracle.run_case(golden_meshes[c["mesh"]], c["materials"], c["bc"], c["settings"], load, c["time_step"])
+    m = mesher.ReadMesh(golden_meshes[c["mesh"]])
+    m.read_gmsh(); m.read_bc(c["bc"]); m.mapping(); m.connectivities()
+
+    class Num:
+        pass
+    num = Num(); num.u, num.v, num.a, num.output_time = U, V, A, tt
+    w = export_results.Write(os.path.join(tmp_path, "out"), m, c["materials"], num)
+    w.pickle(write=True, nodes="all")
+    w.vtk(write=True, binary=False)
+    mine = open(os.path.join(tmp_path, "out", "VTK", "data_7.vtk")).read().splitlines()
+    gold = str(H["hexa8_pulse__vtk_step7"]).splitlines()
+    assert len(mine) == len(gold)
+    for a, b in zip(mine, gold):
+        tb = b.split()
+        try:
+            fb = [float(t) for t in tb]
+        except ValueError:
+            assert a == b, (a, b)
+            continue
+        np.testing.assert_almost_equal([float(t) for t in a.split()], fb, decimal=9)
+    import pickle
+    data = pickle.load(open(os.path.join(tmp_path, "out", "data.pickle"), "rb"))
+    assert set(data) == {"time", "nodes", "position", "displacement", "velocity", "acceleration"}
+    assert set(data["displacement"]["3"]) == {"x", "y", "z"}
+    assert data["displacement"]["1"]["y"].shape == (len(tt),)
+    # binary VTK: header + big-endian payload sizes
+    w.vtk(name="bin", write=True, binary=True)
+    raw = open(os.path.join(tmp_path, "out", "VTK", "bin_0.vtk"), "rb").read()
+    assert raw.startswith(b"# vtk DataFile Version 2.0\nbin_0\nBINARY\nDATASET UNSTRUCTURED_GRID\nPOINTS 804 float\n")
+    # subset pickle (test_benchmark_set_2.py: pickle_nodes=[3])
+    w.pickle(name="sub", write=True, nodes=[3])
+    sub = pickle.load(open(os.path.join(tmp_path, "out", "sub.pickle"), "rb"))
+    assert sub["nodes"] == [3] and list(sub["displacement"].keys()) == ["3"]
+
+
+def test_box_generator_matches_file_reader(tmp_path, oracle):
+    from scatter_b200 import boxmesh, mesher
+    for et in ("hexa8", "hexa20"):
+        path = os.path.join(tmp_path, f"b_{et}.msh")
+        boxmesh.write_box_msh(path, 3, 4, 2, 0.5, et)
+        bc = boxmesh.box_boundaries(3, 4, 2, 0.5)
+        a = boxmesh.box_model(3, 4, 2, 0.5, et); a.connectivities()
+        b = mesher.ReadMesh(path); b.read_gmsh(); b.read_bc(bc); b.mapping(); b.connectivities()
+        assert np.array_equal(a.nodes, b.nodes) and np.array_equal(a.elem, b.elem)
+        assert np.array_equal(np.nan_to_num(a.eq_nb_elem, nan=-1), np.nan_to_num(b.eq_nb_elem, nan=-1))
+        # every element is a positively oriented cube of volume h^3
+        Ke, Me = oracle.element_matrices(et, 2, a.nodes[:, 1:][a.node_rows()], 1.0, 0.2, 1.0)
+        assert np.allclose(Me[:, 0::3, 0::3].sum(axis=(1, 2)), 0.125)
+    # slabs of a box are sub-boxes with shifted z
+    n1, e1 = boxmesh.box_arrays(3, 4, 6, 0.5, "hexa8", z_range=(2, 5))
+    n2, e2 = boxmesh.box_arrays(3, 4, 3, 0.5, "hexa8")
+    assert np.array_equal(e1, e2) and np.allclose(n1[:, 3], n2[:, 3] + 1.0) and np.array_equal(n1[:, 1:3], n2[:, 1:3])
