@@ -706,3 +706,14 @@ def run_case(mesh_file: str, materials: dict, bc: dict, settings: dict, loading:
     else:
         U, V, A, t_out = central_difference(M, C, K, force, time, oi)
     return model, (K, M, C), (U, V, A, t_out)
+
+
+def model_from_readmesh(m) -> Model:
+    """Oracle `Model` view of a product `ReadMesh` object (tests: lets the oracle assemble partitioned / synthetic meshes)."""
+    om = Model(nodes=np.asarray(m.nodes), elem=np.asarray(m.elem), materials_index=np.asarray(m.materials_index),
+               materials=m.materials, element_type=m.element_type, dimension=m.dimension, BC=m.BC, BC_dir=m.BC_dir,
+               eq_nb_dof=m.eq_nb_dof, type_BC=m.type_BC, number_eq=m.number_eq, eq_nb_elem=m.eq_nb_elem,
+               lower_element_type=m.lower_element_type, nb_nodes_lower_elem=m.nb_nodes_lower_elem,
+               nb_nodes_elem=m.nb_nodes_elem)
+    om.extra["node_rows"] = m.node_rows()
+    return om

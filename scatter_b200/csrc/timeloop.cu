@@ -327,11 +327,12 @@ int tl_central_difference(sc_ctx* ctx, double dt, int64_t t0, int64_t n_steps, i
     const double a0 = 1.0 / (dt * dt), a1 = 1.0 / (2.0 * dt);
 
     // lumped damping: c = c0 m + c1 rowsum(K) + rowsum(C_abs)
-    SC_TRY(la_fill(ctx, ub, 1.0, n));
-    SC_TRY(la_spmv(ctx, ctx->d_K, ub, tmp));
+    // (work[0] may hold u(t - dt) of a resumable state: use work[1] as the vector of ones)
+    SC_TRY(la_fill(ctx, uc, 1.0, n));
+    SC_TRY(la_spmv(ctx, ctx->d_K, uc, tmp));
     k_cd_lumped_c<<<nblk(n, 256), 256, 0, st>>>(ctx->d_Ml, tmp, ctx->c0, ctx->c1, cl, n);
     SC_CHECK_LAUNCH(ctx);
-    SC_TRY(la_cabs_spmv_add(ctx, ub, cl, 1.0));
+    SC_TRY(la_cabs_spmv_add(ctx, uc, cl, 1.0));
     k_cd_coeffs<<<nblk(n, 256), 256, 0, st>>>(ctx->d_Ml, cl, a0, a1, inv_d, alpha, n);
     SC_CHECK_LAUNCH(ctx);
 
