@@ -221,6 +221,259 @@ __global__ void k_assemble(AsmParams p, int warps) {
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Register-resident variant for element types whose DIM x (NNE*DIM) row block fits in registers (<= 72 doubles:
+// tri3, tri6, quad4, quad8, tetra4, hexa8).  One *lane* owns one (node, element) pair: it evaluates the Jacobians and
+// the complete row block of the node in that element in registers (integration tables come from constant memory with
+// warp-uniform addresses), so the FP64 pipe, not shared memory, is the limit (ncu of the warp-per-node kernel above:
+// 90 % LSU/shared-memory utilisation, 28 % FP64).  The pairs of one node are then added to the shared-memory image of
+// the node's CSR rows in ascending element order (one barrier-separated round per rank), which keeps the summation
+// order of the reference (system_matrix.py:98-103) and needs no atomics.
+__constant__ double c_tabN[SC_MAX_GP * SC_MAX_NNE];
+__constant__ double c_tabdN[SC_MAX_GP * SC_MAX_NNE * 3];
+__constant__ double c_tabw[SC_MAX_GP];
+
+template <int NNE, int DIM, int NGP, int TPB>
+__global__ void __launch_bounds__(TPB) k_assemble_pairs(AsmParams p, int npb) {
+    constexpr int DD = DIM * DIM, ND = NNE * DIM;
+    extern __shared__ double smem[];
+    double* xs = smem;                                   // [ND][TPB] coordinates, one column per thread
+    double* swj = xs + ND * TPB;                         // [NGP][TPB] detJ*w per Gauss point, one column per thread
+    double* sdN = swj + NGP * TPB;                       // [NGP*NNE*DIM] copy for lane-dependent rows
+    double* sN = sdN + NGP * NNE * DIM;                  // [NGP*NNE]
+    double* Kst = sN + NGP * NNE;                        // CSR image of the block's rows
+    double* Mst = Kst + (size_t)npb * DIM * p.max_rl;    // scalar mass per (node, neighbour)
+    int* s_ptr = reinterpret_cast<int*>(Mst + (size_t)npb * p.max_nbr);   // [npb+1] pair offsets
+
+    const int tid = threadIdx.x;
+    const int64_t a0 = (int64_t)blockIdx.x * npb;
+    const int64_t a1 = min(a0 + npb, p.n_nodes);
+    const int nbn = (int)(a1 - a0);
+    const int64_t P0 = p.n2e_ptr[a0];
+    for (int t = tid; t <= nbn; t += TPB) s_ptr[t] = (int)(p.n2e_ptr[a0 + t] - P0);
+    for (int t = tid; t < NGP * NNE * DIM; t += TPB) sdN[t] = p.tabdN[t];
+    for (int t = tid; t < NGP * NNE; t += TPB) sN[t] = p.tabN[t];
+    const int64_t R0 = p.node_row0[a0], R1 = p.node_row0[a1];
+    const int64_t base = p.rowptr[R0];
+    const int span = (int)(p.rowptr[R1] - base);
+    const int64_t nbr0 = p.nbr_ptr[a0];
+    const int nbr_span = (int)(p.nbr_ptr[a1] - nbr0);
+    for (int t = tid; t < span; t += TPB) Kst[t] = 0.0;
+    for (int t = tid; t < nbr_span; t += TPB) Mst[t] = 0.0;
+    __syncthreads();
+    const int npairs = s_ptr[nbn];
+    int maxval = 0;
+    for (int t = 0; t < nbn; ++t) maxval = max(maxval, s_ptr[t + 1] - s_ptr[t]);
+
+    for (int pb = 0; pb < npairs; pb += TPB) {
+        const int k = pb + tid;
+        const bool valid = k < npairs;
+        double acc[DIM][ND];
+        int an = 0, rank = 0, al = 0, e = 0;
+        double rho = 0.0;
+#pragma unroll
+        for (int i = 0; i < DIM; ++i)
+#pragma unroll
+            for (int c = 0; c < ND; ++c) acc[i][c] = 0.0;
+        if (valid) {
+            int lo = 0, hi = nbn;
+            while (hi - lo > 1) {
+                const int mid = (lo + hi) >> 1;
+                if (s_ptr[mid] <= k) lo = mid; else hi = mid;
+            }
+            an = lo;
+            rank = k - s_ptr[an];
+            const int a = (int)(a0 + an);
+            e = p.n2e[P0 + k];
+#pragma unroll
+            for (int b = 0; b < NNE; ++b) {
+                const int c = p.conn[(int64_t)e * NNE + b];
+                if (c == a) al = b;
+#pragma unroll
+                for (int d = 0; d < DIM; ++d) xs[(b * DIM + d) * TPB + tid] = p.xyz[(int64_t)c * 3 + d];
+            }
+            const double E = p.E[e], nu = p.nu[e];
+            rho = p.rho[e];
+            const double lam = E * nu / ((1.0 + nu) * (1.0 - 2.0 * nu));
+            const double mu = E / (2.0 * (1.0 + nu));
+#pragma unroll 1
+            for (int g = 0; g < NGP; ++g) {
+                double J[DD], inv[DD], det;
+#pragma unroll
+                for (int r = 0; r < DD; ++r) J[r] = 0.0;
+#pragma unroll
+                for (int b = 0; b < NNE; ++b)
+#pragma unroll
+                    for (int d = 0; d < DIM; ++d) {
+                        const double dn = c_tabdN[(g * NNE + b) * DIM + d];
+#pragma unroll
+                        for (int kk = 0; kk < DIM; ++kk) J[d * DIM + kk] += dn * xs[(b * DIM + kk) * TPB + tid];
+                    }
+                invert<DIM>(J, inv, det);
+                const double wj = det * c_tabw[g];
+                swj[g * TPB + tid] = wj;
+                double lga[DIM], mga[DIM];
+#pragma unroll
+                for (int kk = 0; kk < DIM; ++kk) {
+                    double s = 0.0;
+#pragma unroll
+                    for (int d = 0; d < DIM; ++d) s += sdN[(g * NNE + al) * DIM + d] * inv[kk * DIM + d];
+                    lga[kk] = lam * wj * s;
+                    mga[kk] = mu * wj * s;
+                }
+#pragma unroll
+                for (int b = 0; b < NNE; ++b) {
+                    double gb[DIM];
+#pragma unroll
+                    for (int kk = 0; kk < DIM; ++kk) {
+                        double s = 0.0;
+#pragma unroll
+                        for (int d = 0; d < DIM; ++d) s += c_tabdN[(g * NNE + b) * DIM + d] * inv[kk * DIM + d];
+                        gb[kk] = s;
+                    }
+                    double sdot = 0.0;
+#pragma unroll
+                    for (int d = 0; d < DIM; ++d) sdot += mga[d] * gb[d];
+#pragma unroll
+                    for (int i = 0; i < DIM; ++i)
+#pragma unroll
+                        for (int j = 0; j < DIM; ++j) {
+                            double t = lga[i] * gb[j] + mga[j] * gb[i];
+                            if (i == j) t += sdot;
+                            acc[i][b * DIM + j] += t;
+                        }
+                }
+            }
+        }
+        // slot look-ups and the mass entries do not depend on the summation order: do them for all pairs at once
+        int koff[NNE];          // offset of block (a,b) inside a row of node a, bit 16+j = dof j of node b is free
+        int moff[NNE];
+        double mab[NNE];
+        int rowoff[DIM];
+#pragma unroll
+        for (int i = 0; i < DIM; ++i) rowoff[i] = -1;
+#pragma unroll
+        for (int b = 0; b < NNE; ++b) { koff[b] = 0; moff[b] = 0; mab[b] = 0.0; }
+        if (valid) {
+            const int64_t a = a0 + an;
+            const int64_t nb0 = p.nbr_ptr[a];
+            const int nn_a = (int)(p.nbr_ptr[a + 1] - nb0);
+#pragma unroll
+            for (int i = 0; i < DIM; ++i) {
+                const int rr = p.eq[a * DIM + i];
+                rowoff[i] = rr >= 0 ? (int)(p.rowptr[rr] - base) : -1;
+            }
+#pragma unroll
+            for (int b = 0; b < NNE; ++b) {
+                const int nodeb = p.conn[(int64_t)e * NNE + b];
+                int lo = 0, hi = nn_a;
+                while (lo < hi) {
+                    const int mid = (lo + hi) >> 1;
+                    if (p.nbr[nb0 + mid] < nodeb) lo = mid + 1; else hi = mid;
+                }
+                int code = p.nbr_off[nb0 + lo];
+#pragma unroll
+                for (int j = 0; j < DIM; ++j)
+                    if (p.eq[(int64_t)nodeb * DIM + j] >= 0) code |= 1 << (16 + j);
+                koff[b] = code;
+                moff[b] = (int)(nb0 - nbr0) + lo;
+                // consistent mass of the node pair: rho * sum_g detJ w N_a N_b   (discretisation.py:213-214)
+                double m = 0.0;
+#pragma unroll
+                for (int g = 0; g < NGP; ++g) m += swj[g * TPB + tid] * sN[g * NNE + al] * c_tabN[g * NNE + b];
+                mab[b] = rho * m;
+            }
+        }
+        // ordered accumulation: round r adds the r-th element of every node (ascending element id per slot)
+        for (int r = 0; r < maxval; ++r) {
+            if (valid && rank == r) {
+#pragma unroll
+                for (int b = 0; b < NNE; ++b) {
+                    const int off = koff[b] & 0xffff;
+#pragma unroll
+                    for (int i = 0; i < DIM; ++i) {
+                        if (rowoff[i] < 0) continue;
+                        int o = rowoff[i] + off;
+#pragma unroll
+                        for (int j = 0; j < DIM; ++j)
+                            if (koff[b] & (1 << (16 + j))) Kst[o++] += acc[i][b * DIM + j];
+                    }
+                    Mst[moff[b]] += mab[b];
+                }
+            }
+            __syncthreads();
+        }
+    }
+    if (p.K)
+        for (int t = tid; t < span; t += TPB) p.K[base + t] = Kst[t];
+    // mass: one warp per node
+    const int lane = tid & 31, warp = tid >> 5;
+    for (int n = warp; n < nbn; n += TPB / 32) {
+        const int64_t a = a0 + n;
+        if (p.node_rl[a] <= 0) continue;
+        const int64_t nb0 = p.nbr_ptr[a];
+        const int nn_a = (int)(p.nbr_ptr[a + 1] - nb0);
+        const double* mnode = Mst + (nb0 - nbr0);
+        int64_t rowg[DIM];
+#pragma unroll
+        for (int i = 0; i < DIM; ++i) {
+            const int rr = p.eq[a * DIM + i];
+            rowg[i] = rr >= 0 ? p.rowptr[rr] : -1;
+        }
+        if (p.M) {
+            for (int q = lane; q < nn_a; q += 32) {
+                const int nodeb = p.nbr[nb0 + q];
+                const double m = mnode[q];
+                const int off = p.nbr_off[nb0 + q];
+#pragma unroll
+                for (int i = 0; i < DIM; ++i) {
+                    if (rowg[i] < 0) continue;
+                    int64_t o = rowg[i] + off;
+#pragma unroll
+                    for (int j = 0; j < DIM; ++j)
+                        if (p.eq[(int64_t)nodeb * DIM + j] >= 0) p.M[o++] = (i == j) ? m : 0.0;
+                }
+            }
+        }
+        if (p.Ml) {
+#pragma unroll
+            for (int i = 0; i < DIM; ++i) {
+                if (rowg[i] < 0) continue;
+                double s = 0.0;
+                for (int q = lane; q < nn_a; q += 32)
+                    if (p.eq[(int64_t)p.nbr[nb0 + q] * DIM + i] >= 0) s += mnode[q];
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+                if (lane == 0) p.Ml[p.eq[a * DIM + i]] = s;
+            }
+        }
+    }
+}
+
+template <int NNE, int DIM, int NGP>
+int launch_pairs(sc_ctx* ctx, const AsmParams& p, const ShapeTable& t) {
+    constexpr int TPB = 128;
+    SC_CUDA(ctx, cudaMemcpyToSymbolAsync(c_tabN, t.N.data(), t.N.size() * sizeof(double), 0, cudaMemcpyHostToDevice, ctx->stream));
+    SC_CUDA(ctx, cudaMemcpyToSymbolAsync(c_tabdN, t.dN.data(), t.dN.size() * sizeof(double), 0, cudaMemcpyHostToDevice, ctx->stream));
+    SC_CUDA(ctx, cudaMemcpyToSymbolAsync(c_tabw, t.w.data(), t.w.size() * sizeof(double), 0, cudaMemcpyHostToDevice, ctx->stream));
+    const double valence = (double)ctx->n_elem * NNE / (double)ctx->n_nodes;
+    int npb = (int)(TPB / std::max(valence, 1.0));
+    npb = std::max(1, std::min(npb, 64));
+    size_t bytes = 0;
+    for (; npb >= 1; npb >>= 1) {
+        bytes = ((size_t)NNE * DIM * TPB + (size_t)NGP * TPB + (size_t)NGP * NNE * DIM + (size_t)NGP * NNE + (size_t)npb * DIM * p.max_rl +
+                 (size_t)npb * p.max_nbr) * sizeof(double) + (npb + 2) * sizeof(int);
+        if (bytes <= 100 * 1024) break;
+    }
+    if (npb < 1) return sc_fail(ctx, SC_ERR_UNSUPPORTED, "assembly staging does not fit in shared memory (max row length %d)", p.max_rl);
+    auto kern = k_assemble_pairs<NNE, DIM, NGP, TPB>;
+    SC_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    const unsigned grid = (unsigned)((p.n_nodes + npb - 1) / npb);
+    kern<<<grid, TPB, bytes, ctx->stream>>>(p, npb);
+    SC_CHECK_LAUNCH(ctx);
+    return SC_OK;
+}
+
 template <int NNE, int DIM, int NGP>
 int launch(sc_ctx* ctx, const AsmParams& p) {
     constexpr int JS = DIM * DIM + 1;
@@ -279,7 +532,11 @@ int sc_assemble_run(sc_ctx* ctx, int order, int flags, double* seconds) {
     int rc = SC_ERR_UNSUPPORTED;
     const int key = t.nne * 10000 + t.dim * 1000 + t.ngp;
     switch (key) {
-#define SC_CASE(NNE, DIM, NGP) case NNE * 10000 + DIM * 1000 + NGP: rc = launch<NNE, DIM, NGP>(ctx, p); break;
+#define SC_CASE(NNE, DIM, NGP)                                                           \
+    case NNE * 10000 + DIM * 1000 + NGP:                                                 \
+        if (DIM * NNE * DIM <= 72 && !ctx->force_generic_assembly) rc = launch_pairs<NNE, DIM, NGP>(ctx, p, t); \
+        else rc = launch<NNE, DIM, NGP>(ctx, p);                                         \
+        break;
         SC_CASE(3, 2, 1) SC_CASE(3, 2, 3) SC_CASE(3, 2, 4)
         SC_CASE(6, 2, 1) SC_CASE(6, 2, 3) SC_CASE(6, 2, 4)
         SC_CASE(4, 2, 1) SC_CASE(4, 2, 4) SC_CASE(4, 2, 9)

@@ -92,6 +92,7 @@ struct sc_ctx {
     double* d_scal = nullptr;       // small device scalar block
     double* d_partial = nullptr;    // reduction partials
     double* h_pinned = nullptr;     // pinned host scalars
+    bool force_generic_assembly = false;   // test hook: use the warp-per-node kernel for every element type
     bool cd_resume_valid = false;   // work[0] holds u(t - dt) of the central-difference state at step cd_resume_t
     int64_t cd_resume_t = 0;
     double cd_resume_dt = 0.0;

@@ -3,78 +3,120 @@
 // These replace the scipy.sparse products the reference's external solver performs every step
 // (solvers.NewmarkExplicit.calculate called at scatter/scatter.py:159; recurrence in SURVEY.md 3.3).
 //
-// SpMV layout ("CSR stream"): a thread block owns R consecutive rows = one contiguous slice of the value / column
-// arrays.  All threads stream that slice with fully coalesced loads, multiply by the gathered x entries (L2-resident
-// for FEM orderings) and park the products in shared memory; then one thread per row adds its products in column
-// order.  No atomics, fixed order => bit-reproducible, and identical to a sequential CSR row sum.
+// SpMV layout: rows are consecutive slices of the value / column arrays; each warp streams the slices of a few
+// consecutive rows with coalesced loads and multiplies by gathered x entries (L2-resident for FEM orderings).
+// No atomics, fixed summation order => bit-reproducible.
 #include <algorithm>
 #include "common.h"
 
 namespace {
 
 constexpr int SPMV_THREADS = 256;
-constexpr int SPMV_TILE = 4096;      // products staged per pass (32 KB)
-constexpr int SPMV_MAX_ROWS = 256;
+constexpr int SPMV_WARPS = SPMV_THREADS / 32;
 
+// CSR SpMV, one warp per RPW consecutive rows, U chunks of 32 entries in flight per row and pass.
+// There is no shared-memory staging and no block barrier in the streaming part: every warp keeps RPW*U independent
+// (value, column) loads plus their gathers in flight, which is what hides the HBM latency (ncu of the first version --
+// products staged in shared memory, one thread per row adding them -- showed 51 long-scoreboard stalls per issue and
+// 40 % DRAM throughput).  Lane partials are added in entry order, then a fixed xor butterfly: deterministic.
 // MODE 0: y = A xa            MODE 1: y = A xa + B xb
 // MODE 2: central-difference step  un[i] = inv_d[i]*(-sum) + alpha[i]*xa[i] - (alpha[i]-1)*un[i]   (un holds u_prev)
 // MODE 3: PCG product  y = A xa  and per-block partial of xa.y  (partial[blockIdx])
-template <int MODE>
+template <int MODE, int RPW, int U>
 __global__ void __launch_bounds__(SPMV_THREADS)
 k_spmv(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col, const double* __restrict__ va,
        const double* __restrict__ xa, const double* __restrict__ vb, const double* __restrict__ xb,
        double* __restrict__ y, const double* __restrict__ inv_d, const double* __restrict__ alpha,
-       double* __restrict__ partial, int64_t n_rows, int R) {
-    __shared__ double prod[SPMV_TILE];
-    __shared__ int64_t rp[SPMV_MAX_ROWS + 1];
-    __shared__ double red[SPMV_THREADS / 32];
-    const int tid = threadIdx.x;
-    const int64_t r0 = (int64_t)blockIdx.x * R;
-    const int nr = (int)min((int64_t)R, n_rows - r0);
-    for (int t = tid; t <= nr; t += SPMV_THREADS) rp[t] = rowptr[r0 + t];
-    __syncthreads();
-    const int64_t s0 = rp[0], s1 = rp[nr];
-    double acc = 0.0;
-    int64_t rs = 0, re = 0;
-    if (tid < nr) { rs = rp[tid]; re = rp[tid + 1]; }
-    for (int64_t c0 = s0; c0 < s1; c0 += SPMV_TILE) {
-        const int cnt = (int)min((int64_t)SPMV_TILE, s1 - c0);
-#pragma unroll 4
-        for (int k = tid; k < cnt; k += SPMV_THREADS) {
-            const int64_t g = c0 + k;
-            const int c = col[g];
-            double v = va[g] * xa[c];
-            if (MODE == 1) v += vb[g] * xb[c];
-            prod[k] = v;
-        }
-        __syncthreads();
-        if (tid < nr) {
-            const int b = (int)(max(rs, c0) - c0), e = (int)(min(re, c0 + cnt) - c0);
-            for (int k = b; k < e; ++k) acc += prod[k];
-        }
-        __syncthreads();
+       double* __restrict__ partial, int64_t n_rows) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t row0 = ((int64_t)blockIdx.x * SPMV_WARPS + warp) * RPW;
+    // row pointers of the warp's rows: lanes 0..RPW load, everybody reads them through shuffles
+    int64_t rp = 0;
+    if (lane <= RPW && row0 + lane <= n_rows) rp = rowptr[row0 + lane];
+    int64_t rs[RPW], re[RPW];
+    int niter = 0;
+#pragma unroll
+    for (int r = 0; r < RPW; ++r) {
+        rs[r] = __shfl_sync(0xffffffffu, rp, r);
+        re[r] = __shfl_sync(0xffffffffu, rp, r + 1);
+        if (row0 + r >= n_rows) re[r] = rs[r];
+        niter = max(niter, (int)((re[r] - rs[r] + 31) >> 5));
+    }
+    // epilogue operands do not depend on the sums: issue their loads first
+    const int64_t myrow = row0 + lane;
+    const bool owner = lane < RPW && myrow < n_rows;
+    double e_al = 0.0, e_id = 0.0, e_x = 0.0, e_y = 0.0;
+    if (owner) {
+        if (MODE == 2) { e_al = alpha[myrow]; e_id = inv_d[myrow]; e_x = xa[myrow]; e_y = y[myrow]; }
+        if (MODE == 3) e_x = xa[myrow];
+    }
+    double sum[RPW];
+#pragma unroll
+    for (int r = 0; r < RPW; ++r) sum[r] = 0.0;
+    for (int j = 0; j < niter; j += U) {
+        // all loads of the pass are unconditional (inactive lanes read entry 0 and are masked afterwards), so the
+        // compiler issues the RPW*U (value, column) loads back to back, then the gathers, then the FMAs
+        double v[RPW][U], w[RPW][U];
+        int c[RPW][U];
+#pragma unroll
+        for (int r = 0; r < RPW; ++r)
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int64_t k = rs[r] + lane + 32 * (j + u);
+                const bool ok = k < re[r];
+                const int64_t ks = ok ? k : 0;
+                c[r][u] = __ldg(col + ks);
+                const double vv = __ldg(va + ks);
+                v[r][u] = ok ? vv : 0.0;
+                if (MODE == 1) { const double ww = __ldg(vb + ks); w[r][u] = ok ? ww : 0.0; }
+            }
+        __syncwarp();      // scheduling fence: every (value, column) load of the pass is issued before the first gather
+        double xg[RPW][U], xh[RPW][U];
+#pragma unroll
+        for (int r = 0; r < RPW; ++r)
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                xg[r][u] = xa[c[r][u]];
+                if (MODE == 1) xh[r][u] = xb[c[r][u]];
+            }
+        __syncwarp();      // ... and every gather before the first FMA
+#pragma unroll
+        for (int r = 0; r < RPW; ++r)
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                double t = v[r][u] * xg[r][u];
+                if (MODE == 1) t += w[r][u] * xh[r][u];
+                sum[r] += t;
+            }
+    }
+    double mine = 0.0;
+#pragma unroll
+    for (int r = 0; r < RPW; ++r) {
+        double s = sum[r];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (lane == r) mine = s;
     }
     double dotv = 0.0;
-    if (tid < nr) {
-        const int64_t i = r0 + tid;
+    // lane r owns row r in the epilogue; empty rows (ghost dofs of a domain decomposition) are left untouched
+    const int64_t rp_next = __shfl_down_sync(0xffffffffu, rp, 1);
+    if (owner) {
         if (MODE == 2) {
-            if (re > rs) {
-                const double al = alpha[i];
-                y[i] = inv_d[i] * (-acc) + al * xa[i] - (al - 1.0) * y[i];
-            }
+            if (rp_next > rp) y[myrow] = e_id * (-mine) + e_al * e_x - (e_al - 1.0) * e_y;
         } else {
-            y[i] = acc;
-            if (MODE == 3) dotv = xa[i] * acc;
+            y[myrow] = mine;
+            if (MODE == 3) dotv = e_x * mine;
         }
     }
     if (MODE == 3) {
+        __shared__ double red[SPMV_WARPS];
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) dotv += __shfl_down_sync(0xffffffffu, dotv, o);
-        if ((tid & 31) == 0) red[tid >> 5] = dotv;
+        if (lane == 0) red[warp] = dotv;
         __syncthreads();
-        if (tid == 0) {
+        if (threadIdx.x == 0) {
             double s = 0.0;
-            for (int w = 0; w < SPMV_THREADS / 32; ++w) s += red[w];
+            for (int w2 = 0; w2 < SPMV_WARPS; ++w2) s += red[w2];
             partial[blockIdx.x] = s;
         }
     }
@@ -160,10 +202,27 @@ __global__ void k_cabs_add_values(const int64_t* __restrict__ slot, const double
 
 inline unsigned nblk(int64_t n, int t) { return (unsigned)((n + t - 1) / t); }
 
-int spmv_rows_per_block(sc_ctx* ctx) {
-    double avg = ctx->n_eq > 0 ? (double)ctx->nnz / (double)ctx->n_eq : 1.0;
-    int R = (int)(SPMV_TILE / std::max(avg, 1.0));
-    return std::max(8, std::min(R, SPMV_MAX_ROWS));
+// launch configuration from the average row length: U chunks of 32 entries per pass, RPW rows per warp
+template <int MODE>
+int spmv_launch(sc_ctx* ctx, const double* va, const double* xa, const double* vb, const double* xb, double* y,
+                const double* inv_d, const double* alpha, double* partial, unsigned* nblocks_out) {
+    const double avg = ctx->n_eq > 0 ? (double)ctx->nnz / (double)ctx->n_eq : 1.0;
+    const int64_t n = ctx->n_eq;
+    cudaStream_t st = ctx->stream;
+#define SC_SPMV_GO(RPW, U)                                                                                              \
+    {                                                                                                                   \
+        const unsigned nb = (unsigned)((n + (int64_t)SPMV_WARPS * RPW - 1) / ((int64_t)SPMV_WARPS * RPW));             \
+        if (nblocks_out) *nblocks_out = nb;                                                                             \
+        k_spmv<MODE, RPW, U><<<nb, SPMV_THREADS, 0, st>>>(ctx->d_rowptr, ctx->d_col, va, xa, vb, xb, y, inv_d, alpha,   \
+                                                           partial, n);                                                 \
+    }
+    if (avg <= 32.0) SC_SPMV_GO(4, 1)
+    else if (avg <= 64.0) SC_SPMV_GO(2, 2)
+    else if (avg <= 96.0) SC_SPMV_GO(2, 3)
+    else SC_SPMV_GO(2, 4)
+#undef SC_SPMV_GO
+    SC_CHECK_LAUNCH(ctx);
+    return SC_OK;
 }
 
 }  // namespace
@@ -189,38 +248,23 @@ int la_scratch(sc_ctx* ctx) {
 }
 
 int la_spmv(sc_ctx* ctx, const double* vals, const double* x, double* y) {
-    const int R = spmv_rows_per_block(ctx);
-    k_spmv<0><<<nblk(ctx->n_eq, R), SPMV_THREADS, 0, ctx->stream>>>(ctx->d_rowptr, ctx->d_col, vals, x, nullptr, nullptr, y,
-                                                                     nullptr, nullptr, nullptr, ctx->n_eq, R);
-    SC_CHECK_LAUNCH(ctx);
-    return SC_OK;
+    return spmv_launch<0>(ctx, vals, x, nullptr, nullptr, y, nullptr, nullptr, nullptr, nullptr);
 }
 
 int la_spmv2(sc_ctx* ctx, const double* va, const double* xa, const double* vb, const double* xb, double* y) {
-    const int R = spmv_rows_per_block(ctx);
-    k_spmv<1><<<nblk(ctx->n_eq, R), SPMV_THREADS, 0, ctx->stream>>>(ctx->d_rowptr, ctx->d_col, va, xa, vb, xb, y, nullptr,
-                                                                     nullptr, nullptr, ctx->n_eq, R);
-    SC_CHECK_LAUNCH(ctx);
-    return SC_OK;
+    return spmv_launch<1>(ctx, va, xa, vb, xb, y, nullptr, nullptr, nullptr, nullptr);
 }
 
 // u_next (in place over u_prev) = inv_d*(-K u) + alpha*u - (alpha-1)*u_prev
 int la_cd_step(sc_ctx* ctx, const double* K, const double* u, double* uprev_next, const double* inv_d, const double* alpha) {
-    const int R = spmv_rows_per_block(ctx);
-    k_spmv<2><<<nblk(ctx->n_eq, R), SPMV_THREADS, 0, ctx->stream>>>(ctx->d_rowptr, ctx->d_col, K, u, nullptr, nullptr,
-                                                                     uprev_next, inv_d, alpha, nullptr, ctx->n_eq, R);
-    SC_CHECK_LAUNCH(ctx);
-    return SC_OK;
+    return spmv_launch<2>(ctx, K, u, nullptr, nullptr, uprev_next, inv_d, alpha, nullptr, nullptr);
 }
 
 // q = A p and d_out[0] = p.q (device scalar)
 int la_spmv_dot(sc_ctx* ctx, const double* vals, const double* p, double* q, double* d_out) {
     SC_TRY(la_scratch(ctx));
-    const int R = spmv_rows_per_block(ctx);
-    const unsigned nb = nblk(ctx->n_eq, R);
-    k_spmv<3><<<nb, SPMV_THREADS, 0, ctx->stream>>>(ctx->d_rowptr, ctx->d_col, vals, p, nullptr, nullptr, q, nullptr, nullptr,
-                                                    ctx->d_partial, ctx->n_eq, R);
-    SC_CHECK_LAUNCH(ctx);
+    unsigned nb = 0;
+    SC_TRY(spmv_launch<3>(ctx, vals, p, nullptr, nullptr, q, nullptr, nullptr, ctx->d_partial, &nb));
     k_reduce_final<<<1, RED_THREADS, 0, ctx->stream>>>(ctx->d_partial, nb, 1, 0, d_out);
     SC_CHECK_LAUNCH(ctx);
     if (ctx->world > 1) SC_TRY(dist_allreduce_sum(ctx, d_out, 1, ctx->stream));
