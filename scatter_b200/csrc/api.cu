@@ -1,6 +1,7 @@
 // C ABI glue of libscatter_b200.so (see include/scatter_b200.h for the contract of every entry point).
 #include <algorithm>
 #include <cstdarg>
+#include <cstdlib>
 #include <cstring>
 #include <numeric>
 #include "common.h"
@@ -103,6 +104,10 @@ int sc_create(int device, sc_ctx** out) {
         return SC_ERR_CUDA;
     }
     cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
+    const char* no_tma = getenv("SCATTER_B200_NO_TMA");
+    ctx->force_no_tma = no_tma && no_tma[0] == '1';
+    const char* gen_asm = getenv("SCATTER_B200_GENERIC_ASSEMBLY");
+    ctx->force_generic_assembly = gen_asm && gen_asm[0] == '1';
     *out = ctx;
     return SC_OK;
 }

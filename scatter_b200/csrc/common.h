@@ -92,6 +92,7 @@ struct sc_ctx {
     double* d_scal = nullptr;       // small device scalar block
     double* d_partial = nullptr;    // reduction partials
     double* h_pinned = nullptr;     // pinned host scalars
+    bool force_no_tma = false;             // test hook / env SCATTER_B200_NO_TMA: register-staged SpMV instead of the TMA ring
     bool force_generic_assembly = false;   // test hook: use the warp-per-node kernel for every element type
     bool cd_resume_valid = false;   // work[0] holds u(t - dt) of the central-difference state at step cd_resume_t
     int64_t cd_resume_t = 0;
@@ -137,7 +138,8 @@ template <typename T>
 int sc_alloc(sc_ctx* ctx, T** p, size_t n) {
     if (*p) { cudaFree(*p); *p = nullptr; }
     if (n == 0) n = 1;
-    cudaError_t e = cudaMalloc((void**)p, n * sizeof(T));
+    // 64 bytes of slack: the TMA bulk copies round slice ends up to 16 bytes
+    cudaError_t e = cudaMalloc((void**)p, n * sizeof(T) + 64);
     if (e != cudaSuccess) {
         *p = nullptr;
         return sc_fail(ctx, SC_ERR_CUDA, "cudaMalloc of %zu bytes failed: %s", n * sizeof(T), cudaGetErrorString(e));
@@ -167,6 +169,11 @@ int la_dot(sc_ctx* ctx, const double* x, const double* y, double* d_out);     //
 int la_scratch(sc_ctx* ctx);
 int la_cd_step(sc_ctx* ctx, const double* K, const double* u, double* uprev_next, const double* inv_d, const double* alpha);
 int la_spmv_dot(sc_ctx* ctx, const double* vals, const double* p, double* q, double* d_out);
+// spmv_tma.cu
+bool la_tma_usable(sc_ctx* ctx);
+int la_tma_spmv(sc_ctx* ctx, const double* vals, const double* x, double* y);
+int la_tma_cd_step(sc_ctx* ctx, const double* K, const double* u, double* uprev_next, const double* inv_d, const double* alpha);
+int la_tma_spmv_dot(sc_ctx* ctx, const double* vals, const double* p, double* q, double* partial, unsigned* nblocks);
 // timeloop.cu
 int tl_newmark(sc_ctx* ctx, double dt, int64_t t0, int64_t n_steps, int64_t oi, double beta, double gamma, double rtol,
                int maxit, int64_t n_out, double* u_out, double* v_out, double* a_out, sc_stats* st);
