@@ -267,7 +267,7 @@ __global__ void __launch_bounds__(TPB) k_assemble_pairs(AsmParams p, int npb) {
 
     for (int pb = 0; pb < npairs; pb += TPB) {
         const int k = pb + tid;
-        const bool valid = k < npairs;
+        bool valid = k < npairs;
         double acc[DIM][ND];
         int an = 0, rank = 0, al = 0, e = 0;
         double rho = 0.0;
@@ -283,6 +283,9 @@ __global__ void __launch_bounds__(TPB) k_assemble_pairs(AsmParams p, int npb) {
             }
             an = lo;
             rank = k - s_ptr[an];
+            valid = p.node_rl[a0 + an] > 0;      // ghost nodes of a domain decomposition own no rows
+        }
+        if (valid) {
             const int a = (int)(a0 + an);
             e = p.n2e[P0 + k];
 #pragma unroll
