@@ -130,6 +130,13 @@ int sc_run_newmark(sc_ctx* ctx, double dt, int64_t t_start, int64_t n_steps, int
 int sc_run_central_difference(sc_ctx* ctx, double dt, int64_t t_start, int64_t n_steps, int64_t out_interval,
                               int64_t n_out, double* u_out, double* v_out, double* a_out, sc_stats* stats);
 
+/* Bathe composite scheme (solvers.BatheSolver, scatter.py:126-127) and static solver (solvers.StaticSolver.calculate(K, F,
+ * t0, t1), scatter.py:128-129,156).  Neither is pinned by a reference fixture; schemes documented in DESIGN.md. */
+int sc_run_bathe(sc_ctx* ctx, double dt, int64_t t_start, int64_t n_steps, int64_t out_interval, double pcg_rtol,
+                 int pcg_maxit, int64_t n_out, double* u_out, double* v_out, double* a_out, sc_stats* stats);
+int sc_run_static(sc_ctx* ctx, int64_t t_start, int64_t n_steps, int64_t out_interval, double pcg_rtol, int pcg_maxit,
+                  int64_t n_out, double* u_out, sc_stats* stats);
+
 /* ---- multi-GPU (domain decomposition; one context per rank) --------------------------------------------------- */
 int sc_nccl_unique_id(void* out128 /*128 bytes*/);
 int sc_dist_init(sc_ctx* ctx, int rank, int world, const void* nccl_unique_id128);

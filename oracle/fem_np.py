@@ -717,3 +717,44 @@ def model_from_readmesh(m) -> Model:
                nb_nodes_elem=m.nb_nodes_elem)
     om.extra["node_rows"] = m.node_rows()
     return om
+
+
+def bathe(M, C, K, force, time: np.ndarray, output_interval: int = 1):
+    """Bathe composite scheme (trapezoidal rule over dt/2, then 3-point backward Euler).  PARITY UNPINNED: the reference
+    only forwards `Solver.BATHE` to the un-vendored PuggleSolvers class and ships no fixture for it; this is the textbook
+    scheme (Bathe & Baig 2005) with the half-step force taken as the mean of the two step forces."""
+    M, C, K = sp.csc_matrix(M), sp.csc_matrix(C), sp.csc_matrix(K)
+    n = M.shape[0]
+    nt = len(time)
+    dt = (time[-1] - time[0]) / (nt - 1)
+    out_idx = np.arange(0, nt, output_interval)
+    U = np.zeros((len(out_idx), n)); V = np.zeros_like(U); A = np.zeros_like(U)
+    u = np.zeros(n); v = np.zeros(n)
+    a = spla.splu(M).solve(force(0) - C @ v - K @ u)
+    A[0] = a
+    lu1 = spla.splu((K + C * (4 / dt) + M * (16 / dt ** 2)).tocsc())
+    lu2 = spla.splu((K + C * (3 / dt) + M * (9 / dt ** 2)).tocsc())
+    row = 1
+    for t in range(1, nt):
+        f_half = 0.5 * (force(t - 1) + force(t))
+        u1 = lu1.solve(f_half + M @ (16 * u / dt ** 2 + 8 * v / dt + a) + C @ (4 * u / dt + v))
+        v1 = 4 * (u1 - u) / dt - v
+        u2 = lu2.solve(force(t) + M @ (12 * u1 / dt ** 2 - 3 * u / dt ** 2 + 4 * v1 / dt - v / dt) + C @ (4 * u1 / dt - u / dt))
+        v2 = (u - 4 * u1 + 3 * u2) / dt
+        a2 = (v - 4 * v1 + 3 * v2) / dt
+        u, v, a = u2, v2, a2
+        if t % output_interval == 0:
+            U[row], V[row], A[row] = u, v, a
+            row += 1
+    return U, V, A, time[out_idx]
+
+
+def static(K, force, time: np.ndarray, output_interval: int = 1):
+    """K u(t) = F(t) for every time index.  PARITY UNPINNED (no reference fixture for Solver.STATIC)."""
+    lu = spla.splu(sp.csc_matrix(K))
+    nt = len(time)
+    out_idx = np.arange(0, nt, output_interval)
+    U = np.zeros((len(out_idx), K.shape[0]))
+    for row, t in enumerate(out_idx):
+        U[row] = lu.solve(force(int(t)))
+    return U, time[out_idx]

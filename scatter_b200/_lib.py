@@ -26,7 +26,7 @@ SYMBOLS = [
     "sc_host_alloc", "sc_host_free",
     "sc_set_mesh", "sc_set_materials", "sc_build_pattern", "sc_get_pattern", "sc_assemble", "sc_add_entries",
     "sc_set_rayleigh", "sc_get_values", "sc_get_lumped_mass", "sc_spmv", "sc_set_load_schedule", "sc_set_state",
-    "sc_get_state", "sc_run_newmark", "sc_run_central_difference", "sc_nccl_unique_id", "sc_dist_init", "sc_set_halo",
+    "sc_get_state", "sc_run_newmark", "sc_run_central_difference", "sc_run_bathe", "sc_run_static", "sc_nccl_unique_id", "sc_dist_init", "sc_set_halo",
     "sc_halo_exchange",
 ]
 
@@ -87,6 +87,8 @@ def load_library():
     lib.sc_get_state.argtypes = [vp, vp, vp, vp]
     lib.sc_run_newmark.argtypes = [vp, dbl, i64, i64, i64, dbl, dbl, dbl, i32, i64, vp, vp, vp, P(Stats)]
     lib.sc_run_central_difference.argtypes = [vp, dbl, i64, i64, i64, i64, vp, vp, vp, P(Stats)]
+    lib.sc_run_bathe.argtypes = [vp, dbl, i64, i64, i64, dbl, i32, i64, vp, vp, vp, P(Stats)]
+    lib.sc_run_static.argtypes = [vp, i64, i64, i64, dbl, i32, i64, vp, P(Stats)]
     lib.sc_nccl_unique_id.argtypes = [vp]
     lib.sc_dist_init.argtypes = [vp, i32, i32, vp]
     lib.sc_set_halo.argtypes = [vp, i32, vp, vp, vp, vp, vp]
@@ -302,6 +304,24 @@ class Context:
         self._ck(self.lib.sc_run_central_difference(self.h, float(dt), int(t_start), int(n_steps), int(out_interval), n_out,
                                                     _ptr(u_out), _ptr(v_out), _ptr(a_out), C.byref(st)))
         return u_out, v_out, a_out, st.as_dict()
+
+    def run_bathe(self, dt, t_start, n_steps, out_interval=1, rtol=1e-14, maxit=20000, u_out=None, v_out=None, a_out=None):
+        n_out = self.n_output_rows(t_start, n_steps, out_interval)
+        u_out = np.zeros((n_out, self.n_eq)) if u_out is None else u_out
+        v_out = np.zeros((n_out, self.n_eq)) if v_out is None else v_out
+        a_out = np.zeros((n_out, self.n_eq)) if a_out is None else a_out
+        st = Stats()
+        self._ck(self.lib.sc_run_bathe(self.h, float(dt), int(t_start), int(n_steps), int(out_interval), float(rtol), int(maxit),
+                                       n_out, _ptr(u_out), _ptr(v_out), _ptr(a_out), C.byref(st)))
+        return u_out, v_out, a_out, st.as_dict()
+
+    def run_static(self, t_start, n_steps, out_interval=1, rtol=1e-12, maxit=100000, u_out=None):
+        n_out = self.n_output_rows(t_start, n_steps, out_interval)
+        u_out = np.zeros((n_out, self.n_eq)) if u_out is None else u_out
+        st = Stats()
+        self._ck(self.lib.sc_run_static(self.h, int(t_start), int(n_steps), int(out_interval), float(rtol), int(maxit), n_out,
+                                        _ptr(u_out), C.byref(st)))
+        return u_out, st.as_dict()
 
     # ---- multi-GPU
     def dist_init(self, rank: int, world: int, unique_id: bytes | None):

@@ -40,7 +40,7 @@ int upload(sc_ctx* ctx, T** dst, const T* src, size_t n) {
 void free_pattern(sc_ctx* c) {
     sc_free(&c->d_n2e_ptr); sc_free(&c->d_n2e); sc_free(&c->d_nbr_ptr); sc_free(&c->d_nbr); sc_free(&c->d_nbr_off);
     sc_free(&c->d_node_rl); sc_free(&c->d_node_row0); sc_free(&c->d_rowptr); sc_free(&c->d_col);
-    sc_free(&c->d_K); sc_free(&c->d_M); sc_free(&c->d_Ml); sc_free(&c->d_Khat);
+    sc_free(&c->d_K); sc_free(&c->d_M); sc_free(&c->d_Ml); sc_free(&c->d_Khat); sc_free(&c->d_Khat2);
     sc_free(&c->d_cabs_rowid); sc_free(&c->d_cabs_rptr); sc_free(&c->d_cabs_col); sc_free(&c->d_cabs_slot); sc_free(&c->d_cabs_val);
     c->cabs_n = c->cabs_rows = 0;
     c->have_pattern = c->have_K = c->have_M = c->have_Ml = false;
@@ -422,6 +422,26 @@ int sc_run_central_difference(sc_ctx* ctx, double dt, int64_t t_start, int64_t n
     SC_CUDA(ctx, cudaSetDevice(ctx->device));
     if (stats) std::memset(stats, 0, sizeof(*stats));
     return tl_central_difference(ctx, dt, t_start, n_steps, out_interval, n_out, u_out, v_out, a_out, stats);
+}
+
+int sc_run_bathe(sc_ctx* ctx, double dt, int64_t t_start, int64_t n_steps, int64_t out_interval, double pcg_rtol, int pcg_maxit,
+                 int64_t n_out, double* u_out, double* v_out, double* a_out, sc_stats* stats) {
+    if (!ctx || !ctx->have_K || !ctx->have_M) return sc_fail(ctx, SC_ERR_STATE, "Bathe needs assembled K and full M");
+    if (dt <= 0 || n_steps < 0 || out_interval < 1) return sc_fail(ctx, SC_ERR_ARG, "bad time-integration arguments");
+    SC_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (stats) std::memset(stats, 0, sizeof(*stats));
+    ctx->cd_resume_valid = false;
+    return tl_bathe(ctx, dt, t_start, n_steps, out_interval, pcg_rtol, pcg_maxit, n_out, u_out, v_out, a_out, stats);
+}
+
+int sc_run_static(sc_ctx* ctx, int64_t t_start, int64_t n_steps, int64_t out_interval, double pcg_rtol, int pcg_maxit, int64_t n_out,
+                  double* u_out, sc_stats* stats) {
+    if (!ctx || !ctx->have_K) return sc_fail(ctx, SC_ERR_STATE, "the static solver needs assembled K");
+    if (n_steps < 0 || out_interval < 1) return sc_fail(ctx, SC_ERR_ARG, "bad arguments");
+    SC_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (stats) std::memset(stats, 0, sizeof(*stats));
+    ctx->cd_resume_valid = false;
+    return tl_static(ctx, t_start, n_steps, out_interval, pcg_rtol, pcg_maxit, n_out, u_out, stats);
 }
 
 int sc_nccl_unique_id(void* out128) { return out128 ? dist_unique_id(out128) : SC_ERR_ARG; }

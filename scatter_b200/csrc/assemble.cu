@@ -236,67 +236,80 @@ __constant__ double c_tabw[SC_MAX_GP];
 template <int NNE, int DIM, int NGP, int TPB>
 __global__ void __launch_bounds__(TPB) k_assemble_pairs(AsmParams p, int npb) {
     constexpr int DD = DIM * DIM, ND = NNE * DIM;
+    constexpr int SST = DIM * ND + 1;                    // stride of one pair's row block in the staging area (odd: no bank conflicts)
     extern __shared__ double smem[];
-    double* xs = smem;                                   // [ND][TPB] coordinates, one column per thread
-    double* swj = xs + ND * TPB;                         // [NGP][TPB] detJ*w per Gauss point, one column per thread
-    double* sdN = swj + NGP * TPB;                       // [NGP*NNE*DIM] copy for lane-dependent rows
+    // region A is used twice: coordinates + detJ*w during the integration, the staged row blocks afterwards
+    double* xs = smem;                                   // [ND][TPB]   coordinates, one column per thread
+    double* swj = xs + ND * TPB;                         // [NGP][TPB]  detJ*w per Gauss point
+    double* stage = smem;                                // [TPB][SST]  row block of every pair
+    double* stage_m = stage + (size_t)TPB * SST;         // [TPB][NNE]  rho * sum_g detJ w N_a N_b of every pair
+    constexpr size_t REGION_A = (size_t)TPB * SST + (size_t)TPB * NNE;
+    static_assert(REGION_A >= (size_t)(ND + NGP) * TPB, "staging area must cover the integration scratch");
+    double* sdN = smem + REGION_A;                       // [NGP*NNE*DIM] table copy for lane-dependent rows
     double* sN = sdN + NGP * NNE * DIM;                  // [NGP*NNE]
-    double* Kst = sN + NGP * NNE;                        // CSR image of the block's rows
-    double* Mst = Kst + (size_t)npb * DIM * p.max_rl;    // scalar mass per (node, neighbour)
-    int* s_ptr = reinterpret_cast<int*>(Mst + (size_t)npb * p.max_nbr);   // [npb+1] pair offsets
+    double* s_mitem = sN + NGP * NNE;                    // [npb*max_nbr] mass of every (node, neighbour) item
+    int* s_ptr = reinterpret_cast<int*>(s_mitem + (size_t)npb * p.max_nbr);   // [npb+1] pair offsets of the block's nodes
+    int* s_nptr = s_ptr + npb + 1;                       // [npb+1] neighbour-list offsets
+    unsigned char* s_inv = reinterpret_cast<unsigned char*>(s_nptr + npb + 1);   // [TPB][max_nbr] neighbour position -> local node
 
     const int tid = threadIdx.x;
     const int64_t a0 = (int64_t)blockIdx.x * npb;
     const int64_t a1 = min(a0 + npb, p.n_nodes);
     const int nbn = (int)(a1 - a0);
     const int64_t P0 = p.n2e_ptr[a0];
-    for (int t = tid; t <= nbn; t += TPB) s_ptr[t] = (int)(p.n2e_ptr[a0 + t] - P0);
+    const int64_t nbr0 = p.nbr_ptr[a0];
+    for (int t = tid; t <= nbn; t += TPB) {
+        s_ptr[t] = (int)(p.n2e_ptr[a0 + t] - P0);
+        s_nptr[t] = (int)(p.nbr_ptr[a0 + t] - nbr0);
+    }
     for (int t = tid; t < NGP * NNE * DIM; t += TPB) sdN[t] = p.tabdN[t];
     for (int t = tid; t < NGP * NNE; t += TPB) sN[t] = p.tabN[t];
-    const int64_t R0 = p.node_row0[a0], R1 = p.node_row0[a1];
-    const int64_t base = p.rowptr[R0];
-    const int span = (int)(p.rowptr[R1] - base);
-    const int64_t nbr0 = p.nbr_ptr[a0];
-    const int nbr_span = (int)(p.nbr_ptr[a1] - nbr0);
-    for (int t = tid; t < span; t += TPB) Kst[t] = 0.0;
-    for (int t = tid; t < nbr_span; t += TPB) Mst[t] = 0.0;
+    for (int t = tid; t < TPB * p.max_nbr; t += TPB) s_inv[t] = 0xff;
     __syncthreads();
-    const int npairs = s_ptr[nbn];
-    int maxval = 0;
-    for (int t = 0; t < nbn; ++t) maxval = max(maxval, s_ptr[t + 1] - s_ptr[t]);
+    const int npairs = s_ptr[nbn];                       // <= TPB by construction of npb
+    const int n_items = s_nptr[nbn];
 
-    for (int pb = 0; pb < npairs; pb += TPB) {
-        const int k = pb + tid;
-        bool valid = k < npairs;
-        double acc[DIM][ND];
-        int an = 0, rank = 0, al = 0, e = 0;
-        double rho = 0.0;
+    // ---- phase 1: one lane per (node, element) pair, row block in registers ------------------------------------------
+    const int k = tid;
+    bool valid = k < npairs;
+    double acc[DIM][ND];
+    double mab[NNE];
 #pragma unroll
-        for (int i = 0; i < DIM; ++i)
+    for (int i = 0; i < DIM; ++i)
 #pragma unroll
-            for (int c = 0; c < ND; ++c) acc[i][c] = 0.0;
-        if (valid) {
-            int lo = 0, hi = nbn;
-            while (hi - lo > 1) {
-                const int mid = (lo + hi) >> 1;
-                if (s_ptr[mid] <= k) lo = mid; else hi = mid;
-            }
-            an = lo;
-            rank = k - s_ptr[an];
-            valid = p.node_rl[a0 + an] > 0;      // ghost nodes of a domain decomposition own no rows
+        for (int c = 0; c < ND; ++c) acc[i][c] = 0.0;
+#pragma unroll
+    for (int b = 0; b < NNE; ++b) mab[b] = 0.0;
+    if (valid) {
+        int lo = 0, hi = nbn;
+        while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if (s_ptr[mid] <= k) lo = mid; else hi = mid;
         }
+        const int an = lo;
+        valid = p.node_rl[a0 + an] > 0;                  // ghost nodes of a domain decomposition own no rows
         if (valid) {
             const int a = (int)(a0 + an);
-            e = p.n2e[P0 + k];
+            const int e = p.n2e[P0 + k];
+            int al = 0;
+            const int64_t nb0 = p.nbr_ptr[a];
+            const int nn_a = (int)(p.nbr_ptr[a + 1] - nb0);
 #pragma unroll
             for (int b = 0; b < NNE; ++b) {
                 const int c = p.conn[(int64_t)e * NNE + b];
                 if (c == a) al = b;
 #pragma unroll
                 for (int d = 0; d < DIM; ++d) xs[(b * DIM + d) * TPB + tid] = p.xyz[(int64_t)c * 3 + d];
+                // position of node c in the (ascending) neighbour list of a
+                int l2 = 0, h2 = nn_a;
+                while (l2 < h2) {
+                    const int mid = (l2 + h2) >> 1;
+                    if (p.nbr[nb0 + mid] < c) l2 = mid + 1; else h2 = mid;
+                }
+                s_inv[k * p.max_nbr + l2] = (unsigned char)b;
             }
             const double E = p.E[e], nu = p.nu[e];
-            rho = p.rho[e];
+            const double rho = p.rho[e];
             const double lam = E * nu / ((1.0 + nu) * (1.0 - 2.0 * nu));
             const double mu = E / (2.0 * (1.0 + nu));
 #pragma unroll 1
@@ -347,133 +360,108 @@ __global__ void __launch_bounds__(TPB) k_assemble_pairs(AsmParams p, int npb) {
                         }
                 }
             }
-        }
-        // slot look-ups and the mass entries do not depend on the summation order: do them for all pairs at once
-        int koff[NNE];          // offset of block (a,b) inside a row of node a, bit 16+j = dof j of node b is free
-        int moff[NNE];
-        double mab[NNE];
-        int rowoff[DIM];
-#pragma unroll
-        for (int i = 0; i < DIM; ++i) rowoff[i] = -1;
-#pragma unroll
-        for (int b = 0; b < NNE; ++b) { koff[b] = 0; moff[b] = 0; mab[b] = 0.0; }
-        if (valid) {
-            const int64_t a = a0 + an;
-            const int64_t nb0 = p.nbr_ptr[a];
-            const int nn_a = (int)(p.nbr_ptr[a + 1] - nb0);
-#pragma unroll
-            for (int i = 0; i < DIM; ++i) {
-                const int rr = p.eq[a * DIM + i];
-                rowoff[i] = rr >= 0 ? (int)(p.rowptr[rr] - base) : -1;
-            }
+            // consistent mass of the node pairs: rho * sum_g detJ w N_a N_b   (discretisation.py:213-214)
 #pragma unroll
             for (int b = 0; b < NNE; ++b) {
-                const int nodeb = p.conn[(int64_t)e * NNE + b];
-                int lo = 0, hi = nn_a;
-                while (lo < hi) {
-                    const int mid = (lo + hi) >> 1;
-                    if (p.nbr[nb0 + mid] < nodeb) lo = mid + 1; else hi = mid;
-                }
-                int code = p.nbr_off[nb0 + lo];
-#pragma unroll
-                for (int j = 0; j < DIM; ++j)
-                    if (p.eq[(int64_t)nodeb * DIM + j] >= 0) code |= 1 << (16 + j);
-                koff[b] = code;
-                moff[b] = (int)(nb0 - nbr0) + lo;
-                // consistent mass of the node pair: rho * sum_g detJ w N_a N_b   (discretisation.py:213-214)
                 double m = 0.0;
 #pragma unroll
                 for (int g = 0; g < NGP; ++g) m += swj[g * TPB + tid] * sN[g * NNE + al] * c_tabN[g * NNE + b];
                 mab[b] = rho * m;
             }
         }
-        // ordered accumulation: round r adds the r-th element of every node (ascending element id per slot)
-        for (int r = 0; r < maxval; ++r) {
-            if (valid && rank == r) {
-#pragma unroll
-                for (int b = 0; b < NNE; ++b) {
-                    const int off = koff[b] & 0xffff;
-#pragma unroll
-                    for (int i = 0; i < DIM; ++i) {
-                        if (rowoff[i] < 0) continue;
-                        int o = rowoff[i] + off;
-#pragma unroll
-                        for (int j = 0; j < DIM; ++j)
-                            if (koff[b] & (1 << (16 + j))) Kst[o++] += acc[i][b * DIM + j];
-                    }
-                    Mst[moff[b]] += mab[b];
-                }
-            }
-            __syncthreads();
-        }
     }
-    if (p.K)
-        for (int t = tid; t < span; t += TPB) p.K[base + t] = Kst[t];
-    // mass: one warp per node
-    const int lane = tid & 31, warp = tid >> 5;
-    for (int n = warp; n < nbn; n += TPB / 32) {
+    __syncthreads();                                     // everybody is done with xs / swj: region A becomes the staging area
+    if (valid) {
+#pragma unroll
+        for (int i = 0; i < DIM; ++i)
+#pragma unroll
+            for (int c = 0; c < ND; ++c) stage[(size_t)k * SST + i * ND + c] = acc[i][c];
+#pragma unroll
+        for (int b = 0; b < NNE; ++b) stage_m[k * NNE + b] = mab[b];
+    }
+    __syncthreads();
+
+    // ---- phase 2: one thread per (node, neighbour) item = one DIM x DIM block of the global matrix; it adds the staged
+    //      contributions of the node's elements in ascending element id (the reference's summation order) -------------
+    for (int q = tid; q < n_items; q += TPB) {
+        int lo = 0, hi = nbn;
+        while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if (s_nptr[mid] <= q) lo = mid; else hi = mid;
+        }
+        const int n = lo, pidx = q - s_nptr[n];
         const int64_t a = a0 + n;
-        if (p.node_rl[a] <= 0) continue;
-        const int64_t nb0 = p.nbr_ptr[a];
-        const int nn_a = (int)(p.nbr_ptr[a + 1] - nb0);
-        const double* mnode = Mst + (nb0 - nbr0);
-        int64_t rowg[DIM];
+        double blk[DIM][DIM];
+#pragma unroll
+        for (int i = 0; i < DIM; ++i)
+#pragma unroll
+            for (int j = 0; j < DIM; ++j) blk[i][j] = 0.0;
+        double m = 0.0;
+        for (int pr = s_ptr[n]; pr < s_ptr[n + 1]; ++pr) {
+            const int b = s_inv[pr * p.max_nbr + pidx];
+            if (b == 0xff) continue;
+            const double* sp = stage + (size_t)pr * SST + b * DIM;
+#pragma unroll
+            for (int i = 0; i < DIM; ++i)
+#pragma unroll
+                for (int j = 0; j < DIM; ++j) blk[i][j] += sp[i * ND + j];
+            m += stage_m[pr * NNE + b];
+        }
+        s_mitem[q] = m;
+        const int nodeb = p.nbr[nbr0 + q];
+        const int off = p.nbr_off[nbr0 + q];
+        bool fr[DIM];
+#pragma unroll
+        for (int j = 0; j < DIM; ++j) fr[j] = p.eq[(int64_t)nodeb * DIM + j] >= 0;
 #pragma unroll
         for (int i = 0; i < DIM; ++i) {
             const int rr = p.eq[a * DIM + i];
-            rowg[i] = rr >= 0 ? p.rowptr[rr] : -1;
-        }
-        if (p.M) {
-            for (int q = lane; q < nn_a; q += 32) {
-                const int nodeb = p.nbr[nb0 + q];
-                const double m = mnode[q];
-                const int off = p.nbr_off[nb0 + q];
+            if (rr < 0) continue;
+            int64_t o = p.rowptr[rr] + off;
 #pragma unroll
-                for (int i = 0; i < DIM; ++i) {
-                    if (rowg[i] < 0) continue;
-                    int64_t o = rowg[i] + off;
-#pragma unroll
-                    for (int j = 0; j < DIM; ++j)
-                        if (p.eq[(int64_t)nodeb * DIM + j] >= 0) p.M[o++] = (i == j) ? m : 0.0;
-                }
+            for (int j = 0; j < DIM; ++j) {
+                if (!fr[j]) continue;
+                if (p.K) p.K[o] = blk[i][j];
+                if (p.M) p.M[o] = (i == j) ? m : 0.0;
+                ++o;
             }
         }
-        if (p.Ml) {
-#pragma unroll
-            for (int i = 0; i < DIM; ++i) {
-                if (rowg[i] < 0) continue;
-                double s = 0.0;
-                for (int q = lane; q < nn_a; q += 32)
-                    if (p.eq[(int64_t)p.nbr[nb0 + q] * DIM + i] >= 0) s += mnode[q];
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
-                if (lane == 0) p.Ml[p.eq[a * DIM + i]] = s;
-            }
+    }
+    if (p.Ml) {
+        __syncthreads();
+        // row sums of the consistent mass: columns (b,i) that exist, neighbour order
+        for (int t = tid; t < nbn * DIM; t += TPB) {
+            const int n = t / DIM, i = t % DIM;
+            const int64_t a = a0 + n;
+            const int rr = p.eq[a * DIM + i];
+            if (rr < 0 || p.node_rl[a] <= 0) continue;
+            double s = 0.0;
+            for (int q = s_nptr[n]; q < s_nptr[n + 1]; ++q)
+                if (p.eq[(int64_t)p.nbr[nbr0 + q] * DIM + i] >= 0) s += s_mitem[q];
+            p.Ml[rr] = s;
         }
     }
 }
 
 template <int NNE, int DIM, int NGP>
-int launch_pairs(sc_ctx* ctx, const AsmParams& p, const ShapeTable& t) {
+int launch_pairs(sc_ctx* ctx, const AsmParams& p, const ShapeTable& t, bool* handled) {
     constexpr int TPB = 128;
+    constexpr int ND = NNE * DIM, SST = DIM * ND + 1;
+    *handled = false;
+    if (ctx->max_valence <= 0 || ctx->max_valence > TPB || p.max_nbr > 255) return SC_OK;
+    const int npb = std::max(1, TPB / ctx->max_valence);
+    const size_t bytes = ((size_t)TPB * SST + (size_t)TPB * NNE + (size_t)NGP * NNE * DIM + (size_t)NGP * NNE +
+                          (size_t)npb * p.max_nbr) * sizeof(double) + 2 * (size_t)(npb + 1) * sizeof(int) + (size_t)TPB * p.max_nbr + 16;
+    if (bytes > 110 * 1024) return SC_OK;
     SC_CUDA(ctx, cudaMemcpyToSymbolAsync(c_tabN, t.N.data(), t.N.size() * sizeof(double), 0, cudaMemcpyHostToDevice, ctx->stream));
     SC_CUDA(ctx, cudaMemcpyToSymbolAsync(c_tabdN, t.dN.data(), t.dN.size() * sizeof(double), 0, cudaMemcpyHostToDevice, ctx->stream));
     SC_CUDA(ctx, cudaMemcpyToSymbolAsync(c_tabw, t.w.data(), t.w.size() * sizeof(double), 0, cudaMemcpyHostToDevice, ctx->stream));
-    const double valence = (double)ctx->n_elem * NNE / (double)ctx->n_nodes;
-    int npb = (int)(TPB / std::max(valence, 1.0));
-    npb = std::max(1, std::min(npb, 64));
-    size_t bytes = 0;
-    for (; npb >= 1; npb >>= 1) {
-        bytes = ((size_t)NNE * DIM * TPB + (size_t)NGP * TPB + (size_t)NGP * NNE * DIM + (size_t)NGP * NNE + (size_t)npb * DIM * p.max_rl +
-                 (size_t)npb * p.max_nbr) * sizeof(double) + (npb + 2) * sizeof(int);
-        if (bytes <= 100 * 1024) break;
-    }
-    if (npb < 1) return sc_fail(ctx, SC_ERR_UNSUPPORTED, "assembly staging does not fit in shared memory (max row length %d)", p.max_rl);
     auto kern = k_assemble_pairs<NNE, DIM, NGP, TPB>;
     SC_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
     const unsigned grid = (unsigned)((p.n_nodes + npb - 1) / npb);
     kern<<<grid, TPB, bytes, ctx->stream>>>(p, npb);
     SC_CHECK_LAUNCH(ctx);
+    *handled = true;
     return SC_OK;
 }
 
@@ -537,8 +525,12 @@ int sc_assemble_run(sc_ctx* ctx, int order, int flags, double* seconds) {
     switch (key) {
 #define SC_CASE(NNE, DIM, NGP)                                                           \
     case NNE * 10000 + DIM * 1000 + NGP:                                                 \
-        if (DIM * NNE * DIM <= 72 && !ctx->force_generic_assembly) rc = launch_pairs<NNE, DIM, NGP>(ctx, p, t); \
-        else rc = launch<NNE, DIM, NGP>(ctx, p);                                         \
+        {                                                                                \
+            bool done = false;                                                           \
+            rc = SC_OK;                                                                  \
+            if (DIM * NNE * DIM <= 72 && !ctx->force_generic_assembly) rc = launch_pairs<NNE, DIM, NGP>(ctx, p, t, &done); \
+            if (rc == SC_OK && !done) rc = launch<NNE, DIM, NGP>(ctx, p);                \
+        }                                                                                \
         break;
         SC_CASE(3, 2, 1) SC_CASE(3, 2, 3) SC_CASE(3, 2, 4)
         SC_CASE(6, 2, 1) SC_CASE(6, 2, 3) SC_CASE(6, 2, 4)

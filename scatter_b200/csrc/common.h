@@ -56,7 +56,7 @@ struct sc_ctx {
     uint16_t* d_nbr_off = nullptr;  // dof offset of neighbour inside a row of the node
     int32_t* d_node_rl = nullptr;   // [n_nodes] row length of the node's rows (0 if inactive)
     int64_t* d_node_row0 = nullptr; // [n_nodes+1] number of free dofs before the node (= first row of the node)
-    int max_nbr = 0, max_rl = 0;
+    int max_nbr = 0, max_rl = 0, max_valence = 0;   // max neighbours / row length / elements per node
 
     // dof-level CSR
     int64_t nnz = 0;
@@ -68,7 +68,8 @@ struct sc_ctx {
     double* d_K = nullptr;          // [nnz]
     double* d_M = nullptr;          // [nnz] (optional)
     double* d_Ml = nullptr;         // [n_eq] lumped mass (optional)
-    double* d_Khat = nullptr;       // [nnz] effective matrix (Newmark)
+    double* d_Khat = nullptr;       // [nnz] effective matrix (Newmark / Bathe sub-step 1)
+    double* d_Khat2 = nullptr;      // [nnz] effective matrix of Bathe sub-step 2
     bool have_K = false, have_M = false, have_Ml = false;
     double c0 = 0.0, c1 = 0.0;
 
@@ -179,6 +180,9 @@ int tl_newmark(sc_ctx* ctx, double dt, int64_t t0, int64_t n_steps, int64_t oi, 
                int maxit, int64_t n_out, double* u_out, double* v_out, double* a_out, sc_stats* st);
 int tl_central_difference(sc_ctx* ctx, double dt, int64_t t0, int64_t n_steps, int64_t oi, int64_t n_out, double* u_out,
                           double* v_out, double* a_out, sc_stats* st);
+int tl_bathe(sc_ctx* ctx, double dt, int64_t t0, int64_t n_steps, int64_t oi, double rtol, int maxit, int64_t n_out, double* u_out,
+             double* v_out, double* a_out, sc_stats* st);
+int tl_static(sc_ctx* ctx, int64_t t0, int64_t n_steps, int64_t oi, double rtol, int maxit, int64_t n_out, double* u_out, sc_stats* st);
 // dist.cu
 int dist_init(sc_ctx* ctx, int rank, int world, const void* id);
 int dist_unique_id(void* out);

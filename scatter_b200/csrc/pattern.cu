@@ -202,6 +202,7 @@ int sc_pattern_build(sc_ctx* ctx) {
     SC_CUDA(ctx, cudaMemsetAsync(d_cnt, 0, sizeof(int) * (nn + 1), st));
     k_count_node_elems<<<nblk(ne * nne, T), T, 0, st>>>(ctx->d_conn, ne, nne, d_cnt);
     SC_CHECK_LAUNCH(ctx);
+    SC_TRY(max_i32(ctx, d_cnt, nn, &ctx->max_valence));
     k_i32_to_i64<<<nblk(nn + 1, T), T, 0, st>>>(d_cnt, d_tmp64, nn + 1);
     SC_CHECK_LAUNCH(ctx);
     SC_TRY(sc_alloc(ctx, &ctx->d_n2e_ptr, (size_t)nn + 1));

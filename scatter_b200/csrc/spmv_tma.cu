@@ -68,7 +68,11 @@ k_spmv_tma(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col, 
     // layout: [STAGES][cap] doubles | [STAGES][cap] ints | barriers
     double* s_val = reinterpret_cast<double*>(smem_raw);
     int* s_col = reinterpret_cast<int*>(s_val + (size_t)TMA_STAGES * cap);
-    uint64_t* bar_full = reinterpret_cast<uint64_t*>(s_col + (size_t)TMA_STAGES * cap);
+    // per-row operands of the fused epilogue (alpha, inv_d, x[row], y[row]) travel through the same ring: as single
+    // 8-byte global loads they cost 2.5 ms per step on the 50 M-dof box (32-byte DRAM requests), as bulk copies ~0.4 ms
+    constexpr int NVEC = (MODE == 2) ? 4 : (MODE == 3 ? 1 : 0);
+    double* s_vec = reinterpret_cast<double*>(s_col + (size_t)TMA_STAGES * cap);          // [STAGES][NVEC][TR]
+    uint64_t* bar_full = reinterpret_cast<uint64_t*>(s_vec + (size_t)TMA_STAGES * (NVEC > 0 ? NVEC : 1) * TR);
     uint64_t* bar_empty = bar_full + TMA_STAGES;
     __shared__ double red[TMA_CONSUMER_WARPS];
 
@@ -113,9 +117,19 @@ k_spmv_tma(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col, 
                     const uint32_t vb = (uint32_t)(((a1 - v0 + 1) & ~(int64_t)1) * 8);
                     const uint32_t cb = (uint32_t)(((a1 - c0 + 3) & ~(int64_t)3) * 4);
                     if (a1 > a0) {
-                        mbar_expect_tx(&bar_full[stage], vb + cb);
+                        const int64_t r0 = tj * TR;
+                        const uint32_t rb = (uint32_t)(((min((int64_t)TR, n_rows - r0) + 1) & ~(int64_t)1) * 8);
+                        mbar_expect_tx(&bar_full[stage], vb + cb + NVEC * rb);
                         tma_load_1d(s_val + (size_t)stage * cap, va + v0, vb, &bar_full[stage]);
                         tma_load_1d(s_col + (size_t)stage * cap, col + c0, cb, &bar_full[stage]);
+                        double* sv = s_vec + (size_t)stage * (NVEC > 0 ? NVEC : 1) * TR;
+                        if (MODE == 2) {
+                            tma_load_1d(sv, alpha + r0, rb, &bar_full[stage]);
+                            tma_load_1d(sv + TR, inv_d + r0, rb, &bar_full[stage]);
+                            tma_load_1d(sv + 2 * TR, xa + r0, rb, &bar_full[stage]);
+                            tma_load_1d(sv + 3 * TR, y + r0, rb, &bar_full[stage]);
+                        }
+                        if (MODE == 3) tma_load_1d(sv, xa + r0, rb, &bar_full[stage]);
                     } else {
                         mbar_arrive(&bar_full[stage]);                   // empty tile (ghost rows): nothing to copy
                     }
@@ -140,11 +154,6 @@ k_spmv_tma(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col, 
             const int myr = lane / LPR;
             const int64_t myrow = row0 + myr;
             const bool owner = (lane % LPR) == 0 && myrow < n_rows;
-            double e_al = 0.0, e_id = 0.0, e_x = 0.0, e_y = 0.0;
-            if (owner) {
-                if (MODE == 2) { e_al = alpha[myrow]; e_id = inv_d[myrow]; e_x = xa[myrow]; e_y = y[myrow]; }
-                if (MODE == 3) e_x = xa[myrow];
-            }
             const int64_t tile_s0 = __shfl_sync(0xffffffffu, rp, 31);
             const int dvc = (int)((tile_s0 & ~(int64_t)1) - (tile_s0 & ~(int64_t)3));     // value-slice vs column-slice origin
             const int loc = (int)(rp - (tile_s0 & ~(int64_t)1));                         // offset inside the value slice
@@ -161,6 +170,12 @@ k_spmv_tma(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col, 
             const double* sv = s_val + (size_t)stage * cap;
             const int* sc = s_col + (size_t)stage * cap + dvc;
             mbar_wait(&bar_full[stage], phase);
+            double e_al = 0.0, e_id = 0.0, e_x = 0.0, e_y = 0.0;
+            if (NVEC > 0 && owner && maxlen > 0) {
+                const double* svec = s_vec + (size_t)stage * NVEC * TR + warp * RW + myr;
+                if (MODE == 2) { e_al = svec[0]; e_id = svec[TR]; e_x = svec[2 * TR]; e_y = svec[3 * TR]; }
+                if (MODE == 3) e_x = svec[0];
+            }
 
             double sum[RW];
 #pragma unroll
@@ -233,7 +248,7 @@ k_spmv_tma(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col, 
                     if (mylen > 0) y[myrow] = e_id * (-mine) + e_al * e_x - (e_al - 1.0) * e_y;
                 } else {
                     y[myrow] = mine;
-                    if (MODE == 3) dot_acc += e_x * mine;
+                    if (MODE == 3 && mylen > 0) dot_acc += e_x * mine;
                 }
             }
         }
@@ -260,7 +275,8 @@ int launch_tr(sc_ctx* ctx, const double* va, const double* xa, double* y, const 
     const int64_t n_tiles = (n + TR - 1) / TR;
     int cap = TR * ctx->max_rl + 8;
     cap = (cap + 31) & ~31;                                  // stage starts stay 128-byte aligned
-    const size_t bytes = (size_t)TMA_STAGES * cap * (sizeof(double) + sizeof(int)) + 2 * TMA_STAGES * sizeof(uint64_t);
+    const size_t bytes = (size_t)TMA_STAGES * cap * (sizeof(double) + sizeof(int)) + (size_t)TMA_STAGES * 4 * TR * sizeof(double) +
+                         2 * TMA_STAGES * sizeof(uint64_t);
     auto kern = k_spmv_tma<MODE, TR>;
     SC_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
     unsigned grid = (unsigned)std::min<int64_t>(n_tiles, (int64_t)ctx->sm_count * 2);
@@ -279,7 +295,7 @@ bool la_tma_usable(sc_ctx* ctx) {
     if (ctx->force_no_tma || ctx->max_rl <= 0) return false;
     const size_t per_entry = sizeof(double) + sizeof(int);
     const size_t budget = 100 * 1024;                        // per CTA, two CTAs per SM
-    return (size_t)TMA_STAGES * (8 * (size_t)ctx->max_rl + 40) * per_entry <= budget;
+    return (size_t)TMA_STAGES * (8 * (size_t)ctx->max_rl + 40) * per_entry + 4096 <= budget;
 }
 
 template <int MODE>
@@ -287,7 +303,7 @@ static int launch_mode(sc_ctx* ctx, const double* va, const double* xa, double* 
                        double* partial, unsigned* nblocks_out) {
     const size_t per_entry = sizeof(double) + sizeof(int);
     const size_t budget = 100 * 1024;
-    auto fits = [&](int tr) { return (size_t)TMA_STAGES * ((size_t)tr * ctx->max_rl + 40) * per_entry <= budget; };
+    auto fits = [&](int tr) { return (size_t)TMA_STAGES * ((size_t)tr * ctx->max_rl + 40) * per_entry + (size_t)TMA_STAGES * 32 * tr <= budget; };
     if (fits(32)) return launch_tr<MODE, 32>(ctx, va, xa, y, inv_d, alpha, partial, nblocks_out);
     if (fits(16)) return launch_tr<MODE, 16>(ctx, va, xa, y, inv_d, alpha, partial, nblocks_out);
     return launch_tr<MODE, 8>(ctx, va, xa, y, inv_d, alpha, partial, nblocks_out);

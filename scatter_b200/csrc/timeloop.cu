@@ -157,11 +157,39 @@ __global__ void k_neg_add(double* __restrict__ y, int64_t n) {   // y = -y
     if (i < n) y[i] = -y[i];
 }
 
+
+// out = c0 x0 + c1 x1 + c2 x2 + c3 x3 (null pointers are skipped)
+__global__ void k_lincomb(double* __restrict__ out, double c0, const double* __restrict__ x0, double c1, const double* __restrict__ x1,
+                          double c2, const double* __restrict__ x2, double c3, const double* __restrict__ x3, int64_t n) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double s = c0 * x0[i];
+    if (x1) s += c1 * x1[i];
+    if (x2) s += c2 * x2[i];
+    if (x3) s += c3 * x3[i];
+    out[i] = s;
+}
+int lincomb(sc_ctx* ctx, double* out, double c0, const double* x0, double c1, const double* x1, double c2 = 0.0,
+            const double* x2 = nullptr, double c3 = 0.0, const double* x3 = nullptr) {
+    k_lincomb<<<nblk(ctx->n_eq, 256), 256, 0, ctx->stream>>>(out, c0, x0, c1, x1, c2, x2, c3, x3, ctx->n_eq);
+    SC_CHECK_LAUNCH(ctx);
+    return SC_OK;
+}
+// rhs = M xm + C xc with C = C_abs + c0 M + c1 K  ->  M (xm + c0 xc) + K (c1 xc) + C_abs xc   (x1, x2 are scratch)
+int apply_M_C(sc_ctx* ctx, const double* xm, const double* xc, double* x1, double* x2, double* rhs) {
+    SC_TRY(lincomb(ctx, x1, 1.0, xm, ctx->c0, xc));
+    SC_TRY(lincomb(ctx, x2, ctx->c1, xc, 0.0, nullptr));
+    if (ctx->world > 1) { SC_TRY(dist_halo(ctx, x1, ctx->stream)); SC_TRY(dist_halo(ctx, x2, ctx->stream)); }
+    SC_TRY(la_spmv2(ctx, ctx->d_M, x1, ctx->d_K, x2, rhs));
+    SC_TRY(la_cabs_spmv_add(ctx, xc, rhs, 1.0));
+    return SC_OK;
+}
+
 constexpr int PCG_NB = 1024;
 
 // Jacobi-preconditioned CG for A x = b, x0 = 0.  Returns iterations and the relative residual.
 int pcg(sc_ctx* ctx, const double* vals, const double* dinv, const double* b, double* x, double* r, double* p, double* q,
-        double rtol, int maxit, int* iters, double* relres) {
+        double rtol, int maxit, int* iters, double* relres, double ref_norm2 = -1.0) {
     const int64_t n = ctx->n_eq;
     cudaStream_t st = ctx->stream;
     double* sc = ctx->d_scal;
@@ -172,10 +200,14 @@ int pcg(sc_ctx* ctx, const double* vals, const double* dinv, const double* b, do
     if (ctx->world > 1) { SC_TRY(dist_allreduce_sum(ctx, sc + 0, 1, st)); SC_TRY(dist_allreduce_sum(ctx, sc + 4, 1, st)); }
     SC_CUDA(ctx, cudaMemcpyAsync(ctx->h_pinned, sc, 5 * sizeof(double), cudaMemcpyDeviceToHost, st));
     SC_CUDA(ctx, cudaStreamSynchronize(st));
-    const double bb = ctx->h_pinned[4];
+    double bb = ctx->h_pinned[4];
     *iters = 0;
     *relres = 0.0;
     if (!(bb > 0.0)) return SC_OK;   // zero right-hand side: x = 0
+    if (ref_norm2 > 0.0) {           // stopping test relative to a caller-supplied scale (incremental static solve)
+        if (bb <= rtol * rtol * ref_norm2) return SC_OK;
+        bb = ref_norm2;
+    }
     const double target = rtol * rtol * bb;
     for (int it = 1; it <= maxit; ++it) {
         if (ctx->world > 1) SC_TRY(dist_halo(ctx, p, st));
@@ -410,6 +442,150 @@ int tl_central_difference(sc_ctx* ctx, double dt, int64_t t0, int64_t n_steps, i
         stats->kernel_launches = ctx->launches - launches0;
         stats->last_residual = 0.0;
         stats->seconds_halo = 0.0;
+    }
+    return SC_OK;
+}
+
+// Bathe composite scheme (trapezoidal rule over dt/2, then 3-point backward Euler), two PCG solves per step.
+//   sub-step 1:  (K + 4/dt C + 16/dt^2 M) u1 = F(t+dt/2) + M (16 u/dt^2 + 8 v/dt + a) + C (4 u/dt + v)
+//                v1 = 4 (u1 - u)/dt - v
+//   sub-step 2:  (K + 3/dt C + 9/dt^2 M) u2 = F(t+dt) + M (12 u1/dt^2 - 3 u/dt^2 + 4 v1/dt - v/dt) + C (4 u1/dt - u/dt)
+//                v2 = (u - 4 u1 + 3 u2)/dt,  a2 = (v - 4 v1 + 3 v2)/dt
+// The half-step force is the mean of the two step forces (the load schedule is defined on whole steps).
+int tl_bathe(sc_ctx* ctx, double dt, int64_t t0, int64_t n_steps, int64_t oi, double rtol, int maxit, int64_t n_out, double* u_out,
+             double* v_out, double* a_out, sc_stats* stats) {
+    auto wall0 = std::chrono::steady_clock::now();
+    const int64_t n = ctx->n_eq;
+    cudaStream_t st = ctx->stream;
+    const int64_t launches0 = ctx->launches;
+    SC_TRY(la_scratch(ctx));
+    SC_TRY(ensure_state(ctx));
+    double *x1, *x2, *xm, *xc, *rhs, *u1, *v1, *r, *p, *q, *dinv1, *dinv2, *dinvM, *u2;
+    SC_TRY(sc_work(ctx, 0, &x1)); SC_TRY(sc_work(ctx, 1, &x2)); SC_TRY(sc_work(ctx, 2, &xm)); SC_TRY(sc_work(ctx, 3, &rhs));
+    SC_TRY(sc_work(ctx, 4, &u1)); SC_TRY(sc_work(ctx, 5, &r)); SC_TRY(sc_work(ctx, 6, &p)); SC_TRY(sc_work(ctx, 7, &q));
+    SC_TRY(sc_work(ctx, 8, &dinv1)); SC_TRY(sc_work(ctx, 9, &dinvM)); SC_TRY(sc_work(ctx, 10, &xc)); SC_TRY(sc_work(ctx, 11, &v1));
+    SC_TRY(sc_work(ctx, 12, &dinv2)); SC_TRY(sc_work(ctx, 13, &u2));
+    const double c0 = ctx->c0, c1 = ctx->c1;
+    SC_TRY(sc_alloc(ctx, &ctx->d_Khat, (size_t)ctx->nnz));
+    SC_TRY(sc_alloc(ctx, &ctx->d_Khat2, (size_t)ctx->nnz));
+    SC_TRY(la_axpby_vals(ctx, ctx->d_Khat, 1.0 + 4.0 / dt * c1, ctx->d_K, 16.0 / (dt * dt) + 4.0 / dt * c0, ctx->d_M, ctx->nnz));
+    SC_TRY(la_cabs_add_values(ctx, ctx->d_Khat, 4.0 / dt));
+    SC_TRY(la_axpby_vals(ctx, ctx->d_Khat2, 1.0 + 3.0 / dt * c1, ctx->d_K, 9.0 / (dt * dt) + 3.0 / dt * c0, ctx->d_M, ctx->nnz));
+    SC_TRY(la_cabs_add_values(ctx, ctx->d_Khat2, 3.0 / dt));
+    SC_TRY(la_extract_diag(ctx, ctx->d_Khat, dinv1, true));
+    SC_TRY(la_extract_diag(ctx, ctx->d_Khat2, dinv2, true));
+    SC_TRY(la_extract_diag(ctx, ctx->d_M, dinvM, true));
+    int64_t pcg_total = 0, row = 0;
+    int iters = 0;
+    double relres = 0.0;
+    // initial acceleration a = M^-1 (F(t0) - C v - K u)
+    SC_TRY(lincomb(ctx, xm, 0.0, ctx->d_v, 0.0, nullptr));
+    SC_TRY(apply_M_C(ctx, xm, ctx->d_v, x1, x2, rhs));
+    SC_TRY(la_spmv(ctx, ctx->d_K, ctx->d_u, x1));
+    SC_TRY(lincomb(ctx, rhs, -1.0, rhs, -1.0, x1));
+    SC_TRY(apply_load(ctx, t0, 1.0, nullptr, rhs));
+    SC_TRY(pcg(ctx, ctx->d_M, dinvM, rhs, ctx->d_a, r, p, q, rtol, maxit, &iters, &relres));
+    pcg_total += iters;
+    if (t0 % oi == 0 && row < n_out) {
+        SC_TRY(store_row(ctx, u_out, row, ctx->d_u)); SC_TRY(store_row(ctx, v_out, row, ctx->d_v)); SC_TRY(store_row(ctx, a_out, row, ctx->d_a));
+        ++row;
+    }
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    cudaEventRecord(e0, st);
+    double *u = ctx->d_u, *v = ctx->d_v, *a = ctx->d_a;
+    for (int64_t t = t0 + 1; t <= t0 + n_steps; ++t) {
+        // ---- sub-step 1
+        SC_TRY(lincomb(ctx, xm, 16.0 / (dt * dt), u, 8.0 / dt, v, 1.0, a));
+        SC_TRY(lincomb(ctx, xc, 4.0 / dt, u, 1.0, v));
+        SC_TRY(apply_M_C(ctx, xm, xc, x1, x2, rhs));
+        SC_TRY(apply_load(ctx, t - 1, 0.5, nullptr, rhs));
+        SC_TRY(apply_load(ctx, t, 0.5, nullptr, rhs));
+        SC_TRY(pcg(ctx, ctx->d_Khat, dinv1, rhs, u1, r, p, q, rtol, maxit, &iters, &relres));
+        pcg_total += iters;
+        if (ctx->world > 1) SC_TRY(dist_halo(ctx, u1, st));
+        SC_TRY(lincomb(ctx, v1, 4.0 / dt, u1, -4.0 / dt, u, -1.0, v));
+        // ---- sub-step 2
+        SC_TRY(lincomb(ctx, xm, 12.0 / (dt * dt), u1, -3.0 / (dt * dt), u, 4.0 / dt, v1, -1.0 / dt, v));
+        SC_TRY(lincomb(ctx, xc, 4.0 / dt, u1, -1.0 / dt, u));
+        SC_TRY(apply_M_C(ctx, xm, xc, x1, x2, rhs));
+        SC_TRY(apply_load(ctx, t, 1.0, nullptr, rhs));
+        SC_TRY(pcg(ctx, ctx->d_Khat2, dinv2, rhs, u2, r, p, q, rtol, maxit, &iters, &relres));
+        pcg_total += iters;
+        if (ctx->world > 1) SC_TRY(dist_halo(ctx, u2, st));
+        // v2 (into x1), a2, then commit
+        SC_TRY(lincomb(ctx, x1, 1.0 / dt, u, -4.0 / dt, u1, 3.0 / dt, u2));
+        SC_TRY(lincomb(ctx, a, 1.0 / dt, v, -4.0 / dt, v1, 3.0 / dt, x1));
+        SC_CUDA(ctx, cudaMemcpyAsync(v, x1, sizeof(double) * n, cudaMemcpyDeviceToDevice, st));
+        SC_CUDA(ctx, cudaMemcpyAsync(u, u2, sizeof(double) * n, cudaMemcpyDeviceToDevice, st));
+        if (t % oi == 0 && row < n_out) {
+            SC_TRY(store_row(ctx, u_out, row, u)); SC_TRY(store_row(ctx, v_out, row, v)); SC_TRY(store_row(ctx, a_out, row, a));
+            ++row;
+        }
+    }
+    cudaEventRecord(e1, st);
+    SC_CUDA(ctx, cudaStreamSynchronize(st));
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    if (stats) {
+        stats->seconds_device = ms * 1e-3;
+        stats->seconds_total = std::chrono::duration<double>(std::chrono::steady_clock::now() - wall0).count();
+        stats->steps = n_steps;
+        stats->pcg_iterations = pcg_total;
+        stats->kernel_launches = ctx->launches - launches0;
+        stats->last_residual = relres;
+    }
+    return SC_OK;
+}
+
+// Static solver: K u(t) = F(t) for every step, solved incrementally (du = K^-1 (F(t) - K u)) with Jacobi-PCG.
+int tl_static(sc_ctx* ctx, int64_t t0, int64_t n_steps, int64_t oi, double rtol, int maxit, int64_t n_out, double* u_out, sc_stats* stats) {
+    auto wall0 = std::chrono::steady_clock::now();
+    const int64_t n = ctx->n_eq;
+    cudaStream_t st = ctx->stream;
+    const int64_t launches0 = ctx->launches;
+    SC_TRY(la_scratch(ctx));
+    SC_TRY(ensure_state(ctx));
+    double *rhs, *du, *r, *p, *q, *dinv, *f;
+    SC_TRY(sc_work(ctx, 3, &rhs)); SC_TRY(sc_work(ctx, 4, &du)); SC_TRY(sc_work(ctx, 5, &r)); SC_TRY(sc_work(ctx, 6, &p));
+    SC_TRY(sc_work(ctx, 7, &q)); SC_TRY(sc_work(ctx, 8, &dinv)); SC_TRY(sc_work(ctx, 0, &f));
+    SC_TRY(la_extract_diag(ctx, ctx->d_K, dinv, true));
+    SC_CUDA(ctx, cudaMemsetAsync(ctx->d_v, 0, sizeof(double) * n, st));
+    SC_CUDA(ctx, cudaMemsetAsync(ctx->d_a, 0, sizeof(double) * n, st));
+    int64_t pcg_total = 0, row = 0;
+    int iters = 0;
+    double relres = 0.0;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    cudaEventRecord(e0, st);
+    for (int64_t t = t0; t <= t0 + n_steps; ++t) {
+        if (ctx->world > 1) SC_TRY(dist_halo(ctx, ctx->d_u, st));
+        SC_TRY(la_spmv(ctx, ctx->d_K, ctx->d_u, rhs));
+        SC_TRY(la_fill(ctx, f, 0.0, n));
+        SC_TRY(apply_load(ctx, t, 1.0, nullptr, f));
+        SC_TRY(la_dot(ctx, f, f, ctx->d_scal + 8));
+        SC_TRY(lincomb(ctx, rhs, -1.0, rhs, 1.0, f));
+        SC_CUDA(ctx, cudaMemcpyAsync(ctx->h_pinned + 8, ctx->d_scal + 8, sizeof(double), cudaMemcpyDeviceToHost, st));
+        SC_CUDA(ctx, cudaStreamSynchronize(st));
+        const double ff = ctx->h_pinned[8];
+        SC_TRY(pcg(ctx, ctx->d_K, dinv, rhs, du, r, p, q, rtol, maxit, &iters, &relres, ff > 0.0 ? ff : -1.0));
+        pcg_total += iters;
+        SC_TRY(lincomb(ctx, ctx->d_u, 1.0, ctx->d_u, 1.0, du));
+        if (t % oi == 0 && row < n_out) { SC_TRY(store_row(ctx, u_out, row, ctx->d_u)); ++row; }
+    }
+    cudaEventRecord(e1, st);
+    SC_CUDA(ctx, cudaStreamSynchronize(st));
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    if (stats) {
+        stats->seconds_device = ms * 1e-3;
+        stats->seconds_total = std::chrono::duration<double>(std::chrono::steady_clock::now() - wall0).count();
+        stats->steps = n_steps;
+        stats->pcg_iterations = pcg_total;
+        stats->kernel_launches = ctx->launches - launches0;
+        stats->last_residual = relres;
     }
     return SC_OK;
 }

@@ -132,10 +132,36 @@ class CentralDifferenceSolver(_DeviceSolver):
 
 
 class BatheSolver(_DeviceSolver):
-    def calculate(self, *a, **k):
-        raise NotImplementedError("Solver.BATHE has no device implementation yet (no reference fixture pins it)")
+    """Bathe composite scheme (trapezoidal rule over dt/2 + 3-point backward Euler); see csrc/timeloop.cu `tl_bathe`."""
+
+    def __init__(self):
+        super().__init__()
+        self.pcg_rtol = 1e-14
+        self.pcg_maxit = 20000
+
+    def calculate(self, M, C, K, F, t_start_idx, t_end_idx):
+        ctx = self._ctx()
+        self._upload_loads(ctx)
+        ctx.set_state(self.u0, self.v0)
+        uo, vo, ao = self._out_views(int(t_start_idx))
+        _, _, _, st = ctx.run_bathe(self._dt(t_start_idx, t_end_idx), int(t_start_idx), int(t_end_idx) - int(t_start_idx),
+                                    self.output_interval, self.pcg_rtol, self.pcg_maxit, uo, vo, ao)
+        self.stats.append(st)
 
 
 class StaticSolver(_DeviceSolver):
-    def calculate(self, *a, **k):
-        raise NotImplementedError("Solver.STATIC has no device implementation yet (no reference fixture pins it)")
+    """K u(t) = F(t) at every step (`calculate(K, F, t_start_idx, t_end_idx)`, scatter.py:156)."""
+
+    def __init__(self):
+        super().__init__()
+        self.pcg_rtol = 1e-12
+        self.pcg_maxit = 200000
+
+    def calculate(self, K, F, t_start_idx, t_end_idx):
+        ctx = self._ctx()
+        self._upload_loads(ctx)
+        ctx.set_state(self.u0, None)
+        uo, _, _ = self._out_views(int(t_start_idx))
+        _, st = ctx.run_static(int(t_start_idx), int(t_end_idx) - int(t_start_idx), self.output_interval, self.pcg_rtol,
+                               self.pcg_maxit, uo)
+        self.stats.append(st)

@@ -287,6 +287,40 @@ def test_central_difference_vs_oracle(golden_meshes, oracle):
     assert errs[0] <= TOL_HIST and errs[1] <= TOL_HIST and errs[2] <= 1e-7, (errs, rows[:3], rows[24:28], rows[-2:])
 
 
+def test_bathe_and_static_vs_oracle(golden_meshes, oracle):
+    """Solver.BATHE / Solver.STATIC have no reference fixture: compare the device loops with the oracle's textbook
+    restatement, and Bathe with the pinned Newmark oracle (both second order)."""
+    from scatter_b200 import force_external, solvers
+    mesh, bc = "column.msh", cases.BC_COLUMN
+    mat, sett = cases.materials(), cases.settings()
+    load = {"force": [0, -1000, 0], "node": [3, 4, 7, 8], "time": 0.05, "type": "heaviside", "ini_steps": 20}
+    dt = 5e-4
+    om = oracle.build_model(golden_meshes[mesh], bc)
+    K, M, C, _ = oracle.system_matrices(om, mat, sett)
+    time = oracle.time_array(load["time"], dt)
+    force = oracle.LoadSchedule(om, load, time)
+    Ub, Vb, Ab, _ = oracle.bathe(M, C, K, force, time, 2)
+    Un, Vn, An, _ = oracle.newmark(M, C, K, force, time, 2)
+    Us, _ = oracle.static(K, force, time[:12], 1)
+    assert rel_l2(Ub, Un) < 2e-2          # same physics, different second-order schemes
+    for cls, ref in ((solvers.BatheSolver, (Ub, Vb, Ab)), (solvers.StaticSolver, (Us,))):
+        m, mx = build(golden_meshes[mesh], bc, mat, sett)
+        num = cls()
+        static = cls is solvers.StaticSolver
+        tt = time[:12] if static else time
+        num.output_interval = 1 if static else 2
+        num.initialise(m.number_eq, tt); num.bind(mx)
+        F = force_external.Force(); F.initialise_load(load, tt if not static else time, m, num)
+        num.update_rhs_at_time_step_func = F.update_load_at_t
+        if static:
+            num.calculate(None, F.force_vector, 0, len(tt) - 1)
+            assert rel_l2(num.u, ref[0]) <= 1e-8
+        else:
+            num.update(0)
+            num.calculate(None, None, None, F.force_vector, 0, len(tt) - 1)
+            assert rel_l2(num.u, ref[0]) <= TOL_HIST and rel_l2(num.v, ref[1]) <= TOL_HIST and rel_l2(num.a, ref[2]) <= 1e-7
+
+
 def test_scatter_entry_point_writes_reference_layout(golden_meshes, golden_histories, tmp_path):
     from scatter_b200 import scatter
     c = cases.history_case("quad4_heaviside")
