@@ -284,6 +284,8 @@ def run_ours(args):
     for _ in range(args.steps):
         st = stage_device()
         dev_s += st["seconds_device"]
+    if st.get("step_bytes", 0) > 0:
+        step_bytes = int(st["step_bytes"])
     barrier()
     wall = time.perf_counter() - w0
     launches = ctx.kernel_launches() - l0
@@ -343,7 +345,8 @@ def run_ours(args):
                 "warmup": max(args.warmup, 3), "ms_per_step": 1e3 * wall / args.steps, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(args, world),
                 "dof_total": total_dof, "dof_per_gpu": n_owned, "nnz_per_gpu": nnz, "time_steps_timed": n_ts,
-                "roofline": {"bound": "hbm", "kernel": "k_spmv<2> (fused CSR SpMV + central-difference update)",
+                "roofline": {"bound": "hbm", "kernel": st.get("step_kernel", "?") + ": fused SpMV + central-difference update",
+                             "bytes_per_launch_plain_csr": 12 * nnz + 48 * n_owned,
                              "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
                              "bytes_per_launch": step_bytes, "kernel_ms": 1e3 * kernel_s, "traffic": TRAFFIC.get(s)},
                 "assembly": {"seconds": t_asm, "pattern_seconds": t_pattern, "gbs": asm_bytes / t_asm / 1e9,

@@ -37,7 +37,10 @@ class Stats(C.Structure):
                 ("last_residual", C.c_double), ("reserved", C.c_double * 4)]
 
     def as_dict(self):
-        return {k: getattr(self, k) for k, _ in self._fields_ if k != "reserved"}
+        d = {k: getattr(self, k) for k, _ in self._fields_ if k != "reserved"}
+        d["step_bytes"] = self.reserved[0]
+        d["step_kernel"] = {0: "k_spmv (register staged)", 1: "k_spmv_tma (row tiles)", 2: "k_spmv_node (node-blocked, TMA)"}.get(int(self.reserved[1]), "?")
+        return d
 
 
 class ScatterB200Error(RuntimeError):

@@ -56,6 +56,11 @@ struct sc_ctx {
     uint16_t* d_nbr_off = nullptr;  // dof offset of neighbour inside a row of the node
     int32_t* d_node_rl = nullptr;   // [n_nodes] row length of the node's rows (0 if inactive)
     int64_t* d_node_row0 = nullptr; // [n_nodes+1] number of free dofs before the node (= first row of the node)
+    // node-blocked column structure for the time loop: all rows of a node share one column list
+    struct NodeDesc { int64_t val_off; int64_t col_off; int32_t row0; int32_t len_nfree; };   // len | nfree << 24
+    NodeDesc* d_nd = nullptr;       // [n_nodes + 32] (padded with empty descriptors)
+    int32_t* d_ncol = nullptr;      // [sum node_rl] column list per node
+    int64_t ncol_total = 0;
     int max_nbr = 0, max_rl = 0, max_valence = 0;   // max neighbours / row length / elements per node
 
     // dof-level CSR
@@ -93,6 +98,7 @@ struct sc_ctx {
     double* d_scal = nullptr;       // small device scalar block
     double* d_partial = nullptr;    // reduction partials
     double* h_pinned = nullptr;     // pinned host scalars
+    bool force_no_node = false;            // env SCATTER_B200_NO_NODE: row-wise kernels instead of the node-blocked one
     bool force_no_tma = false;             // test hook / env SCATTER_B200_NO_TMA: register-staged SpMV instead of the TMA ring
     bool force_generic_assembly = false;   // test hook: use the warp-per-node kernel for every element type
     bool cd_resume_valid = false;   // work[0] holds u(t - dt) of the central-difference state at step cd_resume_t
@@ -172,6 +178,12 @@ int la_cd_step(sc_ctx* ctx, const double* K, const double* u, double* uprev_next
 int la_spmv_dot(sc_ctx* ctx, const double* vals, const double* p, double* q, double* d_out);
 // spmv_tma.cu
 bool la_tma_usable(sc_ctx* ctx);
+// spmv_node.cu
+bool la_node_usable(sc_ctx* ctx);
+int la_node_spmv(sc_ctx* ctx, const double* vals, const double* x, double* y);
+int la_node_cd_step(sc_ctx* ctx, const double* K, const double* u, double* uprev_next, const double* inv_d, const double* alpha);
+int la_node_spmv_dot(sc_ctx* ctx, const double* vals, const double* p, double* q, double* partial, unsigned* nblocks);
+int64_t la_node_step_bytes(sc_ctx* ctx);
 int la_tma_spmv(sc_ctx* ctx, const double* vals, const double* x, double* y);
 int la_tma_cd_step(sc_ctx* ctx, const double* K, const double* u, double* uprev_next, const double* inv_d, const double* alpha);
 int la_tma_spmv_dot(sc_ctx* ctx, const double* vals, const double* p, double* q, double* partial, unsigned* nblocks);

@@ -248,6 +248,7 @@ int la_scratch(sc_ctx* ctx) {
 }
 
 int la_spmv(sc_ctx* ctx, const double* vals, const double* x, double* y) {
+    if (la_node_usable(ctx)) return la_node_spmv(ctx, vals, x, y);
     if (la_tma_usable(ctx)) return la_tma_spmv(ctx, vals, x, y);
     return spmv_launch<0>(ctx, vals, x, nullptr, nullptr, y, nullptr, nullptr, nullptr, nullptr);
 }
@@ -258,6 +259,7 @@ int la_spmv2(sc_ctx* ctx, const double* va, const double* xa, const double* vb, 
 
 // u_next (in place over u_prev) = inv_d*(-K u) + alpha*u - (alpha-1)*u_prev
 int la_cd_step(sc_ctx* ctx, const double* K, const double* u, double* uprev_next, const double* inv_d, const double* alpha) {
+    if (la_node_usable(ctx)) return la_node_cd_step(ctx, K, u, uprev_next, inv_d, alpha);
     if (la_tma_usable(ctx)) return la_tma_cd_step(ctx, K, u, uprev_next, inv_d, alpha);
     return spmv_launch<2>(ctx, K, u, nullptr, nullptr, uprev_next, inv_d, alpha, nullptr, nullptr);
 }
@@ -266,7 +268,8 @@ int la_cd_step(sc_ctx* ctx, const double* K, const double* u, double* uprev_next
 int la_spmv_dot(sc_ctx* ctx, const double* vals, const double* p, double* q, double* d_out) {
     SC_TRY(la_scratch(ctx));
     unsigned nb = 0;
-    if (la_tma_usable(ctx)) SC_TRY(la_tma_spmv_dot(ctx, vals, p, q, ctx->d_partial, &nb));
+    if (la_node_usable(ctx)) SC_TRY(la_node_spmv_dot(ctx, vals, p, q, ctx->d_partial, &nb));
+    else if (la_tma_usable(ctx)) SC_TRY(la_tma_spmv_dot(ctx, vals, p, q, ctx->d_partial, &nb));
     else SC_TRY(spmv_launch<3>(ctx, vals, p, nullptr, nullptr, q, nullptr, nullptr, ctx->d_partial, &nb));
     k_reduce_final<<<1, RED_THREADS, 0, ctx->stream>>>(ctx->d_partial, nb, 1, 0, d_out);
     SC_CHECK_LAUNCH(ctx);

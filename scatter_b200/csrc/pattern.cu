@@ -142,6 +142,45 @@ __global__ void k_fill_columns(const int32_t* __restrict__ eq, int dim, const in
     }
 }
 
+// node-blocked structure: one column list per node (shared by all its rows) + a 24-byte descriptor per node
+__global__ void k_node_columns(const int32_t* __restrict__ eq, int dim, const int64_t* __restrict__ nbr_ptr,
+                               const int32_t* __restrict__ nbr, const uint16_t* __restrict__ nbr_off,
+                               const int64_t* __restrict__ ncol_ptr, int64_t n_nodes, int32_t* __restrict__ ncol) {
+    int64_t a = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    int lane = threadIdx.x & 31;
+    if (a >= n_nodes) return;
+    const int64_t s = nbr_ptr[a], e = nbr_ptr[a + 1];
+    const int64_t base = ncol_ptr[a];
+    for (int64_t k = s + lane; k < e; k += 32) {
+        const int b = nbr[k];
+        int64_t o = base + nbr_off[k];
+        for (int j = 0; j < dim; ++j) {
+            const int c = eq[(int64_t)b * dim + j];
+            if (c >= 0) ncol[o++] = c;
+        }
+    }
+}
+__global__ void k_node_desc(const int64_t* __restrict__ node_row0, const int32_t* __restrict__ node_rl, const int64_t* __restrict__ rowptr,
+                            const int64_t* __restrict__ ncol_ptr, int64_t n_nodes, int64_t n_pad, sc_ctx::NodeDesc* __restrict__ nd) {
+    int64_t a = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (a >= n_pad) return;
+    sc_ctx::NodeDesc d;
+    if (a < n_nodes) {
+        const int64_t r0 = node_row0[a];
+        const int nfree = (int)(node_row0[a + 1] - r0);
+        d.row0 = (int32_t)r0;
+        d.val_off = rowptr[r0];
+        d.col_off = ncol_ptr[a];
+        d.len_nfree = nfree > 0 ? (node_rl[a] | (nfree << 24)) : 0;     // fully fixed nodes own no rows: nothing to stream
+    } else {   // padding: empty nodes at the end of the value / column arrays
+        d.row0 = (int32_t)node_row0[n_nodes];
+        d.val_off = rowptr[node_row0[n_nodes]];
+        d.col_off = ncol_ptr[n_nodes];
+        d.len_nfree = 0;
+    }
+    nd[a] = d;
+}
+
 __global__ void k_i32_to_i64(const int* __restrict__ in, int64_t* __restrict__ out, int64_t n) {
     int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (i < n) out[i] = in[i];
@@ -282,6 +321,25 @@ int sc_pattern_build(sc_ctx* ctx) {
     SC_TRY(sc_alloc(ctx, &ctx->d_col, (size_t)ctx->nnz));
     k_fill_columns<<<nblk(nn * 32, T), T, 0, st>>>(ctx->d_eq, dim, ctx->d_nbr_ptr, ctx->d_nbr, ctx->d_nbr_off, ctx->d_rowptr, nn, ctx->d_col);
     SC_CHECK_LAUNCH(ctx);
+    // ---- node-blocked column lists + descriptors (time-loop kernels, spmv_node.cu) ------------------------------------
+    {
+        int64_t* d_ncol_ptr = nullptr;
+        SC_TRY(sc_alloc(ctx, &d_ncol_ptr, (size_t)nn + 1));
+        SC_CUDA(ctx, cudaMemsetAsync(d_tmp64, 0, sizeof(int64_t) * (nn + 1), st));
+        k_i32_to_i64<<<nblk(nn, T), T, 0, st>>>(ctx->d_node_rl, d_tmp64, nn);
+        SC_CHECK_LAUNCH(ctx);
+        SC_TRY(scan64(ctx, d_tmp64, d_ncol_ptr, nn));
+        SC_CUDA(ctx, cudaMemcpy(&ctx->ncol_total, d_ncol_ptr + nn, sizeof(int64_t), cudaMemcpyDeviceToHost));
+        SC_TRY(sc_alloc(ctx, &ctx->d_ncol, (size_t)ctx->ncol_total));
+        k_node_columns<<<nblk(nn * 32, T), T, 0, st>>>(ctx->d_eq, dim, ctx->d_nbr_ptr, ctx->d_nbr, ctx->d_nbr_off, d_ncol_ptr, nn, ctx->d_ncol);
+        SC_CHECK_LAUNCH(ctx);
+        const int64_t n_pad = nn + 32;
+        SC_TRY(sc_alloc(ctx, &ctx->d_nd, (size_t)n_pad));
+        k_node_desc<<<nblk(n_pad, T), T, 0, st>>>(ctx->d_node_row0, ctx->d_node_rl, ctx->d_rowptr, d_ncol_ptr, nn, n_pad, ctx->d_nd);
+        SC_CHECK_LAUNCH(ctx);
+        SC_CUDA(ctx, cudaStreamSynchronize(st));
+        sc_free(&d_ncol_ptr);
+    }
     SC_CUDA(ctx, cudaStreamSynchronize(st));
     sc_free(&d_cnt); sc_free(&d_tmp64); sc_free(&d_flag);
     ctx->have_pattern = true;

@@ -1,0 +1,308 @@
+// Node-blocked, TMA-fed SpMV for the time loop (sm_100a).
+//
+// In the reference's CSR (scatter/system_matrix.py:98-121) the rows of one node -- its 1..3 free dofs -- have identical
+// column lists, because two dofs couple iff their nodes share an element.  Storing the list once per node instead of
+// once per row removes 2/3 of the column-index traffic (81*4 -> 27*4 bytes per row for interior hexa8 rows) and, more
+// importantly for the SM, 2/3 of the x gathers and of the per-entry instructions: a lane loads one column index,
+// gathers x once and feeds up to three FMAs (one per row of the node).  The value array is untouched -- it is still the
+// reference CSR value array, row after row -- only the index structure differs (pattern.cu builds `ncol` and the
+// 24-byte node descriptors next to the exported CSR pattern).
+//
+// Data movement follows spmv_tma.cu: persistent CTAs, one producer warp issuing `cp.async.bulk` copies of a tile's
+// contiguous slices (values, node columns, node descriptors, epilogue vectors) into a ring of shared-memory stages,
+// mbarrier full/empty handshakes, eight consumer warps (one node each per tile).  Deterministic: fixed lane partials
+// and a fixed butterfly, no atomics.
+#include <algorithm>
+#include "common.h"
+
+namespace {
+
+constexpr int NB_WARPS = 8;                       // consumer warps
+constexpr int NB_NPW = 2;                         // nodes per consumer warp and tile (their gathers are in flight together)
+constexpr int NB_NODES = NB_WARPS * NB_NPW;       // nodes per tile
+constexpr int NB_THREADS = 32 * (NB_WARPS + 1);
+constexpr int NB_VT = 3 * NB_NODES + 8;           // vector slots per tile (rows + alignment), multiple of 2
+using NodeDesc = sc_ctx::NodeDesc;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    const uint32_t addr = smem_u32(bar);
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t"
+            "}"
+            : "=r"(done)
+            : "r"(addr), "r"(parity)
+            : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void tma_load_1d(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+// MODE 0: y = A xa   MODE 2: central-difference step   MODE 3: y = A xa, partial[blockIdx] = xa.y
+template <int MODE, int STAGES>
+__global__ void __launch_bounds__(NB_THREADS, 2)
+k_spmv_node(const NodeDesc* __restrict__ nd, const int32_t* __restrict__ ncol, const double* __restrict__ va,
+            const double* __restrict__ xa, double* __restrict__ y, const double* __restrict__ inv_d,
+            const double* __restrict__ alpha, double* __restrict__ partial, int64_t n_nodes, int64_t n_rows, int64_t n_tiles,
+            int cap_v, int cap_c) {
+    constexpr int NVEC = (MODE == 2) ? 4 : (MODE == 3 ? 1 : 0);
+    constexpr int NV1 = NVEC > 0 ? NVEC : 1;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    double* s_val = reinterpret_cast<double*>(smem_raw);                         // [STAGES][cap_v]
+    double* s_vec = s_val + (size_t)STAGES * cap_v;                              // [STAGES][NV1][NB_VT]
+    NodeDesc* s_nd = reinterpret_cast<NodeDesc*>(s_vec + (size_t)STAGES * NV1 * NB_VT);   // [STAGES][NB_NODES]
+    int* s_col = reinterpret_cast<int*>(s_nd + (size_t)STAGES * NB_NODES);       // [STAGES][cap_c]
+    uint64_t* bar_full = reinterpret_cast<uint64_t*>(s_col + (size_t)STAGES * cap_c);
+    uint64_t* bar_empty = bar_full + STAGES;
+    __shared__ double red[NB_WARPS];
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&bar_full[s], 1);
+            mbar_init(&bar_empty[s], NB_WARPS);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    const int64_t G = gridDim.x;
+    double dot_acc = 0.0;
+
+    if (warp == NB_WARPS) {
+        // ------------------------------------------------ producer warp ----------------------------------------------
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int64_t ib = 0;; ib += 32) {
+            const int64_t t_first = blockIdx.x + ib * G;
+            if (t_first >= n_tiles) break;
+            // every lane fetches the slice bounds of one upcoming tile (descriptors of its first node and of the node after it)
+            const int64_t t = blockIdx.x + (ib + lane) * G;
+            int64_t v0 = 0, v1 = 0, c0 = 0, c1 = 0;
+            int r0 = 0, r1 = 0;
+            if (t < n_tiles) {
+                const NodeDesc d0 = nd[t * NB_NODES];
+                const NodeDesc d1 = nd[t * NB_NODES + NB_NODES];     // the descriptor array is padded by NB_NODES entries
+                v0 = d0.val_off; v1 = d1.val_off; c0 = d0.col_off; c1 = d1.col_off; r0 = d0.row0; r1 = d1.row0;
+            }
+            for (int j = 0; j < 32; ++j) {
+                const int64_t tj = blockIdx.x + (ib + j) * G;
+                if (tj >= n_tiles) break;
+                const int64_t a_v0 = __shfl_sync(0xffffffffu, v0, j), a_v1 = __shfl_sync(0xffffffffu, v1, j);
+                const int64_t a_c0 = __shfl_sync(0xffffffffu, c0, j), a_c1 = __shfl_sync(0xffffffffu, c1, j);
+                const int a_r0 = __shfl_sync(0xffffffffu, r0, j), a_r1 = __shfl_sync(0xffffffffu, r1, j);
+                if (lane == 0) {
+                    mbar_wait(&bar_empty[stage], phase ^ 1u);
+                    const int64_t vs = a_v0 & ~(int64_t)1, cs = a_c0 & ~(int64_t)3;
+                    const int rs = a_r0 & ~1;
+                    const uint32_t vb = (uint32_t)(((a_v1 - vs + 1) & ~(int64_t)1) * 8);
+                    const uint32_t cb = (uint32_t)(((a_c1 - cs + 3) & ~(int64_t)3) * 4);
+                    const uint32_t rb = (uint32_t)(((a_r1 - rs + 1) & ~1) * 8);
+                    const uint32_t db = NB_NODES * (uint32_t)sizeof(NodeDesc);
+                    const bool has = a_v1 > a_v0;
+                    mbar_expect_tx(&bar_full[stage], db + (has ? vb + cb + NVEC * rb : 0u));
+                    tma_load_1d(s_nd + (size_t)stage * NB_NODES, nd + tj * NB_NODES, db, &bar_full[stage]);
+                    if (has) {
+                        tma_load_1d(s_val + (size_t)stage * cap_v, va + vs, vb, &bar_full[stage]);
+                        tma_load_1d(s_col + (size_t)stage * cap_c, ncol + cs, cb, &bar_full[stage]);
+                        double* sv = s_vec + (size_t)stage * NV1 * NB_VT;
+                        if (MODE == 2) {
+                            tma_load_1d(sv, alpha + rs, rb, &bar_full[stage]);
+                            tma_load_1d(sv + NB_VT, inv_d + rs, rb, &bar_full[stage]);
+                            tma_load_1d(sv + 2 * NB_VT, xa + rs, rb, &bar_full[stage]);
+                            tma_load_1d(sv + 3 * NB_VT, y + rs, rb, &bar_full[stage]);
+                        }
+                        if (MODE == 3) tma_load_1d(sv, xa + rs, rb, &bar_full[stage]);
+                    }
+                }
+                if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+            }
+        }
+    } else {
+        // ------------------------------------------------ consumer warps: NB_NPW nodes each per tile -----------------
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int64_t t = blockIdx.x; t < n_tiles; t += G) {
+            mbar_wait(&bar_full[stage], phase);
+            const NodeDesc* snd = s_nd + (size_t)stage * NB_NODES;
+            const NodeDesc d0 = snd[0];
+            const int myr = lane >> 3;                       // lanes 0, 8, 16 own rows 0, 1, 2 of a node after the reduction
+            int L[NB_NPW], nfree[NB_NPW], row0[NB_NPW];
+            const double* sv[NB_NPW];
+            const int* sc[NB_NPW];
+            double e_al[NB_NPW], e_id[NB_NPW], e_x[NB_NPW], e_y[NB_NPW];
+            bool owner[NB_NPW];
+            int maxL = 0;
+#pragma unroll
+            for (int q = 0; q < NB_NPW; ++q) {
+                const NodeDesc d = snd[warp * NB_NPW + q];
+                nfree[q] = d.len_nfree >> 24;
+                L[q] = nfree[q] > 0 ? (d.len_nfree & 0xffffff) : 0;
+                row0[q] = d.row0;
+                maxL = max(maxL, L[q]);
+                sv[q] = s_val + (size_t)stage * cap_v + (int)(d.val_off - (d0.val_off & ~(int64_t)1)) + lane;
+                sc[q] = s_col + (size_t)stage * cap_c + (int)(d.col_off - (d0.col_off & ~(int64_t)3)) + lane;
+                owner[q] = (lane & 7) == 0 && myr < nfree[q] && L[q] > 0;
+                e_al[q] = e_id[q] = e_x[q] = e_y[q] = 0.0;
+                if (NVEC > 0 && owner[q]) {
+                    const double* svec = s_vec + (size_t)stage * NV1 * NB_VT + (d.row0 - (d0.row0 & ~1)) + myr;
+                    if (MODE == 2) { e_al[q] = svec[0]; e_id[q] = svec[NB_VT]; e_x[q] = svec[2 * NB_VT]; e_y[q] = svec[3 * NB_VT]; }
+                    if (MODE == 3) e_x[q] = svec[0];
+                }
+            }
+            double s0[NB_NPW], s1[NB_NPW], s2[NB_NPW];
+#pragma unroll
+            for (int q = 0; q < NB_NPW; ++q) { s0[q] = 0.0; s1[q] = 0.0; s2[q] = 0.0; }
+            constexpr int U = 3;
+            for (int kb = 0; kb < maxL; kb += 32 * U) {
+                int c[NB_NPW][U];
+                double xg[NB_NPW][U], v0[NB_NPW][U], v1[NB_NPW][U], v2[NB_NPW][U];
+#pragma unroll
+                for (int q = 0; q < NB_NPW; ++q)
+#pragma unroll
+                    for (int u = 0; u < U; ++u) {
+                        const int k = kb + 32 * u;
+                        const bool ok = k + lane < L[q];
+                        c[q][u] = 0; v0[q][u] = 0.0; v1[q][u] = 0.0; v2[q][u] = 0.0;
+                        if (ok) {
+                            c[q][u] = sc[q][k];
+                            v0[q][u] = sv[q][k];
+                            if (nfree[q] > 1) v1[q][u] = sv[q][L[q] + k];
+                            if (nfree[q] > 2) v2[q][u] = sv[q][2 * L[q] + k];
+                        }
+                    }
+#pragma unroll
+                for (int q = 0; q < NB_NPW; ++q)
+#pragma unroll
+                    for (int u = 0; u < U; ++u) xg[q][u] = __ldg(xa + c[q][u]);
+                __syncwarp();      // scheduling fence: all gathers of the pass are issued before the first FMA
+#pragma unroll
+                for (int q = 0; q < NB_NPW; ++q)
+#pragma unroll
+                    for (int u = 0; u < U; ++u) {
+                        s0[q] += v0[q][u] * xg[q][u];
+                        s1[q] += v1[q][u] * xg[q][u];
+                        s2[q] += v2[q][u] * xg[q][u];
+                    }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bar_empty[stage]);
+            if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+
+            // three-row butterfly per node (a fourth, empty row keeps the 4-row pattern): row r ends up in lanes [8r, 8r+8)
+            const bool h16 = (lane & 16) != 0, h8 = (lane & 8) != 0;
+#pragma unroll
+            for (int q = 0; q < NB_NPW; ++q) {
+                double k0 = h16 ? s2[q] : s0[q], k1 = h16 ? 0.0 : s1[q];
+                const double g0 = h16 ? s0[q] : s2[q], g1 = h16 ? s1[q] : 0.0;
+                k0 += __shfl_xor_sync(0xffffffffu, g0, 16);
+                k1 += __shfl_xor_sync(0xffffffffu, g1, 16);
+                double mine = h8 ? k1 : k0;
+                const double g = h8 ? k0 : k1;
+                mine += __shfl_xor_sync(0xffffffffu, g, 8);
+                mine += __shfl_xor_sync(0xffffffffu, mine, 4);
+                mine += __shfl_xor_sync(0xffffffffu, mine, 2);
+                mine += __shfl_xor_sync(0xffffffffu, mine, 1);
+                if (owner[q]) {
+                    const int64_t row = (int64_t)row0[q] + myr;
+                    if (MODE == 2) {
+                        y[row] = e_id[q] * (-mine) + e_al[q] * e_x[q] - (e_al[q] - 1.0) * e_y[q];
+                    } else {
+                        y[row] = mine;
+                        if (MODE == 3) dot_acc += e_x[q] * mine;
+                    }
+                }
+            }
+        }
+    }
+    if (MODE == 3) {
+        if (warp < NB_WARPS) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) dot_acc += __shfl_down_sync(0xffffffffu, dot_acc, o);
+            if (lane == 0) red[warp] = dot_acc;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double s = 0.0;
+            for (int w = 0; w < NB_WARPS; ++w) s += red[w];
+            partial[blockIdx.x] = s;
+        }
+    }
+}
+
+struct NodeCfg { int cap_v, cap_c, stages; size_t bytes; };
+
+bool node_cfg(sc_ctx* ctx, NodeCfg& c) {
+    if (ctx->force_no_node || !ctx->d_nd || ctx->max_rl <= 0 || ctx->dim > 3) return false;
+    c.cap_v = (NB_NODES * 3 * ctx->max_rl + 2 + 15) & ~15;
+    c.cap_c = (NB_NODES * ctx->max_rl + 4 + 31) & ~31;
+    const size_t per_stage = (size_t)c.cap_v * 8 + (size_t)c.cap_c * 4 + 4 * NB_VT * 8 + NB_NODES * sizeof(NodeDesc);
+    for (int st = 4; st >= 2; --st) {
+        const size_t bytes = st * per_stage + 2 * st * sizeof(uint64_t) + 64;
+        if (bytes <= 104 * 1024) { c.stages = st; c.bytes = bytes; return true; }
+    }
+    return false;
+}
+
+template <int MODE, int STAGES>
+int launch_node(sc_ctx* ctx, const NodeCfg& c, const double* va, const double* xa, double* y, const double* inv_d, const double* alpha,
+                double* partial, unsigned* nblocks_out) {
+    const int64_t n_tiles = (ctx->n_nodes + NB_NODES - 1) / NB_NODES;
+    auto kern = k_spmv_node<MODE, STAGES>;
+    SC_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.bytes));
+    unsigned grid = (unsigned)std::min<int64_t>(n_tiles, (int64_t)ctx->sm_count * 2);
+    if (grid == 0) grid = 1;
+    if (nblocks_out) *nblocks_out = grid;
+    kern<<<grid, NB_THREADS, c.bytes, ctx->stream>>>(ctx->d_nd, ctx->d_ncol, va, xa, y, inv_d, alpha, partial, ctx->n_nodes, ctx->n_eq,
+                                                     n_tiles, c.cap_v, c.cap_c);
+    SC_CHECK_LAUNCH(ctx);
+    return SC_OK;
+}
+
+template <int MODE>
+int launch_mode(sc_ctx* ctx, const double* va, const double* xa, double* y, const double* inv_d, const double* alpha, double* partial,
+                unsigned* nblocks_out) {
+    NodeCfg c;
+    if (!node_cfg(ctx, c)) return sc_fail(ctx, SC_ERR_UNSUPPORTED, "node-blocked SpMV not usable for this pattern");
+    if (c.stages == 4) return launch_node<MODE, 4>(ctx, c, va, xa, y, inv_d, alpha, partial, nblocks_out);
+    if (c.stages == 3) return launch_node<MODE, 3>(ctx, c, va, xa, y, inv_d, alpha, partial, nblocks_out);
+    return launch_node<MODE, 2>(ctx, c, va, xa, y, inv_d, alpha, partial, nblocks_out);
+}
+
+}  // namespace
+
+bool la_node_usable(sc_ctx* ctx) {
+    NodeCfg c;
+    return node_cfg(ctx, c);
+}
+int la_node_spmv(sc_ctx* ctx, const double* vals, const double* x, double* y) {
+    return launch_mode<0>(ctx, vals, x, y, nullptr, nullptr, nullptr, nullptr);
+}
+int la_node_cd_step(sc_ctx* ctx, const double* K, const double* u, double* uprev_next, const double* inv_d, const double* alpha) {
+    return launch_mode<2>(ctx, K, u, uprev_next, inv_d, alpha, nullptr, nullptr);
+}
+int la_node_spmv_dot(sc_ctx* ctx, const double* vals, const double* p, double* q, double* partial, unsigned* nblocks) {
+    return launch_mode<3>(ctx, vals, p, q, nullptr, nullptr, partial, nblocks);
+}
+// bytes one fused central-difference launch has to move with this format: values, node column lists, node descriptors,
+// and five vector passes (alpha, inv_d, u gathered once, u_prev read, u_next written)
+int64_t la_node_step_bytes(sc_ctx* ctx) {
+    return ctx->nnz * 8 + ctx->ncol_total * 4 + ctx->n_nodes * (int64_t)sizeof(NodeDesc) + ctx->n_eq * 40;
+}

@@ -438,6 +438,10 @@ int tl_central_difference(sc_ctx* ctx, double dt, int64_t t0, int64_t n_steps, i
         stats->seconds_device = ms * 1e-3;
         stats->seconds_total = std::chrono::duration<double>(std::chrono::steady_clock::now() - wall0).count();
         stats->steps = steps_done;
+        // algorithmic bytes of one fused step launch for the index format in use (reported by bench.py)
+        stats->reserved[0] = la_node_usable(ctx) ? (double)la_node_step_bytes(ctx)
+                                                 : (double)(ctx->nnz * 12 + ctx->n_eq * 48);
+        stats->reserved[1] = la_node_usable(ctx) ? 2.0 : (la_tma_usable(ctx) ? 1.0 : 0.0);
         stats->pcg_iterations = 0;
         stats->kernel_launches = ctx->launches - launches0;
         stats->last_residual = 0.0;
