@@ -1,0 +1,100 @@
+"""Size-independent properties at BASELINE.json's full single-GPU size (hexa8 box 255^3 elements, 49.9 M DOF), where the
+CPU oracle cannot run: symmetry, rigid-translation null space away from the supports, the analytic lumped mass of an
+interior node, bit-reproducible assembly, and exact linearity of the explicit time loop in the load."""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+SIZE = int(os.environ.get("SCATTER_B200_FULLSIZE", "255"))
+H, RHO, NU = 0.5, 1500.0, 0.2
+
+
+@pytest.fixture(scope="module")
+def big():
+    from scatter_b200 import _lib, boxmesh
+    s = SIZE
+    model = boxmesh.box_model(s, s, s, H, "hexa8")
+    ne = len(model.elem)
+    E = boxmesh.lognormal_young(ne, 30e6, 1e6)
+    ctx = _lib.Context(0)
+    ctx.set_mesh("hexa8", model.nodes[:, 1:], model.node_rows(), model.equation_table_int(), model.number_eq, None)
+    ctx.set_materials(E, np.full(ne, NU), np.full(ne, RHO))
+    nnz = ctx.build_pattern()
+    ctx.assemble(2, _lib.ASM_K | _lib.ASM_M_LUMPED)
+    yield model, ctx, nnz
+    ctx.close()
+
+
+def test_pattern_size(big):
+    model, ctx, nnz = big
+    s = SIZE
+    # interior rows couple with 27 nodes x 3 dofs; the total is below that because of boundaries and fixed dofs
+    assert model.number_eq == ctx.n_eq
+    assert 0.95 * 81 * ctx.n_eq < nnz < 81 * ctx.n_eq
+    assert nnz > 2 ** 31 or s < 255            # the full-size pattern needs 64-bit row pointers
+
+
+def test_symmetry_and_translation_null_space(big):
+    model, ctx, nnz = big
+    n = ctx.n_eq
+    rng = np.random.default_rng(5)
+    x = rng.standard_normal(n); y = rng.standard_normal(n)
+    Kx = ctx.spmv(0, x); Ky = ctx.spmv(0, y)
+    a, b = float(y @ Kx), float(x @ Ky)
+    assert abs(a - b) <= 1e-11 * max(abs(a), abs(b))
+    assert float(x @ Kx) > 0                    # positive definite on the restrained box
+    # vertical rigid translation: zero force on every row that does not touch the fixed bottom layer
+    eq = model.equation_table_int()
+    t = np.zeros(n)
+    t[eq[:, 1][eq[:, 1] >= 0]] = 1.0
+    f = ctx.spmv(0, t)
+    j = np.rint(model.nodes[:, 2] / H).astype(int)
+    far = j >= 2
+    rows = eq[far].ravel(); rows = rows[rows >= 0]
+    kmax = np.abs(Kx).max() / np.abs(x).max()
+    assert np.abs(f[rows]).max() <= 1e-9 * 30e6
+
+
+def test_lumped_mass_of_interior_node(big):
+    model, ctx, nnz = big
+    ml = ctx.get_lumped_mass()
+    s = SIZE
+    node = (s // 2) + (s + 1) * ((s // 2) + (s + 1) * (s // 2))
+    eq = model.equation_table_int()
+    for d in range(3):
+        assert abs(ml[eq[node, d]] - RHO * H ** 3) <= 1e-12 * RHO * H ** 3
+
+
+def test_assembly_bit_reproducible_at_scale(big):
+    from scatter_b200 import _lib
+    model, ctx, nnz = big
+    x = np.random.default_rng(1).standard_normal(ctx.n_eq)
+    y1 = ctx.spmv(0, x)
+    ctx.assemble(2, _lib.ASM_K | _lib.ASM_M_LUMPED)
+    y2 = ctx.spmv(0, x)
+    assert np.array_equal(y1, y2)
+
+
+def test_explicit_loop_is_exactly_linear_in_the_load(big):
+    model, ctx, nnz = big
+    from scatter_b200 import boxmesh, system_matrix
+    s = SIZE
+    c0, c1 = system_matrix.rayleigh_coefficients([1, 0.01, 30, 0.01])
+    ctx.set_rayleigh(c0, c1)
+    d = int(model.eq_nb_dof[boxmesh.top_centre_node(s, s, s) - 1, 1])
+    nt = 12
+    dt = 0.3 * H / np.sqrt(36e6 * 0.9 / (1.2 * 0.6) / RHO)
+    res = []
+    for scale in (1.0, 2.0):
+        ctx.set_load_schedule(np.arange(nt + 1, dtype=np.int64), np.full(nt, d, dtype=np.int64), np.full(nt, -1000.0 * scale))
+        ctx.set_state(None, None)
+        u, v, a, st = ctx.run_central_difference(dt, 0, nt - 2, nt - 2)
+        res.append((u[-1].copy(), v[-1].copy()))
+    assert np.isfinite(res[0][0]).all() and np.abs(res[0][0]).max() > 0
+    assert np.array_equal(2.0 * res[0][0], res[1][0])
+    assert np.array_equal(2.0 * res[0][1], res[1][1])
+    # the wave has only travelled ~ (nt * dt * vp / h) elements from the load: far-away dofs are still exactly at rest
+    assert res[0][0][0] == 0.0

@@ -52,6 +52,18 @@ def _worker(rank, world, port, mesh_path, out_dir):
     y = ctx.halo_exchange(x)
     free = leq >= 0
     assert np.array_equal(y[leq[free]], geq_all[free].astype(float)), "halo exchange delivered wrong ghost values"
+    # the rows a rank owns equal the corresponding rows of the single-domain matrix (values and global columns)
+    rowptr, col = mx.pattern()
+    kv = ctx.get_values(0)
+    l2g = np.full(loc.number_eq, -1, dtype=np.int64)
+    l2g[leq[free]] = geq_all[free]
+    out_rows = {}
+    for le, ge in zip(dom.owned_eq[::7], dom.global_eq_of_owned[::7]):
+        sl = slice(rowptr[le], rowptr[le + 1])
+        out_rows[int(ge)] = (l2g[col[sl]], kv[sl])
+    np.savez(os.path.join(out_dir, f"rows{rank}.npz"), ge=np.array(list(out_rows.keys())),
+             cols=np.concatenate([v[0] for v in out_rows.values()]), vals=np.concatenate([v[1] for v in out_rows.values()]),
+             ptr=np.cumsum([0] + [len(v[0]) for v in out_rows.values()]))
     # load on global node 8, owner rank only
     nt = 61
     grow = int(np.where(m.nodes[:, 0] == 8)[0][0])
@@ -104,6 +116,14 @@ def test_two_gpu_time_loops_match_single_domain_oracle(golden_meshes, tmp_path):
         z = np.load(os.path.join(tmp_path, f"rank{r}.npz"))
         for k in got:
             got[k][:, z["geq"]] = z[k]
+    Kc = K.tocsr()
+    for r in range(world):
+        z = np.load(os.path.join(tmp_path, f"rows{r}.npz"))
+        for i, ge in enumerate(z["ge"]):
+            sl = slice(z["ptr"][i], z["ptr"][i + 1])
+            ref_sl = slice(Kc.indptr[ge], Kc.indptr[ge + 1])
+            assert np.array_equal(z["cols"][sl], Kc.indices[ref_sl])
+            assert np.abs(z["vals"][sl] - Kc.data[ref_sl]).max() <= 1e-12 * np.abs(Kc.data).max()
     for k, ref in (("cd_u", Ucd), ("cd_v", Vcd), ("nm_u", Unm), ("nm_v", Vnm), ("nm_a", Anm)):
         assert not np.isnan(got[k]).any()
         err = np.linalg.norm(got[k] - ref) / np.linalg.norm(ref)
