@@ -101,6 +101,9 @@ struct sc_ctx {
     bool force_no_node = false;            // env SCATTER_B200_NO_NODE: row-wise kernels instead of the node-blocked one
     bool force_no_tma = false;             // test hook / env SCATTER_B200_NO_TMA: register-staged SpMV instead of the TMA ring
     bool force_generic_assembly = false;   // test hook: use the warp-per-node kernel for every element type
+    bool nm_resume_valid = false;   // d_a holds the Newmark acceleration of step nm_resume_t (stage continuation)
+    int64_t nm_resume_t = 0;
+    double khat_a1 = -1.0, khat_a4 = -1.0;   // parameters d_Khat was built with (-1: invalid)
     bool cd_resume_valid = false;   // work[0] holds u(t - dt) of the central-difference state at step cd_resume_t
     int64_t cd_resume_t = 0;
     double cd_resume_dt = 0.0;

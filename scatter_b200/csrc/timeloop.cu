@@ -276,30 +276,37 @@ int tl_newmark(sc_ctx* ctx, double dt, int64_t t0, int64_t n_steps, int64_t oi, 
     const double c0 = ctx->c0, c1 = ctx->c1;
     const bool cabs = ctx->cabs_n > 0;
 
-    // effective matrix Khat = (1 + a4 c1) K + (a1 + a4 c0) M + a4 C_abs
-    SC_TRY(sc_alloc(ctx, &ctx->d_Khat, (size_t)ctx->nnz));
-    SC_TRY(la_axpby_vals(ctx, ctx->d_Khat, 1.0 + a4 * c1, ctx->d_K, a1 + a4 * c0, ctx->d_M, ctx->nnz));
-    SC_TRY(la_cabs_add_values(ctx, ctx->d_Khat, a4));
+    // effective matrix Khat = (1 + a4 c1) K + (a1 + a4 c0) M + a4 C_abs (kept across stages with the same dt)
+    if (!ctx->d_Khat || ctx->khat_a1 != a1 || ctx->khat_a4 != a4) {
+        SC_TRY(sc_alloc(ctx, &ctx->d_Khat, (size_t)ctx->nnz));
+        SC_TRY(la_axpby_vals(ctx, ctx->d_Khat, 1.0 + a4 * c1, ctx->d_K, a1 + a4 * c0, ctx->d_M, ctx->nnz));
+        SC_TRY(la_cabs_add_values(ctx, ctx->d_Khat, a4));
+        ctx->khat_a1 = a1; ctx->khat_a4 = a4;
+    }
     SC_TRY(la_extract_diag(ctx, ctx->d_Khat, dinv, true));
-    SC_TRY(la_extract_diag(ctx, ctx->d_M, dinvM, true));
 
     int64_t pcg_total = 0;
     int iters = 0;
     double relres = 0.0;
     int64_t row = 0;
 
-    // initial acceleration a = M^-1 (F(t0) - C v - K u) = M^-1 (F - M (c0 v) - K (c1 v + u) - C_abs v)
-    SC_TRY(la_axpby_vals(ctx, x1, c0, ctx->d_v, 0.0, nullptr, n));
-    SC_TRY(la_axpby_vals(ctx, x2, c1, ctx->d_v, 1.0, ctx->d_u, n));
-    if (ctx->world > 1) { SC_TRY(dist_halo(ctx, x1, st)); SC_TRY(dist_halo(ctx, x2, st)); }
-    SC_TRY(la_spmv2(ctx, ctx->d_M, x1, ctx->d_K, x2, rhs));
-    SC_TRY(la_cabs_spmv_add(ctx, ctx->d_v, rhs, 1.0));
-    k_neg_add<<<nblk(n, 256), 256, 0, st>>>(rhs, n);
-    SC_CHECK_LAUNCH(ctx);
-    SC_TRY(apply_load(ctx, t0, 1.0, nullptr, rhs));
-    SC_TRY(pcg(ctx, ctx->d_M, dinvM, rhs, ctx->d_a, r, p, q, rtol, maxit, &iters, &relres));
-    pcg_total += iters;
-    if (ctx->world > 1) SC_TRY(dist_halo(ctx, ctx->d_a, st));
+    const bool resume = ctx->nm_resume_valid && ctx->nm_resume_t == t0;
+    ctx->nm_resume_valid = false;
+    if (!resume) {
+        // initial acceleration a = M^-1 (F(t0) - C v - K u) = M^-1 (F - M (c0 v) - K (c1 v + u) - C_abs v)
+        SC_TRY(la_extract_diag(ctx, ctx->d_M, dinvM, true));
+        SC_TRY(la_axpby_vals(ctx, x1, c0, ctx->d_v, 0.0, nullptr, n));
+        SC_TRY(la_axpby_vals(ctx, x2, c1, ctx->d_v, 1.0, ctx->d_u, n));
+        if (ctx->world > 1) { SC_TRY(dist_halo(ctx, x1, st)); SC_TRY(dist_halo(ctx, x2, st)); }
+        SC_TRY(la_spmv2(ctx, ctx->d_M, x1, ctx->d_K, x2, rhs));
+        SC_TRY(la_cabs_spmv_add(ctx, ctx->d_v, rhs, 1.0));
+        k_neg_add<<<nblk(n, 256), 256, 0, st>>>(rhs, n);
+        SC_CHECK_LAUNCH(ctx);
+        SC_TRY(apply_load(ctx, t0, 1.0, nullptr, rhs));
+        SC_TRY(pcg(ctx, ctx->d_M, dinvM, rhs, ctx->d_a, r, p, q, rtol, maxit, &iters, &relres));
+        pcg_total += iters;
+        if (ctx->world > 1) SC_TRY(dist_halo(ctx, ctx->d_a, st));
+    }
 
     if (t0 % oi == 0 && row < n_out) {
         SC_TRY(store_row(ctx, u_out, row, ctx->d_u)); SC_TRY(store_row(ctx, v_out, row, ctx->d_v)); SC_TRY(store_row(ctx, a_out, row, ctx->d_a));
@@ -342,6 +349,8 @@ int tl_newmark(sc_ctx* ctx, double dt, int64_t t0, int64_t n_steps, int64_t oi, 
         stats->last_residual = relres;
         stats->seconds_halo = 0.0;
     }
+    ctx->nm_resume_valid = true;
+    ctx->nm_resume_t = t0 + n_steps;
     return SC_OK;
 }
 

@@ -105,7 +105,9 @@ class NewmarkExplicit(_DeviceSolver):
     def calculate(self, M, C, K, F, t_start_idx, t_end_idx):
         ctx = self._ctx()
         self._upload_loads(ctx)
-        ctx.set_state(self.u0, self.v0)
+        if getattr(self, "_state_dirty", True):      # a stage that continues the previous one keeps u, v, a on the device
+            ctx.set_state(self.u0, self.v0)
+            self._state_dirty = False
         n_steps = int(t_end_idx) - int(t_start_idx)
         uo, vo, ao = self._out_views(int(t_start_idx))
         _, _, _, st = ctx.run_newmark(self._dt(t_start_idx, t_end_idx), int(t_start_idx), n_steps, self.output_interval,
