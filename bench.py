@@ -400,9 +400,12 @@ def run_secondary_newmark(args, local_rank):
     ctx.run_newmark(dt, 0, 2, 1, rtol=rtol, store=False)                       # warm-up (also builds Khat)
     _, _, _, st = ctx.run_newmark(dt, 2, nsteps, 1, rtol=rtol, store=False)
     its = st["pcg_iterations"] / max(nsteps, 1)
-    # bytes per step: rhs two-matrix SpMV (values of M and K, columns once) + per PCG iteration one SpMV + ~13 vector passes
+    # bytes per step: rhs two-matrix SpMV (values of M and K, CSR columns once) + per PCG iteration one SpMV (node-blocked
+    # index: one column list per node) + 14 vector passes (SpMV x/y, fused update, direction update)
+    ps = ctx.pattern_stats()
+    idx_bytes = ps["node_col_entries"] * 4 + ps["n_nodes"] * 24 if ps["node_blocked"] else nnz * 4 + n * 8
     rhs_bytes = nnz * 20 + n * 8 * 12
-    it_bytes = nnz * 12 + n * 8 * 14
+    it_bytes = nnz * 8 + idx_bytes + n * 8 * 14
     step_bytes = rhs_bytes + its * it_bytes
     sec = st["seconds_device"] / nsteps
     peak, _ = measured_peak()

@@ -91,6 +91,9 @@ int sc_set_materials(sc_ctx* ctx, const double* young, const double* poisson, co
 /* ---- structural CSR pattern (the key set of k_dict, system_matrix.py:98-121): sorted rows, sorted columns ----- */
 int sc_build_pattern(sc_ctx* ctx, int64_t* nnz_out);
 int sc_get_pattern(sc_ctx* ctx, int64_t* rowptr /*[n_eq+1]*/, int32_t* col /*[nnz]*/);
+/* sizes of the device structures: out[0] nnz, [1] entries of the node-blocked column lists, [2] n_nodes, [3] longest row,
+ * [4] most neighbour nodes, [5] most elements per node, [6] 1 if the node-blocked SpMV is in use, [7] reserved */
+int sc_pattern_stats(sc_ctx* ctx, int64_t* out8);
 
 /* ---- element integration + deterministic assembly (GenerateMatrix.generate_stiffness_and_mass,
  *      system_matrix.py:35-121 over discretisation.py:83-222,290-417) -------------------------------------------- */

@@ -24,7 +24,7 @@ ASM_K, ASM_M_FULL, ASM_M_LUMPED = 1, 2, 4
 SYMBOLS = [
     "sc_create", "sc_destroy", "sc_last_error", "sc_version", "sc_device_info", "sc_kernel_launches", "sc_shape_table",
     "sc_host_alloc", "sc_host_free",
-    "sc_set_mesh", "sc_set_materials", "sc_build_pattern", "sc_get_pattern", "sc_assemble", "sc_add_entries",
+    "sc_set_mesh", "sc_set_materials", "sc_build_pattern", "sc_get_pattern", "sc_pattern_stats", "sc_assemble", "sc_add_entries",
     "sc_set_rayleigh", "sc_get_values", "sc_get_lumped_mass", "sc_spmv", "sc_set_load_schedule", "sc_set_state",
     "sc_get_state", "sc_run_newmark", "sc_run_central_difference", "sc_run_bathe", "sc_run_static", "sc_nccl_unique_id", "sc_dist_init", "sc_set_halo",
     "sc_halo_exchange",
@@ -79,6 +79,7 @@ def load_library():
     lib.sc_set_materials.argtypes = [vp, vp, vp, vp]
     lib.sc_build_pattern.argtypes = [vp, P(i64)]
     lib.sc_get_pattern.argtypes = [vp, vp, vp]
+    lib.sc_pattern_stats.argtypes = [vp, vp]
     lib.sc_assemble.argtypes = [vp, i32, i32, P(dbl)]
     lib.sc_add_entries.argtypes = [vp, i32, i64, vp, vp, vp]
     lib.sc_set_rayleigh.argtypes = [vp, dbl, dbl]
@@ -235,6 +236,12 @@ class Context:
         col = np.empty(self.nnz, dtype=np.int32)
         self._ck(self.lib.sc_get_pattern(self.h, _ptr(rowptr), _ptr(col)))
         return rowptr, col
+
+    def pattern_stats(self) -> dict:
+        out = np.zeros(8, dtype=np.int64)
+        self._ck(self.lib.sc_pattern_stats(self.h, _ptr(out)))
+        keys = ("nnz", "node_col_entries", "n_nodes", "max_row_len", "max_node_neighbours", "max_elems_per_node", "node_blocked")
+        return {k: int(v) for k, v in zip(keys, out)}
 
     def assemble(self, order: int, flags: int = ASM_K | ASM_M_FULL) -> float:
         sec = C.c_double()

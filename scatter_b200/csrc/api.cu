@@ -236,6 +236,13 @@ int sc_get_pattern(sc_ctx* ctx, int64_t* rowptr, int32_t* col) {
     return SC_OK;
 }
 
+int sc_pattern_stats(sc_ctx* ctx, int64_t* out8) {
+    if (!ctx || !ctx->have_pattern || !out8) return sc_fail(ctx, SC_ERR_STATE, "sc_build_pattern must be called first");
+    out8[0] = ctx->nnz; out8[1] = ctx->ncol_total; out8[2] = ctx->n_nodes; out8[3] = ctx->max_rl; out8[4] = ctx->max_nbr;
+    out8[5] = ctx->max_valence; out8[6] = la_node_usable(ctx) ? 1 : 0; out8[7] = 0;
+    return SC_OK;
+}
+
 int sc_assemble(sc_ctx* ctx, int gauss_order, int flags, double* seconds_device) {
     if (!ctx || !ctx->have_pattern) return sc_fail(ctx, SC_ERR_STATE, "sc_build_pattern must be called first");
     if (!ctx->have_mat) return sc_fail(ctx, SC_ERR_STATE, "sc_set_materials must be called first");

@@ -18,10 +18,7 @@
 namespace {
 
 constexpr int NB_WARPS = 8;                       // consumer warps
-constexpr int NB_NPW = 2;                         // nodes per consumer warp and tile (their gathers are in flight together)
-constexpr int NB_NODES = NB_WARPS * NB_NPW;       // nodes per tile
 constexpr int NB_THREADS = 32 * (NB_WARPS + 1);
-constexpr int NB_VT = 3 * NB_NODES + 8;           // vector slots per tile (rows + alignment), multiple of 2
 using NodeDesc = sc_ctx::NodeDesc;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -56,12 +53,14 @@ __device__ __forceinline__ void tma_load_1d(void* dst_smem, const void* src_gmem
 }
 
 // MODE 0: y = A xa   MODE 2: central-difference step   MODE 3: y = A xa, partial[blockIdx] = xa.y
-template <int MODE, int STAGES>
+template <int MODE, int STAGES, int NB_NPW>
 __global__ void __launch_bounds__(NB_THREADS, 2)
 k_spmv_node(const NodeDesc* __restrict__ nd, const int32_t* __restrict__ ncol, const double* __restrict__ va,
             const double* __restrict__ xa, double* __restrict__ y, const double* __restrict__ inv_d,
             const double* __restrict__ alpha, double* __restrict__ partial, int64_t n_nodes, int64_t n_rows, int64_t n_tiles,
             int cap_v, int cap_c) {
+    constexpr int NB_NODES = NB_WARPS * NB_NPW;      // nodes per tile; NB_NPW nodes per consumer warp (gathers in flight together)
+    constexpr int NB_VT = 3 * NB_NODES + 8;          // vector slots per tile (rows + alignment), multiple of 2
     constexpr int NVEC = (MODE == 2) ? 4 : (MODE == 3 ? 1 : 0);
     constexpr int NV1 = NVEC > 0 ? NVEC : 1;
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -247,25 +246,31 @@ k_spmv_node(const NodeDesc* __restrict__ nd, const int32_t* __restrict__ ncol, c
     }
 }
 
-struct NodeCfg { int cap_v, cap_c, stages; size_t bytes; };
+struct NodeCfg { int cap_v, cap_c, stages, npw; size_t bytes; };
 
 bool node_cfg(sc_ctx* ctx, NodeCfg& c) {
     if (ctx->force_no_node || !ctx->d_nd || ctx->max_rl <= 0 || ctx->dim > 3) return false;
-    c.cap_v = (NB_NODES * 3 * ctx->max_rl + 2 + 15) & ~15;
-    c.cap_c = (NB_NODES * ctx->max_rl + 4 + 31) & ~31;
-    const size_t per_stage = (size_t)c.cap_v * 8 + (size_t)c.cap_c * 4 + 4 * NB_VT * 8 + NB_NODES * sizeof(NodeDesc);
-    for (int st = 4; st >= 2; --st) {
-        const size_t bytes = st * per_stage + 2 * st * sizeof(uint64_t) + 64;
-        if (bytes <= 104 * 1024) { c.stages = st; c.bytes = bytes; return true; }
+    // two nodes per consumer warp when the stages fit (short rows), one node per warp for long rows (hexa20, tetra10)
+    for (int npw = 2; npw >= 1; --npw) {
+        const int nodes = NB_WARPS * npw, vt = 3 * nodes + 8;
+        c.cap_v = (nodes * 3 * ctx->max_rl + 2 + 15) & ~15;
+        c.cap_c = (nodes * ctx->max_rl + 4 + 31) & ~31;
+        const size_t per_stage = (size_t)c.cap_v * 8 + (size_t)c.cap_c * 4 + 4 * (size_t)vt * 8 + nodes * sizeof(NodeDesc);
+        const size_t budget = (npw == 2 ? 104 : 112) * 1024;
+        for (int st = 4; st >= 2; --st) {
+            const size_t bytes = st * per_stage + 2 * st * sizeof(uint64_t) + 64;
+            if (bytes <= budget) { c.stages = st; c.npw = npw; c.bytes = bytes; return true; }
+        }
     }
     return false;
 }
 
-template <int MODE, int STAGES>
+template <int MODE, int STAGES, int NPW>
 int launch_node(sc_ctx* ctx, const NodeCfg& c, const double* va, const double* xa, double* y, const double* inv_d, const double* alpha,
                 double* partial, unsigned* nblocks_out) {
-    const int64_t n_tiles = (ctx->n_nodes + NB_NODES - 1) / NB_NODES;
-    auto kern = k_spmv_node<MODE, STAGES>;
+    constexpr int NODES = NB_WARPS * NPW;
+    const int64_t n_tiles = (ctx->n_nodes + NODES - 1) / NODES;
+    auto kern = k_spmv_node<MODE, STAGES, NPW>;
     SC_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.bytes));
     unsigned grid = (unsigned)std::min<int64_t>(n_tiles, (int64_t)ctx->sm_count * 2);
     if (grid == 0) grid = 1;
@@ -281,9 +286,14 @@ int launch_mode(sc_ctx* ctx, const double* va, const double* xa, double* y, cons
                 unsigned* nblocks_out) {
     NodeCfg c;
     if (!node_cfg(ctx, c)) return sc_fail(ctx, SC_ERR_UNSUPPORTED, "node-blocked SpMV not usable for this pattern");
-    if (c.stages == 4) return launch_node<MODE, 4>(ctx, c, va, xa, y, inv_d, alpha, partial, nblocks_out);
-    if (c.stages == 3) return launch_node<MODE, 3>(ctx, c, va, xa, y, inv_d, alpha, partial, nblocks_out);
-    return launch_node<MODE, 2>(ctx, c, va, xa, y, inv_d, alpha, partial, nblocks_out);
+    if (c.npw == 2) {
+        if (c.stages == 4) return launch_node<MODE, 4, 2>(ctx, c, va, xa, y, inv_d, alpha, partial, nblocks_out);
+        if (c.stages == 3) return launch_node<MODE, 3, 2>(ctx, c, va, xa, y, inv_d, alpha, partial, nblocks_out);
+        return launch_node<MODE, 2, 2>(ctx, c, va, xa, y, inv_d, alpha, partial, nblocks_out);
+    }
+    if (c.stages == 4) return launch_node<MODE, 4, 1>(ctx, c, va, xa, y, inv_d, alpha, partial, nblocks_out);
+    if (c.stages == 3) return launch_node<MODE, 3, 1>(ctx, c, va, xa, y, inv_d, alpha, partial, nblocks_out);
+    return launch_node<MODE, 2, 1>(ctx, c, va, xa, y, inv_d, alpha, partial, nblocks_out);
 }
 
 }  // namespace
