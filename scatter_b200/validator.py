@@ -1,14 +1,16 @@
-"""Load-dictionary validation -- mirror of the reference's `scatter/validator.py:4-57`."""
-from typing import Dict
+"""Checks on the loading dictionary -- behaviour of the reference's `scatter/validator.py:34-57`: an unknown load type
+raises, `ini_steps` defaults to 5 (the dict is updated in place, as the reference does)."""
 
-_KNOWN = ("pulse", "heaviside", "moving", "moving_at_plane", "rose")
+LOAD_TYPES = frozenset({"pulse", "heaviside", "moving", "moving_at_plane", "rose"})
+DEFAULTS = {"ini_steps": 5}
 
 
 class ValidateLoad:
     @staticmethod
-    def validate(loading: Dict):
-        """Checks the load type and fills in defaults (`ini_steps` = 5, validator.py:57)."""
+    def validate(loading: dict) -> None:
         assert "type" in loading
-        if loading["type"] not in _KNOWN:
-            raise Exception(f'Error: Load type {loading["type"]} not supported')
-        loading.setdefault("ini_steps", 5)
+        kind = loading["type"]
+        if kind not in LOAD_TYPES:
+            raise Exception(f'Error: Load type {kind} not supported')
+        for key, value in DEFAULTS.items():
+            loading.setdefault(key, value)
