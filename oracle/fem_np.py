@@ -758,3 +758,92 @@ def static(K, force, time: np.ndarray, output_interval: int = 1):
     for row, t in enumerate(out_idx):
         U[row] = lu.solve(force(int(t)))
     return U, time[out_idx]
+
+
+# ---- boundary faces / top surface / moving load on the top plane (plain loops; small cases only) -----------------
+_HEX8_FACES = [[0, 1, 2, 3], [0, 1, 4, 5], [4, 5, 6, 7], [2, 3, 6, 7], [0, 3, 4, 7], [1, 2, 5, 6]]
+
+
+def boundary_faces_hexa8(model: Model) -> np.ndarray:
+    """mesher.py:328-391 -- faces (node ids) whose nodes all touch fewer than 8 elements, unique rows."""
+    ids = model.nodes[:, 0].astype(int)
+    is_bnd = np.array([np.count_nonzero(model.elem == n) < 8 for n in ids])
+    bnd_ids = set(ids[is_bnd].tolist())
+    faces = []
+    for el in model.elem:
+        flags = np.array([int(n) in bnd_ids for n in el])
+        if not flags.any():
+            continue
+        if flags.sum() > 4:
+            for f in _HEX8_FACES:
+                if flags[f].all():
+                    faces.append(el[f])
+        elif flags.sum() == 4:
+            faces.append(el[flags])
+    return np.unique(np.array(faces), axis=0)
+
+
+def top_surface_faces(model: Model, faces: np.ndarray) -> np.ndarray:
+    """mesher.py:393-424 -- boundary faces whose centroid is strictly inside the x/z extent and above the bottom."""
+    eps = 1e-10
+    cen = np.array([model.nodes[f - 1, 1:].mean(axis=0) for f in faces])
+    keep = [(c[0] > cen[:, 0].min() + eps) and (c[0] < cen[:, 0].max() - eps) and (c[1] > cen[:, 1].min() + eps)
+            and (c[2] > cen[:, 2].min() + eps) and (c[2] < cen[:, 2].max() - eps) for c in cen]
+    return faces[np.array(keep)]
+
+
+def _inside_convex(poly, pt) -> bool:
+    """strict interior test by ray casting on the angularly sorted polygon"""
+    c = poly.mean(axis=0)
+    order = np.argsort(np.arctan2(poly[:, 1] - c[1], poly[:, 0] - c[0]))
+    p = poly[order]
+    inside = False
+    n = len(p)
+    for i in range(n):
+        x1, y1 = p[i]
+        x2, y2 = p[(i + 1) % n]
+        if (y1 > pt[1]) != (y2 > pt[1]):
+            xi = x1 + (pt[1] - y1) * (x2 - x1) / (y2 - y1)
+            if xi > pt[0]:
+                inside = not inside
+    return inside
+
+
+class MovingAtPlaneLoad:
+    """force_external.py:151-212, 281-318 -- point load travelling over the top surface, bilinear-like nodal weights."""
+
+    def __init__(self, model: Model, loading: dict, time: np.ndarray, top_faces: np.ndarray):
+        self.model, self.time = model, time
+        s = loading.get("ini_steps", 5)
+        self.sf = np.ones(len(time)); self.sf[:s] = np.linspace(0, 1, s)
+        self.factor = loading["force"]
+        dist = np.zeros(len(time))
+        dist[s:] = np.append(0, np.cumsum(loading["speed"] * np.diff(time[s:])))
+        d = loading["direction"]
+        ang = (0.5 * np.pi if d[1] > 0 else -0.5 * np.pi) if np.isclose(d[0], 0) else np.arctan(d[1] / d[0])
+        self.pos = np.array([np.cos(ang) * dist + loading["start_coord"][0], np.sin(ang) * dist + loading["start_coord"][1]])
+        self.active = []
+        for p in self.pos.T:
+            hit = None
+            for f in top_faces:
+                if _inside_convex(model.nodes[f - 1][:, [1, 3]], p):
+                    hit = f
+                    break
+            self.active.append(hit)
+
+    def __call__(self, t: int) -> np.ndarray:
+        f = np.zeros(self.model.number_eq)
+        el = self.active[t]
+        xz = self.model.nodes[el - 1][:, [1, 3]]
+        dx, dz = np.abs(xz[:, 0] - self.pos[0, t]), np.abs(xz[:, 1] - self.pos[1, t])
+        wx = (dx < 1e-10) * 1 if np.any(dx < 1e-10) else 1 / dx
+        wz = (dz < 1e-10) * 1 if np.any(dz < 1e-10) else 1 / dz
+        w = wx * wz
+        w = w / w.sum()
+        load = np.array(self.factor) * self.sf[t]
+        eq = self.model.eq_nb_dof[el - 1]
+        for a in range(len(el)):
+            for d in range(3):
+                if not np.isnan(eq[a, d]):
+                    f[int(eq[a, d])] = w[a] * load[d]
+        return f

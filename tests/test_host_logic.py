@@ -138,6 +138,30 @@ def test_load_schedule_matches_oracle(kind, golden_meshes, oracle):
         assert np.array_equal(F.update_load_at_t(t), expect)
 
 
+def test_moving_at_plane_load_matches_oracle(golden_meshes, oracle):
+    """integration_test.py:551-602 (moving load on the top surface of cube.msh)."""
+    from scatter_b200 import force_external, mesher
+    m = mesher.ReadMesh(golden_meshes["cube.msh"])
+    m.read_gmsh(); m.read_bc(cases.BC_CUBE); m.mapping(); m.connectivities(); m.get_mesh_edges()
+    om = oracle.build_model(golden_meshes["cube.msh"], cases.BC_CUBE)
+    faces = oracle.boundary_faces_hexa8(om)
+    assert np.array_equal(faces, m.boundary_elem)
+    top = oracle.top_surface_faces(om, faces)
+    assert np.array_equal(top, m.get_top_surface())
+    time = np.linspace(0, 1, 201)
+    load = {"force": [0, -1000, 0], "start_coord": [0.5, -0.5], "time": 1, "type": "moving_at_plane", "direction": [0.5, -1],
+            "speed": 10, "ini_steps": 50}
+    F = force_external.Force()
+    F.initialise_load(load, time, m, None, top_surface_elements=m.get_top_surface())
+    ref = oracle.MovingAtPlaneLoad(om, load, time, top)
+    ptr, dof, val = F.compile_schedule()
+    for t in (0, 10, 49, 50, 51, 77, 120, 200):
+        dense = np.zeros(m.number_eq)
+        dense[dof[ptr[t]:ptr[t + 1]]] = val[ptr[t]:ptr[t + 1]]
+        assert np.allclose(dense, ref(t), rtol=1e-13, atol=1e-13), t
+        assert abs(dense.sum() - (-1000.0 * ref.sf[t])) < 1e-9          # the nodal forces add up to the point load
+
+
 def test_validator():
     from scatter_b200 import validator
     load = {"type": "pulse"}
