@@ -27,6 +27,7 @@ struct AsmParams {
     const int64_t* nbr_ptr; const int32_t* nbr; const uint16_t* nbr_off;
     const int32_t* node_rl; const int64_t* node_row0; const int64_t* rowptr;
     const double *tabN, *tabdN, *tabw;
+    const uint8_t *pair_pos, *pair_al;
     double *K, *M, *Ml;
     int64_t n_nodes;
     int max_rl, max_nbr;
@@ -233,24 +234,30 @@ __constant__ double c_tabN[SC_MAX_GP * SC_MAX_NNE];
 __constant__ double c_tabdN[SC_MAX_GP * SC_MAX_NNE * 3];
 __constant__ double c_tabw[SC_MAX_GP];
 
-template <int NNE, int DIM, int NGP, int TPB>
-__global__ void __launch_bounds__(TPB) k_assemble_pairs(AsmParams p, int npb) {
+// LPP lanes share one (node, element) pair: every lane evaluates the Jacobians (redundantly) and NNE/LPP of the NNE
+// node blocks of the row block.  LPP = 2 halves the register-resident accumulators of hexa8 (72 -> 36 doubles), which
+// doubles the resident warps per SM; the extra Jacobian work costs less than the latency it hides.
+template <int NNE, int DIM, int NGP, int TPB, int LPP>
+__global__ void __launch_bounds__(TPB, (LPP > 1 ? 3 : 2)) k_assemble_pairs(AsmParams p, int npb) {
     constexpr int DD = DIM * DIM, ND = NNE * DIM;
+    constexpr int NBB = NNE / LPP;                       // node blocks per lane
+    constexpr int PPB = TPB / LPP;                       // pairs per block
     constexpr int SST = DIM * ND + 1;                    // stride of one pair's row block in the staging area (odd: no bank conflicts)
+    static_assert(NNE % LPP == 0, "lanes per pair must divide the node count");
     extern __shared__ double smem[];
     // region A is used twice: coordinates + detJ*w during the integration, the staged row blocks afterwards
     double* xs = smem;                                   // [ND][TPB]   coordinates, one column per thread
     double* swj = xs + ND * TPB;                         // [NGP][TPB]  detJ*w per Gauss point
-    double* stage = smem;                                // [TPB][SST]  row block of every pair
-    double* stage_m = stage + (size_t)TPB * SST;         // [TPB][NNE]  rho * sum_g detJ w N_a N_b of every pair
-    constexpr size_t REGION_A = (size_t)TPB * SST + (size_t)TPB * NNE;
-    static_assert(REGION_A >= (size_t)(ND + NGP) * TPB, "staging area must cover the integration scratch");
+    double* stage = smem;                                // [PPB][SST]  row block of every pair
+    double* stage_m = stage + (size_t)PPB * SST;         // [PPB][NNE]  rho * sum_g detJ w N_a N_b of every pair
+    constexpr size_t SZ_STAGE = (size_t)PPB * SST + (size_t)PPB * NNE, SZ_INT = (size_t)(ND + NGP) * TPB;
+    constexpr size_t REGION_A = SZ_STAGE > SZ_INT ? SZ_STAGE : SZ_INT;
     double* sdN = smem + REGION_A;                       // [NGP*NNE*DIM] table copy for lane-dependent rows
     double* sN = sdN + NGP * NNE * DIM;                  // [NGP*NNE]
     double* s_mitem = sN + NGP * NNE;                    // [npb*max_nbr] mass of every (node, neighbour) item
     int* s_ptr = reinterpret_cast<int*>(s_mitem + (size_t)npb * p.max_nbr);   // [npb+1] pair offsets of the block's nodes
     int* s_nptr = s_ptr + npb + 1;                       // [npb+1] neighbour-list offsets
-    unsigned char* s_inv = reinterpret_cast<unsigned char*>(s_nptr + npb + 1);   // [TPB][max_nbr] neighbour position -> local node
+    unsigned char* s_inv = reinterpret_cast<unsigned char*>(s_nptr + npb + 1);   // [PPB][max_nbr] neighbour position -> local node
 
     const int tid = threadIdx.x;
     const int64_t a0 = (int64_t)blockIdx.x * npb;
@@ -264,49 +271,41 @@ __global__ void __launch_bounds__(TPB) k_assemble_pairs(AsmParams p, int npb) {
     }
     for (int t = tid; t < NGP * NNE * DIM; t += TPB) sdN[t] = p.tabdN[t];
     for (int t = tid; t < NGP * NNE; t += TPB) sN[t] = p.tabN[t];
-    for (int t = tid; t < TPB * p.max_nbr; t += TPB) s_inv[t] = 0xff;
+    for (int t = tid; t < PPB * p.max_nbr; t += TPB) s_inv[t] = 0xff;
     __syncthreads();
-    const int npairs = s_ptr[nbn];                       // <= TPB by construction of npb
+    const int npairs = s_ptr[nbn];                       // <= PPB by construction of npb
     const int n_items = s_nptr[nbn];
 
-    // ---- phase 1: one lane per (node, element) pair, row block in registers ------------------------------------------
-    const int k = tid;
+    // ---- phase 1: LPP lanes per (node, element) pair, their part of the row block in registers -----------------------
+    const int k = tid / LPP, half = tid % LPP;
     bool valid = k < npairs;
-    double acc[DIM][ND];
-    double mab[NNE];
+    double acc[DIM][NBB * DIM];
+    double mab[NBB];
 #pragma unroll
     for (int i = 0; i < DIM; ++i)
 #pragma unroll
-        for (int c = 0; c < ND; ++c) acc[i][c] = 0.0;
+        for (int c = 0; c < NBB * DIM; ++c) acc[i][c] = 0.0;
 #pragma unroll
-    for (int b = 0; b < NNE; ++b) mab[b] = 0.0;
+    for (int b = 0; b < NBB; ++b) mab[b] = 0.0;
     if (valid) {
         int lo = 0, hi = nbn;
         while (hi - lo > 1) {
             const int mid = (lo + hi) >> 1;
             if (s_ptr[mid] <= k) lo = mid; else hi = mid;
         }
-        const int an = lo;
-        valid = p.node_rl[a0 + an] > 0;                  // ghost nodes of a domain decomposition own no rows
+        valid = p.node_rl[a0 + lo] > 0;                  // ghost nodes of a domain decomposition own no rows
         if (valid) {
-            const int a = (int)(a0 + an);
             const int e = p.n2e[P0 + k];
-            int al = 0;
-            const int64_t nb0 = p.nbr_ptr[a];
-            const int nn_a = (int)(p.nbr_ptr[a + 1] - nb0);
+            const int al = p.pair_al[P0 + k];
 #pragma unroll
             for (int b = 0; b < NNE; ++b) {
                 const int c = p.conn[(int64_t)e * NNE + b];
-                if (c == a) al = b;
 #pragma unroll
                 for (int d = 0; d < DIM; ++d) xs[(b * DIM + d) * TPB + tid] = p.xyz[(int64_t)c * 3 + d];
-                // position of node c in the (ascending) neighbour list of a
-                int l2 = 0, h2 = nn_a;
-                while (l2 < h2) {
-                    const int mid = (l2 + h2) >> 1;
-                    if (p.nbr[nb0 + mid] < c) l2 = mid + 1; else h2 = mid;
-                }
-                s_inv[k * p.max_nbr + l2] = (unsigned char)b;
+            }
+            if (half == 0) {
+#pragma unroll
+                for (int b = 0; b < NNE; ++b) s_inv[k * p.max_nbr + p.pair_pos[(P0 + k) * NNE + b]] = (unsigned char)b;
             }
             const double E = p.E[e], nu = p.nu[e];
             const double rho = p.rho[e];
@@ -338,13 +337,15 @@ __global__ void __launch_bounds__(TPB) k_assemble_pairs(AsmParams p, int npb) {
                     mga[kk] = mu * wj * s;
                 }
 #pragma unroll
-                for (int b = 0; b < NNE; ++b) {
+                for (int bb = 0; bb < NBB; ++bb) {
+                    // node block b = half * NBB + bb: the table row is lane dependent for LPP > 1 -> shared-memory copy
+                    const double* dnb = (LPP > 1) ? (sdN + (g * NNE + half * NBB + bb) * DIM) : (c_tabdN + (g * NNE + bb) * DIM);
                     double gb[DIM];
 #pragma unroll
                     for (int kk = 0; kk < DIM; ++kk) {
                         double s = 0.0;
 #pragma unroll
-                        for (int d = 0; d < DIM; ++d) s += c_tabdN[(g * NNE + b) * DIM + d] * inv[kk * DIM + d];
+                        for (int d = 0; d < DIM; ++d) s += dnb[d] * inv[kk * DIM + d];
                         gb[kk] = s;
                     }
                     double sdot = 0.0;
@@ -356,17 +357,17 @@ __global__ void __launch_bounds__(TPB) k_assemble_pairs(AsmParams p, int npb) {
                         for (int j = 0; j < DIM; ++j) {
                             double t = lga[i] * gb[j] + mga[j] * gb[i];
                             if (i == j) t += sdot;
-                            acc[i][b * DIM + j] += t;
+                            acc[i][bb * DIM + j] += t;
                         }
                 }
             }
             // consistent mass of the node pairs: rho * sum_g detJ w N_a N_b   (discretisation.py:213-214)
 #pragma unroll
-            for (int b = 0; b < NNE; ++b) {
+            for (int bb = 0; bb < NBB; ++bb) {
                 double m = 0.0;
 #pragma unroll
-                for (int g = 0; g < NGP; ++g) m += swj[g * TPB + tid] * sN[g * NNE + al] * c_tabN[g * NNE + b];
-                mab[b] = rho * m;
+                for (int g = 0; g < NGP; ++g) m += swj[g * TPB + tid] * sN[g * NNE + al] * sN[g * NNE + half * NBB + bb];
+                mab[bb] = rho * m;
             }
         }
     }
@@ -375,9 +376,9 @@ __global__ void __launch_bounds__(TPB) k_assemble_pairs(AsmParams p, int npb) {
 #pragma unroll
         for (int i = 0; i < DIM; ++i)
 #pragma unroll
-            for (int c = 0; c < ND; ++c) stage[(size_t)k * SST + i * ND + c] = acc[i][c];
+            for (int c = 0; c < NBB * DIM; ++c) stage[(size_t)k * SST + i * ND + half * NBB * DIM + c] = acc[i][c];
 #pragma unroll
-        for (int b = 0; b < NNE; ++b) stage_m[k * NNE + b] = mab[b];
+        for (int bb = 0; bb < NBB; ++bb) stage_m[k * NNE + half * NBB + bb] = mab[bb];
     }
     __syncthreads();
 
@@ -446,17 +447,20 @@ __global__ void __launch_bounds__(TPB) k_assemble_pairs(AsmParams p, int npb) {
 template <int NNE, int DIM, int NGP>
 int launch_pairs(sc_ctx* ctx, const AsmParams& p, const ShapeTable& t, bool* handled) {
     constexpr int TPB = 128;
+    constexpr int LPP = (DIM * NNE * DIM > 36 && NNE % 2 == 0) ? 2 : 1;       // two lanes per pair for hexa8 / quad8
+    constexpr int PPB = TPB / LPP;
     constexpr int ND = NNE * DIM, SST = DIM * ND + 1;
     *handled = false;
-    if (ctx->max_valence <= 0 || ctx->max_valence > TPB || p.max_nbr > 255) return SC_OK;
-    const int npb = std::max(1, TPB / ctx->max_valence);
-    const size_t bytes = ((size_t)TPB * SST + (size_t)TPB * NNE + (size_t)NGP * NNE * DIM + (size_t)NGP * NNE +
-                          (size_t)npb * p.max_nbr) * sizeof(double) + 2 * (size_t)(npb + 1) * sizeof(int) + (size_t)TPB * p.max_nbr + 16;
+    if (!p.pair_pos || ctx->max_valence <= 0 || ctx->max_valence > PPB || p.max_nbr > 255) return SC_OK;
+    const int npb = std::max(1, PPB / ctx->max_valence);
+    const size_t region_a = std::max((size_t)PPB * SST + (size_t)PPB * NNE, (size_t)(ND + NGP) * TPB);
+    const size_t bytes = (region_a + (size_t)NGP * NNE * DIM + (size_t)NGP * NNE + (size_t)npb * p.max_nbr) * sizeof(double) +
+                         2 * (size_t)(npb + 1) * sizeof(int) + (size_t)PPB * p.max_nbr + 16;
     if (bytes > 110 * 1024) return SC_OK;
     SC_CUDA(ctx, cudaMemcpyToSymbolAsync(c_tabN, t.N.data(), t.N.size() * sizeof(double), 0, cudaMemcpyHostToDevice, ctx->stream));
     SC_CUDA(ctx, cudaMemcpyToSymbolAsync(c_tabdN, t.dN.data(), t.dN.size() * sizeof(double), 0, cudaMemcpyHostToDevice, ctx->stream));
     SC_CUDA(ctx, cudaMemcpyToSymbolAsync(c_tabw, t.w.data(), t.w.size() * sizeof(double), 0, cudaMemcpyHostToDevice, ctx->stream));
-    auto kern = k_assemble_pairs<NNE, DIM, NGP, TPB>;
+    auto kern = k_assemble_pairs<NNE, DIM, NGP, TPB, LPP>;
     SC_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
     const unsigned grid = (unsigned)((p.n_nodes + npb - 1) / npb);
     kern<<<grid, TPB, bytes, ctx->stream>>>(p, npb);
@@ -515,6 +519,7 @@ int sc_assemble_run(sc_ctx* ctx, int order, int flags, double* seconds) {
     p.K = (flags & SC_ASM_K) ? ctx->d_K : nullptr;
     p.M = (flags & SC_ASM_M_FULL) ? ctx->d_M : nullptr;
     p.Ml = (flags & SC_ASM_M_LUMPED) ? ctx->d_Ml : nullptr;
+    p.pair_pos = ctx->d_pair_pos; p.pair_al = ctx->d_pair_al;
     p.n_nodes = ctx->n_nodes; p.max_rl = ctx->max_rl; p.max_nbr = ctx->max_nbr;
 
     cudaEvent_t e0, e1;

@@ -60,6 +60,8 @@ struct sc_ctx {
     struct NodeDesc { int64_t val_off; int64_t col_off; int32_t row0; int32_t len_nfree; };   // len | nfree << 24
     NodeDesc* d_nd = nullptr;       // [n_nodes + 32] (padded with empty descriptors)
     int32_t* d_ncol = nullptr;      // [sum node_rl] column list per node
+    uint8_t* d_pair_pos = nullptr;  // [n_pairs*nne] position of every element node in the pair's node neighbour list (or null)
+    uint8_t* d_pair_al = nullptr;   // [n_pairs] local index of the pair's node in its element
     int64_t ncol_total = 0;
     int max_nbr = 0, max_rl = 0, max_valence = 0;   // max neighbours / row length / elements per node
 

@@ -181,6 +181,30 @@ __global__ void k_node_desc(const int64_t* __restrict__ node_row0, const int32_t
     nd[a] = d;
 }
 
+// pair map for the assembly kernel: for pair k = (node a, element e) the position of every node of e in the (ascending)
+// neighbour list of a, and the local index of a in e
+__global__ void k_pair_map(const int32_t* __restrict__ conn, int nne, const int64_t* __restrict__ n2e_ptr, const int32_t* __restrict__ n2e,
+                           const int64_t* __restrict__ nbr_ptr, const int32_t* __restrict__ nbr, int64_t n_nodes,
+                           uint8_t* __restrict__ pos, uint8_t* __restrict__ al) {
+    int64_t a = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (a >= n_nodes) return;
+    const int64_t nb0 = nbr_ptr[a];
+    const int nn = (int)(nbr_ptr[a + 1] - nb0);
+    for (int64_t k = n2e_ptr[a]; k < n2e_ptr[a + 1]; ++k) {
+        const int32_t* c = conn + (int64_t)n2e[k] * nne;
+        for (int b = 0; b < nne; ++b) {
+            const int v = c[b];
+            int lo = 0, hi = nn;
+            while (lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                if (nbr[nb0 + mid] < v) lo = mid + 1; else hi = mid;
+            }
+            pos[k * nne + b] = (uint8_t)lo;
+            if (v == (int)a) al[k] = (uint8_t)b;
+        }
+    }
+}
+
 __global__ void k_i32_to_i64(const int* __restrict__ in, int64_t* __restrict__ out, int64_t n) {
     int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (i < n) out[i] = in[i];
@@ -321,6 +345,15 @@ int sc_pattern_build(sc_ctx* ctx) {
     SC_TRY(sc_alloc(ctx, &ctx->d_col, (size_t)ctx->nnz));
     k_fill_columns<<<nblk(nn * 32, T), T, 0, st>>>(ctx->d_eq, dim, ctx->d_nbr_ptr, ctx->d_nbr, ctx->d_nbr_off, ctx->d_rowptr, nn, ctx->d_col);
     SC_CHECK_LAUNCH(ctx);
+    // ---- pair map (assembly kernel) ------------------------------------------------------------------------------------
+    sc_free(&ctx->d_pair_pos); sc_free(&ctx->d_pair_al);
+    if (ctx->max_nbr <= 255) {
+        SC_TRY(sc_alloc(ctx, &ctx->d_pair_pos, (size_t)ne * nne * nne));
+        SC_TRY(sc_alloc(ctx, &ctx->d_pair_al, (size_t)ne * nne));
+        k_pair_map<<<nblk(nn, 128), 128, 0, st>>>(ctx->d_conn, nne, ctx->d_n2e_ptr, ctx->d_n2e, ctx->d_nbr_ptr, ctx->d_nbr, nn,
+                                                  ctx->d_pair_pos, ctx->d_pair_al);
+        SC_CHECK_LAUNCH(ctx);
+    }
     // ---- node-blocked column lists + descriptors (time-loop kernels, spmv_node.cu) ------------------------------------
     {
         int64_t* d_ncol_ptr = nullptr;
