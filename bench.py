@@ -420,7 +420,7 @@ def run_secondary_newmark(args, local_rank):
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum of one k_spmv<2> launch from the committed ncu capture (profiles/), by box size
-TRAFFIC = {}
+TRAFFIC = {255: 41377949000 + 420294000}      # profiles/r1_v4_k_spmv_node_mode2_255cube.txt (k_spmv_node<2,2,2>, 1 GPU)
 
 
 def main():
