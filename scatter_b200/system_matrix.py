@@ -82,48 +82,81 @@ def face_mass(face_type: str, order: int, xy: np.ndarray) -> np.ndarray:
     return np.einsum("ga,gb,g->ab", N, N, det * w)
 
 
-def absorbing_entries(data, E, nu, rho, order: int, viscous, stiff: float):
-    """COO entries of C_abs and K_abs/stiff, duplicates summed in element order (system_matrix.py:256-376)."""
+def _absorbing_faces(data):
+    """(element, direction, node rows[nl]) of every absorbing face, in the reference's element / direction order
+    (system_matrix.py:274-316): a face exists where exactly `nb_nodes_lower_elem` nodes of an element absorb in a direction."""
     type_bc = np.asarray(data.type_BC)
-    absorb_node = (type_bc == "Absorb").any(axis=1)
-    cdict, kdict = {}, {}
-    if not absorb_node.any():
-        return cdict, kdict
+    absorb = type_bc == "Absorb"                                   # (Nn, dim)
     rows = data.node_rows()
+    nl, dim = data.nb_nodes_lower_elem, data.dimension
+    touched = np.where(absorb.any(axis=1)[rows].any(axis=1))[0]
+    out = []
+    if len(touched) == 0:
+        return out
+    fl = absorb[rows[touched]]                                     # (nt, nne, dim)
+    cnt = fl.sum(axis=1)                                           # (nt, dim)
+    for t, d in zip(*np.where(cnt == nl)):                         # row-major: element order, then direction
+        e = touched[t]
+        out.append((e, d, rows[e][fl[t, :, d]]))
+    return out
+
+
+def absorbing_entries(data, E, nu, rho, order: int, viscous, stiff: float):
+    """COO entries of C_abs and K_abs/stiff, duplicates summed in face order (system_matrix.py:256-376).
+
+    quad4 faces (hexa8 meshes) are processed with whole-array numpy so that large boxes stay cheap; other face types use
+    the per-face path."""
+    faces = _absorbing_faces(data)
+    cdict, kdict = {}, {}
+    if not faces:
+        return cdict, kdict
     dim, nl = data.dimension, data.nb_nodes_lower_elem
-    touched = np.where(absorb_node[rows].any(axis=1))[0]
+    if dim == 2:
+        raise SystemExit("Absorbing boundaries not implemented for 2D yet")
     eq = data.eq_nb_dof
-    eq_to_dir = {}
-    for e in touched:
-        Ec = E[e] * (1 - nu[e]) / ((1 + nu[e]) * (1 - 2 * nu[e]))
-        G = E[e] / (2 * (1 + nu[e]))
-        vp, vs = np.sqrt(Ec / rho[e]), np.sqrt(G / rho[e])
-        nodes_e = rows[e][absorb_node[rows[e]]]           # element-local order, absorbing nodes only
-        for d in range(dim):
-            sel = nodes_e[type_bc[nodes_e, d] == "Absorb"]
-            if len(sel) != nl:
-                continue
-            if dim == 2:
-                raise SystemExit("Absorbing boundaries not implemented for 2D yet")
-            xy = gmsh_face_order(np.delete(data.nodes[sel, 1:], d, axis=1))
-            S = face_mass(data.lower_element_type, order, xy)
-            i1 = np.sort(eq[sel, d]).astype(np.int64)
-            fct = np.full(nl, viscous[1] * rho[e] * vs)
-            fct2 = np.full(nl, G)
-            for k, val in enumerate(i1):
-                if val not in eq_to_dir:
-                    n_, d_ = np.where(eq == val)
-                    eq_to_dir[val] = int(data.BC_dir[n_[0], d_[0]])
-                if eq_to_dir[val] == 1:
-                    fct[k] = viscous[0] * rho[e] * vp
-                    fct2[k] = Ec
-            for r in range(nl):
-                for c in range(nl):
-                    key = (int(i1[r]), int(i1[c]))
-                    cdict[key] = cdict.get(key, 0.0) + S[r, c] * fct[c]
-                    kdict[key] = kdict.get(key, 0.0) + abs(S[r, c]) * fct2[c]
-    for key in kdict:
-        kdict[key] = kdict[key] / stiff
+    el = np.array([f[0] for f in faces]); dr = np.array([f[1] for f in faces]); nodes = np.array([f[2] for f in faces])
+    nf = len(faces)
+    Ec = E[el] * (1 - nu[el]) / ((1 + nu[el]) * (1 - 2 * nu[el]))
+    G = E[el] / (2 * (1 + nu[el]))
+    vp, vs = np.sqrt(Ec / rho[el]), np.sqrt(G / rho[el])
+    # unit face matrices in the reference's face-node order
+    S = np.empty((nf, nl, nl))
+    if data.lower_element_type == "quad4":
+        keep = np.array([[1, 2], [0, 2], [0, 1]])[dr]              # in-plane coordinate columns after dropping `d`
+        xy = np.take_along_axis(data.nodes[nodes, 1:], keep[:, None, :], axis=2)     # (nf, 4, 2)
+        low = np.argmin(xy[:, :, 1], axis=1)                        # first lowest point
+        ref = xy[np.arange(nf), low]
+        ang = np.arctan2(xy[:, :, 1] - ref[:, None, 1], xy[:, :, 0] - ref[:, None, 0])
+        srt = np.argsort(ang, axis=1, kind="stable")
+        xy = np.take_along_axis(xy, srt[:, :, None], axis=1)        # counter-clockwise from the lowest point
+        N, dN, w = _lib.shape_table("quad4", order)
+        J = np.einsum("gad,fak->fgdk", dN, xy)
+        det = J[..., 0, 0] * J[..., 1, 1] - J[..., 0, 1] * J[..., 1, 0]
+        S = np.einsum("ga,gb,fg->fab", N, N, det * w[None, :])
+    else:
+        for k, (e, d, nd) in enumerate(faces):
+            S[k] = face_mass(data.lower_element_type, order, gmsh_face_order(np.delete(data.nodes[nd, 1:], d, axis=1)))
+    # equation numbers of the face dofs, sorted (the reference pairs them with the face-node order as is)
+    i1 = np.sort(eq[nodes, dr[:, None]], axis=1).astype(np.int64)  # (nf, nl)
+    eqi = np.where(np.isnan(eq), -1, eq).astype(np.int64)
+    dir_of_eq = np.zeros(data.number_eq, dtype=np.int64)
+    dir_of_eq[eqi[eqi >= 0]] = np.asarray(data.BC_dir)[eqi >= 0]
+    perp = dir_of_eq[i1] == 1
+    fct = np.where(perp, (viscous[0] * rho[el] * vp)[:, None], (viscous[1] * rho[el] * vs)[:, None])
+    fct2 = np.where(perp, Ec[:, None], G[:, None])
+    r = np.repeat(i1[:, :, None], nl, axis=2).ravel()
+    c = np.repeat(i1[:, None, :], nl, axis=1).ravel()
+    cv = (S * fct[:, None, :]).ravel()
+    kv = (np.abs(S) * fct2[:, None, :]).ravel()
+    # sum duplicates in face order (np.add.at is sequential) on the unique key set
+    key = r * data.number_eq + c
+    uniq, inv = np.unique(key, return_inverse=True)
+    csum = np.zeros(len(uniq)); ksum = np.zeros(len(uniq))
+    np.add.at(csum, inv, cv)
+    np.add.at(ksum, inv, kv)
+    keys = [(int(u // data.number_eq), int(u % data.number_eq)) for u in uniq]
+    cdict = dict(zip(keys, csum))
+    kdict = dict(zip(keys, ksum / stiff))
     return cdict, kdict
 
 

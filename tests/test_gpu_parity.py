@@ -263,6 +263,24 @@ def test_newmark_absorbing_and_hexa20_vs_oracle(golden_meshes, oracle):
         assert rel_l2(num.u, U) <= TOL_HIST and rel_l2(num.v, V) <= TOL_HIST and rel_l2(num.a, A) <= 1e-7
 
 
+def test_newmark_moving_load_vs_oracle(golden_meshes, oracle):
+    """integration_test.py:493-545 (moving load on cube.msh); the reference's golden pickle is a missing blob, so the
+    history is compared with the pinned oracle (first 60 of the 201 steps)."""
+    from scatter_b200 import force_external, solvers
+    mat = cases.materials(); mat["solid"]["Young"] = 10e6
+    sett = cases.settings(damping=[1, 0.0, 30, 0.0])
+    load = {"force": [0, -1000, 0], "node": 8, "time": 0.3, "type": "moving", "speed": 10, "ini_steps": 20}
+    model, mats, (U, V, A, tt) = oracle.run_case(golden_meshes["cube.msh"], mat, cases.BC_CUBE, sett, load, 0.5e-2)
+    m, mx = build(golden_meshes["cube.msh"], cases.BC_CUBE, mat, sett)
+    time = oracle.time_array(load["time"], 0.5e-2)
+    num = solvers.NewmarkExplicit(); num.initialise(m.number_eq, time); num.bind(mx)
+    F = force_external.Force(); F.initialise_load(load, time, m, num)
+    num.update_rhs_at_time_step_func = F.update_load_at_t
+    num.update(0); num.calculate(None, None, None, F.force_vector, 0, len(time) - 1)
+    assert np.abs(U).max() > 0
+    assert rel_l2(num.u, U) <= TOL_HIST and rel_l2(num.v, V) <= TOL_HIST and rel_l2(num.a, A) <= 1e-7
+
+
 def test_central_difference_vs_oracle(golden_meshes, oracle):
     from scatter_b200 import force_external, solvers
     mesh, bc = "cube.msh", cases.BC_CUBE
