@@ -52,6 +52,8 @@ void free_vectors(sc_ctx* c) {
     for (auto& w : c->work) sc_free(&w);
     c->work.clear();
     sc_free(&c->d_partial);
+    for (int k = 0; k < 3; ++k) sc_free(&c->d_snap[k]);
+    c->rows_pending = false;
     c->cd_resume_valid = false; c->nm_resume_valid = false;
 }
 
@@ -126,6 +128,8 @@ void sc_destroy(sc_ctx* ctx) {
     sc_free(&ctx->d_load_dof); sc_free(&ctx->d_load_val); sc_free(&ctx->d_scal);
     sc_free(&ctx->d_send_idx); sc_free(&ctx->d_recv_idx); sc_free(&ctx->d_send_buf); sc_free(&ctx->d_recv_buf);
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
+    if (ctx->ev_rows_ready) cudaEventDestroy(ctx->ev_rows_ready);
+    if (ctx->ev_rows_done) cudaEventDestroy(ctx->ev_rows_done);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     delete ctx;
