@@ -237,8 +237,6 @@ def run_ours(args):
     if world > 1:
         ctx.set_halo(dom.neighbor_rank, dom.send_ptr, dom.send_idx, dom.recv_ptr, dom.recv_idx)
     n_owned = int(len(dom.owned_eq))
-    n_owned_nodes = int(dom.active.sum())
-    n_owned_elem_equiv = n_owned_nodes                       # one element per node on a periodic-like count (reporting only)
     # algorithmic bytes of the assembly: xyz 24 B/node + conn 32 B/elem + material 24 B/elem +
     # K values 8 B/nnz + lumped mass 8 B/dof
     asm_bytes = 24 * len(model.nodes) + (32 + 24) * ne + 8 * nnz + 8 * n_owned
@@ -279,7 +277,7 @@ def run_ours(args):
         sampler.start()
     barrier()
     l0 = ctx.kernel_launches()
-    dev_s, halo_s = 0.0, 0.0
+    dev_s = 0.0
     w0 = time.perf_counter()
     for _ in range(args.steps):
         st = stage_device()

@@ -20,7 +20,7 @@ ELEM_DIM = {"tri3": 2, "tri6": 2, "quad4": 2, "quad8": 2, "tetra4": 3, "tetra10"
 MAT_K, MAT_M, MAT_C, MAT_KHAT = 0, 1, 2, 3
 ASM_K, ASM_M_FULL, ASM_M_LUMPED = 1, 2, 4
 
-# every symbol include/scatter_b200.h declares (checked by tests/test_cabi_symbols.py)
+# every symbol include/scatter_b200.h declares (checked by tests/test_host_logic.py)
 SYMBOLS = [
     "sc_create", "sc_destroy", "sc_last_error", "sc_version", "sc_device_info", "sc_kernel_launches", "sc_shape_table",
     "sc_host_alloc", "sc_host_free",

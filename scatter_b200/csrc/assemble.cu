@@ -5,11 +5,13 @@
 //                 (scatter/discretisation.py:83-222, :290-417), D from material_models.py:5-43
 //   scatter       k_dict[i,k] += Ke[j,l]; mass_dict[i,k] += Me[j,l] in element order (system_matrix.py:98-103)
 //
-// Formulation ("row gather"): one warp owns one node = DIM consecutive matrix rows.  It walks the elements touching
-// the node in ascending element id -- the same order in which the reference adds them to a slot -- and for each
-// element evaluates only the DIM x (NNE*DIM) row block of Ke that belongs to its node, accumulating into a shared
-// memory image of its CSR rows.  Nobody else writes those rows, so the sum order is fixed and the result is
-// reproducible bit for bit; the block then streams its contiguous CSR segment to HBM with coalesced stores.
+// Formulation ("row gather"): every node owns DIM consecutive matrix rows and a row only receives contributions from
+// the elements touching its node.  A block of consecutive nodes therefore produces its CSR rows alone: it walks the
+// elements of each node in ascending element id -- the order in which the reference adds them to a slot -- evaluates
+// only the DIM x (NNE*DIM) row block of Ke that belongs to the node, and sums per slot in that order.  Nobody else
+// writes those rows, so the result is reproducible bit for bit.  Two kernels implement it: `k_assemble_pairs`
+// (row block in registers, one or two lanes per (node, element) pair; tri3..hexa8) and `k_assemble` (one warp per
+// node, shared-memory staging; tetra10 / hexa20 and very high node valences).
 //
 // Isotropic elasticity lets the row block be formed without B or D:
 //   K[(a,i),(b,j)] = sum_g w_g detJ_g ( lam dNa_i dNb_j + mu dNa_j dNb_i + delta_ij mu dNa.dNb )

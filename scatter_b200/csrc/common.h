@@ -171,7 +171,6 @@ int sc_pattern_build(sc_ctx* ctx);
 // assemble.cu
 int sc_assemble_run(sc_ctx* ctx, int order, int flags, double* seconds);
 // linalg.cu
-enum { SC_SPMV_PLAIN = 0 };
 int sc_work(sc_ctx* ctx, int idx, double** out);                       // work vector idx
 int la_spmv(sc_ctx* ctx, const double* vals, const double* x, double* y);                 // y = A x
 int la_spmv2(sc_ctx* ctx, const double* va, const double* xa, const double* vb, const double* xb, double* y); // y = A xa + B xb

@@ -280,7 +280,6 @@ int sc_pattern_build(sc_ctx* ctx) {
     // ---- node -> nodes ------------------------------------------------------------------------------------------
     // capacity tiers for the per-thread sorted set
     int tier = 0;
-    const int caps[3] = {64, 256, 1024};
     for (;; ++tier) {
         if (tier == 3) { sc_free(&d_cnt); sc_free(&d_tmp64); sc_free(&d_flag);
             return sc_fail(ctx, SC_ERR_UNSUPPORTED, "a node has more than 1024 neighbour nodes"); }
@@ -294,7 +293,6 @@ int sc_pattern_build(sc_ctx* ctx) {
         SC_CUDA(ctx, cudaStreamSynchronize(st));
         if (!flag) break;
     }
-    (void)caps;
     SC_CUDA(ctx, cudaMemsetAsync(d_cnt + nn, 0, sizeof(int), st));
     SC_TRY(max_i32(ctx, d_cnt, nn, &ctx->max_nbr));
     k_i32_to_i64<<<nblk(nn + 1, T), T, 0, st>>>(d_cnt, d_tmp64, nn + 1);

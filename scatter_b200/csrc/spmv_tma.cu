@@ -289,8 +289,7 @@ int launch_tr(sc_ctx* ctx, const double* va, const double* xa, double* y, const 
 
 }  // namespace
 
-// Returns SC_ERR_UNSUPPORTED (without touching ctx->err) when the rows are too long for the staging ring; the caller then
-// uses the register-staged kernel.
+// false when the rows are too long for the staging ring: the caller then uses the register-staged kernel (linalg.cu)
 bool la_tma_usable(sc_ctx* ctx) {
     if (ctx->force_no_tma || ctx->max_rl <= 0) return false;
     const size_t per_entry = sizeof(double) + sizeof(int);
