@@ -26,7 +26,7 @@ struct AsmParams {
     const double* xyz; const int32_t* conn; const int32_t* eq;
     const double *E, *nu, *rho;
     const int64_t* n2e_ptr; const int32_t* n2e;
-    const int64_t* nbr_ptr; const int32_t* nbr; const uint16_t* nbr_off;
+    const int64_t* nbr_ptr; const int32_t* nbr; const uint16_t* nbr_off; const uint8_t* nbr_free;
     const int32_t* node_rl; const int64_t* node_row0; const int64_t* rowptr;
     const double *tabN, *tabdN, *tabw;
     const uint8_t *pair_pos, *pair_al;
@@ -257,7 +257,8 @@ __global__ void __launch_bounds__(TPB, (LPP > 1 ? 3 : 2)) k_assemble_pairs(AsmPa
     double* sdN = smem + REGION_A;                       // [NGP*NNE*DIM] table copy for lane-dependent rows
     double* sN = sdN + NGP * NNE * DIM;                  // [NGP*NNE]
     double* s_mitem = sN + NGP * NNE;                    // [npb*max_nbr] mass of every (node, neighbour) item
-    int* s_ptr = reinterpret_cast<int*>(s_mitem + (size_t)npb * p.max_nbr);   // [npb+1] pair offsets of the block's nodes
+    long long* s_rowbase = reinterpret_cast<long long*>(s_mitem + (size_t)npb * p.max_nbr);   // [npb*DIM] first slot of row (a,i) or -1
+    int* s_ptr = reinterpret_cast<int*>(s_rowbase + (size_t)npb * DIM);   // [npb+1] pair offsets of the block's nodes
     int* s_nptr = s_ptr + npb + 1;                       // [npb+1] neighbour-list offsets
     unsigned char* s_inv = reinterpret_cast<unsigned char*>(s_nptr + npb + 1);   // [PPB][max_nbr] neighbour position -> local node
 
@@ -274,6 +275,10 @@ __global__ void __launch_bounds__(TPB, (LPP > 1 ? 3 : 2)) k_assemble_pairs(AsmPa
     for (int t = tid; t < NGP * NNE * DIM; t += TPB) sdN[t] = p.tabdN[t];
     for (int t = tid; t < NGP * NNE; t += TPB) sN[t] = p.tabN[t];
     for (int t = tid; t < PPB * p.max_nbr; t += TPB) s_inv[t] = 0xff;
+    for (int t = tid; t < nbn * DIM; t += TPB) {
+        const int rr = p.eq[(a0 + t / DIM) * DIM + t % DIM];
+        s_rowbase[t] = (rr >= 0 && p.node_rl[a0 + t / DIM] > 0) ? (long long)p.rowptr[rr] : -1;
+    }
     __syncthreads();
     const int npairs = s_ptr[nbn];                       // <= PPB by construction of npb
     const int n_items = s_nptr[nbn];
@@ -411,19 +416,16 @@ __global__ void __launch_bounds__(TPB, (LPP > 1 ? 3 : 2)) k_assemble_pairs(AsmPa
             m += stage_m[pr * NNE + b];
         }
         s_mitem[q] = m;
-        const int nodeb = p.nbr[nbr0 + q];
         const int off = p.nbr_off[nbr0 + q];
-        bool fr[DIM];
-#pragma unroll
-        for (int j = 0; j < DIM; ++j) fr[j] = p.eq[(int64_t)nodeb * DIM + j] >= 0;
+        const int fmask = p.nbr_free[nbr0 + q];
 #pragma unroll
         for (int i = 0; i < DIM; ++i) {
-            const int rr = p.eq[a * DIM + i];
-            if (rr < 0) continue;
-            int64_t o = p.rowptr[rr] + off;
+            const long long rb = s_rowbase[n * DIM + i];
+            if (rb < 0) continue;
+            int64_t o = rb + off;
 #pragma unroll
             for (int j = 0; j < DIM; ++j) {
-                if (!fr[j]) continue;
+                if (!(fmask & (1 << j))) continue;
                 if (p.K) p.K[o] = blk[i][j];
                 if (p.M) p.M[o] = (i == j) ? m : 0.0;
                 ++o;
@@ -435,13 +437,11 @@ __global__ void __launch_bounds__(TPB, (LPP > 1 ? 3 : 2)) k_assemble_pairs(AsmPa
         // row sums of the consistent mass: columns (b,i) that exist, neighbour order
         for (int t = tid; t < nbn * DIM; t += TPB) {
             const int n = t / DIM, i = t % DIM;
-            const int64_t a = a0 + n;
-            const int rr = p.eq[a * DIM + i];
-            if (rr < 0 || p.node_rl[a] <= 0) continue;
+            if (s_rowbase[t] < 0) continue;
             double s = 0.0;
             for (int q = s_nptr[n]; q < s_nptr[n + 1]; ++q)
-                if (p.eq[(int64_t)p.nbr[nbr0 + q] * DIM + i] >= 0) s += s_mitem[q];
-            p.Ml[rr] = s;
+                if (p.nbr_free[nbr0 + q] & (1 << i)) s += s_mitem[q];
+            p.Ml[p.eq[(a0 + n) * DIM + i]] = s;
         }
     }
 }
@@ -456,7 +456,7 @@ int launch_pairs(sc_ctx* ctx, const AsmParams& p, const ShapeTable& t, bool* han
     if (!p.pair_pos || ctx->max_valence <= 0 || ctx->max_valence > PPB || p.max_nbr > 255) return SC_OK;
     const int npb = std::max(1, PPB / ctx->max_valence);
     const size_t region_a = std::max((size_t)PPB * SST + (size_t)PPB * NNE, (size_t)(ND + NGP) * TPB);
-    const size_t bytes = (region_a + (size_t)NGP * NNE * DIM + (size_t)NGP * NNE + (size_t)npb * p.max_nbr) * sizeof(double) +
+    const size_t bytes = (region_a + (size_t)NGP * NNE * DIM + (size_t)NGP * NNE + (size_t)npb * p.max_nbr + (size_t)npb * DIM) * sizeof(double) +
                          2 * (size_t)(npb + 1) * sizeof(int) + (size_t)PPB * p.max_nbr + 16;
     if (bytes > 110 * 1024) return SC_OK;
     SC_CUDA(ctx, cudaMemcpyToSymbolAsync(c_tabN, t.N.data(), t.N.size() * sizeof(double), 0, cudaMemcpyHostToDevice, ctx->stream));
@@ -515,7 +515,7 @@ int sc_assemble_run(sc_ctx* ctx, int order, int flags, double* seconds) {
     p.xyz = ctx->d_xyz; p.conn = ctx->d_conn; p.eq = ctx->d_eq;
     p.E = ctx->d_E; p.nu = ctx->d_nu; p.rho = ctx->d_rho;
     p.n2e_ptr = ctx->d_n2e_ptr; p.n2e = ctx->d_n2e;
-    p.nbr_ptr = ctx->d_nbr_ptr; p.nbr = ctx->d_nbr; p.nbr_off = ctx->d_nbr_off;
+    p.nbr_ptr = ctx->d_nbr_ptr; p.nbr = ctx->d_nbr; p.nbr_off = ctx->d_nbr_off; p.nbr_free = ctx->d_nbr_free;
     p.node_rl = ctx->d_node_rl; p.node_row0 = ctx->d_node_row0; p.rowptr = ctx->d_rowptr;
     p.tabN = dN; p.tabdN = ddN; p.tabw = dw;
     p.K = (flags & SC_ASM_K) ? ctx->d_K : nullptr;

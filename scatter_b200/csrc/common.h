@@ -54,6 +54,7 @@ struct sc_ctx {
     int64_t* d_nbr_ptr = nullptr;   // [n_nodes+1]
     int32_t* d_nbr = nullptr;       // neighbour node rows (incl. self), ascending
     uint16_t* d_nbr_off = nullptr;  // dof offset of neighbour inside a row of the node
+    uint8_t* d_nbr_free = nullptr;  // bit j set: dof j of the neighbour node is free (has a column)
     int32_t* d_node_rl = nullptr;   // [n_nodes] row length of the node's rows (0 if inactive)
     int64_t* d_node_row0 = nullptr; // [n_nodes+1] number of free dofs before the node (= first row of the node)
     // node-blocked column structure for the time loop: all rows of a node share one column list

@@ -94,15 +94,19 @@ __global__ void k_node_free(const int32_t* __restrict__ eq, int dim, int64_t n_n
 
 // per node: dof offset of every neighbour inside the node's rows and the row length
 __global__ void k_node_rowlen(const int64_t* __restrict__ nbr_ptr, const int32_t* __restrict__ nbr, const int* __restrict__ nfree,
-                              int64_t n_nodes, uint16_t* __restrict__ nbr_off, int32_t* __restrict__ node_rl,
-                              int* __restrict__ overflow) {
+                              const int32_t* __restrict__ eq, int dim, int64_t n_nodes, uint16_t* __restrict__ nbr_off,
+                              uint8_t* __restrict__ nbr_free, int32_t* __restrict__ node_rl, int* __restrict__ overflow) {
     int64_t a = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (a >= n_nodes) return;
     int off = 0;
     for (int64_t k = nbr_ptr[a]; k < nbr_ptr[a + 1]; ++k) {
         if (off > 65535) { atomicExch(overflow, 2); break; }
         nbr_off[k] = (uint16_t)off;
-        off += nfree[nbr[k]];
+        const int b = nbr[k];
+        int mask = 0;
+        for (int j = 0; j < dim; ++j) mask |= (eq[(int64_t)b * dim + j] >= 0) << j;
+        nbr_free[k] = (uint8_t)mask;
+        off += nfree[b];
     }
     node_rl[a] = off;
 }
@@ -303,6 +307,7 @@ int sc_pattern_build(sc_ctx* ctx) {
     SC_CUDA(ctx, cudaMemcpy(&total_nbr, ctx->d_nbr_ptr + nn, sizeof(int64_t), cudaMemcpyDeviceToHost));
     SC_TRY(sc_alloc(ctx, &ctx->d_nbr, (size_t)total_nbr));
     SC_TRY(sc_alloc(ctx, &ctx->d_nbr_off, (size_t)total_nbr));
+    SC_TRY(sc_alloc(ctx, &ctx->d_nbr_free, (size_t)total_nbr));
     if (tier == 0) k_node_neighbours<64, true><<<nblk(nn, 128), 128, 0, st>>>(ctx->d_conn, nne, ctx->d_n2e_ptr, ctx->d_n2e, nn, ctx->d_active, nullptr, ctx->d_nbr_ptr, ctx->d_nbr, d_flag);
     if (tier == 1) k_node_neighbours<256, true><<<nblk(nn, 128), 128, 0, st>>>(ctx->d_conn, nne, ctx->d_n2e_ptr, ctx->d_n2e, nn, ctx->d_active, nullptr, ctx->d_nbr_ptr, ctx->d_nbr, d_flag);
     if (tier == 2) k_node_neighbours<1024, true><<<nblk(nn, 64), 64, 0, st>>>(ctx->d_conn, nne, ctx->d_n2e_ptr, ctx->d_n2e, nn, ctx->d_active, nullptr, ctx->d_nbr_ptr, ctx->d_nbr, d_flag);
@@ -326,7 +331,8 @@ int sc_pattern_build(sc_ctx* ctx) {
     }
     SC_TRY(sc_alloc(ctx, &ctx->d_node_rl, (size_t)nn));
     SC_CUDA(ctx, cudaMemsetAsync(d_flag, 0, sizeof(int), st));
-    k_node_rowlen<<<nblk(nn, T), T, 0, st>>>(ctx->d_nbr_ptr, ctx->d_nbr, d_nfree, nn, ctx->d_nbr_off, ctx->d_node_rl, d_flag);
+    k_node_rowlen<<<nblk(nn, T), T, 0, st>>>(ctx->d_nbr_ptr, ctx->d_nbr, d_nfree, ctx->d_eq, dim, nn, ctx->d_nbr_off, ctx->d_nbr_free,
+                                              ctx->d_node_rl, d_flag);
     SC_CHECK_LAUNCH(ctx);
     int flag = 0;
     SC_CUDA(ctx, cudaMemcpyAsync(&flag, d_flag, sizeof(int), cudaMemcpyDeviceToHost, st));
