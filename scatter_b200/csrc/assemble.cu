@@ -18,6 +18,7 @@
 //   M[(a,i),(b,j)] = delta_ij rho sum_g w_g detJ_g Na Nb          (consistent mass; zeros kept in the pattern)
 // which equals B^T D B with the reference's Voigt ordering; detJ is used signed (discretisation.py:126).
 #include <algorithm>
+#include <cstdlib>
 #include "common.h"
 
 namespace {
@@ -239,8 +240,8 @@ __constant__ double c_tabw[SC_MAX_GP];
 // LPP lanes share one (node, element) pair: every lane evaluates the Jacobians (redundantly) and NNE/LPP of the NNE
 // node blocks of the row block.  LPP = 2 halves the register-resident accumulators of hexa8 (72 -> 36 doubles), which
 // doubles the resident warps per SM; the extra Jacobian work costs less than the latency it hides.
-template <int NNE, int DIM, int NGP, int TPB, int LPP>
-__global__ void __launch_bounds__(TPB, (LPP > 1 ? 3 : 2)) k_assemble_pairs(AsmParams p, int npb) {
+template <int NNE, int DIM, int NGP, int TPB, int LPP, int MINB, int UG>
+__global__ void __launch_bounds__(TPB, MINB) k_assemble_pairs(AsmParams p, int npb) {
     constexpr int DD = DIM * DIM, ND = NNE * DIM;
     constexpr int NBB = NNE / LPP;                       // node blocks per lane
     constexpr int PPB = TPB / LPP;                       // pairs per block
@@ -318,7 +319,7 @@ __global__ void __launch_bounds__(TPB, (LPP > 1 ? 3 : 2)) k_assemble_pairs(AsmPa
             const double rho = p.rho[e];
             const double lam = E * nu / ((1.0 + nu) * (1.0 - 2.0 * nu));
             const double mu = E / (2.0 * (1.0 + nu));
-#pragma unroll 1
+#pragma unroll UG
             for (int g = 0; g < NGP; ++g) {
                 double J[DD], inv[DD], det;
 #pragma unroll
@@ -462,9 +463,12 @@ int launch_pairs(sc_ctx* ctx, const AsmParams& p, const ShapeTable& t, bool* han
     SC_CUDA(ctx, cudaMemcpyToSymbolAsync(c_tabN, t.N.data(), t.N.size() * sizeof(double), 0, cudaMemcpyHostToDevice, ctx->stream));
     SC_CUDA(ctx, cudaMemcpyToSymbolAsync(c_tabdN, t.dN.data(), t.dN.size() * sizeof(double), 0, cudaMemcpyHostToDevice, ctx->stream));
     SC_CUDA(ctx, cudaMemcpyToSymbolAsync(c_tabw, t.w.data(), t.w.size() * sizeof(double), 0, cudaMemcpyHostToDevice, ctx->stream));
-    auto kern = k_assemble_pairs<NNE, DIM, NGP, TPB, LPP>;
-    SC_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
     const unsigned grid = (unsigned)((p.n_nodes + npb - 1) / npb);
+    // (measured on B200, hexa8: 4 blocks/SM with a 128-register cap spills and is 1.45x slower; unrolling the Gauss-point
+    //  loop x2 is 1.09x slower -- instruction cache)
+    constexpr int MINB = LPP > 1 ? 3 : 2;
+    auto kern = k_assemble_pairs<NNE, DIM, NGP, TPB, LPP, MINB, 1>;
+    SC_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
     kern<<<grid, TPB, bytes, ctx->stream>>>(p, npb);
     SC_CHECK_LAUNCH(ctx);
     *handled = true;
