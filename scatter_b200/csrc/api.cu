@@ -111,6 +111,10 @@ int sc_create(int device, sc_ctx** out) {
     ctx->force_no_tma = no_tma && no_tma[0] == '1';
     const char* no_node = getenv("SCATTER_B200_NO_NODE");
     ctx->force_no_node = no_node && no_node[0] == '1';
+    // the software-pipelined node kernel measured 2 % slower than the two-nodes-per-warp kernel on the 50 M-dof box
+    // (8.22 vs 8.08 ms): opt-in only
+    const char* pipe = getenv("SCATTER_B200_PIPE");
+    ctx->force_no_pipe = !(pipe && pipe[0] == '1');
     const char* gen_asm = getenv("SCATTER_B200_GENERIC_ASSEMBLY");
     ctx->force_generic_assembly = gen_asm && gen_asm[0] == '1';
     *out = ctx;

@@ -104,6 +104,7 @@ struct sc_ctx {
     cudaEvent_t ev_rows_ready = nullptr, ev_rows_done = nullptr;   // output rows: snapshot ready / D2H finished
     bool rows_pending = false;
     double* d_snap[3] = {nullptr, nullptr, nullptr};               // snapshots of u, v, a while their D2H copy is in flight
+    bool force_no_pipe = true;             // env SCATTER_B200_PIPE=1 selects the software-pipelined node kernel (experimental)
     bool force_no_node = false;            // env SCATTER_B200_NO_NODE: row-wise kernels instead of the node-blocked one
     bool force_no_tma = false;             // test hook / env SCATTER_B200_NO_TMA: register-staged SpMV instead of the TMA ring
     bool force_generic_assembly = false;   // test hook: use the warp-per-node kernel for every element type
