@@ -21,6 +21,10 @@
 #include <cstdlib>
 #include "common.h"
 
+#ifndef SC_BLK_UG
+#define SC_BLK_UG 2
+#endif
+
 namespace {
 
 struct AsmParams {
@@ -467,6 +471,7 @@ __global__ void __launch_bounds__(TPB, MINB) k_assemble_blk(AsmParams p, int npb
     constexpr int GC = NGP <= 9 ? NGP : 9;               // Gauss points per chunk (27 = 3 x 9)
     constexpr int IST = DD + 1;                          // J^-1 and detJ*w
     constexpr int UST = GC * IST + 1;                    // per-element stride (odd: no bank conflicts across elements)
+    constexpr int UGB = SC_BLK_UG;                       // unroll factor of the Gauss-point loop of the pair lanes
     constexpr int HBITS = 8, HSIZE = 1 << HBITS;         // hash table of the block's elements (load <= 1/2)
     static_assert(NNE % LPP == 0 && NGP % GC == 0 && (TPB / 32) % LPP == 0 && PPB * 2 <= HSIZE, "unsupported split");
     extern __shared__ double smem[];
@@ -530,11 +535,21 @@ __global__ void __launch_bounds__(TPB, MINB) k_assemble_blk(AsmParams p, int npb
     for (int t = tid; t < (PPB * p.max_nbr + 3) / 4; t += TPB) reinterpret_cast<unsigned*>(s_inv)[t] = 0xffffffffu;
     for (int t = tid; t < HSIZE; t += TPB) s_hkey[t] = -1;
     if (tid == 0) s_wcnt[0] = 0;
-    for (int t = tid; t < nbn * DIM; t += TPB) {
-        const int rr = p.eq[(a0 + t / DIM) * DIM + t % DIM];
-        s_rowbase[t] = (rr >= 0 && p.node_rl[a0 + t / DIM] > 0) ? (long long)p.rowptr[rr] : -1;
+    // first slot of the block's rows: a two-level load chain that is only needed in phase 2 -> stored after the barrier
+    long long rb_reg[DIM];                               // nbn <= PPB <= TPB, so DIM strided passes cover nbn * DIM rows
+#pragma unroll
+    for (int c = 0; c < DIM; ++c) {
+        const int t = tid + c * TPB;
+        rb_reg[c] = -1;
+        if (t < nbn * DIM) {
+            const int rr = p.eq[a0 * DIM + t];
+            if (rr >= 0 && p.node_rl[a0 + t / DIM] > 0) rb_reg[c] = (long long)p.rowptr[rr];
+        }
     }
     __syncthreads();
+#pragma unroll
+    for (int c = 0; c < DIM; ++c)
+        if (tid + c * TPB < nbn * DIM) s_rowbase[tid + c * TPB] = rb_reg[c];
     const int n_items = s_nptr[nbn];
 
     // ---- distinct elements of the block -----------------------------------------------------------------------------
@@ -626,7 +641,7 @@ __global__ void __launch_bounds__(TPB, MINB) k_assemble_blk(AsmParams p, int npb
         }
         __syncthreads();
         if (valid) {
-#pragma unroll 1
+#pragma unroll UGB
             for (int gl = 0; gl < GC; ++gl) {
                 const int g = g0 + gl;
                 const double* si = sinv + (size_t)ui * UST + gl * IST;
