@@ -117,8 +117,6 @@ int sc_create(int device, sc_ctx** out) {
     ctx->force_no_pipe = !(pipe && pipe[0] == '1');
     const char* gen_asm = getenv("SCATTER_B200_GENERIC_ASSEMBLY");
     ctx->force_generic_assembly = gen_asm && gen_asm[0] == '1';
-    const char* asm_cfg = getenv("SCATTER_B200_ASM_CFG");
-    ctx->asm_cfg = asm_cfg ? atoi(asm_cfg) : 0;
     const char* pair_asm = getenv("SCATTER_B200_PAIR_ASSEMBLY");
     ctx->force_pair_assembly = pair_asm && pair_asm[0] == '1';
     *out = ctx;

@@ -9,9 +9,11 @@
 // the elements touching its node.  A block of consecutive nodes therefore produces its CSR rows alone: it walks the
 // elements of each node in ascending element id -- the order in which the reference adds them to a slot -- evaluates
 // only the DIM x (NNE*DIM) row block of Ke that belongs to the node, and sums per slot in that order.  Nobody else
-// writes those rows, so the result is reproducible bit for bit.  Two kernels implement it: `k_assemble_pairs`
-// (row block in registers, one or two lanes per (node, element) pair; tri3..hexa8) and `k_assemble` (one warp per
-// node, shared-memory staging; tetra10 / hexa20 and very high node valences).
+// writes those rows, so the result is reproducible bit for bit.  Three kernels implement it: `k_assemble_blk` (default
+// for tri3..hexa8: row block in registers, one or two lanes per (node, element) pair, Jacobian set-up shared by the
+// pairs of a block), `k_assemble_pairs` (its predecessor: set-up repeated per lane; kept as a cross-check behind
+// SCATTER_B200_PAIR_ASSEMBLY=1) and `k_assemble` (one warp per node, shared-memory staging; tetra10 / hexa20 and very
+// high node valences).
 //
 // Isotropic elasticity lets the row block be formed without B or D:
 //   K[(a,i),(b,j)] = sum_g w_g detJ_g ( lam dNa_i dNb_j + mu dNa_j dNb_i + delta_ij mu dNa.dNb )
@@ -790,9 +792,10 @@ int launch_blk_cfg(sc_ctx* ctx, const AsmParams& p, const ShapeTable& t, bool* h
 
 template <int NNE, int DIM, int NGP>
 int launch_blk(sc_ctx* ctx, const AsmParams& p, const ShapeTable& t, bool* handled) {
-    if constexpr (DIM * NNE * DIM > 36 && NNE % 4 == 0) {
-        if (ctx->asm_cfg == 1) return launch_blk_cfg<NNE, DIM, NGP, 256, 4, 3>(ctx, p, t, handled);
-        if (ctx->asm_cfg == 2) return launch_blk_cfg<NNE, DIM, NGP, 256, 2, 2>(ctx, p, t, handled);
+    // measured on B200 (hexa8, 128^3 elements): 128 threads x 2 lanes per pair x 4 CTAs/SM 7.4 ms; 256 x 4 x 3 9.5 ms;
+    // 128 x 4 x 6 9.4 ms (both spill at 80 registers and do 14 % more flops); 256 x 2 x 2 8.3 ms; coordinates re-read
+    // per set-up task instead of held in registers 7.9 ms
+    if constexpr (DIM * NNE * DIM > 36 && NNE % 2 == 0) {
         return launch_blk_cfg<NNE, DIM, NGP, 128, 2, 4>(ctx, p, t, handled);
     } else {
         return launch_blk_cfg<NNE, DIM, NGP, 128, 1, 2>(ctx, p, t, handled);

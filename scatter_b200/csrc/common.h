@@ -107,7 +107,6 @@ struct sc_ctx {
     bool force_no_pipe = true;             // env SCATTER_B200_PIPE=1 selects the software-pipelined node kernel (experimental)
     bool force_no_node = false;            // env SCATTER_B200_NO_NODE: row-wise kernels instead of the node-blocked one
     bool force_no_tma = false;             // test hook / env SCATTER_B200_NO_TMA: register-staged SpMV instead of the TMA ring
-    int asm_cfg = 0;                       // tuning hook: launch configuration of k_assemble_blk
     bool force_pair_assembly = false;      // test hook: previous generation (set-up repeated per pair lane)
     bool force_generic_assembly = false;   // test hook: use the warp-per-node kernel for every element type
     bool nm_resume_valid = false;   // d_a holds the Newmark acceleration of step nm_resume_t (stage continuation)

@@ -157,6 +157,28 @@ def test_assembly_is_bit_reproducible(golden_meshes):
     assert sha(k1) != "" and np.array_equal(k1, a.ctx.get_values(0))
 
 
+@pytest.mark.parametrize("case", ["cube", "column_3D_tetra4", "column_2D", "column_2D_tri6"])
+def test_assembly_kernel_generations_agree(case, golden_meshes, monkeypatch):
+    """k_assemble_blk (default), k_assemble_pairs and the warp-per-node k_assemble sum the same contributions in the same
+    order; they differ only in how a single element contribution is rounded (material law per Gauss point vs once)."""
+    if case not in cases.MATRIX_CASES:
+        pytest.skip("case not in the fixture set")
+    fn, bc = cases.MATRIX_CASES[case]
+    vals = {}
+    for name, env in (("blk", None), ("pairs", "SCATTER_B200_PAIR_ASSEMBLY"), ("generic", "SCATTER_B200_GENERIC_ASSEMBLY")):
+        if env:
+            monkeypatch.setenv(env, "1")
+        _, mx = build(golden_meshes[fn], bc, cases.materials(), cases.settings())
+        vals[name] = (mx.ctx.get_values(0), mx.ctx.get_values(1), mx.ctx.get_lumped_mass())
+        mx.ctx.close()
+        if env:
+            monkeypatch.delenv(env)
+    for other in ("pairs", "generic"):
+        for a, b in zip(vals["blk"], vals[other]):
+            assert a.shape == b.shape
+            assert np.abs(a - b).max() <= 1e-13 * np.abs(b).max()
+
+
 def test_box_mesh_random_field(oracle, tmp_path):
     """Synthetic structured boxes (the benchmark generator) with per-element random Young's modulus."""
     from scatter_b200 import boxmesh, system_matrix
