@@ -188,6 +188,13 @@ int apply_M_C(sc_ctx* ctx, const double* xm, const double* xc, double* x1, doubl
 constexpr int PCG_NB = 1024;
 
 // Jacobi-preconditioned CG for A x = b, x0 = 0.  Returns iterations and the relative residual.
+// non-finite detector for the explicit schemes: one pass over u at the end of a stage (0.07 ms for 50 M dofs)
+__global__ void k_flag_nonfinite(const double* __restrict__ u, int64_t n, double* __restrict__ flag) {
+    bool bad = false;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) bad |= !isfinite(u[i]);
+    if (__syncthreads_or(bad) && threadIdx.x == 0) *flag = 1.0;
+}
+
 int pcg(sc_ctx* ctx, const double* vals, const double* dinv, const double* b, double* x, double* r, double* p, double* q,
         double rtol, int maxit, int* iters, double* relres, double ref_norm2 = -1.0) {
     const int64_t n = ctx->n_eq;
@@ -476,11 +483,28 @@ int tl_central_difference(sc_ctx* ctx, double dt, int64_t t0, int64_t n_steps, i
     ctx->cd_resume_valid = true;
     ctx->cd_resume_t = t_end;
     ctx->cd_resume_dt = dt;
+    // the scheme is only conditionally stable: report a blown-up state instead of handing back NaN/Inf histories
+    SC_CUDA(ctx, cudaMemsetAsync(ctx->d_scal + 9, 0, sizeof(double), st));
+    k_flag_nonfinite<<<592, 256, 0, st>>>(ctx->d_u, n, ctx->d_scal + 9);
+    SC_CHECK_LAUNCH(ctx);
+    SC_CUDA(ctx, cudaMemcpyAsync(ctx->h_pinned + 9, ctx->d_scal + 9, sizeof(double), cudaMemcpyDeviceToHost, st));
     SC_TRY(finish_rows(ctx));
     SC_CUDA(ctx, cudaStreamSynchronize(st));
     float ms = 0.f;
     cudaEventElapsedTime(&ms, e0, e1);
     cudaEventDestroy(e0); cudaEventDestroy(e1);
+    double diverged = ctx->h_pinned[9];
+    if (ctx->world > 1) {                                // every rank must take the same exit
+        SC_TRY(dist_allreduce_sum(ctx, ctx->d_scal + 9, 1, st));
+        SC_CUDA(ctx, cudaMemcpyAsync(ctx->h_pinned + 9, ctx->d_scal + 9, sizeof(double), cudaMemcpyDeviceToHost, st));
+        SC_CUDA(ctx, cudaStreamSynchronize(st));
+        diverged = ctx->h_pinned[9];
+    }
+    if (diverged != 0.0) {
+        ctx->cd_resume_valid = false;
+        return sc_fail(ctx, SC_ERR_NOCONV, "central difference diverged (non-finite displacements after step %lld): the time step %g "
+                       "exceeds the stability limit of the mesh", (long long)t_end, dt);
+    }
     if (stats) {
         stats->seconds_device = ms * 1e-3;
         stats->seconds_total = std::chrono::duration<double>(std::chrono::steady_clock::now() - wall0).count();

@@ -325,6 +325,25 @@ def test_central_difference_vs_oracle(golden_meshes, oracle):
     assert errs[0] <= TOL_HIST and errs[1] <= TOL_HIST and errs[2] <= 1e-7, (errs, rows[:3], rows[24:28], rows[-2:])
 
 
+def test_central_difference_reports_divergence(golden_meshes):
+    """A time step far above the stability limit must raise, not hand back NaN/Inf histories."""
+    from scatter_b200 import force_external, solvers
+    from scatter_b200._lib import ScatterB200Error
+    mesh, bc = "cube.msh", cases.BC_CUBE
+    mat, sett = cases.materials(), cases.settings(damping=[1, 0.01, 30, 0.01])
+    dt = 0.5
+    load = {"force": [0, -1000, 0], "node": [8], "time": 200.0, "type": "heaviside", "ini_steps": 5}
+    m, mx = build(golden_meshes[mesh], bc, mat, sett)
+    time = np.linspace(0, load["time"], int(np.ceil(load["time"] / dt) + 1))
+    num = solvers.CentralDifferenceSolver(); num.output_interval = 50
+    num.initialise(m.number_eq, time); num.bind(mx)
+    F = force_external.Force(); F.initialise_load(load, time, m, num)
+    num.update_rhs_at_time_step_func = F.update_load_at_t
+    num.update(0)
+    with pytest.raises(ScatterB200Error, match="diverged"):
+        num.calculate(None, None, None, F.force_vector, 0, len(time) - 1)
+
+
 def test_bathe_and_static_vs_oracle(golden_meshes, oracle):
     """Solver.BATHE / Solver.STATIC have no reference fixture: compare the device loops with the oracle's textbook
     restatement, and Bathe with the pinned Newmark oracle (both second order)."""
