@@ -158,7 +158,9 @@ k_spmv_node(const NodeDesc* __restrict__ nd, const int32_t* __restrict__ ncol, c
                 maxL = max(maxL, L[q]);
                 sv[q] = s_val + (size_t)stage * cap_v + (int)(d.val_off - (d0.val_off & ~(int64_t)1)) + lane;
                 sc[q] = s_col + (size_t)stage * cap_c + (int)(d.col_off - (d0.col_off & ~(int64_t)3)) + lane;
-                owner[q] = (lane & 7) == 0 && myr < nfree[q] && L[q] > 0;
+                // rows without entries (ghost nodes of a domain decomposition) still get y = 0: PCG reads q on every local
+                // row; the fused central-difference step leaves them alone (their u comes from the halo exchange)
+                owner[q] = (lane & 7) == 0 && myr < nfree[q] && (L[q] > 0 || MODE != 2);
                 e_al[q] = e_id[q] = e_x[q] = e_y[q] = 0.0;
                 if (NVEC > 0 && owner[q]) {
                     const double* svec = s_vec + (size_t)stage * NV1 * NB_VT + (d.row0 - (d0.row0 & ~1)) + myr;
@@ -363,7 +365,7 @@ k_spmv_node_pipe(const NodeDesc* __restrict__ nd, const int32_t* __restrict__ nc
             const int nfree = d.len_nfree >> 24;
             const int L = nfree > 0 ? (d.len_nfree & 0xffffff) : 0;
             const double* sv = s_val + (size_t)stage * cap_v + (int)(d.val_off - (d0.val_off & ~(int64_t)1)) + lane;
-            const bool owner = (lane & 7) == 0 && myr < nfree && L > 0;
+            const bool owner = (lane & 7) == 0 && myr < nfree && (L > 0 || MODE != 2);
             double e_al = 0.0, e_id = 0.0, e_x = 0.0, e_y = 0.0;
             if (NVEC > 0 && owner) {
                 const double* svec = s_vec + (size_t)stage * NV1 * NB_VT + (d.row0 - (d0.row0 & ~1)) + myr;
