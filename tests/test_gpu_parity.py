@@ -344,6 +344,53 @@ def test_central_difference_reports_divergence(golden_meshes):
         num.calculate(None, None, None, F.force_vector, 0, len(time) - 1)
 
 
+def test_rows_without_entries_do_not_disturb_pcg(golden_meshes, oracle):
+    """Rank 0's sub-domain of a two-way decomposition, run alone on one GPU with no halo exchange: ghost nodes own equation
+    numbers but empty rows, so the system reduces to the owned block with the ghost dofs held at zero.  Regression test:
+    the SpMV must write q = 0 on the empty rows, otherwise stale values leak into the PCG residual norms."""
+    from scatter_b200 import mesher, partition, system_matrix
+    m = mesher.ReadMesh(golden_meshes["cube.msh"])
+    m.read_gmsh(); m.read_bc(cases.BC_CUBE); m.mapping(); m.connectivities()
+    owner = partition.owner_by_slabs(m, 2, axis=2)
+    dom = partition.partition_model(m, owner, 0)
+    loc = dom.model
+    ne = len(loc.elem)
+    mx = system_matrix.GenerateMatrix(loc.number_eq, 2)
+    mx.generate_stiffness_and_mass(loc, None, elem_props=(np.full(ne, 10e6), np.full(ne, 0.2), np.full(ne, 1500.0)), active=dom.active)
+    mx.damping_Rayleigh([1, 0.01, 30, 0.01])
+    ctx = mx.ctx
+    own = np.asarray(dom.owned_eq)
+    ghost = np.setdiff1d(np.arange(loc.number_eq), own)
+    assert len(ghost) > 0
+    nt = 21
+    d = int(own[len(own) // 2])
+    ramp = np.ones(nt); ramp[:5] = np.linspace(0, 1, 5)
+    ctx.set_load_schedule(np.arange(nt + 1, dtype=np.int64), np.full(nt, d, dtype=np.int64), -1000.0 * ramp)
+    # dirty the scratch vectors on the ghost rows first (an explicit run with a non-zero initial velocity leaves
+    # non-zero accelerations there and shares its scratch with the PCG), then the implicit solve from rest
+    ctx.set_state(None, np.ones(loc.number_eq))
+    ctx.run_central_difference(2e-4, 0, 10, 5)
+    ctx.set_state(None, None)
+    u, v, a, st = ctx.run_newmark(5e-3, 0, nt - 1, 5)
+    assert np.all(u[:, ghost] == 0.0)
+    # oracle: the owned block of the single-domain matrices
+    om = oracle.model_from_readmesh(m)
+    neg = len(m.elem)
+    K, M = oracle.assemble_global(om, np.full(neg, 10e6), np.full(neg, 0.2), np.full(neg, 1500.0), 2)
+    c0, c1 = oracle.rayleigh_coefficients([1, 0.01, 30, 0.01])
+    g = np.asarray(dom.global_eq_of_owned)
+    Koo = sp.csr_matrix(K)[g][:, g]; Moo = sp.csr_matrix(M)[g][:, g]
+    Coo = c0 * Moo + c1 * Koo
+    k = int(np.where(own == d)[0][0])
+
+    def force(t):
+        f = np.zeros(len(g)); f[k] = -1000.0 * ramp[min(t, nt - 1)]
+        return f
+    U, V, A = oracle.newmark(Moo, Coo, Koo, force, np.arange(nt) * 5e-3, output_interval=5)[:3]
+    assert rel_l2(u[:, own], U) <= TOL_HIST and rel_l2(v[:, own], V) <= TOL_HIST
+    ctx.close()
+
+
 def test_bathe_and_static_vs_oracle(golden_meshes, oracle):
     """Solver.BATHE / Solver.STATIC have no reference fixture: compare the device loops with the oracle's textbook
     restatement, and Bathe with the pinned Newmark oracle (both second order)."""
