@@ -38,6 +38,7 @@ int upload(sc_ctx* ctx, T** dst, const T* src, size_t n) {
 }
 
 void free_pattern(sc_ctx* c) {
+    pcg_graph_drop(c);
     sc_free(&c->d_n2e_ptr); sc_free(&c->d_n2e); sc_free(&c->d_nbr_ptr); sc_free(&c->d_nbr); sc_free(&c->d_nbr_off); sc_free(&c->d_nbr_free);
     sc_free(&c->d_node_rl); sc_free(&c->d_node_row0); sc_free(&c->d_rowptr); sc_free(&c->d_col); sc_free(&c->d_nd); sc_free(&c->d_ncol); sc_free(&c->d_pair_pos); sc_free(&c->d_pair_al);
     sc_free(&c->d_K); sc_free(&c->d_M); sc_free(&c->d_Ml); sc_free(&c->d_Khat); sc_free(&c->d_Khat2);
@@ -48,6 +49,7 @@ void free_pattern(sc_ctx* c) {
     c->nnz = 0;
 }
 void free_vectors(sc_ctx* c) {
+    pcg_graph_drop(c);
     sc_free(&c->d_u); sc_free(&c->d_v); sc_free(&c->d_a);
     for (auto& w : c->work) sc_free(&w);
     c->work.clear();
@@ -117,6 +119,8 @@ int sc_create(int device, sc_ctx** out) {
     ctx->force_no_pipe = !(pipe && pipe[0] == '1');
     const char* gen_asm = getenv("SCATTER_B200_GENERIC_ASSEMBLY");
     ctx->force_generic_assembly = gen_asm && gen_asm[0] == '1';
+    const char* no_graph = getenv("SCATTER_B200_NO_GRAPH");
+    ctx->no_graph = no_graph && no_graph[0] == '1';
     const char* pair_asm = getenv("SCATTER_B200_PAIR_ASSEMBLY");
     ctx->force_pair_assembly = pair_asm && pair_asm[0] == '1';
     *out = ctx;

@@ -107,6 +107,11 @@ struct sc_ctx {
     bool force_no_pipe = true;             // env SCATTER_B200_PIPE=1 selects the software-pipelined node kernel (experimental)
     bool force_no_node = false;            // env SCATTER_B200_NO_NODE: row-wise kernels instead of the node-blocked one
     bool force_no_tma = false;             // test hook / env SCATTER_B200_NO_TMA: register-staged SpMV instead of the TMA ring
+    bool no_graph = false;                 // SCATTER_B200_NO_GRAPH=1: launch the PCG iteration kernel by kernel
+    cudaGraphExec_t pcg_graph = nullptr;   // captured PCG iteration (single-GPU), valid for the pointers in pcg_graph_key
+    const void* pcg_graph_key[8] = {};
+    int64_t pcg_graph_n = 0;
+    int pcg_graph_launches = 0;
     bool force_pair_assembly = false;      // test hook: previous generation (set-up repeated per pair lane)
     bool force_generic_assembly = false;   // test hook: use the warp-per-node kernel for every element type
     bool nm_resume_valid = false;   // d_a holds the Newmark acceleration of step nm_resume_t (stage continuation)
@@ -184,6 +189,7 @@ int la_extract_diag(sc_ctx* ctx, const double* vals, double* diag, bool invert);
 int la_fill(sc_ctx* ctx, double* x, double v, int64_t n);
 int la_dot(sc_ctx* ctx, const double* x, const double* y, double* d_out);     // deterministic 2-stage, result on device
 int la_scratch(sc_ctx* ctx);
+void pcg_graph_drop(sc_ctx* ctx);                                        // timeloop.cu: forget the captured PCG iteration
 int la_cd_step(sc_ctx* ctx, const double* K, const double* u, double* uprev_next, const double* inv_d, const double* alpha);
 int la_spmv_dot(sc_ctx* ctx, const double* vals, const double* p, double* q, double* d_out);
 // spmv_tma.cu

@@ -46,7 +46,7 @@ __global__ void k_pcg_update(const double* __restrict__ scal, const double* __re
                              const double* __restrict__ dinv, double* __restrict__ x, double* __restrict__ r, int64_t n,
                              double* __restrict__ partial, int nb) {
     __shared__ double sh[2][8];
-    const double alpha = scal[0] / scal[1];
+    const double alpha = scal[1] != 0.0 ? scal[0] / scal[1] : 0.0;   // p.Ap = 0 only once r = 0 (iterations past convergence)
     const int64_t chunk = (n + nb - 1) / nb;
     const int64_t s = blockIdx.x * chunk, e = min(s + chunk, n);
     double rz = 0.0, rr = 0.0;
@@ -89,7 +89,7 @@ __global__ void k_pcg_p(const double* __restrict__ scal, const double* __restric
                         double* __restrict__ p, int64_t n) {
     int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const double beta = scal[2] / scal[0];
+    const double beta = scal[0] != 0.0 ? scal[2] / scal[0] : 0.0;
     p[i] = dinv[i] * r[i] + beta * p[i];
 }
 __global__ void k_shift(double* scal) { scal[0] = scal[2]; }
@@ -195,6 +195,15 @@ __global__ void k_flag_nonfinite(const double* __restrict__ u, int64_t n, double
     if (__syncthreads_or(bad) && threadIdx.x == 0) *flag = 1.0;
 }
 
+}  // namespace
+
+void pcg_graph_drop(sc_ctx* ctx) {
+    if (ctx->pcg_graph) cudaGraphExecDestroy(ctx->pcg_graph);
+    ctx->pcg_graph = nullptr;
+}
+
+namespace {
+
 int pcg(sc_ctx* ctx, const double* vals, const double* dinv, const double* b, double* x, double* r, double* p, double* q,
         double rtol, int maxit, int* iters, double* relres, double ref_norm2 = -1.0) {
     const int64_t n = ctx->n_eq;
@@ -216,7 +225,9 @@ int pcg(sc_ctx* ctx, const double* vals, const double* dinv, const double* b, do
         bb = ref_norm2;
     }
     const double target = rtol * rtol * bb;
-    for (int it = 1; it <= maxit; ++it) {
+    // one iteration = six small launches + a 40-byte read-back; on small and mid-size meshes the launch overhead is
+    // the iteration time, so the sequence is captured once into a CUDA graph (single-GPU runs; NCCL calls stay eager)
+    auto iteration = [&]() -> int {
         if (ctx->world > 1) SC_TRY(dist_halo(ctx, p, st));
         SC_TRY(la_spmv_dot(ctx, vals, p, q, sc + 1));
         k_pcg_update<<<PCG_NB, 256, 0, st>>>(sc, p, q, dinv, x, r, n, ctx->d_partial, PCG_NB);
@@ -229,6 +240,42 @@ int pcg(sc_ctx* ctx, const double* vals, const double* dinv, const double* b, do
         SC_CHECK_LAUNCH(ctx);
         k_shift<<<1, 1, 0, st>>>(sc);
         SC_CHECK_LAUNCH(ctx);
+        return SC_OK;
+    };
+    const bool use_graph = ctx->world == 1 && !ctx->no_graph;
+    if (use_graph) {
+        const void* key[8] = {vals, dinv, x, r, p, q, ctx->d_nd, ctx->d_partial};
+        bool same = ctx->pcg_graph != nullptr && ctx->pcg_graph_n == n;
+        for (int k = 0; k < 8 && same; ++k) same = ctx->pcg_graph_key[k] == key[k];
+        if (!same) {
+            pcg_graph_drop(ctx);
+            const int64_t l0 = ctx->launches;
+            cudaGraph_t graph = nullptr;
+            SC_CUDA(ctx, cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+            const int rc = iteration();
+            const cudaError_t ce = cudaStreamEndCapture(st, &graph);
+            if (rc != SC_OK) { if (graph) cudaGraphDestroy(graph); return rc; }
+            SC_CUDA(ctx, ce);
+            const cudaError_t ie = cudaGraphInstantiate(&ctx->pcg_graph, graph, 0);
+            cudaGraphDestroy(graph);
+            SC_CUDA(ctx, ie);
+            ctx->pcg_graph_launches = (int)(ctx->launches - l0);
+            ctx->launches = l0;
+            ctx->pcg_graph_n = n;
+            for (int k = 0; k < 8; ++k) ctx->pcg_graph_key[k] = key[k];
+        }
+    }
+    // small systems: the stopping test (a stream synchronisation) costs as much as an iteration, so it is made every
+    // fourth iteration; the up to three extra iterations only tighten the solution (alpha, beta are guarded against r = 0)
+    const int check_every = (use_graph && n < 100000) ? 4 : 1;
+    for (int it = 1; it <= maxit; ++it) {
+        if (use_graph) {
+            SC_CUDA(ctx, cudaGraphLaunch(ctx->pcg_graph, st));
+            ctx->launches += ctx->pcg_graph_launches;
+        } else {
+            SC_TRY(iteration());
+        }
+        if (it % check_every != 0 && it != maxit) continue;
         SC_CUDA(ctx, cudaStreamSynchronize(st));
         const double rr = ctx->h_pinned[3];
         *iters = it;
