@@ -119,6 +119,8 @@ int sc_create(int device, sc_ctx** out) {
     ctx->force_no_pipe = !(pipe && pipe[0] == '1');
     const char* gen_asm = getenv("SCATTER_B200_GENERIC_ASSEMBLY");
     ctx->force_generic_assembly = gen_asm && gen_asm[0] == '1';
+    const char* no_small = getenv("SCATTER_B200_NO_SMALL_PCG");
+    ctx->no_small_pcg = no_small && no_small[0] == '1';
     const char* no_graph = getenv("SCATTER_B200_NO_GRAPH");
     ctx->no_graph = no_graph && no_graph[0] == '1';
     const char* pair_asm = getenv("SCATTER_B200_PAIR_ASSEMBLY");

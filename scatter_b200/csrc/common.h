@@ -107,6 +107,8 @@ struct sc_ctx {
     bool force_no_pipe = true;             // env SCATTER_B200_PIPE=1 selects the software-pipelined node kernel (experimental)
     bool force_no_node = false;            // env SCATTER_B200_NO_NODE: row-wise kernels instead of the node-blocked one
     bool force_no_tma = false;             // test hook / env SCATTER_B200_NO_TMA: register-staged SpMV instead of the TMA ring
+    bool no_small_pcg = false;             // SCATTER_B200_NO_SMALL_PCG=1: never use the cooperative single-kernel PCG
+    int small_pcg_grid = 0;                // co-resident grid limit of k_pcg_small (0: not queried yet)
     bool no_graph = false;                 // SCATTER_B200_NO_GRAPH=1: launch the PCG iteration kernel by kernel
     cudaGraphExec_t pcg_graph = nullptr;   // captured PCG iteration (single-GPU), valid for the pointers in pcg_graph_key
     const void* pcg_graph_key[8] = {};
@@ -189,6 +191,12 @@ int la_extract_diag(sc_ctx* ctx, const double* vals, double* diag, bool invert);
 int la_fill(sc_ctx* ctx, double* x, double v, int64_t n);
 int la_dot(sc_ctx* ctx, const double* x, const double* y, double* d_out);     // deterministic 2-stage, result on device
 int la_scratch(sc_ctx* ctx);
+constexpr size_t SC_PARTIAL_DOUBLES = 4096;                              // lower bound of the size of sc_ctx::d_partial
+constexpr int64_t SMALL_PCG_MAX_N = 250000;                              // largest system solved by the cooperative PCG
+// pcg_small.cu
+bool pcg_small_usable(sc_ctx* ctx);
+int pcg_small(sc_ctx* ctx, const double* vals, const double* dinv, const double* b, double* x, double* r, double* p, double* q,
+              double rtol, int maxit, int* iters, double* relres, double ref_norm2);
 void pcg_graph_drop(sc_ctx* ctx);                                        // timeloop.cu: forget the captured PCG iteration
 int la_cd_step(sc_ctx* ctx, const double* K, const double* u, double* uprev_next, const double* inv_d, const double* alpha);
 int la_spmv_dot(sc_ctx* ctx, const double* vals, const double* p, double* q, double* d_out);

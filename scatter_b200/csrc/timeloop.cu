@@ -206,6 +206,7 @@ namespace {
 
 int pcg(sc_ctx* ctx, const double* vals, const double* dinv, const double* b, double* x, double* r, double* p, double* q,
         double rtol, int maxit, int* iters, double* relres, double ref_norm2 = -1.0) {
+    if (pcg_small_usable(ctx)) return pcg_small(ctx, vals, dinv, b, x, r, p, q, rtol, maxit, iters, relres, ref_norm2);
     const int64_t n = ctx->n_eq;
     cudaStream_t st = ctx->stream;
     double* sc = ctx->d_scal;

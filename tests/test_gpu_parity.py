@@ -238,7 +238,14 @@ def test_newmark_hexa8_pulse_vs_reference_golden(golden_meshes, golden_histories
     assert num.stats[0]["pcg_iterations"] > 0
 
 
-def test_newmark_quad4_heaviside_vs_reference_golden(golden_meshes, golden_histories):
+@pytest.mark.parametrize("pcg_path", ["cooperative", "graph", "eager"])
+def test_newmark_quad4_heaviside_vs_reference_golden(pcg_path, golden_meshes, golden_histories, monkeypatch):
+    # the three PCG drivers (one cooperative kernel for small systems; stream-ordered iterations replayed from a CUDA
+    # graph, or launched one by one as on multi-GPU runs) must all reproduce the reference history
+    if pcg_path != "cooperative":
+        monkeypatch.setenv("SCATTER_B200_NO_SMALL_PCG", "1")
+    if pcg_path == "eager":
+        monkeypatch.setenv("SCATTER_B200_NO_GRAPH", "1")
     H = golden_histories
     m, mx, num = run_history("quad4_heaviside", golden_meshes)
     ids = list(m.nodes[:, 0].astype(int))
