@@ -348,6 +348,7 @@ def run_ours(args):
             secondary = {"error": repr(exc)}
     if rank == 0:
         info = info0 if secondary is not None else ctx.device_info()
+        sm_max_hz = 1e6 * float(clocks.get("sm_max_mhz") or 1965.0)
         line = {"metric": "dof_timesteps_per_s", "value": value, "unit": "DOF*steps/s", "n_gpus": world, "steps": args.steps,
                 "warmup": max(args.warmup, 3), "ms_per_step": 1e3 * wall / args.steps, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(args, world),
@@ -358,7 +359,11 @@ def run_ours(args):
                              "bytes_per_launch": step_bytes, "kernel_ms": 1e3 * kernel_s, "traffic": TRAFFIC.get(s)},
                 "assembly": {"seconds": t_asm, "pattern_seconds": t_pattern, "gbs": asm_bytes / t_asm / 1e9,
                              "frac_hbm": asm_bytes / t_asm / 1e9 / peak, "elements_per_s": ne / t_asm, "algorithmic_bytes": asm_bytes,
-                             "host_mesh_seconds": t_mesh},
+                             "host_mesh_seconds": t_mesh,
+                             # the kernel is FP64 bound, not HBM bound: modelled FMA count of
+                             # k_assemble_blk per hexa8 element against 64 FMA/clk/SM at the maximum SM clock
+                             "fma_per_element": ASM_FMA_PER_HEXA8,
+                             "frac_fp64_peak": ne * ASM_FMA_PER_HEXA8 / t_asm / (64.0 * info["sm_count"] * sm_max_hz)},
                 "cpu_baseline": cpu,
                 "e2e": {"value": e2e_value, "unit": "DOF*steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "ms_per_step": 1e3 * e2e_wall / args.steps},
@@ -416,6 +421,10 @@ def run_secondary_newmark(args, local_rank):
     ctx.close()
     return out
 
+
+# FP64 FMAs k_assemble_blk spends per hexa8 element (order 2): per Gauss point 121 for J, J^-1, detJ evaluated ~4 times per
+# element (once per block that sees it) and 84 in each of the 16 pair lanes
+ASM_FMA_PER_HEXA8 = 8 * (4 * 121 + 16 * 84)
 
 # dram__bytes_read.sum + dram__bytes_write.sum of one k_spmv<2> launch from the committed ncu capture (profiles/), by box size
 TRAFFIC = {255: 41377949000 + 420294000}      # profiles/r1_v4_k_spmv_node_mode2_255cube.txt (k_spmv_node<2,2,2>, 1 GPU)

@@ -9,11 +9,10 @@
 // the elements touching its node.  A block of consecutive nodes therefore produces its CSR rows alone: it walks the
 // elements of each node in ascending element id -- the order in which the reference adds them to a slot -- evaluates
 // only the DIM x (NNE*DIM) row block of Ke that belongs to the node, and sums per slot in that order.  Nobody else
-// writes those rows, so the result is reproducible bit for bit.  Three kernels implement it: `k_assemble_blk` (default
-// for tri3..hexa8: row block in registers, one or two lanes per (node, element) pair, Jacobian set-up shared by the
-// pairs of a block), `k_assemble_pairs` (its predecessor: set-up repeated per lane; kept as a cross-check behind
-// SCATTER_B200_PAIR_ASSEMBLY=1) and `k_assemble` (one warp per node, shared-memory staging; tetra10 / hexa20 and very
-// high node valences).
+// writes those rows, so the result is reproducible bit for bit.  Three kernels implement it: `k_assemble_blk` (default:
+// row block in registers, one, two or five lanes per (node, element) pair, Jacobian set-up shared by the pairs of a
+// block), `k_assemble_pairs` (its predecessor for tri3..hexa8: set-up repeated per lane; kept as a cross-check behind
+// SCATTER_B200_PAIR_ASSEMBLY=1) and `k_assemble` (one warp per node, shared-memory staging; very high node valences).
 //
 // Isotropic elasticity lets the row block be formed without B or D:
 //   K[(a,i),(b,j)] = sum_g w_g detJ_g ( lam dNa_i dNb_j + mu dNa_j dNb_i + delta_ij mu dNa.dNb )
@@ -795,7 +794,10 @@ int launch_blk(sc_ctx* ctx, const AsmParams& p, const ShapeTable& t, bool* handl
     // measured on B200 (hexa8, 128^3 elements): 128 threads x 2 lanes per pair x 4 CTAs/SM 7.4 ms; 256 x 4 x 3 9.5 ms;
     // 128 x 4 x 6 9.4 ms (both spill at 80 registers and do 14 % more flops); 256 x 2 x 2 8.3 ms; coordinates re-read
     // per set-up task instead of held in registers 7.9 ms
-    if constexpr (DIM * NNE * DIM > 36 && NNE % 2 == 0) {
+    if constexpr (DIM * NNE * DIM > 72 && NNE % 5 == 0) {
+        // tetra10 / hexa20: five lanes per pair (2 / 4 node blocks each), 160-thread blocks of 32 pairs
+        return launch_blk_cfg<NNE, DIM, NGP, 160, 5, 3>(ctx, p, t, handled);
+    } else if constexpr (DIM * NNE * DIM > 36 && NNE % 2 == 0) {
         return launch_blk_cfg<NNE, DIM, NGP, 128, 2, 4>(ctx, p, t, handled);
     } else {
         return launch_blk_cfg<NNE, DIM, NGP, 128, 1, 2>(ctx, p, t, handled);
@@ -894,7 +896,7 @@ int sc_assemble_run(sc_ctx* ctx, int order, int flags, double* seconds) {
         {                                                                                \
             bool done = false;                                                           \
             rc = SC_OK;                                                                  \
-            if (DIM * NNE * DIM <= 72 && !ctx->force_generic_assembly && !ctx->force_pair_assembly)          \
+            if (!ctx->force_generic_assembly && !ctx->force_pair_assembly)                                   \
                 rc = launch_blk<NNE, DIM, NGP>(ctx, p, t, &done);                        \
             if (rc == SC_OK && !done && DIM * NNE * DIM <= 72 && !ctx->force_generic_assembly)               \
                 rc = launch_pairs<NNE, DIM, NGP>(ctx, p, t, &done);                      \

@@ -157,7 +157,7 @@ def test_assembly_is_bit_reproducible(golden_meshes):
     assert sha(k1) != "" and np.array_equal(k1, a.ctx.get_values(0))
 
 
-@pytest.mark.parametrize("case", ["cube", "column_3D_tetra4", "column_2D", "column_2D_tri6"])
+@pytest.mark.parametrize("case", ["cube", "column_3D_tetra4", "column_2D", "column_2D_tri6", "column_high_order", "column_3D_tetra10"])
 def test_assembly_kernel_generations_agree(case, golden_meshes, monkeypatch):
     """k_assemble_blk (default), k_assemble_pairs and the warp-per-node k_assemble sum the same contributions in the same
     order; they differ only in how a single element contribution is rounded (material law per Gauss point vs once)."""
