@@ -20,27 +20,34 @@ _CORNER_OFF = np.array([[0, 0, 0], [1, 0, 0], [1, 1, 0], [0, 1, 0], [0, 0, 1], [
 
 
 def box_arrays(nx: int, ny: int, nz: int, h: float = 0.5, element_type: str = "hexa8", z_range=None):
-    """-> nodes (Nn,4) [id,x,y,z], elem (Ne,nne) 1-based ids, with ids local to the slab `z_range` = (k0, k1)."""
+    """-> nodes (Nn,4) [id,x,y,z], elem (Ne,nne) 1-based ids, with ids local to the slab `z_range` = (k0, k1).
+
+    Everything is generated in (k, j, i) C order, which is the id order (x fastest), so no scatter is needed."""
     k0, k1 = (0, nz) if z_range is None else z_range
     nzl = k1 - k0
     NX, NY, NZ = nx + 1, ny + 1, nzl + 1
-    ii, jj, kk = np.meshgrid(np.arange(NX), np.arange(NY), np.arange(NZ), indexing="ij")
-    # x fastest: flatten in (k, j, i) order
-    order = (kk * NY + jj) * NX + ii
+
+    def lattice(nk, nj, ni, off=(0.0, 0.0, 0.0)):
+        """coordinates of an (nk, nj, ni) lattice, x fastest; `off` shifts it by a fraction of h along (x, y, z)"""
+        out = np.empty((nk, nj, ni, 3))
+        out[..., 0] = (np.arange(ni) + off[0]) * h
+        out[..., 1] = ((np.arange(nj) + off[1]) * h)[:, None]
+        out[..., 2] = ((np.arange(nk) + k0 + off[2]) * h)[:, None, None]
+        return out.reshape(-1, 3)
+
     n_corner = NX * NY * NZ
-    xyz = np.empty((n_corner, 3))
-    xyz[order.ravel(), 0] = ii.ravel() * h
-    xyz[order.ravel(), 1] = jj.ravel() * h
-    xyz[order.ravel(), 2] = (kk.ravel() + k0) * h
-    ei, ej, ek = np.meshgrid(np.arange(nx), np.arange(ny), np.arange(nzl), indexing="ij")
-    eorder = ((ek * ny + ej) * nx + ei).ravel()
+    # element (ek, ej, ei) in id order; its first corner on the node lattice
+    ek, ej, ei = (a.ravel() for a in np.meshgrid(np.arange(nzl), np.arange(ny), np.arange(nx), indexing="ij"))
     ne = nx * ny * nzl
+    first = (ek * NY + ej) * NX + ei
     corner = np.empty((ne, 8), dtype=np.int64)
     for a, (di, dj, dk) in enumerate(_CORNER_OFF):
-        corner[eorder, a] = (((ek + dk) * NY + (ej + dj)) * NX + (ei + di)).ravel()
+        corner[:, a] = first + ((dk * NY + dj) * NX + di)
     if element_type == "hexa8":
-        ids = np.arange(1, n_corner + 1, dtype=float)
-        return np.column_stack([ids, xyz]), corner + 1
+        nodes = np.empty((n_corner, 4))
+        nodes[:, 0] = np.arange(1, n_corner + 1)
+        nodes[:, 1:] = lattice(NZ, NY, NX)
+        return nodes, corner + 1
     if element_type != "hexa20":
         raise ValueError("box meshes are hexa8 or hexa20")
     # mid-edge nodes: x-edges, then y-edges, then z-edges, each group x fastest
@@ -55,23 +62,20 @@ def box_arrays(nx: int, ny: int, nz: int, h: float = 0.5, element_type: str = "h
         return base[2] + (k * NY + j) * NX + i
 
     n_total = n_corner + nxe + nye + NX * NY * nzl
-    xyz_all = np.empty((n_total, 3))
-    xyz_all[:n_corner] = xyz
-    for axis, (ni, nj, nk) in enumerate([(nx, NY, NZ), (NX, ny, NZ), (NX, NY, nzl)]):
-        a, b, c = np.meshgrid(np.arange(ni), np.arange(nj), np.arange(nk), indexing="ij")
-        idx = edge_id(axis, a, b, c).ravel()
-        p = np.stack([a.ravel() * h, b.ravel() * h, (c.ravel() + k0) * h], axis=1).astype(float)
-        p[:, axis] += 0.5 * h
-        xyz_all[idx] = p
+    nodes = np.empty((n_total, 4))
+    nodes[:, 0] = np.arange(1, n_total + 1)
+    nodes[:n_corner, 1:] = lattice(NZ, NY, NX)
+    nodes[base[0]:base[1], 1:] = lattice(NZ, NY, nx, (0.5, 0.0, 0.0))
+    nodes[base[1]:base[2], 1:] = lattice(NZ, ny, NX, (0.0, 0.5, 0.0))
+    nodes[base[2]:, 1:] = lattice(nzl, NY, NX, (0.0, 0.0, 0.5))
     elem = np.empty((ne, 20), dtype=np.int64)
     elem[:, :8] = corner
     for m, (ca, cb) in enumerate(_HEX20_EDGES):
         oa, ob = _CORNER_OFF[ca], _CORNER_OFF[cb]
         axis = int(np.nonzero(ob - oa)[0][0])
         lo = np.minimum(oa, ob)
-        elem[eorder, 8 + m] = edge_id(axis, ei + lo[0], ej + lo[1], ek + lo[2]).ravel()
-    ids = np.arange(1, n_total + 1, dtype=float)
-    return np.column_stack([ids, xyz_all]), elem + 1
+        elem[:, 8 + m] = edge_id(axis, ei + lo[0], ej + lo[1], ek + lo[2])
+    return nodes, elem + 1
 
 
 def box_boundaries(nx: int, ny: int, nz: int, h: float = 0.5, bottom: str = "111") -> dict:

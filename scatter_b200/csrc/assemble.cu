@@ -885,9 +885,8 @@ int sc_assemble_run(sc_ctx* ctx, int order, int flags, double* seconds) {
     p.pair_pos = ctx->d_pair_pos; p.pair_al = ctx->d_pair_al;
     p.n_nodes = ctx->n_nodes; p.max_rl = ctx->max_rl; p.max_nbr = ctx->max_nbr;
 
-    cudaEvent_t e0, e1;
-    cudaEventCreate(&e0); cudaEventCreate(&e1);
-    cudaEventRecord(e0, ctx->stream);
+    sc_gpu_timer timer(ctx->stream);
+    timer.start();
     int rc = SC_ERR_UNSUPPORTED;
     const int key = t.nne * 10000 + t.dim * 1000 + t.ngp;
     switch (key) {
@@ -914,11 +913,9 @@ int sc_assemble_run(sc_ctx* ctx, int order, int flags, double* seconds) {
 #undef SC_CASE
         default: rc = sc_fail(ctx, SC_ERR_UNSUPPORTED, "no assembly kernel for nne=%d dim=%d ngp=%d", t.nne, t.dim, t.ngp);
     }
-    cudaEventRecord(e1, ctx->stream);
+    timer.stop();
     cudaError_t se = cudaStreamSynchronize(ctx->stream);
-    float ms = 0.f;
-    cudaEventElapsedTime(&ms, e0, e1);
-    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    const float ms = timer.ms();
     sc_free(&dN); sc_free(&ddN); sc_free(&dw);
     if (rc != SC_OK) return rc;
     if (se != cudaSuccess) return sc_fail(ctx, SC_ERR_CUDA, "assembly kernel failed: %s", cudaGetErrorString(se));

@@ -159,6 +159,19 @@ void sc_set_global_error(const char* msg);
         SC_CUDA((ctx), cudaGetLastError());                    \
     } while (0)
 
+// Pair of timing events on one stream; destroyed on every exit path of the caller (the SC_TRY / SC_CUDA macros return early).
+struct sc_gpu_timer {
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    cudaStream_t st;
+    explicit sc_gpu_timer(cudaStream_t s) : st(s) { cudaEventCreate(&e0); cudaEventCreate(&e1); }
+    ~sc_gpu_timer() { if (e0) cudaEventDestroy(e0); if (e1) cudaEventDestroy(e1); }
+    sc_gpu_timer(const sc_gpu_timer&) = delete;
+    sc_gpu_timer& operator=(const sc_gpu_timer&) = delete;
+    void start() { cudaEventRecord(e0, st); }
+    void stop() { cudaEventRecord(e1, st); }
+    float ms() const { float v = 0.f; cudaEventElapsedTime(&v, e0, e1); return v; }   // after the stream was synchronised
+};
+
 template <typename T>
 int sc_alloc(sc_ctx* ctx, T** p, size_t n) {
     if (*p) { cudaFree(*p); *p = nullptr; }

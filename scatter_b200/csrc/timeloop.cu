@@ -402,9 +402,8 @@ int tl_newmark(sc_ctx* ctx, double dt, int64_t t0, int64_t n_steps, int64_t oi, 
         SC_TRY(store_rows_async(ctx, u_out, v_out, a_out, row, ctx->d_u, ctx->d_v, ctx->d_a, true, true, true));
         ++row;
     }
-    cudaEvent_t e0, e1;
-    cudaEventCreate(&e0); cudaEventCreate(&e1);
-    cudaEventRecord(e0, st);
+    sc_gpu_timer timer(st);
+    timer.start();
     const double pv = 1.0 / (beta * dt), pa = 1.0 / (2.0 * beta);
     const double qvv = gamma / beta, qa = dt * (gamma / (2.0 * beta) - 1.0);
     for (int64_t t = t0 + 1; t <= t0 + n_steps; ++t) {
@@ -425,12 +424,10 @@ int tl_newmark(sc_ctx* ctx, double dt, int64_t t0, int64_t n_steps, int64_t oi, 
             ++row;
         }
     }
-    cudaEventRecord(e1, st);
+    timer.stop();
     SC_CUDA(ctx, cudaStreamSynchronize(st));
     SC_TRY(finish_rows(ctx));
-    float ms = 0.f;
-    cudaEventElapsedTime(&ms, e0, e1);
-    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    const float ms = timer.ms();
     if (stats) {
         stats->seconds_device = ms * 1e-3;
         stats->seconds_total = std::chrono::duration<double>(std::chrono::steady_clock::now() - wall0).count();
@@ -488,9 +485,8 @@ int tl_central_difference(sc_ctx* ctx, double dt, int64_t t0, int64_t n_steps, i
     const bool want_out = (u_out || v_out || a_out) && n_out > 0;
     if (want_out) { SC_TRY(sc_work(ctx, 6, &vv)); SC_TRY(sc_work(ctx, 7, &aa)); }
     int64_t row = 0;
-    cudaEvent_t e0, e1;
-    cudaEventCreate(&e0); cudaEventCreate(&e1);
-    cudaEventRecord(e0, st);
+    sc_gpu_timer timer(st);
+    timer.start();
     int64_t steps_done = 0;
     const int64_t t_end = t0 + n_steps;
     for (int64_t t = t0; t <= t_end; ++t) {
@@ -521,7 +517,7 @@ int tl_central_difference(sc_ctx* ctx, double dt, int64_t t0, int64_t n_steps, i
         double* t_ = cur; cur = prev; prev = t_;
         ++steps_done;
     }
-    cudaEventRecord(e1, st);
+    timer.stop();
     // normalise the buffers: d_u = u(t_end), work[0] = u(t_end - dt)
     if (cur != ctx->d_u) {
         SC_CUDA(ctx, cudaMemcpyAsync(uc, prev, sizeof(double) * n, cudaMemcpyDeviceToDevice, st));     // prev lives in d_u
@@ -538,9 +534,7 @@ int tl_central_difference(sc_ctx* ctx, double dt, int64_t t0, int64_t n_steps, i
     SC_CUDA(ctx, cudaMemcpyAsync(ctx->h_pinned + 9, ctx->d_scal + 9, sizeof(double), cudaMemcpyDeviceToHost, st));
     SC_TRY(finish_rows(ctx));
     SC_CUDA(ctx, cudaStreamSynchronize(st));
-    float ms = 0.f;
-    cudaEventElapsedTime(&ms, e0, e1);
-    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    const float ms = timer.ms();
     double diverged = ctx->h_pinned[9];
     if (ctx->world > 1) {                                // every rank must take the same exit
         SC_TRY(dist_allreduce_sum(ctx, ctx->d_scal + 9, 1, st));
@@ -613,9 +607,8 @@ int tl_bathe(sc_ctx* ctx, double dt, int64_t t0, int64_t n_steps, int64_t oi, do
         SC_TRY(store_row(ctx, u_out, row, ctx->d_u)); SC_TRY(store_row(ctx, v_out, row, ctx->d_v)); SC_TRY(store_row(ctx, a_out, row, ctx->d_a));
         ++row;
     }
-    cudaEvent_t e0, e1;
-    cudaEventCreate(&e0); cudaEventCreate(&e1);
-    cudaEventRecord(e0, st);
+    sc_gpu_timer timer(st);
+    timer.start();
     double *u = ctx->d_u, *v = ctx->d_v, *a = ctx->d_a;
     for (int64_t t = t0 + 1; t <= t0 + n_steps; ++t) {
         // ---- sub-step 1
@@ -646,11 +639,9 @@ int tl_bathe(sc_ctx* ctx, double dt, int64_t t0, int64_t n_steps, int64_t oi, do
             ++row;
         }
     }
-    cudaEventRecord(e1, st);
+    timer.stop();
     SC_CUDA(ctx, cudaStreamSynchronize(st));
-    float ms = 0.f;
-    cudaEventElapsedTime(&ms, e0, e1);
-    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    const float ms = timer.ms();
     if (stats) {
         stats->seconds_device = ms * 1e-3;
         stats->seconds_total = std::chrono::duration<double>(std::chrono::steady_clock::now() - wall0).count();
@@ -679,9 +670,8 @@ int tl_static(sc_ctx* ctx, int64_t t0, int64_t n_steps, int64_t oi, double rtol,
     int64_t pcg_total = 0, row = 0;
     int iters = 0;
     double relres = 0.0;
-    cudaEvent_t e0, e1;
-    cudaEventCreate(&e0); cudaEventCreate(&e1);
-    cudaEventRecord(e0, st);
+    sc_gpu_timer timer(st);
+    timer.start();
     for (int64_t t = t0; t <= t0 + n_steps; ++t) {
         if (ctx->world > 1) SC_TRY(dist_halo(ctx, ctx->d_u, st));
         SC_TRY(la_spmv(ctx, ctx->d_K, ctx->d_u, rhs));
@@ -697,11 +687,9 @@ int tl_static(sc_ctx* ctx, int64_t t0, int64_t n_steps, int64_t oi, double rtol,
         SC_TRY(lincomb(ctx, ctx->d_u, 1.0, ctx->d_u, 1.0, du));
         if (t % oi == 0 && row < n_out) { SC_TRY(store_row(ctx, u_out, row, ctx->d_u)); ++row; }
     }
-    cudaEventRecord(e1, st);
+    timer.stop();
     SC_CUDA(ctx, cudaStreamSynchronize(st));
-    float ms = 0.f;
-    cudaEventElapsedTime(&ms, e0, e1);
-    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    const float ms = timer.ms();
     if (stats) {
         stats->seconds_device = ms * 1e-3;
         stats->seconds_total = std::chrono::duration<double>(std::chrono::steady_clock::now() - wall0).count();
