@@ -146,6 +146,105 @@ def test_quad8_elements(oracle, tmp_path):
         ctx.close()
 
 
+def _dense_from_elements(oracle, etype, order, xyz, conn, eq, n_eq, E, nu, rho):
+    Ke, Me = oracle.element_matrices(etype, order, xyz[conn], E, nu, rho)
+    Kd = np.zeros((n_eq, n_eq)); Md = np.zeros((n_eq, n_eq))
+    for e in range(len(conn)):
+        g = eq[conn[e]].ravel()
+        ok = g >= 0
+        Kd[np.ix_(g[ok], g[ok])] += Ke[e][np.ix_(ok, ok)]
+        Md[np.ix_(g[ok], g[ok])] += Me[e][np.ix_(ok, ok)]
+    return Kd, Md
+
+
+def _gpu_dense(etype, order, xyz, conn, eq, n_eq, E, nu, rho):
+    from scatter_b200 import _lib
+    ctx = _lib.Context(0)
+    ctx.set_mesh(etype, xyz, conn, eq, n_eq)
+    ctx.set_materials(E, nu, rho)
+    ctx.build_pattern()
+    ctx.assemble(order, _lib.ASM_K | _lib.ASM_M_FULL | _lib.ASM_M_LUMPED)
+    rowptr, col = ctx.get_pattern()
+    K = sp.csr_matrix((ctx.get_values(0), col, rowptr), shape=(n_eq, n_eq)).toarray()
+    M = sp.csr_matrix((ctx.get_values(1), col, rowptr), shape=(n_eq, n_eq)).toarray()
+    Ml = ctx.get_lumped_mass()
+    ctx.close()
+    return K, M, Ml
+
+
+@pytest.mark.parametrize("etype,mesh,orders", [("tri3", "column_2D_tri3.msh", (1, 2)), ("tri6", "column_2D_tri6.msh", (2, 3)),
+                                               ("quad4", "column_2D.msh", (1, 2, 3)), ("tetra4", "column_3D_tetra4.msh", (1, 2)),
+                                               ("tetra10", "column_3D_tetra10.msh", (1, 2)), ("hexa8", "cube.msh", (1, 2, 3)),
+                                               ("hexa20", "column_high_order.msh", (1, 2, 3))])
+def test_single_distorted_element(etype, mesh, orders, golden_meshes, oracle):
+    """Smallest possible mesh (one element, every dof free) with perturbed nodes: the Jacobian differs at every Gauss point
+    and the assembled matrices are Ke / Me themselves."""
+    from scatter_b200 import mesher
+    m = mesher.ReadMesh(golden_meshes[mesh]); m.read_gmsh()
+    rng = np.random.default_rng(11)
+    rows = m.node_rows()[0]
+    xyz = m.nodes[rows, 1:].copy()
+    dim = m.dimension
+    size = np.ptp(xyz[:, :dim], axis=0).max()
+    xyz[:, :dim] += 0.06 * size * rng.uniform(-1, 1, (len(rows), dim))
+    nne = len(rows)
+    conn = np.arange(nne, dtype=np.int32)[None, :]
+    eq = np.arange(nne * dim).reshape(nne, dim)
+    n_eq = nne * dim
+    E, nu, rho = np.array([12.5e6]), np.array([0.31]), np.array([1830.0])
+    for order in orders:
+        K, M, Ml = _gpu_dense(etype, order, xyz, conn, eq, n_eq, E, nu, rho)
+        Kd, Md = _dense_from_elements(oracle, etype, order, xyz, conn, eq, n_eq, E, nu, rho)
+        assert np.abs(K - Kd).max() <= TOL_MAT * np.abs(Kd).max(), (etype, order)
+        assert np.abs(M - Md).max() <= TOL_MAT * np.abs(Md).max(), (etype, order)
+        assert np.abs(Ml - Md.sum(axis=1)).max() <= TOL_MAT * np.abs(Md).max(), (etype, order)
+        assert np.abs(K - K.T).max() <= 1e-13 * np.abs(K).max()
+
+
+@pytest.mark.parametrize("nt", [150, 300])
+def test_high_valence_node_uses_the_warp_per_node_kernel(nt, oracle):
+    """A fan of 150 / 300 triangles around one node: more (node, element) pairs than a block of the pair kernels holds, so the
+    assembly falls back to the warp-per-node kernel; neighbour lists of 151 nodes exercise the long-list paths of the
+    pattern builder as well."""
+    rng = np.random.default_rng(5)
+    ang = np.linspace(0, 2 * np.pi, nt, endpoint=False)
+    r = 1.0 + 0.2 * rng.uniform(-1, 1, nt)
+    xyz = np.zeros((nt + 1, 3))
+    xyz[1:, 0] = r * np.cos(ang); xyz[1:, 1] = r * np.sin(ang)
+    conn = np.array([[0, 1 + i, 1 + (i + 1) % nt] for i in range(nt)], dtype=np.int32)
+    free = np.ones((nt + 1, 2), dtype=bool)
+    free[1, :] = False; free[40, 1] = False
+    eq = np.where(free.ravel(), np.cumsum(free.ravel()) - 1, -1).reshape(nt + 1, 2)
+    n_eq = int(free.sum())
+    E = 30e6 * rng.uniform(0.5, 2, nt); nu = rng.uniform(0.1, 0.35, nt); rho = 1500 * rng.uniform(0.8, 1.2, nt)
+    K, M, Ml = _gpu_dense("tri3", 2, xyz, conn, eq, n_eq, E, nu, rho)
+    Kd, Md = _dense_from_elements(oracle, "tri3", 2, xyz, conn, eq, n_eq, E, nu, rho)
+    assert np.abs(K - Kd).max() <= TOL_MAT * np.abs(Kd).max()
+    assert np.abs(M - Md).max() <= TOL_MAT * np.abs(Md).max()
+    assert np.abs(Ml - Md.sum(axis=1)).max() <= TOL_MAT * np.abs(Md).max()
+
+
+def test_zero_load_and_zero_steps(golden_meshes):
+    """Degenerate runs: no load at all (PCG sees a zero right-hand side), zero time steps, free vibration from an initial
+    velocity only."""
+    m, mx = build(golden_meshes["cube.msh"], cases.BC_CUBE, cases.materials(), cases.settings(damping=[1, 0.01, 30, 0.01]))
+    ctx = mx.ctx
+    n = m.number_eq
+    ctx.set_load_schedule(np.zeros(12, dtype=np.int64), np.zeros(0, dtype=np.int64), np.zeros(0))
+    ctx.set_state(None, None)
+    u, v, a, st = ctx.run_newmark(1e-3, 0, 10, 5)
+    assert u.shape == (3, n) and not u.any() and not v.any() and not a.any()
+    u, v, a, st = ctx.run_central_difference(2e-4, 0, 10, 5)
+    assert u.shape == (3, n) and not u.any() and not v.any()
+    u, v, a, st = ctx.run_newmark(1e-3, 0, 0, 1)
+    assert u.shape == (1, n) and not u.any()
+    v0 = np.zeros(n); v0[n // 2] = 1e-3
+    ctx.set_state(None, v0)
+    u, v, a, st = ctx.run_newmark(1e-3, 0, 10, 5)
+    assert np.isfinite(u).all() and np.abs(u[-1]).max() > 0 and np.array_equal(v[0], v0)
+    ctx.close()
+
+
 def test_assembly_is_bit_reproducible(golden_meshes):
     fn, bc = cases.MATRIX_CASES["cube"]
     _, a = build(golden_meshes[fn], bc, cases.materials(), cases.settings())
