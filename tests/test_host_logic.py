@@ -230,3 +230,20 @@ def test_box_generator_matches_file_reader(tmp_path, oracle):
     n1, e1 = boxmesh.box_arrays(3, 4, 6, 0.5, "hexa8", z_range=(2, 5))
     n2, e2 = boxmesh.box_arrays(3, 4, 3, 0.5, "hexa8")
     assert np.array_equal(e1, e2) and np.allclose(n1[:, 3], n2[:, 3] + 1.0) and np.array_equal(n1[:, 1:3], n2[:, 1:3])
+
+
+def test_bench_reference_arm_runs_without_gpu():
+    """`bench.py --impl reference` (the CPU path on the host cores) needs no GPU and prints the contract's JSON line."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                          "--cpu-size", "6", "--cpu-steps", "3"], capture_output=True, text=True, timeout=600, cwd=root)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["metric"] == "dof_timesteps_per_s" and line["unit"] == "DOF*steps/s"
+    assert line["value"] > 0 and line["higher_is_better"] is True and line["dtype"] == "f64"
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1 and "sample" in line["cpu_baseline"]
+    assert line["e2e"] == {"value": line["value"], "unit": "DOF*steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert "workload" in line["config"]
