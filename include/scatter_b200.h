@@ -29,7 +29,7 @@ enum sc_status {
     SC_ERR_ARG = -2,       /* invalid argument / call order */
     SC_ERR_STATE = -3,     /* required earlier step missing (mesh, pattern, assembly ...) */
     SC_ERR_UNSUPPORTED = -4,
-    SC_ERR_NOCONV = -5,    /* PCG did not reach the requested tolerance */
+    SC_ERR_NOCONV = -5,    /* PCG did not reach the requested tolerance, or an explicit run diverged (non-finite state) */
     SC_ERR_NCCL = -6
 };
 
