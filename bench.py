@@ -307,7 +307,7 @@ def run_ours(args):
     n_out = len(num.output_time)
     num.u = _lib.pinned_zeros((n_out, model.number_eq)); num.v = _lib.pinned_zeros((n_out, model.number_eq))
     num.a = _lib.pinned_zeros((n_out, model.number_eq))
-    num.u0 = _lib.pinned_zeros(model.number_eq); num.v0 = _lib.pinned_zeros(model.number_eq)
+    num.u0 = num.u[0]; num.v0 = num.v[0]
     num.bind(mx)
     num.load_schedule = (ptr, dofs, vals)
     h2d = 2 * 8 * model.number_eq + int(ptr.nbytes + dofs.nbytes + vals.nbytes)

@@ -43,8 +43,16 @@ def probe_vector(n):
 
 # ---- meshes ---------------------------------------------------------------------------------------------------
 mesh_out = {}
-for fn in sorted(os.listdir(os.path.join(IT, "mesh"))):
-    m = ref.mesher.ReadMesh(os.path.join(IT, "mesh", fn))
+RUN_MESH = "/root/reference/mesh"                 # meshes of the reference's run scripts
+EXTRA = ["rose_2D_side.msh", "embankment_rose2D.msh", "box2d.msh"]
+
+
+def mesh_path(fn):
+    return os.path.join(RUN_MESH if fn in EXTRA else os.path.join(IT, "mesh"), fn)
+
+
+for fn in sorted(os.listdir(os.path.join(IT, "mesh"))) + EXTRA:
+    m = ref.mesher.ReadMesh(mesh_path(fn))
     m.read_gmsh()
     key = fn[:-4]
     gm = {"tri3": 2, "tri6": 9, "quad4": 3, "hexa8": 5, "hexa20": 17, "tetra4": 4, "tetra10": 11}[m.element_type]
@@ -60,8 +68,9 @@ mat_out = {}
 MAT = cases.materials()
 SETT = cases.settings()
 for key, (fn, bc) in cases.MATRIX_CASES.items():
-    m = ref.mesher.ReadMesh(os.path.join(IT, "mesh", fn))
+    m = ref.mesher.ReadMesh(mesh_path(fn))
     m.read_gmsh(); m.read_bc(bc); m.mapping(); m.connectivities()
+    MAT = cases.case_materials(key)
     mx = ref.system_matrix.GenerateMatrix(m.number_eq, 2)
     mx.generate_stiffness_and_mass(m, MAT)
     Ks = sp.csr_matrix(mx.K); Ms = sp.csr_matrix(mx.M)

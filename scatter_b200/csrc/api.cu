@@ -45,7 +45,7 @@ void free_pattern(sc_ctx* c) {
     sc_free(&c->d_cabs_rowid); sc_free(&c->d_cabs_rptr); sc_free(&c->d_cabs_col); sc_free(&c->d_cabs_slot); sc_free(&c->d_cabs_val);
     c->cabs_n = c->cabs_rows = 0;
     c->have_pattern = c->have_K = c->have_M = c->have_Ml = false;
-    c->khat_a1 = c->khat_a4 = -1.0;
+    c->khat_a1 = c->khat_a4 = -1.0; c->cd_coef_dt = -1.0;
     c->nnz = 0;
 }
 void free_vectors(sc_ctx* c) {
@@ -56,7 +56,7 @@ void free_vectors(sc_ctx* c) {
     sc_free(&c->d_partial);
     for (int k = 0; k < 3; ++k) sc_free(&c->d_snap[k]);
     c->rows_pending = false;
-    c->cd_resume_valid = false; c->nm_resume_valid = false;
+    c->cd_resume_valid = false; c->nm_resume_valid = false; c->cd_coef_dt = -1.0;
 }
 
 // values of C = C_abs + c0 M + c1 K into a fresh device buffer
@@ -264,7 +264,7 @@ int sc_assemble(sc_ctx* ctx, int gauss_order, int flags, double* seconds_device)
     if (!ctx->have_mat) return sc_fail(ctx, SC_ERR_STATE, "sc_set_materials must be called first");
     if (!(flags & (SC_ASM_K | SC_ASM_M_FULL | SC_ASM_M_LUMPED))) return sc_fail(ctx, SC_ERR_ARG, "nothing to assemble");
     SC_CUDA(ctx, cudaSetDevice(ctx->device));
-    ctx->cd_resume_valid = false; ctx->nm_resume_valid = false; ctx->khat_a1 = ctx->khat_a4 = -1.0;
+    ctx->cd_resume_valid = false; ctx->nm_resume_valid = false; ctx->khat_a1 = ctx->khat_a4 = -1.0; ctx->cd_coef_dt = -1.0;
     return sc_assemble_run(ctx, gauss_order, flags, seconds_device);
 }
 
@@ -329,14 +329,14 @@ int sc_add_entries(sc_ctx* ctx, int which, int64_t n, const int64_t* rows, const
         }
     }
     sc_free(&d_r); sc_free(&d_c); sc_free(&d_v); sc_free(&d_slot); sc_free(&d_flag);
-    ctx->cd_resume_valid = false; ctx->nm_resume_valid = false; ctx->khat_a1 = ctx->khat_a4 = -1.0;
+    ctx->cd_resume_valid = false; ctx->nm_resume_valid = false; ctx->khat_a1 = ctx->khat_a4 = -1.0; ctx->cd_coef_dt = -1.0;
     return rc;
 }
 
 int sc_set_rayleigh(sc_ctx* ctx, double c0, double c1) {
     if (!ctx) return SC_ERR_ARG;
     ctx->c0 = c0; ctx->c1 = c1;
-    ctx->cd_resume_valid = false; ctx->nm_resume_valid = false; ctx->khat_a1 = ctx->khat_a4 = -1.0;
+    ctx->cd_resume_valid = false; ctx->nm_resume_valid = false; ctx->khat_a1 = ctx->khat_a4 = -1.0; ctx->cd_coef_dt = -1.0;
     return SC_OK;
 }
 
@@ -437,7 +437,7 @@ int sc_run_newmark(sc_ctx* ctx, double dt, int64_t t_start, int64_t n_steps, int
     if (dt <= 0 || n_steps < 0 || out_interval < 1 || beta <= 0) return sc_fail(ctx, SC_ERR_ARG, "bad time-integration arguments");
     SC_CUDA(ctx, cudaSetDevice(ctx->device));
     if (stats) std::memset(stats, 0, sizeof(*stats));
-    ctx->cd_resume_valid = false;
+    ctx->cd_resume_valid = false; ctx->cd_coef_dt = -1.0;   // Newmark reuses the work vectors of the cached coefficients
     if (beta != 0.25 || gamma != 0.5) ctx->khat_a1 = -1.0;   // (a1, a4) identify the matrix only together with beta, gamma
     return tl_newmark(ctx, dt, t_start, n_steps, out_interval, beta, gamma, pcg_rtol, pcg_maxit, n_out, u_out, v_out, a_out, stats);
 }
@@ -458,7 +458,7 @@ int sc_run_bathe(sc_ctx* ctx, double dt, int64_t t_start, int64_t n_steps, int64
     if (dt <= 0 || n_steps < 0 || out_interval < 1) return sc_fail(ctx, SC_ERR_ARG, "bad time-integration arguments");
     SC_CUDA(ctx, cudaSetDevice(ctx->device));
     if (stats) std::memset(stats, 0, sizeof(*stats));
-    ctx->cd_resume_valid = false; ctx->nm_resume_valid = false; ctx->khat_a1 = ctx->khat_a4 = -1.0;
+    ctx->cd_resume_valid = false; ctx->nm_resume_valid = false; ctx->khat_a1 = ctx->khat_a4 = -1.0; ctx->cd_coef_dt = -1.0;
     return tl_bathe(ctx, dt, t_start, n_steps, out_interval, pcg_rtol, pcg_maxit, n_out, u_out, v_out, a_out, stats);
 }
 
@@ -468,7 +468,7 @@ int sc_run_static(sc_ctx* ctx, int64_t t_start, int64_t n_steps, int64_t out_int
     if (n_steps < 0 || out_interval < 1) return sc_fail(ctx, SC_ERR_ARG, "bad arguments");
     SC_CUDA(ctx, cudaSetDevice(ctx->device));
     if (stats) std::memset(stats, 0, sizeof(*stats));
-    ctx->cd_resume_valid = false; ctx->nm_resume_valid = false;
+    ctx->cd_resume_valid = false; ctx->nm_resume_valid = false; ctx->cd_coef_dt = -1.0;
     return tl_static(ctx, t_start, n_steps, out_interval, pcg_rtol, pcg_maxit, n_out, u_out, stats);
 }
 

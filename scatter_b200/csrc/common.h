@@ -119,6 +119,7 @@ struct sc_ctx {
     bool nm_resume_valid = false;   // d_a holds the Newmark acceleration of step nm_resume_t (stage continuation)
     int64_t nm_resume_t = 0;
     double khat_a1 = -1.0, khat_a4 = -1.0;   // parameters d_Khat was built with (-1: invalid)
+    double cd_coef_dt = -1.0;       // work[2..4] hold inv_d, alpha, lumped c of the central difference for this dt (-1: invalid)
     bool cd_resume_valid = false;   // work[0] holds u(t - dt) of the central-difference state at step cd_resume_t
     int64_t cd_resume_t = 0;
     double cd_resume_dt = 0.0;

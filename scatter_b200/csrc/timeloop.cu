@@ -457,13 +457,18 @@ int tl_central_difference(sc_ctx* ctx, double dt, int64_t t0, int64_t n_steps, i
 
     // lumped damping: c = c0 m + c1 rowsum(K) + rowsum(C_abs)
     // (work[0] may hold u(t - dt) of a resumable state: use work[1] as the vector of ones)
-    SC_TRY(la_fill(ctx, uc, 1.0, n));
-    SC_TRY(la_spmv(ctx, ctx->d_K, uc, tmp));
-    k_cd_lumped_c<<<nblk(n, 256), 256, 0, st>>>(ctx->d_Ml, tmp, ctx->c0, ctx->c1, cl, n);
-    SC_CHECK_LAUNCH(ctx);
-    SC_TRY(la_cabs_spmv_add(ctx, uc, cl, 1.0));
-    k_cd_coeffs<<<nblk(n, 256), 256, 0, st>>>(ctx->d_Ml, cl, a0, a1, inv_d, alpha, n);
-    SC_CHECK_LAUNCH(ctx);
+    // The three vectors only depend on (K, m, C_abs, c0, c1, dt): a stage that follows another one with the same dt reuses
+    // them (`cd_coef_dt` is reset by every call that changes a matrix or borrows work[2..4]).
+    if (ctx->cd_coef_dt != dt) {
+        SC_TRY(la_fill(ctx, uc, 1.0, n));
+        SC_TRY(la_spmv(ctx, ctx->d_K, uc, tmp));
+        k_cd_lumped_c<<<nblk(n, 256), 256, 0, st>>>(ctx->d_Ml, tmp, ctx->c0, ctx->c1, cl, n);
+        SC_CHECK_LAUNCH(ctx);
+        SC_TRY(la_cabs_spmv_add(ctx, uc, cl, 1.0));
+        k_cd_coeffs<<<nblk(n, 256), 256, 0, st>>>(ctx->d_Ml, cl, a0, a1, inv_d, alpha, n);
+        SC_CHECK_LAUNCH(ctx);
+        ctx->cd_coef_dt = dt;
+    }
 
     // rotating buffers: cur = u(t), prev = u(t-dt) (overwritten by u(t+dt) each step)
     double* cur = ctx->d_u;

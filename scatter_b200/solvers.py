@@ -44,13 +44,11 @@ class _DeviceSolver:
         self.v0 = np.zeros(self.number_equations)
 
     def update(self, t_start_idx):
+        """Restart hook (`scatter.py:158`): u0, v0 <- stored row.  The rows are taken as views, so the next `calculate`
+        uploads them straight from the (possibly page-locked) history arrays without an extra host copy."""
         row = int(t_start_idx) // self.output_interval
-        if self.u0 is not None and self.u0.shape == self.u[row].shape:
-            self.u0[...] = self.u[row]          # keeps (possibly page-locked) staging buffers
-            self.v0[...] = self.v[row]
-        else:
-            self.u0 = np.array(self.u[row])
-            self.v0 = np.array(self.v[row])
+        self.u0 = self.u[row]
+        self.v0 = self.v[row]
         self._state_dirty = True
 
     def bind(self, matrix):

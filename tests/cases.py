@@ -56,6 +56,31 @@ MATRIX_CASES = {
     "column_3D_tetra10": ("column_3D_tetra10.msh", BC_B2_3D),
 }
 
+# meshes of the reference's run scripts (mesh/*.msh; settings from run_scatter_rose_2D.py:22-41): unstructured,
+# multi-material plane-strain triangle / quad meshes that also carry 1-D "rose" line elements the reader must skip
+def _bc_2d(x, y0, y1):
+    return {"bottom": ["11", [[0, y0, 0], [x, y0, 0]]], "left": ["10", [[0, y0, 0], [0, y1, 0]]],
+            "right": ["10", [[x, y0, 0], [x, y1, 0]]]}
+
+
+MATRIX_CASES.update({
+    "rose_2D_side": ("rose_2D_side.msh", _bc_2d(90, -3, 0.5)),
+    "embankment_rose2D": ("embankment_rose2D.msh", _bc_2d(10, -5, 0.5)),
+    "box2d": ("box2d.msh", _bc_2d(120, 0, 1.8)),
+})
+
+
+def materials_embankment():
+    return {"embankment": {"density": 2000, "Young": 100e6, "poisson": 0.2},
+            "soil1": {"density": 1700, "Young": 500e5, "poisson": 0.2},
+            "soil2": {"density": 2000, "Young": 200e5, "poisson": 0.2}}
+
+
+def case_materials(case):
+    """Material dictionary of a MATRIX_CASE."""
+    return materials_embankment() if case in ("rose_2D_side", "embankment_rose2D") else materials()
+
+
 B2_NODES = {
     "tri3": ([3, 4, 25], 2),
     "tri6": ([3, 4, 47, 48, 49], 2),

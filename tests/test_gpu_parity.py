@@ -40,7 +40,7 @@ def build(path, bc, materials, settings, explicit=False, elem_props=None):
 def test_assembly_matches_oracle_and_reference(case, golden_meshes, golden_matrices, oracle):
     fn, bc = cases.MATRIX_CASES[case]
     G = golden_matrices
-    mat, sett = cases.materials(), cases.settings()
+    mat, sett = cases.case_materials(case), cases.settings()
     m, mx = build(golden_meshes[fn], bc, mat, sett)
     # numbering (bit-exact with the reference)
     assert m.number_eq == int(G[case + "__n_eq"])
@@ -256,7 +256,8 @@ def test_assembly_is_bit_reproducible(golden_meshes):
     assert sha(k1) != "" and np.array_equal(k1, a.ctx.get_values(0))
 
 
-@pytest.mark.parametrize("case", ["cube", "column_3D_tetra4", "column_2D", "column_2D_tri6", "column_high_order", "column_3D_tetra10"])
+@pytest.mark.parametrize("case", ["cube", "column_3D_tetra4", "column_2D", "column_2D_tri6", "column_high_order", "column_3D_tetra10",
+                                  "rose_2D_side"])
 def test_assembly_kernel_generations_agree(case, golden_meshes, monkeypatch):
     """k_assemble_blk (default), k_assemble_pairs and the warp-per-node k_assemble sum the same contributions in the same
     order; they differ only in how a single element contribution is rounded (material law per Gauss point vs once)."""
@@ -267,7 +268,7 @@ def test_assembly_kernel_generations_agree(case, golden_meshes, monkeypatch):
     for name, env in (("blk", None), ("pairs", "SCATTER_B200_PAIR_ASSEMBLY"), ("generic", "SCATTER_B200_GENERIC_ASSEMBLY")):
         if env:
             monkeypatch.setenv(env, "1")
-        _, mx = build(golden_meshes[fn], bc, cases.materials(), cases.settings())
+        _, mx = build(golden_meshes[fn], bc, cases.case_materials(case), cases.settings())
         vals[name] = (mx.ctx.get_values(0), mx.ctx.get_values(1), mx.ctx.get_lumped_mass())
         mx.ctx.close()
         if env:

@@ -63,6 +63,27 @@ def test_mesher_numbering_is_bit_exact(case, golden_meshes, golden_matrices, ora
     assert m.lower_element_type == om.lower_element_type and m.nb_nodes_lower_elem == om.nb_nodes_lower_elem
 
 
+def test_reader_skips_lower_dimensional_elements(golden_meshes, tmp_path):
+    """The run-script meshes (mesh/rose_2D_side.msh, box2d.msh) list 1-D "rose" line elements before the domain elements;
+    the reader keeps the elements of the highest dimension only (mesher.py:150-228)."""
+    from scatter_b200 import mesher
+    src = open(golden_meshes["box2d.msh"]).read().splitlines()
+    i0 = src.index("$Elements")
+    ne = int(src[i0 + 1])
+    lines = [f"{k + 1} 1 2 2 7 {k + 1} {k + 2}" for k in range(5)]                 # 5 two-node lines, physical group 2 ("rose")
+    body = []
+    for k, l in enumerate(src[i0 + 2:i0 + 2 + ne]):
+        t = l.split()
+        body.append(" ".join([str(k + 6)] + t[1:]))
+    out = src[:i0 + 1] + [str(ne + 5)] + lines + body + src[i0 + 2 + ne:]
+    p = os.path.join(tmp_path, "mixed.msh")
+    open(p, "w").write("\n".join(out) + "\n")
+    a = mesher.ReadMesh(golden_meshes["box2d.msh"]); a.read_gmsh()
+    b = mesher.ReadMesh(p); b.read_gmsh()
+    assert b.element_type == "quad4" and np.array_equal(a.elem, b.elem) and np.array_equal(a.materials_index, b.materials_index)
+    assert np.array_equal(a.nodes, b.nodes)
+
+
 def test_mesher_errors(tmp_path):
     from scatter_b200 import mesher
     with pytest.raises(SystemExit, match="Mesh file does not exit"):
