@@ -85,6 +85,16 @@ int         sc_shape_table(int elem_type, int order, int* nne, int* dim, int* ng
 int sc_set_mesh(sc_ctx* ctx, int elem_type, int64_t n_nodes, const double* xyz, int64_t n_elem, const int32_t* conn,
                 const int64_t* eq, int64_t n_eq, const uint8_t* active);
 
+/* ---- random material field (random_fields.py:59-104: gstools SRF sampled at the element centroids; gstools==1.7.0 is
+ *      un-vendored, its RandMeth generator is restated here).  Randomisation method:
+ *        out[p] = mean + scale * sum_j ( z1[j] cos(k_j . x_p) + z2[j] sin(k_j . x_p) ),   scale = sqrt(var / n_modes)
+ *      and out = exp(out) when `lognormal` (random_fields.py:103-104).  The sum runs over j in order (reproducible).
+ *  pos [n_points*3] row-major point coordinates (already divided by the anisotropic length scales),
+ *  k [n_modes*3] wave vectors of the unit-length-scale covariance model, z1/z2 [n_modes] standard-normal amplitudes,
+ *  out [n_points] host buffer -> per-element values that go into sc_set_materials                                   */
+int sc_srf_sample(sc_ctx* ctx, int64_t n_points, const double* pos, int n_modes, const double* k, const double* z1,
+                  const double* z2, double scale, double mean, int lognormal, double* out, double* seconds_device /*may be NULL*/);
+
 /* per-element Young's modulus, Poisson ratio, density (system_matrix.py:64-71; random_fields.py:46-57) */
 int sc_set_materials(sc_ctx* ctx, const double* young, const double* poisson, const double* density);
 

@@ -847,3 +847,18 @@ class MovingAtPlaneLoad:
                 if not np.isnan(eq[a, d]):
                     f[int(eq[a, d])] = w[a] * load[d]
         return f
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Random field by the randomisation method (scatter/random_fields.py:59-104 calls gstools SRF; gstools==1.7.0 is an
+# un-vendored dependency -- **parity unpinned** against it.  Restated from its published algorithm (Hesse et al. 2014,
+# gstools.field.generator.RandMeth): field(x) = mean + sqrt(var/N) sum_j (z1_j cos(k_j.x) + z2_j sin(k_j.x)).
+def srf_field(pos: np.ndarray, k: np.ndarray, z1: np.ndarray, z2: np.ndarray, scale: float, mean: float, lognormal: bool) -> np.ndarray:
+    """Sequential sum over the modes (the order gstools' `summate` and the CUDA kernel use)."""
+    pos = np.asarray(pos, dtype=float)
+    acc = np.zeros(len(pos))
+    for j in range(len(z1)):
+        ph = (k[j, 0] * pos[:, 0] + k[j, 1] * pos[:, 1]) + k[j, 2] * pos[:, 2]
+        acc = acc + (z1[j] * np.cos(ph) + z2[j] * np.sin(ph))
+    f = mean + scale * acc
+    return np.exp(f) if lognormal else f

@@ -146,6 +146,84 @@ for et, unit in UNIT.items():
         el_out[p + "W"] = np.array(el.W)
 np.savez_compressed(os.path.join(OUT, "elements.npz"), **el_out)
 
+# ---- random-field bookkeeping (reference random_fields.RF, unmodified, with a stub in place of the gstools sampler) -----
+import types  # noqa: E402
+
+
+def stub_field(cen, mean, var):
+    """Deterministic stand-in for one SRF realisation at the cell centres (shared with tests/test_host_logic.py)."""
+    return mean + np.sqrt(var) * np.sin(cen @ np.array([1.3, 0.7, 0.4]) + 0.2)
+
+
+class _StubModel:
+    def __init__(self, dim, var, len_scale, angles):
+        self.args = dict(dim=dim, var=float(var), len_scale=np.asarray(len_scale, dtype=float), angles=float(angles))
+
+
+class _StubSRF:
+    last = None
+
+    def __init__(self, model, mean, seed):
+        self.model, self.mean, self.seed = model, float(mean), int(seed)
+        _StubSRF.last = self
+
+    def mesh(self, mesh, points, name, seed):
+        assert points == "centroids"
+        (ctype, cells), = mesh.cells.items()
+        cen = mesh.points[cells].mean(axis=1)
+        self.cell_type = ctype
+        mesh.cell_data = {name: [stub_field(cen, self.mean, self.model.args["var"])]}
+
+
+class _StubMesh:
+    def __init__(self, points, cells):
+        self.points, self.cells, self.cell_data = np.asarray(points), cells, {}
+
+
+gs = sys.modules["gstools"]
+gs.SRF = _StubSRF
+for _n in ("Exponential", "Gaussian", "Linear", "Matern"):
+    setattr(gs, _n, type(_n, (_StubModel,), {}))
+sys.modules["meshio"].Mesh = _StubMesh
+import importlib  # noqa: E402
+ref_rf = importlib.import_module("scatter.random_fields")
+rf_out = {}
+for key, model_name in (("rose_2D_side", "Gaussian"), ("cube", "Exponential")):
+    fn, bc = cases.MATRIX_CASES[key]
+    m = ref.mesher.ReadMesh(mesh_path(fn))
+    m.read_gmsh(); m.read_bc(bc); m.mapping(); m.connectivities()
+    mats = cases.case_materials(key)
+    props = cases.rf_properties(key, model_name)
+    out_dir = os.path.join("/tmp", "rf_" + key)
+    rf = ref_rf.RF(props, mats, out_dir, m.element_type)
+    idx = [mm[1] for mm in m.materials if mm[2] == props["material"]][0]
+    rf.generate_gstools_rf(m.nodes, m.elem[m.materials_index == idx], m.dimension, angles=0.0)
+    rf.dump()
+    rf.update_material_list(mats, m, idx)
+    mats.update(rf.new_material)
+    srf = _StubSRF.last
+    p = key + "__"
+    rf_out[p + "model_args"] = np.concatenate([[srf.model.args["dim"], srf.model.args["var"], srf.model.args["angles"], srf.mean, srf.seed],
+                                               srf.model.args["len_scale"]])
+    rf_out[p + "model_class"] = np.array(type(srf.model).__name__)
+    rf_out[p + "cell_type"] = np.array(srf.cell_type)
+    rf_out[p + "field"] = np.asarray(rf.fields[0])
+    rf_out[p + "materials_index"] = np.asarray(m.materials_index, dtype=np.int64)
+    rf_out[p + "model_materials"] = np.array([f"{mm[0]}|{mm[1]}|{mm[2]}" for mm in m.materials])
+    names = sorted(mats)
+    rf_out[p + "material_names"] = np.array(names)
+    rf_out[p + "material_values"] = np.array([[mats[n]["density"], mats[n]["Young"], mats[n]["poisson"]] for n in names], dtype=float)
+    rf_out[p + "dump"] = np.array(open(os.path.join(out_dir, "rf_props.txt")).read())
+    Er, nur, rhor = [], [], []
+    dm = dict(np.array(m.materials)[:, 1:])                      # system_matrix.py:52 look-up
+    for t in m.materials_index:
+        nm = dm[str(t)]
+        Er.append(mats[nm]["Young"]); nur.append(mats[nm]["poisson"]); rhor.append(mats[nm]["density"])
+    rf_out[p + "E_elem"] = np.array(Er, dtype=float)
+    rf_out[p + "rho_elem"] = np.array(rhor, dtype=float)
+    print("rf", key, model_name, len(rf.fields[0]), rf_out[p + "model_args"])
+np.savez_compressed(os.path.join(OUT, "random_field.npz"), **rf_out)
+
 # ---- histories ------------------------------------------------------------------------------------------------
 h = {}
 

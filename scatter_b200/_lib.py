@@ -27,7 +27,7 @@ SYMBOLS = [
     "sc_set_mesh", "sc_set_materials", "sc_build_pattern", "sc_get_pattern", "sc_pattern_stats", "sc_assemble", "sc_add_entries",
     "sc_set_rayleigh", "sc_get_values", "sc_get_lumped_mass", "sc_spmv", "sc_set_load_schedule", "sc_set_state",
     "sc_get_state", "sc_run_newmark", "sc_run_central_difference", "sc_run_bathe", "sc_run_static", "sc_nccl_unique_id", "sc_dist_init", "sc_set_halo",
-    "sc_halo_exchange",
+    "sc_halo_exchange", "sc_srf_sample",
 ]
 
 
@@ -97,6 +97,7 @@ def load_library():
     lib.sc_dist_init.argtypes = [vp, i32, i32, vp]
     lib.sc_set_halo.argtypes = [vp, i32, vp, vp, vp, vp, vp]
     lib.sc_halo_exchange.argtypes = [vp, vp]
+    lib.sc_srf_sample.argtypes = [vp, i64, vp, i32, vp, vp, vp, dbl, dbl, i32, vp, P(dbl)]
     for name in SYMBOLS:
         fn = getattr(lib, name)
         if name not in ("sc_destroy", "sc_last_error", "sc_kernel_launches"):
@@ -270,6 +271,17 @@ class Context:
         y = np.empty(self.n_eq, dtype=np.float64)
         self._ck(self.lib.sc_spmv(self.h, which, _ptr(x), _ptr(y)))
         return y
+
+    def srf_sample(self, pos, k, z1, z2, scale: float, mean: float, lognormal: bool):
+        """Random field at `pos` (n,3) from wave vectors k (m,3) and amplitudes z1, z2 (m,) -> (values (n,), kernel seconds)."""
+        pos = _arr(pos, np.float64); k = _arr(k, np.float64); z1 = _arr(z1, np.float64); z2 = _arr(z2, np.float64)
+        if pos.ndim != 2 or pos.shape[1] != 3 or k.shape != (len(z1), 3) or z2.shape != z1.shape:
+            raise ValueError("pos must be (n,3), k (m,3), z1 and z2 (m,)")
+        out = np.empty(pos.shape[0], dtype=np.float64)
+        sec = C.c_double()
+        self._ck(self.lib.sc_srf_sample(self.h, pos.shape[0], _ptr(pos), len(z1), _ptr(k), _ptr(z1), _ptr(z2), float(scale),
+                                        float(mean), int(bool(lognormal)), _ptr(out), C.byref(sec)))
+        return out, sec.value
 
     # ---- loads / state / time loop
     def set_load_schedule(self, step_ptr, dof, val):

@@ -472,6 +472,17 @@ int sc_run_static(sc_ctx* ctx, int64_t t_start, int64_t n_steps, int64_t out_int
     return tl_static(ctx, t_start, n_steps, out_interval, pcg_rtol, pcg_maxit, n_out, u_out, stats);
 }
 
+int sc_srf_sample(sc_ctx* ctx, int64_t n_points, const double* pos, int n_modes, const double* k, const double* z1, const double* z2,
+                  double scale, double mean, int lognormal, double* out, double* seconds_device) {
+    if (!ctx) return SC_ERR_ARG;
+    if (n_points < 0 || n_modes <= 0 || n_modes > (1 << 20)) return sc_fail(ctx, SC_ERR_ARG, "bad random-field sizes (%lld points, %d modes)", (long long)n_points, n_modes);
+    if (seconds_device) *seconds_device = 0.0;
+    if (n_points == 0) return SC_OK;
+    if (!pos || !k || !z1 || !z2 || !out) return sc_fail(ctx, SC_ERR_ARG, "null argument");
+    SC_CUDA(ctx, cudaSetDevice(ctx->device));
+    return srf_sample(ctx, n_points, pos, n_modes, k, z1, z2, scale, mean, lognormal, out, seconds_device);
+}
+
 int sc_nccl_unique_id(void* out128) { return out128 ? dist_unique_id(out128) : SC_ERR_ARG; }
 
 int sc_dist_init(sc_ctx* ctx, int rank, int world, const void* id) {

@@ -233,6 +233,9 @@ int tl_central_difference(sc_ctx* ctx, double dt, int64_t t0, int64_t n_steps, i
 int tl_bathe(sc_ctx* ctx, double dt, int64_t t0, int64_t n_steps, int64_t oi, double rtol, int maxit, int64_t n_out, double* u_out,
              double* v_out, double* a_out, sc_stats* st);
 int tl_static(sc_ctx* ctx, int64_t t0, int64_t n_steps, int64_t oi, double rtol, int maxit, int64_t n_out, double* u_out, sc_stats* st);
+// srf.cu
+int srf_sample(sc_ctx* ctx, int64_t n_points, const double* pos, int n_modes, const double* k, const double* z1, const double* z2,
+               double scale, double mean, int lognormal, double* out, double* seconds);
 // dist.cu
 int dist_init(sc_ctx* ctx, int rank, int world, const void* id);
 int dist_unique_id(void* out);

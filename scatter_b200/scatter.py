@@ -68,11 +68,13 @@ class Pipeline:
         if not rp:
             return self
         print("Generating random field")
-        rf = random_fields.RF(rp, self.materials, out_folder, self.model.element_type)
+        rf = random_fields.RF(rp, self.materials, out_folder, self.model.element_type, device=self.device)
+        # physical tag of the material that gets the field, its elements, the field, the re-indexed material list
         tag = [m[1] for m in self.model.materials if m[2] == rp["material"]][0]
         rf.generate_gstools_rf(self.model.nodes, self.model.elem[self.model.materials_index == tag], self.model.dimension, angles=0.0)
         rf.dump()
         rf.update_material_list(self.materials, self.model, tag)
+        self.rf = rf
         self.materials.update(rf.new_material)
         return self
 

@@ -81,6 +81,13 @@ def case_materials(case):
     return materials_embankment() if case in ("rose_2D_side", "embankment_rose2D") else materials()
 
 
+def rf_properties(case, model_name="Gaussian"):
+    """Random-field settings in the shape of run_scatter_rose_2D.py:62-73 / integration_test.py:148-158."""
+    return {"number_realisations": 1, "element_size": 1, "theta": 1.5, "seed_number": -26021981,
+            "material": "soil1" if case in ("rose_2D_side", "embankment_rose2D") else "solid", "key_material": "Young",
+            "std_value": 3e6, "aniso_x": 10, "aniso_z": 2, "model_name": model_name}
+
+
 B2_NODES = {
     "tri3": ([3, 4, 25], 2),
     "tri6": ([3, 4, 47, 48, 49], 2),

@@ -302,6 +302,60 @@ def test_box_mesh_random_field(oracle, tmp_path):
         assert np.abs(mx.ctx.get_values(1) - Mo.data).max() <= TOL_MAT * np.abs(Mo.data).max()
 
 
+@pytest.mark.parametrize("model_name", ["Gaussian", "Exponential", "Matern"])
+def test_random_field_kernel_vs_oracle(model_name, oracle):
+    """k_srf (randomisation method) against the sequential CPU restatement on the same modes; anisotropic 3-D and 2-D."""
+    from scatter_b200 import _lib, random_fields
+    rng = np.random.default_rng(3)
+    ctx = _lib.Context(0)
+    for dim, n in ((3, 3001), (2, 517), (3, 1)):
+        pos = rng.uniform(-40, 60, (n, 3))
+        if dim == 2:
+            pos[:, 2] = 0.0
+        sf = random_fields.SpectralField(model_name, dim, var=0.01, mean=17.2, len_scale=[15.0, 1.5, 3.0], angles=0.3 if dim == 2 else 0.0,
+                                         seed=26021981)
+        for logn in (False, True):
+            ref = oracle.srf_field(sf.isometrize(pos), sf.k, sf.z1, sf.z2, np.sqrt(sf.var / sf.mode_no), sf.mean, logn)
+            got = sf(pos, lognormal=logn, ctx=ctx)
+            assert got.shape == ref.shape and np.isfinite(got).all()
+            assert np.abs(got - ref).max() <= 1e-11 * np.abs(ref).max(), (model_name, dim, logn, np.abs(got - ref).max())
+            assert np.array_equal(got, sf(pos, lognormal=logn, ctx=ctx))                 # reproducible
+    out, sec = ctx.srf_sample(np.zeros((0, 3)), sf.k, sf.z1, sf.z2, 1.0, 0.0, False)      # no points: no launch
+    assert out.shape == (0,)
+    ctx.close()
+
+
+def test_scatter_with_random_field(golden_meshes, oracle, tmp_path):
+    """BASELINE config 2/3 shape: multi-material embankment mesh, lognormal random Young's modulus in one soil layer
+    (run_scatter_rose_2D.py:62-76 without the train).  The field itself is pinned in test_random_field_kernel_vs_oracle;
+    here the whole entry point is checked against the oracle run with the materials the field produced."""
+    from scatter_b200 import scatter
+    case = "rose_2D_side"
+    fn, bc = cases.MATRIX_CASES[case]
+    mats = cases.case_materials(case)
+    sett = cases.settings(damping=[1, 0.005, 20, 0.005], VTK=True, VTK_binary=False, output_interval=5)
+    load = {"force": [0, -1e4, 0], "node": [4], "time": 0.1, "type": "heaviside", "ini_steps": 5}
+    out = os.path.join(tmp_path, "rf2d")
+    res = scatter(golden_meshes[fn], out, mats, bc, sett, dict(load), time_step=1e-3, random_props=cases.rf_properties(case, "Gaussian"))
+    young = np.array([v["Young"] for k, v in mats.items() if k.startswith("material_")])
+    assert len(young) == 602 and abs(young.mean() / 500e5 - 1) < 0.05 and 0.2 < young.std() / 3e6 < 3.0
+    assert os.path.isfile(os.path.join(out, "rf_props.txt"))
+    # oracle with the same per-element materials (tags 0..N-1 = field elements, the others shifted)
+    om = oracle.build_model(golden_meshes[fn], bc)
+    tag_soil = [m[1] for m in om.materials if m[2] == "soil1"][0]
+    base = cases.case_materials(case)
+    E, nu, rho = oracle.element_properties(om, base)
+    E[np.asarray(om.materials_index) == tag_soil] = young
+    _, _, (U, V, A, _) = oracle.run_case(golden_meshes[fn], base, bc, sett, load, 1e-3, elem_props=(E, nu, rho))
+    assert np.abs(U).max() > 0
+    assert rel_l2(res.dis, U) <= TOL_HIST and rel_l2(res.vel, V) <= TOL_HIST
+    with open(os.path.join(out, "VTK", "data_2.vtk")) as f:
+        txt = f.read().splitlines()
+    i = txt.index("SCALARS material_prop_Young double")
+    vtk_young = np.array([float(t) for t in txt[i + 2:i + 2 + len(om.elem)]])
+    assert np.abs(vtk_young - E).max() <= 1e-9 * E.max()
+
+
 # ---- time histories ----------------------------------------------------------------------------------------------
 def run_history(name, golden_meshes, solver="newmark"):
     from scatter_b200 import force_external, solvers

@@ -183,6 +183,90 @@ def test_moving_at_plane_load_matches_oracle(golden_meshes, oracle):
         assert abs(dense.sum() - (-1000.0 * ref.sf[t])) < 1e-9          # the nodal forces add up to the point load
 
 
+def _stub_field(cen, mean, var):
+    # the stand-in sampler oracle/make_golden.py gave the unmodified reference RF class
+    return mean + np.sqrt(var) * np.sin(cen @ np.array([1.3, 0.7, 0.4]) + 0.2)
+
+
+@pytest.mark.parametrize("case,model_name", [("rose_2D_side", "Gaussian"), ("cube", "Exponential")])
+def test_random_field_bookkeeping_matches_reference(case, model_name, golden_meshes, tmp_path, monkeypatch):
+    """Everything around the sampler -- length scales, lognormal parameters, centroids, one material per element, the tag
+    re-indexing, rf_props.txt, the per-element look-up of system_matrix.py:52-71 -- against the reference's RF class run
+    with the same stand-in sampler (tests/golden/random_field.npz)."""
+    from scatter_b200 import mesher, random_fields, system_matrix
+    G = np.load(os.path.join(ROOT, "tests", "golden", "random_field.npz"))
+    fn, bc = cases.MATRIX_CASES[case]
+    m = mesher.ReadMesh(golden_meshes[fn])
+    m.read_gmsh(); m.read_bc(bc); m.mapping(); m.connectivities()
+    mats = cases.case_materials(case)
+    props = cases.rf_properties(case, model_name)
+    seen = {}
+
+    def fake_call(self, pos, lognormal=False, device=0, ctx=None):
+        seen.update(dim=self.dim, var=self.var, mean=self.mean, angles=self.angles, seed=self.seed, len_scale=self.len_scale,
+                    model=self.model_name)
+        f = _stub_field(np.asarray(pos), self.mean, self.var)
+        return np.exp(f) if lognormal else f
+
+    monkeypatch.setattr(random_fields.SpectralField, "__call__", fake_call)
+    rf = random_fields.RF(props, mats, str(tmp_path), m.element_type)
+    idx = [mm[1] for mm in m.materials if mm[2] == props["material"]][0]
+    rf.generate_gstools_rf(m.nodes, m.elem[m.materials_index == idx], m.dimension, angles=0.0)
+    E_arr, _, rho_arr = rf.element_properties(m, idx)            # array path, before the tags are re-indexed
+    rf.dump()
+    rf.update_material_list(mats, m, idx)
+    mats.update(rf.new_material)
+    p = case + "__"
+    a = G[p + "model_args"]
+    assert seen["dim"] == int(a[0]) and seen["angles"] == a[2] and seen["seed"] == int(a[4]) and seen["model"] == str(G[p + "model_class"])
+    assert abs(seen["var"] - a[1]) <= 1e-15 * a[1] and abs(seen["mean"] - a[3]) <= 1e-15 * abs(a[3])
+    assert np.array_equal(seen["len_scale"], a[5:5 + seen["dim"]])
+    assert rf.element_type_to_meshio_element_type() == str(G[p + "cell_type"])
+    assert np.abs(rf.fields[0] - G[p + "field"]).max() <= 1e-13 * np.abs(G[p + "field"]).max()
+    assert np.array_equal(np.asarray(m.materials_index), G[p + "materials_index"])
+    assert [f"{mm[0]}|{mm[1]}|{mm[2]}" for mm in m.materials] == list(G[p + "model_materials"])
+    names = sorted(mats)
+    assert names == list(G[p + "material_names"])
+    vals = np.array([[mats[n]["density"], mats[n]["Young"], mats[n]["poisson"]] for n in names], dtype=float)
+    assert np.abs(vals - G[p + "material_values"]).max() <= 1e-13 * np.abs(vals).max()
+    assert open(os.path.join(tmp_path, "rf_props.txt")).read() == str(G[p + "dump"])
+    E, nu, rho = system_matrix.resolve_element_properties(m, mats)
+    assert np.abs(E - G[p + "E_elem"]).max() <= 1e-13 * E.max() and np.array_equal(rho, G[p + "rho_elem"])
+    assert np.array_equal(E_arr, E) and np.array_equal(rho_arr, rho)
+
+
+@pytest.mark.parametrize("model_name", ["Gaussian", "Exponential", "Matern"])
+@pytest.mark.parametrize("dim", [2, 3])
+def test_mode_sampler_has_the_model_spectrum(model_name, dim):
+    """Bochner: E[cos(k . h)] over the sampled wave vectors is the correlation function of the covariance model."""
+    from scatter_b200 import random_fields
+    k, z1, z2 = random_fields.sample_modes(model_name, dim, seed=11, mode_no=400000)
+    assert abs(z1.mean()) < 0.01 and abs(z1.std() - 1) < 0.01 and abs(np.mean(z1 * z2)) < 0.01
+    if dim == 2:
+        assert np.all(k[:, 2] == 0)
+    for dist in (0.25, 0.7, 1.5, 3.0):
+        for direction in ([1, 0, 0], [0.6, 0.8, 0], [0, 0, 1] if dim == 3 else [0, 1, 0]):
+            h = dist * np.array(direction, dtype=float)
+            assert abs(np.cos(k @ h).mean() - random_fields.correlation(model_name, dist)) < 6e-3
+    with pytest.raises(NotImplementedError):
+        random_fields.sample_modes("Linear", dim, 1)
+
+
+def test_oracle_random_field_statistics(oracle):
+    """The restated randomisation method reproduces mean, variance and the correlation at one lag (spatial averages over
+    a domain of many correlation lengths)."""
+    from scatter_b200 import random_fields
+    sf = random_fields.SpectralField("Gaussian", 2, var=0.04, mean=1.5, len_scale=[2.0, 0.5, 1.0], angles=0.0, seed=5)
+    gx, gy = np.meshgrid(np.arange(0, 400, 1.0), np.arange(0, 100, 0.25))
+    pos = np.c_[gx.ravel(), gy.ravel(), np.zeros(gx.size)]
+    f = oracle.srf_field(sf.isometrize(pos), sf.k, sf.z1, sf.z2, np.sqrt(sf.var / sf.mode_no), sf.mean, False).reshape(gx.shape)
+    assert abs(f.mean() - 1.5) < 0.02 and abs(f.var() - 0.04) < 0.008
+    c = ((f[:, 2:] - f.mean()) * (f[:, :-2] - f.mean())).mean() / f.var()           # lag 2 along x = one length scale
+    assert abs(c - random_fields.correlation("Gaussian", 1.0)) < 0.08
+    c = ((f[4:, :] - f.mean()) * (f[:-4, :] - f.mean())).mean() / f.var()           # lag 1 along y = two length scales
+    assert abs(c - random_fields.correlation("Gaussian", 2.0)) < 0.08
+
+
 def test_validator():
     from scatter_b200 import validator
     load = {"type": "pulse"}
