@@ -337,6 +337,28 @@ def run_ours(args):
                          f"SpMV (single thread) after numpy assembly at {r['elem_per_s']:.0f} elem/s; oracle/fem_np.py",
                "assembly_elem_per_s": r["elem_per_s"], "host_cores": os.cpu_count()}
 
+    # --- random material field at scale: Gaussian SRF, 1000 modes, at every element centroid of this
+    #     rank's box; outside the timed region, reported next to the assembly (the headline E stays the seeded lognormal)
+    rf = None
+    if rank == 0 and args.random_field:
+        try:
+            from scatter_b200 import random_fields
+            sf = random_fields.SpectralField("Gaussian", 3, var=np.log((E_STD / E_MEAN) ** 2 + 1),
+                                             mean=np.log(E_MEAN ** 2 / np.sqrt(E_MEAN ** 2 + E_STD ** 2)),
+                                             len_scale=[10 * 2.0, 2.0, 10 * 2.0], angles=0.0, seed=26021981)
+            t0 = time.perf_counter()
+            cen = random_fields.RF.centroids(model.nodes, model.elem)
+            t_cen = time.perf_counter() - t0
+            t0 = time.perf_counter()
+            field = sf(cen, lognormal=True, ctx=ctx)
+            t_all = time.perf_counter() - t0
+            rf = {"points": int(len(cen)), "modes": sf.mode_no, "kernel_seconds": sf.seconds_device, "call_seconds": t_all,
+                  "centroid_host_seconds": t_cen, "sincos_per_s": len(cen) * sf.mode_no / max(sf.seconds_device, 1e-12),
+                  "mean": float(field.mean()), "std": float(field.std())}
+            del cen, field
+        except Exception as exc:
+            rf = {"error": repr(exc)}
+
     secondary = None
     if rank == 0 and world == 1 and args.secondary:
         info0 = ctx.device_info()
@@ -364,6 +386,7 @@ def run_ours(args):
                              # k_assemble_blk per hexa8 element against 64 FMA/clk/SM at the maximum SM clock
                              "fma_per_element": ASM_FMA_PER_HEXA8,
                              "frac_fp64_peak": ne * ASM_FMA_PER_HEXA8 / t_asm / (64.0 * info["sm_count"] * sm_max_hz)},
+                "random_field": rf,
                 "cpu_baseline": cpu,
                 "e2e": {"value": e2e_value, "unit": "DOF*steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "ms_per_step": 1e3 * e2e_wall / args.steps},
@@ -442,6 +465,7 @@ def main():
     ap.add_argument("--cpu-steps", type=int, default=20)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--secondary", type=int, default=1, help="also run the hexa20 Newmark/PCG workload (N = 1 only)")
+    ap.add_argument("--random-field", type=int, default=1, help="also time the random-field sampler on this rank's elements")
     ap.add_argument("--size20", type=int, default=94, help="hexa20 box edge (elements) of the secondary workload")
     ap.add_argument("--steps20", type=int, default=5)
     args = ap.parse_args()

@@ -127,22 +127,33 @@ def reference_system(mesh, bc, mat, sett):
     return m, mx, Ks, Ms, t_asm
 
 
-for mesh, bc in CASES:
-    path = os.path.join(IT, "mesh", mesh)
-    m, mx, Ks, Ms, t_asm = reference_system(path, bc, MAT, SETT)
+# meshes of the reference's run scripts (mesh/*.msh, run_scatter_rose_2D.py:22-41): multi-material tri3 / quad4
+def _bc2(xx, y0, y1):
+    return {"bottom": ["11", [[0, y0, 0], [xx, y0, 0]]], "left": ["10", [[0, y0, 0], [0, y1, 0]]], "right": ["10", [[xx, y0, 0], [xx, y1, 0]]]}
+
+
+MAT_EMB = {"embankment": {"density": 2000, "Young": 100e6, "poisson": 0.2}, "soil1": {"density": 1700, "Young": 500e5, "poisson": 0.2},
+           "soil2": {"density": 2000, "Young": 200e5, "poisson": 0.2}}
+RUN_CASES = [("rose_2D_side.msh", _bc2(90, -3, 0.5), MAT_EMB), ("embankment_rose2D.msh", _bc2(10, -5, 0.5), MAT_EMB),
+             ("box2d.msh", _bc2(120, 0, 1.8), MAT)]
+ALL_CASES = [(os.path.join(IT, "mesh", mesh), bc, MAT) for mesh, bc in CASES] + \
+            [(os.path.join("/root/reference/mesh", mesh), bc, mat) for mesh, bc, mat in RUN_CASES]
+for path, bc, MAT_CASE in ALL_CASES:
+    mesh = os.path.basename(path)
+    m, mx, Ks, Ms, t_asm = reference_system(path, bc, MAT_CASE, SETT)
     om = orc.build_model(path, bc)
     assert om.number_eq == m.number_eq and om.element_type == m.element_type
     assert np.array_equal(np.nan_to_num(om.eq_nb_dof, nan=-1), np.nan_to_num(m.eq_nb_dof, nan=-1))
     assert np.array_equal(np.nan_to_num(om.eq_nb_elem, nan=-1), np.nan_to_num(m.eq_nb_elem, nan=-1))
     assert np.array_equal(om.BC, m.BC) and np.array_equal(om.BC_dir, m.BC_dir)
     assert np.array_equal(om.type_BC, m.type_BC)
-    E, nu, rho = orc.element_properties(om, MAT)
+    E, nu, rho = orc.element_properties(om, MAT_CASE)
     Ko, Mo = orc.assemble_global(om, E, nu, rho, 2)
     pat_ok = (np.array_equal(Ko.indptr, Ks.indptr) and np.array_equal(Ko.indices, Ks.indices)
               and np.array_equal(Mo.indptr, Ms.indptr) and np.array_equal(Mo.indices, Ms.indices))
     assert pat_ok, mesh
     ek, em = rel(Ko.data, Ks.data), rel(Mo.data, Ms.data)
-    Kf, Mf, Cf, _ = orc.system_matrices(om, MAT, SETT)
+    Kf, Mf, Cf, _ = orc.system_matrices(om, MAT_CASE, SETT)
     ekf = abs(Kf - sp.csr_matrix(mx.K)).max() / abs(mx.K).max()
     ecf = abs(Cf - sp.csr_matrix(mx.C)).max() / abs(sp.csr_matrix(mx.C)).max()
     nabs = int((om.type_BC == "Absorb").sum())
