@@ -10,7 +10,8 @@ Metric (BASELINE.json): DOF*timesteps/s of the time loop (+ assembly GB/s), next
   sides, lognormal per-element Young's modulus, Rayleigh damping, heaviside point load on the top surface,
   explicit central difference with lumped mass at dt = 0.5 h / vp.  N GPUs: the box grows along z (weak scaling),
   one z-slab per rank, one halo exchange (NCCL send/recv of the two interface planes) per time step.
-* one bench "step" = one solver stage of `--stage` time steps (`sc_run_central_difference`).
+* one bench "step" = one solver stage of `--stage` time steps (`sc_run_central_difference`; default 100 = the
+  `output_interval` of the reference's run scripts, run_scatter_rose_2D.py:19).
   `value`   : stages with everything resident in HBM, no host traffic; timed with CUDA events inside the library on
               the launching stream, max over ranks.
   `e2e`     : the same stage through the reference-facing solver object (`CentralDifferenceSolver.update/calculate`):
@@ -460,7 +461,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--size", type=int, default=255, help="elements per box edge per GPU")
-    ap.add_argument("--stage", type=int, default=50, help="time steps per bench step")
+    ap.add_argument("--stage", type=int, default=100, help="time steps per bench step = output interval of the e2e arm "
+                                                             "(the reference's run scripts store every 100th step, run_scatter_rose_2D.py:19)")
     ap.add_argument("--cpu-size", type=int, default=40)
     ap.add_argument("--cpu-steps", type=int, default=20)
     ap.add_argument("--no-cpu", action="store_true")

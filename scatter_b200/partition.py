@@ -54,6 +54,41 @@ def owner_by_slabs(model: ReadMesh, world: int, axis: int = 2) -> np.ndarray:
     return owner
 
 
+def owner_by_rcb(model: ReadMesh, world: int) -> np.ndarray:
+    """Owner rank of every node by recursive coordinate bisection (any world size, unstructured meshes): a group of ranks
+    is split in two halves of floor / ceil size, the nodes in proportion, along the longest axis of the group's bounding
+    box; ties are broken by node row, so the result is deterministic and every rank gets within one node of its share."""
+    xyz = model.nodes[:, 1:4]
+    owner = np.empty(len(xyz), dtype=np.int32)
+    stack = [(np.arange(len(xyz)), 0, world)]
+    while stack:
+        idx, r0, nr = stack.pop()
+        if nr == 1:
+            owner[idx] = r0
+            continue
+        left = nr // 2
+        pts = xyz[idx]
+        axis = int(np.argmax(pts.max(axis=0) - pts.min(axis=0))) if len(idx) else 0
+        order = np.argsort(pts[:, axis], kind="stable")
+        cut = (len(idx) * left) // nr
+        stack.append((idx[order[:cut]], r0, left))
+        stack.append((idx[order[cut:]], r0 + left, nr - left))
+    return owner
+
+
+def localise_schedule(dom: "LocalDomain", step_ptr, dof, val):
+    """Restrict a global load schedule (CSR over time steps of (global equation, value), `Force.compile_schedule`) to the
+    dofs `dom` owns, renumbered to its local equations -- every load entry is applied by exactly one rank."""
+    step_ptr = np.asarray(step_ptr, dtype=np.int64); dof = np.asarray(dof, dtype=np.int64); val = np.asarray(val, dtype=float)
+    g2l = -np.ones(max(int(dom.n_global_eq), int(dof.max()) + 1 if len(dof) else 0), dtype=np.int64)
+    g2l[dom.global_eq_of_owned] = dom.owned_eq
+    loc = g2l[dof]
+    keep = loc >= 0
+    step = np.repeat(np.arange(len(step_ptr) - 1), np.diff(step_ptr))
+    counts = np.bincount(step[keep], minlength=len(step_ptr) - 1)
+    return np.concatenate([[0], np.cumsum(counts)]).astype(np.int64), loc[keep], val[keep]
+
+
 def partition_model(model: ReadMesh, owner: np.ndarray, rank: int) -> LocalDomain:
     """Local domain of `rank` for a global model whose BC / equation numbering are already set."""
     rows = model.node_rows()

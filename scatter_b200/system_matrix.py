@@ -186,15 +186,20 @@ class GenerateMatrix:
         self.assembly_seconds = self.ctx.assemble(self.order, flags)
         self._pattern = None
 
-    def absorbing_boundaries(self, data, material: dict, parameters_viscous: list, parameters_stiff: float) -> None:
-        """system_matrix.py:256-376 -- Lysmer-Kuhlemeyer dashpots into C, springs into K."""
+    def absorbing_boundaries(self, data, material: dict, parameters_viscous: list, parameters_stiff: float, owned_rows=None) -> None:
+        """system_matrix.py:256-376 -- Lysmer-Kuhlemeyer dashpots into C, springs into K.  `owned_rows` (domain-decomposed
+        runs): local equation numbers whose rows this rank assembles; entries of ghost rows are left to their owner."""
         E, nu, rho = self._props if self._props is not None else resolve_element_properties(data, material)
         cdict, kdict = absorbing_entries(data, E, nu, rho, self.order, parameters_viscous, parameters_stiff)
         if cdict:
             keys = np.array(list(cdict.keys()), dtype=np.int64)
-            self.ctx.add_entries(_lib.MAT_C, keys[:, 0], keys[:, 1], np.array(list(cdict.values())))
-            keys = np.array(list(kdict.keys()), dtype=np.int64)
-            self.ctx.add_entries(_lib.MAT_K, keys[:, 0], keys[:, 1], np.array(list(kdict.values())))
+            cv, kv = np.array(list(cdict.values())), np.array([kdict[tuple(k)] for k in keys])
+            if owned_rows is not None:
+                keep = np.isin(keys[:, 0], np.asarray(owned_rows))
+                keys, cv, kv = keys[keep], cv[keep], kv[keep]
+            if len(keys):
+                self.ctx.add_entries(_lib.MAT_C, keys[:, 0], keys[:, 1], cv)
+                self.ctx.add_entries(_lib.MAT_K, keys[:, 0], keys[:, 1], kv)
 
     def damping_Rayleigh(self, damp) -> None:
         """system_matrix.py:166-198 -- C = C + c0 M + c1 K (applied on the fly on the device)."""

@@ -128,3 +128,47 @@ def test_two_gpu_time_loops_match_single_domain_oracle(golden_meshes, tmp_path):
         assert not np.isnan(got[k]).any()
         err = np.linalg.norm(got[k] - ref) / np.linalg.norm(ref)
         assert err <= (1e-8 if k != "nm_a" else 1e-7), (k, err)
+
+
+def _dist_entry_worker(rank, world, port, mesh_path, out_dir, solver_name):
+    sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    from scatter_b200 import Solver
+    from scatter_b200.distributed import scatter_distributed
+    sett = cases.settings(damping=[1, 0.01, 30, 0.01], output_interval=5, VTK=True, VTK_binary=False)
+    load = {"force": [0, -1000, 0], "node": [8], "time": 0.05 if solver_name == "newmark" else 0.02, "type": "heaviside", "ini_steps": 5}
+    dt = 1e-3 if solver_name == "newmark" else 2e-4
+    res = scatter_distributed(mesh_path, os.path.join(out_dir, f"out_{solver_name}"), cases.materials(), cases.BC_CUBE_ABS, sett, load,
+                              time_step=dt, solver=Solver.NEWMARK_EXPLICIT if solver_name == "newmark" else Solver.CENTRAL_DIFFERENCE)
+    if rank == 0:
+        np.savez(os.path.join(out_dir, f"dist_{solver_name}.npz"), u=res.dis, v=res.vel, a=res.acc, t=res.time)
+    else:
+        assert res is None
+    import torch.distributed as dist
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("solver_name", ["newmark", "cd"])
+def test_scatter_distributed_matches_serial(solver_name, golden_meshes, tmp_path):
+    """The multi-GPU entry point (RCB partition, absorbing faces on owned rows, localised loads, gathered histories, rank-0
+    export) against the single-domain oracle run of the same case."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import torch.multiprocessing as mp
+    oracle = load_oracle()
+    world = 2
+    mesh_path = golden_meshes["cube.msh"]
+    mp.spawn(_dist_entry_worker, args=(world, _free_port(), mesh_path, str(tmp_path), solver_name), nprocs=world, join=True)
+    sett = cases.settings(damping=[1, 0.01, 30, 0.01], output_interval=5)
+    load = {"force": [0, -1000, 0], "node": [8], "time": 0.05 if solver_name == "newmark" else 0.02, "type": "heaviside", "ini_steps": 5}
+    dt = 1e-3 if solver_name == "newmark" else 2e-4
+    _, _, (U, V, A, tt) = oracle.run_case(mesh_path, cases.materials(), cases.BC_CUBE_ABS, sett, load, dt,
+                                          solver="newmark" if solver_name == "newmark" else "cd")
+    z = np.load(os.path.join(tmp_path, f"dist_{solver_name}.npz"))
+    assert z["u"].shape == U.shape and np.abs(U).max() > 0
+    for got, ref, tol in ((z["u"], U, 1e-8), (z["v"], V, 1e-8), (z["a"], A, 1e-7)):
+        assert np.linalg.norm(got - ref) / np.linalg.norm(ref) <= tol
+    assert os.path.isfile(os.path.join(tmp_path, f"out_{solver_name}", "data.pickle"))
+    assert os.path.isfile(os.path.join(tmp_path, f"out_{solver_name}", "VTK", "data_1.vtk"))
