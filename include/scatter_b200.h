@@ -113,6 +113,20 @@ int sc_assemble(sc_ctx* ctx, int gauss_order, int flags, double* seconds_device 
  * separate term C_abs), absorbing springs -> which = SC_MAT_K (system_matrix.py:360-376) */
 int sc_add_entries(sc_ctx* ctx, int which, int64_t n, const int64_t* rows, const int64_t* cols, const double* vals);
 
+/* absorbing boundary faces (GenerateMatrix.absorbing_boundaries, system_matrix.py:256-376, with the face matrices of
+ * compute_abs_bound, discretisation.py:419-433).  The caller plans, the device computes:
+ *   face_nodes [n_faces*nl] node rows of every absorbing face in the reference's face-node order (utils.py:141-175),
+ *   face_elem / face_dir [n_faces] element (material) and normal direction 0..2 of the face,
+ *   perp [n_faces*nl] 1 where the dof paired with face position b is perpendicular to its boundary (p0 rho vp, Ec) else
+ *        (p1 rho vs, G),
+ *   rows/cols [n_unique] sorted, unique matrix positions that receive entries; grp_ptr [n_unique+1] / grp_entry: the
+ *        per-face entries (id = (face*nl + a)*nl + b) of every position, ascending = the reference's accumulation order.
+ * Result: C_abs := sum of S_ab * coefficient_b (replaces any earlier C_abs), K += sum |S_ab| * modulus_b / stiff.      */
+int sc_add_absorbing_faces(sc_ctx* ctx, int face_type, int gauss_order, int64_t n_faces, const int32_t* face_nodes,
+                           const int32_t* face_elem, const int32_t* face_dir, const uint8_t* perp, int64_t n_unique,
+                           const int64_t* rows, const int64_t* cols, const int64_t* grp_ptr, const int64_t* grp_entry,
+                           double p0, double p1, double stiff);
+
 /* Rayleigh damping C = C_abs + c0 M + c1 K (system_matrix.py:198); never materialised in the time loop */
 int sc_set_rayleigh(sc_ctx* ctx, double c0, double c1);
 

@@ -27,7 +27,7 @@ SYMBOLS = [
     "sc_set_mesh", "sc_set_materials", "sc_build_pattern", "sc_get_pattern", "sc_pattern_stats", "sc_assemble", "sc_add_entries",
     "sc_set_rayleigh", "sc_get_values", "sc_get_lumped_mass", "sc_spmv", "sc_set_load_schedule", "sc_set_state",
     "sc_get_state", "sc_run_newmark", "sc_run_central_difference", "sc_run_bathe", "sc_run_static", "sc_nccl_unique_id", "sc_dist_init", "sc_set_halo",
-    "sc_halo_exchange", "sc_srf_sample",
+    "sc_halo_exchange", "sc_srf_sample", "sc_add_absorbing_faces",
 ]
 
 
@@ -97,6 +97,7 @@ def load_library():
     lib.sc_dist_init.argtypes = [vp, i32, i32, vp]
     lib.sc_set_halo.argtypes = [vp, i32, vp, vp, vp, vp, vp]
     lib.sc_halo_exchange.argtypes = [vp, vp]
+    lib.sc_add_absorbing_faces.argtypes = [vp, i32, i32, i64, vp, vp, vp, vp, i64, vp, vp, vp, vp, dbl, dbl, dbl]
     lib.sc_srf_sample.argtypes = [vp, i64, vp, i32, vp, vp, vp, dbl, dbl, i32, vp, P(dbl)]
     for name in SYMBOLS:
         fn = getattr(lib, name)
@@ -252,6 +253,12 @@ class Context:
     def add_entries(self, which: int, rows, cols, vals):
         rows = _arr(rows, np.int64); cols = _arr(cols, np.int64); vals = _arr(vals, np.float64)
         self._ck(self.lib.sc_add_entries(self.h, which, len(vals), _ptr(rows), _ptr(cols), _ptr(vals)))
+
+    def add_absorbing_faces(self, plan, order: int, p0: float, p1: float, stiff: float):
+        """Evaluate an `system_matrix.AbsorbingPlan` on the device: C_abs and the spring terms of K."""
+        self._ck(self.lib.sc_add_absorbing_faces(self.h, ELEM_TYPE_ID[plan.face_type], int(order), len(plan.elem), _ptr(plan.nodes),
+                                                 _ptr(plan.elem), _ptr(plan.direction), _ptr(plan.perp), len(plan.rows), _ptr(plan.rows),
+                                                 _ptr(plan.cols), _ptr(plan.grp_ptr), _ptr(plan.grp_entry), float(p0), float(p1), float(stiff)))
 
     def set_rayleigh(self, c0: float, c1: float):
         self._ck(self.lib.sc_set_rayleigh(self.h, float(c0), float(c1)))

@@ -268,6 +268,55 @@ int sc_assemble(sc_ctx* ctx, int gauss_order, int flags, double* seconds_device)
     return sc_assemble_run(ctx, gauss_order, flags, seconds_device);
 }
 
+// (row, col) keys sorted and free of duplicates on the host, their values already on the device: slots by binary search in
+// the structural pattern, then K[slot] += v, or C_abs := the row-compressed list (takes ownership of *d_v)
+static int add_sorted_entries(sc_ctx* ctx, int which, int64_t n, const std::vector<int64_t>& r, const std::vector<int32_t>& c, double** d_v) {
+    int64_t *d_r = nullptr, *d_slot = nullptr;
+    int32_t* d_c = nullptr;
+    int* d_flag = nullptr;
+    int rc = SC_OK;
+    auto body = [&]() -> int {
+        SC_TRY(upload(ctx, &d_r, r.data(), (size_t)n));
+        SC_TRY(upload(ctx, &d_c, c.data(), (size_t)n));
+        SC_TRY(sc_alloc(ctx, &d_slot, (size_t)n));
+        SC_TRY(sc_alloc(ctx, &d_flag, 1));
+        SC_CUDA(ctx, cudaMemsetAsync(d_flag, 0, sizeof(int), ctx->stream));
+        k_find_slots<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(ctx->d_rowptr, ctx->d_col, d_r, d_c, n, d_slot, d_flag);
+        SC_CHECK_LAUNCH(ctx);
+        int flag = 0;
+        SC_CUDA(ctx, cudaMemcpyAsync(&flag, d_flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        SC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        if (flag) return sc_fail(ctx, SC_ERR_ARG, "an added entry lies outside the structural pattern");
+        if (which == SC_MAT_K) {
+            if (!ctx->have_K) return sc_fail(ctx, SC_ERR_STATE, "K is not assembled");
+            k_add_at<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(ctx->d_K, d_slot, *d_v, n);
+            SC_CHECK_LAUNCH(ctx);
+            SC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            return SC_OK;
+        }
+        // C_abs replaces any previous list: row-compressed form
+        std::vector<int64_t> rowid, rptr;
+        for (int64_t i = 0; i < n; ++i) {
+            if (i == 0 || r[i] != r[i - 1]) { rowid.push_back(r[i]); rptr.push_back(i); }
+        }
+        rptr.push_back(n);
+        sc_free(&ctx->d_cabs_rowid); sc_free(&ctx->d_cabs_rptr); sc_free(&ctx->d_cabs_col); sc_free(&ctx->d_cabs_slot); sc_free(&ctx->d_cabs_val);
+        ctx->cabs_n = ctx->cabs_rows = 0;
+        SC_TRY(upload(ctx, &ctx->d_cabs_rowid, rowid.data(), rowid.size()));
+        SC_TRY(upload(ctx, &ctx->d_cabs_rptr, rptr.data(), rptr.size()));
+        ctx->d_cabs_col = d_c; d_c = nullptr;
+        ctx->d_cabs_slot = d_slot; d_slot = nullptr;
+        ctx->d_cabs_val = *d_v; *d_v = nullptr;
+        ctx->cabs_n = n;
+        ctx->cabs_rows = (int64_t)rowid.size();
+        return SC_OK;
+    };
+    rc = body();
+    sc_free(&d_r); sc_free(&d_c); sc_free(&d_slot); sc_free(&d_flag);
+    ctx->cd_resume_valid = false; ctx->nm_resume_valid = false; ctx->khat_a1 = ctx->khat_a4 = -1.0; ctx->cd_coef_dt = -1.0;
+    return rc;
+}
+
 int sc_add_entries(sc_ctx* ctx, int which, int64_t n, const int64_t* rows, const int64_t* cols, const double* vals) {
     if (!ctx || !ctx->have_pattern) return sc_fail(ctx, SC_ERR_STATE, "sc_build_pattern must be called first");
     if (which != SC_MAT_K && which != SC_MAT_C) return sc_fail(ctx, SC_ERR_ARG, "entries can be added to K or C only");
@@ -286,50 +335,43 @@ int sc_add_entries(sc_ctx* ctx, int which, int64_t n, const int64_t* rows, const
         r[i] = rows[o]; c[i] = (int32_t)cols[o]; v[i] = vals[o];
         if (i > 0 && r[i] == r[i - 1] && c[i] == c[i - 1]) return sc_fail(ctx, SC_ERR_ARG, "duplicate entry (%lld, %lld)", (long long)r[i], (long long)c[i]);
     }
-    int64_t *d_r = nullptr, *d_slot = nullptr;
-    int32_t* d_c = nullptr;
     double* d_v = nullptr;
-    int* d_flag = nullptr;
-    SC_TRY(upload(ctx, &d_r, r.data(), (size_t)n));
-    SC_TRY(upload(ctx, &d_c, c.data(), (size_t)n));
     SC_TRY(upload(ctx, &d_v, v.data(), (size_t)n));
-    SC_TRY(sc_alloc(ctx, &d_slot, (size_t)n));
-    SC_TRY(sc_alloc(ctx, &d_flag, 1));
-    SC_CUDA(ctx, cudaMemsetAsync(d_flag, 0, sizeof(int), ctx->stream));
-    k_find_slots<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(ctx->d_rowptr, ctx->d_col, d_r, d_c, n, d_slot, d_flag);
-    SC_CHECK_LAUNCH(ctx);
-    int flag = 0;
-    SC_CUDA(ctx, cudaMemcpyAsync(&flag, d_flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-    SC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    int rc = SC_OK;
-    if (flag) rc = sc_fail(ctx, SC_ERR_ARG, "an added entry lies outside the structural pattern");
-    else if (which == SC_MAT_K) {
-        if (!ctx->have_K) rc = sc_fail(ctx, SC_ERR_STATE, "K is not assembled");
-        else {
-            k_add_at<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(ctx->d_K, d_slot, d_v, n);
-            ctx->launches++;
-            if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) rc = sc_fail(ctx, SC_ERR_CUDA, "add entries failed");
-        }
-    } else {
-        // C_abs replaces any previous list: row-compressed form
-        std::vector<int64_t> rowid, rptr;
-        for (int64_t i = 0; i < n; ++i) {
-            if (i == 0 || r[i] != r[i - 1]) { rowid.push_back(r[i]); rptr.push_back(i); }
-        }
-        rptr.push_back(n);
-        sc_free(&ctx->d_cabs_rowid); sc_free(&ctx->d_cabs_rptr); sc_free(&ctx->d_cabs_col); sc_free(&ctx->d_cabs_slot); sc_free(&ctx->d_cabs_val);
-        rc = upload(ctx, &ctx->d_cabs_rowid, rowid.data(), rowid.size());
-        if (rc == SC_OK) rc = upload(ctx, &ctx->d_cabs_rptr, rptr.data(), rptr.size());
-        if (rc == SC_OK) {
-            ctx->d_cabs_col = d_c; d_c = nullptr;
-            ctx->d_cabs_slot = d_slot; d_slot = nullptr;
-            ctx->d_cabs_val = d_v; d_v = nullptr;
-            ctx->cabs_n = n;
-            ctx->cabs_rows = (int64_t)rowid.size();
-        }
+    const int rc = add_sorted_entries(ctx, which, n, r, c, &d_v);
+    sc_free(&d_v);
+    return rc;
+}
+
+int sc_add_absorbing_faces(sc_ctx* ctx, int face_type, int gauss_order, int64_t n_faces, const int32_t* face_nodes, const int32_t* face_elem,
+                           const int32_t* face_dir, const uint8_t* perp, int64_t n_unique, const int64_t* rows, const int64_t* cols,
+                           const int64_t* grp_ptr, const int64_t* grp_entry, double p0, double p1, double stiff) {
+    if (!ctx || !ctx->have_pattern || !ctx->have_mat) return sc_fail(ctx, SC_ERR_STATE, "mesh, materials and pattern must be set first");
+    if (!ctx->have_K) return sc_fail(ctx, SC_ERR_STATE, "K is not assembled");
+    if (ctx->dim != 3) return sc_fail(ctx, SC_ERR_UNSUPPORTED, "absorbing faces exist for 3-D meshes only (system_matrix.py:324-326)");
+    if (n_faces <= 0 || n_unique <= 0) return SC_OK;
+    if (!face_nodes || !face_elem || !face_dir || !perp || !rows || !cols || !grp_ptr || !grp_entry || stiff == 0.0)
+        return sc_fail(ctx, SC_ERR_ARG, "null argument");
+    const int nl = sc_elem_nne(face_type);
+    if (nl <= 0 || sc_elem_dim(face_type) != 2) return sc_fail(ctx, SC_ERR_ARG, "the face element must be a 2-D element type");
+    const int64_t n_entries = n_faces * nl * nl;
+    if (grp_ptr[0] != 0 || grp_ptr[n_unique] > n_entries) return sc_fail(ctx, SC_ERR_ARG, "bad entry grouping");
+    std::vector<int64_t> r((size_t)n_unique);
+    std::vector<int32_t> c((size_t)n_unique);
+    for (int64_t i = 0; i < n_unique; ++i) {
+        if (rows[i] < 0 || rows[i] >= ctx->n_eq || cols[i] < 0 || cols[i] >= ctx->n_eq) return sc_fail(ctx, SC_ERR_ARG, "key %lld out of range", (long long)i);
+        if (grp_ptr[i + 1] < grp_ptr[i]) return sc_fail(ctx, SC_ERR_ARG, "bad entry grouping");
+        r[i] = rows[i]; c[i] = (int32_t)cols[i];
+        if (i > 0 && !(r[i] > r[i - 1] || (r[i] == r[i - 1] && c[i] > c[i - 1]))) return sc_fail(ctx, SC_ERR_ARG, "keys must be sorted and unique");
     }
-    sc_free(&d_r); sc_free(&d_c); sc_free(&d_v); sc_free(&d_slot); sc_free(&d_flag);
-    ctx->cd_resume_valid = false; ctx->nm_resume_valid = false; ctx->khat_a1 = ctx->khat_a4 = -1.0; ctx->cd_coef_dt = -1.0;
+    for (int64_t i = 0; i < n_faces; ++i)
+        if (face_elem[i] < 0 || face_elem[i] >= ctx->n_elem || face_dir[i] < 0 || face_dir[i] > 2) return sc_fail(ctx, SC_ERR_ARG, "face %lld out of range", (long long)i);
+    SC_CUDA(ctx, cudaSetDevice(ctx->device));
+    double *d_c = nullptr, *d_k = nullptr;
+    int rc = abs_faces_eval(ctx, face_type, gauss_order, n_faces, face_nodes, face_elem, face_dir, perp, n_unique, grp_ptr, grp_entry,
+                            p0, p1, stiff, &d_c, &d_k);
+    if (rc == SC_OK) rc = add_sorted_entries(ctx, SC_MAT_C, n_unique, r, c, &d_c);
+    if (rc == SC_OK) rc = add_sorted_entries(ctx, SC_MAT_K, n_unique, r, c, &d_k);
+    sc_free(&d_c); sc_free(&d_k);
     return rc;
 }
 

@@ -233,6 +233,10 @@ int tl_central_difference(sc_ctx* ctx, double dt, int64_t t0, int64_t n_steps, i
 int tl_bathe(sc_ctx* ctx, double dt, int64_t t0, int64_t n_steps, int64_t oi, double rtol, int maxit, int64_t n_out, double* u_out,
              double* v_out, double* a_out, sc_stats* st);
 int tl_static(sc_ctx* ctx, int64_t t0, int64_t n_steps, int64_t oi, double rtol, int maxit, int64_t n_out, double* u_out, sc_stats* st);
+// absorb.cu: face matrices, dashpot / spring coefficients and the ordered per-key sums -> device arrays [n_unique]
+int abs_faces_eval(sc_ctx* ctx, int face_type, int order, int64_t n_faces, const int32_t* face_nodes, const int32_t* face_elem,
+                   const int32_t* face_dir, const uint8_t* perp, int64_t n_unique, const int64_t* grp_ptr, const int64_t* grp_entry,
+                   double p0, double p1, double stiff, double** d_csum, double** d_ksum);
 // srf.cu
 int srf_sample(sc_ctx* ctx, int64_t n_points, const double* pos, int n_modes, const double* k, const double* z1, const double* z2,
                double scale, double mean, int lognormal, double* out, double* seconds);

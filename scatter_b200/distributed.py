@@ -9,9 +9,9 @@ exchange per matrix-vector product, and sends the stored rows of its own dofs to
 `data.pickle` / VTK files as the serial entry point.  Host-side plumbing (NCCL id, result gather) goes through a gloo
 group of `torch.distributed`; the data path between GPUs is the library's own NCCL communicator (`sc_dist_init`).
 
-Status: the pieces (partitioning, halo plan, schedule localisation, result gather) are covered by the world_size 2/3 gloo
-tests on CPU and the library calls are the sequence `tests/test_gpu_multirank.py` runs on two GPUs; the entry point as a
-whole is exercised by `tests/test_gpu_multirank.py::test_scatter_distributed_matches_serial` (needs >= 2 GPUs).
+Tests: the pieces (partitioning, halo plan, schedule localisation, result gather) run in the world_size 2/3 gloo tests on
+CPU; the entry point as a whole is compared with the single-domain oracle on two GPUs in
+`tests/test_gpu_multirank.py::test_scatter_distributed_matches_serial` (Newmark and central difference, absorbing faces).
 """
 from __future__ import annotations
 

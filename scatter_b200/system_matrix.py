@@ -101,63 +101,107 @@ def _absorbing_faces(data):
     return out
 
 
-def absorbing_entries(data, E, nu, rho, order: int, viscous, stiff: float):
-    """COO entries of C_abs and K_abs/stiff, duplicates summed in face order (system_matrix.py:256-376).
+class AbsorbingPlan:
+    """Index plan of the absorbing faces (all integer / ordering work of system_matrix.py:274-358; no arithmetic).
 
-    quad4 faces (hexa8 meshes) are processed with whole-array numpy so that large boxes stay cheap; other face types use
-    the per-face path."""
+    faces_nodes (nf, nl) node rows in the reference's face-node order (utils.py:141-175), elem (nf,), direction (nf,),
+    i1 (nf, nl) sorted equation numbers of the face dofs -- paired positionally with the face-node order, as the reference
+    does -- perp (nf, nl) 1 where the dof is perpendicular to its boundary (BC_dir == 1: compression wave, else shear),
+    and the grouping of the nf*nl*nl entries (face, a, b) -> key (i1[a], i1[b]) in face order: rows/cols (sorted unique
+    keys), grp_ptr / grp_entry (entry ids of every key, ascending = the order in which the reference accumulates)."""
+
+    def __init__(self, face_type, nodes, elem, direction, i1, perp, n_eq):
+        self.face_type = face_type
+        self.nodes = np.ascontiguousarray(nodes, dtype=np.int32)
+        self.elem = np.ascontiguousarray(elem, dtype=np.int32)
+        self.direction = np.ascontiguousarray(direction, dtype=np.int32)
+        self.i1 = np.ascontiguousarray(i1, dtype=np.int64)
+        self.perp = np.ascontiguousarray(perp, dtype=np.uint8)
+        nf, nl = self.i1.shape
+        r = np.repeat(self.i1[:, :, None], nl, axis=2).ravel()
+        c = np.repeat(self.i1[:, None, :], nl, axis=1).ravel()
+        key = r * int(n_eq) + c
+        order = np.argsort(key, kind="stable")                    # entries of one key stay in face order
+        uniq, first = np.unique(key[order], return_index=True)
+        self.rows = (uniq // int(n_eq)).astype(np.int64)
+        self.cols = (uniq % int(n_eq)).astype(np.int64)
+        self.grp_ptr = np.append(first, len(key)).astype(np.int64)
+        self.grp_entry = order.astype(np.int64)
+
+    def restrict_rows(self, owned_rows):
+        """Keep the keys whose row is in `owned_rows` (domain-decomposed runs: ghost rows belong to another rank)."""
+        keep = np.isin(self.rows, np.asarray(owned_rows))
+        lens = np.diff(self.grp_ptr)[keep]
+        sel = np.concatenate([np.arange(a, b) for a, b in zip(self.grp_ptr[:-1][keep], self.grp_ptr[1:][keep])]) if keep.any() \
+            else np.zeros(0, dtype=np.int64)
+        self.grp_entry = self.grp_entry[sel]
+        self.grp_ptr = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+        self.rows, self.cols = self.rows[keep], self.cols[keep]
+        return self
+
+
+def absorbing_plan(data):
+    """-> AbsorbingPlan or None when the model has no absorbing face."""
     faces = _absorbing_faces(data)
-    cdict, kdict = {}, {}
     if not faces:
-        return cdict, kdict
-    dim, nl = data.dimension, data.nb_nodes_lower_elem
-    if dim == 2:
-        raise SystemExit("Absorbing boundaries not implemented for 2D yet")
+        return None
+    if data.dimension == 2:
+        raise SystemExit("Absorbing boundaries not implemented for 2D yet")      # system_matrix.py:324-326
     eq = data.eq_nb_dof
     el = np.array([f[0] for f in faces]); dr = np.array([f[1] for f in faces]); nodes = np.array([f[2] for f in faces])
     nf = len(faces)
-    Ec = E[el] * (1 - nu[el]) / ((1 + nu[el]) * (1 - 2 * nu[el]))
-    G = E[el] / (2 * (1 + nu[el]))
-    vp, vs = np.sqrt(Ec / rho[el]), np.sqrt(G / rho[el])
-    # unit face matrices in the reference's face-node order
-    S = np.empty((nf, nl, nl))
     if data.lower_element_type == "quad4":
+        # whole-array version of utils.py:141-175 for four-node faces: counter-clockwise by angle about the first lowest point
         keep = np.array([[1, 2], [0, 2], [0, 1]])[dr]              # in-plane coordinate columns after dropping `d`
         xy = np.take_along_axis(data.nodes[nodes, 1:], keep[:, None, :], axis=2)     # (nf, 4, 2)
-        low = np.argmin(xy[:, :, 1], axis=1)                        # first lowest point
+        low = np.argmin(xy[:, :, 1], axis=1)
         ref = xy[np.arange(nf), low]
         ang = np.arctan2(xy[:, :, 1] - ref[:, None, 1], xy[:, :, 0] - ref[:, None, 0])
-        srt = np.argsort(ang, axis=1, kind="stable")
-        xy = np.take_along_axis(xy, srt[:, :, None], axis=1)        # counter-clockwise from the lowest point
-        N, dN, w = _lib.shape_table("quad4", order)
-        J = np.einsum("gad,fak->fgdk", dN, xy)
-        det = J[..., 0, 0] * J[..., 1, 1] - J[..., 0, 1] * J[..., 1, 0]
-        S = np.einsum("ga,gb,fg->fab", N, N, det * w[None, :])
+        ordered = np.take_along_axis(nodes, np.argsort(ang, axis=1, kind="stable"), axis=1)
     else:
+        ordered = np.empty_like(nodes)
         for k, (e, d, nd) in enumerate(faces):
-            S[k] = face_mass(data.lower_element_type, order, gmsh_face_order(np.delete(data.nodes[nd, 1:], d, axis=1)))
-    # equation numbers of the face dofs, sorted (the reference pairs them with the face-node order as is)
-    i1 = np.sort(eq[nodes, dr[:, None]], axis=1).astype(np.int64)  # (nf, nl)
+            pts = np.delete(data.nodes[nd, 1:], d, axis=1)
+            srt = gmsh_face_order(pts)
+            perm = [int(np.where((pts == q).all(axis=1))[0][0]) for q in srt]
+            ordered[k] = nd[perm]
+    i1 = np.sort(eq[nodes, dr[:, None]], axis=1).astype(np.int64)  # (nf, nl): sorted, not in face-node order (reference quirk)
     eqi = np.where(np.isnan(eq), -1, eq).astype(np.int64)
     dir_of_eq = np.zeros(data.number_eq, dtype=np.int64)
     dir_of_eq[eqi[eqi >= 0]] = np.asarray(data.BC_dir)[eqi >= 0]
-    perp = dir_of_eq[i1] == 1
+    return AbsorbingPlan(data.lower_element_type, ordered, el, dr, i1, dir_of_eq[i1] == 1, data.number_eq)
+
+
+def absorbing_entries(data, E, nu, rho, order: int, viscous, stiff: float):
+    """Host evaluation of an `absorbing_plan` -> ({(row, col): C_abs value}, {(row, col): K_abs value / stiff}).
+
+    CPU tests use it to pin the index plan against the oracle; the product path (`GenerateMatrix.absorbing_boundaries`)
+    hands the same plan to the device (`sc_add_absorbing_faces`), which does this arithmetic in `k_abs_faces`."""
+    plan = absorbing_plan(data)
+    if plan is None:
+        return {}, {}
+    el, dr = plan.elem, plan.direction
+    nf, nl = plan.i1.shape
+    Ec = E[el] * (1 - nu[el]) / ((1 + nu[el]) * (1 - 2 * nu[el]))
+    G = E[el] / (2 * (1 + nu[el]))
+    vp, vs = np.sqrt(Ec / rho[el]), np.sqrt(G / rho[el])
+    keep = np.array([[1, 2], [0, 2], [0, 1]])[dr]
+    xy = np.take_along_axis(data.nodes[plan.nodes, 1:], keep[:, None, :], axis=2)   # (nf, nl, 2) in face-node order
+    N, dN, w = _lib.shape_table(plan.face_type, order)
+    J = np.einsum("gad,fak->fgdk", dN, xy)
+    det = J[..., 0, 0] * J[..., 1, 1] - J[..., 0, 1] * J[..., 1, 0]
+    S = np.einsum("ga,gb,fg->fab", N, N, det * w[None, :])
+    perp = plan.perp.astype(bool)
     fct = np.where(perp, (viscous[0] * rho[el] * vp)[:, None], (viscous[1] * rho[el] * vs)[:, None])
     fct2 = np.where(perp, Ec[:, None], G[:, None])
-    r = np.repeat(i1[:, :, None], nl, axis=2).ravel()
-    c = np.repeat(i1[:, None, :], nl, axis=1).ravel()
     cv = (S * fct[:, None, :]).ravel()
     kv = (np.abs(S) * fct2[:, None, :]).ravel()
-    # sum duplicates in face order (np.add.at is sequential) on the unique key set
-    key = r * data.number_eq + c
-    uniq, inv = np.unique(key, return_inverse=True)
-    csum = np.zeros(len(uniq)); ksum = np.zeros(len(uniq))
-    np.add.at(csum, inv, cv)
-    np.add.at(ksum, inv, kv)
-    keys = [(int(u // data.number_eq), int(u % data.number_eq)) for u in uniq]
-    cdict = dict(zip(keys, csum))
-    kdict = dict(zip(keys, ksum / stiff))
-    return cdict, kdict
+    grp = np.repeat(np.arange(len(plan.rows)), np.diff(plan.grp_ptr))
+    csum = np.zeros(len(plan.rows)); ksum = np.zeros(len(plan.rows))
+    np.add.at(csum, grp, cv[plan.grp_entry])                      # sequential: face order inside every key
+    np.add.at(ksum, grp, kv[plan.grp_entry])
+    keys = list(zip(plan.rows.tolist(), plan.cols.tolist()))
+    return dict(zip(keys, csum)), dict(zip(keys, ksum / stiff))
 
 
 class GenerateMatrix:
@@ -187,19 +231,16 @@ class GenerateMatrix:
         self._pattern = None
 
     def absorbing_boundaries(self, data, material: dict, parameters_viscous: list, parameters_stiff: float, owned_rows=None) -> None:
-        """system_matrix.py:256-376 -- Lysmer-Kuhlemeyer dashpots into C, springs into K.  `owned_rows` (domain-decomposed
-        runs): local equation numbers whose rows this rank assembles; entries of ghost rows are left to their owner."""
-        E, nu, rho = self._props if self._props is not None else resolve_element_properties(data, material)
-        cdict, kdict = absorbing_entries(data, E, nu, rho, self.order, parameters_viscous, parameters_stiff)
-        if cdict:
-            keys = np.array(list(cdict.keys()), dtype=np.int64)
-            cv, kv = np.array(list(cdict.values())), np.array([kdict[tuple(k)] for k in keys])
-            if owned_rows is not None:
-                keep = np.isin(keys[:, 0], np.asarray(owned_rows))
-                keys, cv, kv = keys[keep], cv[keep], kv[keep]
-            if len(keys):
-                self.ctx.add_entries(_lib.MAT_C, keys[:, 0], keys[:, 1], cv)
-                self.ctx.add_entries(_lib.MAT_K, keys[:, 0], keys[:, 1], kv)
+        """system_matrix.py:256-376 -- Lysmer-Kuhlemeyer dashpots into C, springs into K.  The host only plans (which faces,
+        node order, equation numbers); face matrices, wave speeds and the ordered accumulation run on the device.
+        `owned_rows` (domain-decomposed runs): local equations whose rows this rank assembles."""
+        plan = absorbing_plan(data)
+        if plan is None:
+            return
+        if owned_rows is not None:
+            plan.restrict_rows(owned_rows)
+        if len(plan.rows):
+            self.ctx.add_absorbing_faces(plan, self.order, parameters_viscous[0], parameters_viscous[1], parameters_stiff)
 
     def damping_Rayleigh(self, damp) -> None:
         """system_matrix.py:166-198 -- C = C + c0 M + c1 K (applied on the fly on the device)."""

@@ -5,7 +5,10 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from scatter_b200 import _lib, boxmesh, system_matrix
 
-for et, s, dt in (("hexa8", 128, 5e-4), ("hexa8", 128, 2e-3), ("hexa20", 48, 5e-4)):
+# usage: newmark_probe.py [element_type size dt]   (default: three small boxes)
+CASES = [(sys.argv[1], int(sys.argv[2]), float(sys.argv[3]))] if len(sys.argv) > 3 else \
+    [("hexa8", 128, 5e-4), ("hexa8", 128, 2e-3), ("hexa20", 48, 5e-4)]
+for et, s, dt in CASES:
     model = boxmesh.box_model(s, s, s, 0.5, et)
     ne = len(model.elem)
     mx = system_matrix.GenerateMatrix(model.number_eq, 2)
@@ -19,6 +22,7 @@ for et, s, dt in (("hexa8", 128, 5e-4), ("hexa8", 128, 2e-3), ("hexa20", 48, 5e-
     nt = 16
     ctx.set_load_schedule(np.arange(nt + 1, dtype=np.int64), np.full(nt, d, dtype=np.int64), -1000.0 * np.minimum(np.arange(nt) / 4.0, 1.0))
     ctx.set_state(None, None)
+    print(f"device memory after assembly: {ctx.device_info()['free_mem'] / 1e9:.1f} GB free of {ctx.device_info()['total_mem'] / 1e9:.1f} GB", flush=True)
     for rtol in (1e-10, 1e-14):
         ctx.set_state(None, None)
         ctx.run_newmark(dt, 0, 2, 1, rtol=rtol, store=False)

@@ -184,6 +184,13 @@ def test_absorbing_entries_of_a_partition_cover_the_global_ones(golden_meshes, o
         l2g = np.full(dom.model.number_eq, -1, dtype=np.int64)
         l2g[leq[leq >= 0]] = geq[leq >= 0]
         owned = set(dom.owned_eq.tolist())
+        plan = system_matrix.absorbing_plan(dom.model)                                  # what the device path receives
+        if plan is None:
+            assert not cl
+        else:
+            plan.restrict_rows(dom.owned_eq)
+            assert set(zip(plan.rows.tolist(), plan.cols.tolist())) == {k for k in cl if k[0] in owned}
+            assert plan.grp_ptr[0] == 0 and plan.grp_ptr[-1] == len(plan.grp_entry) and (np.diff(plan.grp_ptr) > 0).all()
         for (i, j), v in cl.items():
             if i in owned:
                 key = (int(l2g[i]), int(l2g[j]))
