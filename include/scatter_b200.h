@@ -102,7 +102,8 @@ int sc_set_materials(sc_ctx* ctx, const double* young, const double* poisson, co
 int sc_build_pattern(sc_ctx* ctx, int64_t* nnz_out);
 int sc_get_pattern(sc_ctx* ctx, int64_t* rowptr /*[n_eq+1]*/, int32_t* col /*[nnz]*/);
 /* sizes of the device structures: out[0] nnz, [1] entries of the node-blocked column lists, [2] n_nodes, [3] longest row,
- * [4] most neighbour nodes, [5] most elements per node, [6] 1 if the node-blocked SpMV is in use, [7] reserved */
+ * [4] most neighbour nodes, [5] most elements per node, [6] 1 if the node-blocked SpMV is in use, [7] entries of the
+ * column-pattern dictionary (nodes whose relative column list is in it have no explicit list: [1] counts the rest) */
 int sc_pattern_stats(sc_ctx* ctx, int64_t* out8);
 
 /* ---- element integration + deterministic assembly (GenerateMatrix.generate_stiffness_and_mass,

@@ -242,7 +242,7 @@ class Context:
     def pattern_stats(self) -> dict:
         out = np.zeros(8, dtype=np.int64)
         self._ck(self.lib.sc_pattern_stats(self.h, _ptr(out)))
-        keys = ("nnz", "node_col_entries", "n_nodes", "max_row_len", "max_node_neighbours", "max_elems_per_node", "node_blocked")
+        keys = ("nnz", "node_col_entries", "n_nodes", "max_row_len", "max_node_neighbours", "max_elems_per_node", "node_blocked", "dict_patterns")
         return {k: int(v) for k, v in zip(keys, out)}
 
     def assemble(self, order: int, flags: int = ASM_K | ASM_M_FULL) -> float:

@@ -40,7 +40,7 @@ int upload(sc_ctx* ctx, T** dst, const T* src, size_t n) {
 void free_pattern(sc_ctx* c) {
     pcg_graph_drop(c);
     sc_free(&c->d_n2e_ptr); sc_free(&c->d_n2e); sc_free(&c->d_nbr_ptr); sc_free(&c->d_nbr); sc_free(&c->d_nbr_off); sc_free(&c->d_nbr_free);
-    sc_free(&c->d_node_rl); sc_free(&c->d_node_row0); sc_free(&c->d_rowptr); sc_free(&c->d_col); sc_free(&c->d_nd); sc_free(&c->d_ncol); sc_free(&c->d_pair_pos); sc_free(&c->d_pair_al);
+    sc_free(&c->d_node_rl); sc_free(&c->d_node_row0); sc_free(&c->d_rowptr); sc_free(&c->d_col); sc_free(&c->d_nd); sc_free(&c->d_ncol); sc_free(&c->d_dict); c->n_dict = 0; sc_free(&c->d_pair_pos); sc_free(&c->d_pair_al);
     sc_free(&c->d_K); sc_free(&c->d_M); sc_free(&c->d_Ml); sc_free(&c->d_Khat); sc_free(&c->d_Khat2);
     sc_free(&c->d_cabs_rowid); sc_free(&c->d_cabs_rptr); sc_free(&c->d_cabs_col); sc_free(&c->d_cabs_slot); sc_free(&c->d_cabs_val);
     c->cabs_n = c->cabs_rows = 0;
@@ -123,6 +123,8 @@ int sc_create(int device, sc_ctx** out) {
     ctx->no_small_pcg = no_small && no_small[0] == '1';
     const char* no_graph = getenv("SCATTER_B200_NO_GRAPH");
     ctx->no_graph = no_graph && no_graph[0] == '1';
+    const char* no_dict = getenv("SCATTER_B200_NO_DICT");
+    ctx->no_dict = no_dict && no_dict[0] == '1';
     const char* pair_asm = getenv("SCATTER_B200_PAIR_ASSEMBLY");
     ctx->force_pair_assembly = pair_asm && pair_asm[0] == '1';
     *out = ctx;
@@ -255,7 +257,7 @@ int sc_get_pattern(sc_ctx* ctx, int64_t* rowptr, int32_t* col) {
 int sc_pattern_stats(sc_ctx* ctx, int64_t* out8) {
     if (!ctx || !ctx->have_pattern || !out8) return sc_fail(ctx, SC_ERR_STATE, "sc_build_pattern must be called first");
     out8[0] = ctx->nnz; out8[1] = ctx->ncol_total; out8[2] = ctx->n_nodes; out8[3] = ctx->max_rl; out8[4] = ctx->max_nbr;
-    out8[5] = ctx->max_valence; out8[6] = la_node_usable(ctx) ? 1 : 0; out8[7] = 0;
+    out8[5] = ctx->max_valence; out8[6] = la_node_usable(ctx) ? 1 : 0; out8[7] = ctx->n_dict;
     return SC_OK;
 }
 

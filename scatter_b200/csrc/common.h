@@ -58,12 +58,15 @@ struct sc_ctx {
     int32_t* d_node_rl = nullptr;   // [n_nodes] row length of the node's rows (0 if inactive)
     int64_t* d_node_row0 = nullptr; // [n_nodes+1] number of free dofs before the node (= first row of the node)
     // node-blocked column structure for the time loop: all rows of a node share one column list
-    struct NodeDesc { int64_t val_off; int64_t col_off; int32_t row0; int32_t len_nfree; };   // len | nfree << 24
+    struct NodeDesc { int64_t val_off; int64_t col_off; int32_t row0; int32_t len_nfree; };   // len | pattern id << 16 | nfree << 24
     NodeDesc* d_nd = nullptr;       // [n_nodes + 32] (padded with empty descriptors)
     int32_t* d_ncol = nullptr;      // [sum node_rl] column list per node
     uint8_t* d_pair_pos = nullptr;  // [n_pairs*nne] position of every element node in the pair's node neighbour list (or null)
     uint8_t* d_pair_al = nullptr;   // [n_pairs] local index of the pair's node in its element
     int64_t ncol_total = 0;
+    int32_t* d_dict = nullptr;      // [n_dict*dict_stride] most frequent relative column lists (node_dict.cu); nodes with one of
+    int n_dict = 0, dict_stride = 0;   // them carry its id in their descriptor and have no explicit list in d_ncol
+    bool no_dict = false;           // SCATTER_B200_NO_DICT=1: keep every explicit node column list
     int max_nbr = 0, max_rl = 0, max_valence = 0;   // max neighbours / row length / elements per node
 
     // dof-level CSR
@@ -237,6 +240,10 @@ int tl_static(sc_ctx* ctx, int64_t t0, int64_t n_steps, int64_t oi, double rtol,
 int abs_faces_eval(sc_ctx* ctx, int face_type, int order, int64_t n_faces, const int32_t* face_nodes, const int32_t* face_elem,
                    const int32_t* face_dir, const uint8_t* perp, int64_t n_unique, const int64_t* grp_ptr, const int64_t* grp_entry,
                    double p0, double p1, double stiff, double** d_csum, double** d_ksum);
+// node_dict.cu / spmv_node.cu
+constexpr int SC_DICT_MAX = 32;
+int node_dict_build(sc_ctx* ctx);
+int64_t node_dict_room(sc_ctx* ctx);
 // srf.cu
 int srf_sample(sc_ctx* ctx, int64_t n_points, const double* pos, int n_modes, const double* k, const double* z1, const double* z2,
                double scale, double mean, int lognormal, double* out, double* seconds);

@@ -379,6 +379,7 @@ int sc_pattern_build(sc_ctx* ctx) {
     }
     SC_CUDA(ctx, cudaStreamSynchronize(st));
     sc_free(&d_cnt); sc_free(&d_tmp64); sc_free(&d_flag);
+    SC_TRY(node_dict_build(ctx));     // frequent relative column lists -> dictionary, explicit lists only for the rest
     ctx->have_pattern = true;
     return SC_OK;
 }

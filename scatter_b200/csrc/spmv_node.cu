@@ -58,7 +58,7 @@ __global__ void __launch_bounds__(NB_THREADS, 2)
 k_spmv_node(const NodeDesc* __restrict__ nd, const int32_t* __restrict__ ncol, const double* __restrict__ va,
             const double* __restrict__ xa, double* __restrict__ y, const double* __restrict__ inv_d,
             const double* __restrict__ alpha, double* __restrict__ partial, int64_t n_nodes, int64_t n_rows, int64_t n_tiles,
-            int cap_v, int cap_c) {
+            int cap_v, int cap_c, const int32_t* __restrict__ dict, int n_dict, int dict_stride) {
     constexpr int NB_NODES = NB_WARPS * NB_NPW;      // nodes per tile; NB_NPW nodes per consumer warp (gathers in flight together)
     constexpr int NB_VT = 3 * NB_NODES + 8;          // vector slots per tile (rows + alignment), multiple of 2
     constexpr int NVEC = (MODE == 2) ? 4 : (MODE == 3 ? 1 : 0);
@@ -70,6 +70,7 @@ k_spmv_node(const NodeDesc* __restrict__ nd, const int32_t* __restrict__ ncol, c
     int* s_col = reinterpret_cast<int*>(s_nd + (size_t)STAGES * NB_NODES);       // [STAGES][cap_c]
     uint64_t* bar_full = reinterpret_cast<uint64_t*>(s_col + (size_t)STAGES * cap_c);
     uint64_t* bar_empty = bar_full + STAGES;
+    int* s_dict = reinterpret_cast<int*>(bar_empty + STAGES);                     // [n_dict][dict_stride] relative column lists (node_dict.cu)
     __shared__ double red[NB_WARPS];
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -80,6 +81,7 @@ k_spmv_node(const NodeDesc* __restrict__ nd, const int32_t* __restrict__ ncol, c
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    for (int t = threadIdx.x; t < n_dict * dict_stride; t += NB_THREADS) s_dict[t] = dict[t];
     __syncthreads();
 
     const int64_t G = gridDim.x;
@@ -120,7 +122,7 @@ k_spmv_node(const NodeDesc* __restrict__ nd, const int32_t* __restrict__ ncol, c
                     tma_load_1d(s_nd + (size_t)stage * NB_NODES, nd + tj * NB_NODES, db, &bar_full[stage]);
                     if (has) {
                         tma_load_1d(s_val + (size_t)stage * cap_v, va + vs, vb, &bar_full[stage]);
-                        tma_load_1d(s_col + (size_t)stage * cap_c, ncol + cs, cb, &bar_full[stage]);
+                        if (cb) tma_load_1d(s_col + (size_t)stage * cap_c, ncol + cs, cb, &bar_full[stage]);   // empty when the dictionary covers the tile
                         double* sv = s_vec + (size_t)stage * NV1 * NB_VT;
                         if (MODE == 2) {
                             tma_load_1d(sv, alpha + rs, rb, &bar_full[stage]);
@@ -143,7 +145,7 @@ k_spmv_node(const NodeDesc* __restrict__ nd, const int32_t* __restrict__ ncol, c
             const NodeDesc* snd = s_nd + (size_t)stage * NB_NODES;
             const NodeDesc d0 = snd[0];
             const int myr = lane >> 3;                       // lanes 0, 8, 16 own rows 0, 1, 2 of a node after the reduction
-            int L[NB_NPW], nfree[NB_NPW], row0[NB_NPW];
+            int L[NB_NPW], nfree[NB_NPW], row0[NB_NPW], cadd[NB_NPW];
             const double* sv[NB_NPW];
             const int* sc[NB_NPW];
             double e_al[NB_NPW], e_id[NB_NPW], e_x[NB_NPW], e_y[NB_NPW];
@@ -153,11 +155,15 @@ k_spmv_node(const NodeDesc* __restrict__ nd, const int32_t* __restrict__ ncol, c
             for (int q = 0; q < NB_NPW; ++q) {
                 const NodeDesc d = snd[warp * NB_NPW + q];
                 nfree[q] = d.len_nfree >> 24;
-                L[q] = nfree[q] > 0 ? (d.len_nfree & 0xffffff) : 0;
+                L[q] = nfree[q] > 0 ? (d.len_nfree & 0xffff) : 0;
                 row0[q] = d.row0;
                 maxL = max(maxL, L[q]);
                 sv[q] = s_val + (size_t)stage * cap_v + (int)(d.val_off - (d0.val_off & ~(int64_t)1)) + lane;
-                sc[q] = s_col + (size_t)stage * cap_c + (int)(d.col_off - (d0.col_off & ~(int64_t)3)) + lane;
+                // columns: the node's explicit list in the ring, or row0 + a relative list of the dictionary (bits 16..23: pattern id)
+                const int pid = (d.len_nfree >> 16) & 0xff;
+                sc[q] = pid ? s_dict + (pid - 1) * dict_stride + lane
+                            : s_col + (size_t)stage * cap_c + (int)(d.col_off - (d0.col_off & ~(int64_t)3)) + lane;
+                cadd[q] = pid ? d.row0 : 0;
                 // rows without entries (ghost nodes of a domain decomposition) still get y = 0: PCG reads q on every local
                 // row; the fused central-difference step leaves them alone (their u comes from the halo exchange)
                 owner[q] = (lane & 7) == 0 && myr < nfree[q] && (L[q] > 0 || MODE != 2);
@@ -183,7 +189,7 @@ k_spmv_node(const NodeDesc* __restrict__ nd, const int32_t* __restrict__ ncol, c
                         const bool ok = k + lane < L[q];
                         c[q][u] = 0; v0[q][u] = 0.0; v1[q][u] = 0.0; v2[q][u] = 0.0;
                         if (ok) {
-                            c[q][u] = sc[q][k];
+                            c[q][u] = sc[q][k] + cadd[q];
                             v0[q][u] = sv[q][k];
                             if (nfree[q] > 1) v1[q][u] = sv[q][L[q] + k];
                             if (nfree[q] > 2) v2[q][u] = sv[q][2 * L[q] + k];
@@ -347,7 +353,7 @@ k_spmv_node_pipe(const NodeDesc* __restrict__ nd, const int32_t* __restrict__ nc
             const NodeDesc* snd = s_nd + (size_t)stage * NB_NODES;
             const NodeDesc d0 = snd[0], d = snd[warp];
             const int nfree = d.len_nfree >> 24;
-            const int L = nfree > 0 ? (d.len_nfree & 0xffffff) : 0;
+            const int L = nfree > 0 ? (d.len_nfree & 0xffff) : 0;
             const int* sc = s_col + (size_t)stage * cap_c + (int)(d.col_off - (d0.col_off & ~(int64_t)3)) + lane;
 #pragma unroll
             for (int u = 0; u < U; ++u) {
@@ -363,7 +369,7 @@ k_spmv_node_pipe(const NodeDesc* __restrict__ nd, const int32_t* __restrict__ nc
             const NodeDesc* snd = s_nd + (size_t)stage * NB_NODES;
             const NodeDesc d0 = snd[0], d = snd[warp];
             const int nfree = d.len_nfree >> 24;
-            const int L = nfree > 0 ? (d.len_nfree & 0xffffff) : 0;
+            const int L = nfree > 0 ? (d.len_nfree & 0xffff) : 0;
             const double* sv = s_val + (size_t)stage * cap_v + (int)(d.val_off - (d0.val_off & ~(int64_t)1)) + lane;
             const bool owner = (lane & 7) == 0 && myr < nfree && (L > 0 || MODE != 2);
             double e_al = 0.0, e_id = 0.0, e_x = 0.0, e_y = 0.0;
@@ -431,11 +437,13 @@ k_spmv_node_pipe(const NodeDesc* __restrict__ nd, const int32_t* __restrict__ nc
 }
 
 struct NodeCfg { int cap_v, cap_c, stages, npw; size_t bytes; bool pipe; };
+constexpr size_t NODE_SMEM_MAX = 112 * 1024;       // two CTAs per SM
 
+// ring configuration (dictionary not counted: `node_dict_room` sizes the dictionary into what is left)
 bool node_cfg(sc_ctx* ctx, NodeCfg& c) {
     if (ctx->force_no_node || !ctx->d_nd || ctx->max_rl <= 0 || ctx->dim > 3) return false;
     c.pipe = false;
-    if (ctx->max_rl <= 96 && !ctx->force_no_pipe) {
+    if (ctx->max_rl <= 96 && !ctx->force_no_pipe && ctx->n_dict == 0) {
         // software-pipelined kernel: one node per warp, 8-node tiles, as many stages as fit (needs >= 4 for the look-ahead of 2)
         const int nodes = NB_WARPS, vt = 3 * nodes + 8;
         c.cap_v = (nodes * 3 * ctx->max_rl + 2 + 15) & ~15;
@@ -467,12 +475,13 @@ int launch_node(sc_ctx* ctx, const NodeCfg& c, const double* va, const double* x
     constexpr int NODES = NB_WARPS * NPW;
     const int64_t n_tiles = (ctx->n_nodes + NODES - 1) / NODES;
     auto kern = k_spmv_node<MODE, STAGES, NPW>;
-    SC_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.bytes));
+    const size_t bytes = c.bytes + (size_t)ctx->n_dict * ctx->dict_stride * sizeof(int32_t);
+    SC_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
     unsigned grid = (unsigned)std::min<int64_t>(n_tiles, (int64_t)ctx->sm_count * 2);
     if (grid == 0) grid = 1;
     if (nblocks_out) *nblocks_out = grid;
-    kern<<<grid, NB_THREADS, c.bytes, ctx->stream>>>(ctx->d_nd, ctx->d_ncol, va, xa, y, inv_d, alpha, partial, ctx->n_nodes, ctx->n_eq,
-                                                     n_tiles, c.cap_v, c.cap_c);
+    kern<<<grid, NB_THREADS, bytes, ctx->stream>>>(ctx->d_nd, ctx->d_ncol, va, xa, y, inv_d, alpha, partial, ctx->n_nodes, ctx->n_eq,
+                                                   n_tiles, c.cap_v, c.cap_c, ctx->d_dict, ctx->n_dict, ctx->dict_stride);
     SC_CHECK_LAUNCH(ctx);
     return SC_OK;
 }
@@ -516,6 +525,16 @@ int launch_mode(sc_ctx* ctx, const double* va, const double* xa, double* y, cons
 bool la_node_usable(sc_ctx* ctx) {
     NodeCfg c;
     return node_cfg(ctx, c);
+}
+// shared memory (bytes) the column dictionary may take without changing the ring configuration or the two CTAs per SM
+int64_t node_dict_room(sc_ctx* ctx) {
+    NodeCfg c;
+    const int keep = ctx->n_dict;
+    ctx->n_dict = 0;
+    const bool ok = node_cfg(ctx, c) && !c.pipe;
+    ctx->n_dict = keep;
+    if (!ok || c.bytes + 64 >= NODE_SMEM_MAX) return 0;
+    return (int64_t)(NODE_SMEM_MAX - c.bytes - 64);
 }
 int la_node_spmv(sc_ctx* ctx, const double* vals, const double* x, double* y) {
     return launch_mode<0>(ctx, vals, x, y, nullptr, nullptr, nullptr, nullptr);

@@ -35,6 +35,10 @@ def test_pattern_size(big):
     assert model.number_eq == ctx.n_eq
     assert 0.95 * 81 * ctx.n_eq < nnz < 81 * ctx.n_eq
     assert nnz > 2 ** 31 or s < 255            # the full-size pattern needs 64-bit row pointers
+    st = ctx.pattern_stats()
+    if s >= 64:
+        # the column dictionary covers the interior: fewer than 10 % of the node column entries stay explicit
+        assert st["dict_patterns"] > 0 and st["node_col_entries"] < 0.1 * nnz / 3
 
 
 def test_symmetry_and_translation_null_space(big):

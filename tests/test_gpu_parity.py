@@ -302,6 +302,50 @@ def test_box_mesh_random_field(oracle, tmp_path):
         assert np.abs(mx.ctx.get_values(1) - Mo.data).max() <= TOL_MAT * np.abs(Mo.data).max()
 
 
+@pytest.mark.parametrize("case", ["cube", "cube_abs", "rose_2D_side", "column_3D_tetra4", "box"])
+def test_column_dictionary_is_bitwise_neutral(case, golden_meshes, monkeypatch, tmp_path):
+    """node_dict.cu replaces the explicit column lists of nodes with a frequent relative list by a dictionary id: SpMV, the
+    fused central-difference step and a Newmark stage must give bit-identical results with and without it."""
+    from scatter_b200 import boxmesh, solvers, system_matrix
+    out = {}
+    for mode in ("dict", "explicit"):
+        if mode == "explicit":
+            monkeypatch.setenv("SCATTER_B200_NO_DICT", "1")
+        if case == "box":
+            model = boxmesh.box_model(14, 9, 11, 0.5, "hexa8")
+            model.connectivities()
+            ne = len(model.elem)
+            mx = system_matrix.GenerateMatrix(model.number_eq, 2)
+            mx.generate_stiffness_and_mass(model, None, elem_props=(boxmesh.lognormal_young(ne), np.full(ne, 0.2), np.full(ne, 1500.0)))
+            mx.damping_Rayleigh([1, 0.01, 30, 0.01])
+            m = model
+        else:
+            fn, bc = cases.MATRIX_CASES[case]
+            m, mx = build(golden_meshes[fn], bc, cases.case_materials(case), cases.settings(damping=[1, 0.01, 30, 0.01]))
+        ctx = mx.ctx
+        st = ctx.pattern_stats()
+        n = m.number_eq
+        x = probe_vector(n)
+        y = ctx.spmv(0, x)
+        ptr = np.arange(41, dtype=np.int64)
+        ctx.set_load_schedule(ptr, np.full(40, n // 2, dtype=np.int64), np.full(40, -1000.0))
+        ctx.set_state(None, None)
+        ucd, vcd, _, _ = ctx.run_central_difference(1e-5, 0, 30, 10)
+        ctx.set_state(None, None)
+        unm, _, anm, _ = ctx.run_newmark(1e-3, 0, 6, 3)
+        out[mode] = (st, y, ucd, vcd, unm, anm)
+        ctx.close()
+        if mode == "explicit":
+            monkeypatch.delenv("SCATTER_B200_NO_DICT")
+    sd, se = out["dict"][0], out["explicit"][0]
+    assert se["dict_patterns"] == 0 and sd["nnz"] == se["nnz"]
+    if case in ("cube", "cube_abs", "box"):
+        assert sd["node_blocked"] == 1 and sd["dict_patterns"] > 0 and sd["node_col_entries"] < se["node_col_entries"]
+    for a, b in zip(out["dict"][1:], out["explicit"][1:]):
+        assert np.isfinite(a).all() and np.abs(a).max() > 0
+        assert np.array_equal(a, b)
+
+
 @pytest.mark.parametrize("model_name", ["Gaussian", "Exponential", "Matern"])
 def test_random_field_kernel_vs_oracle(model_name, oracle):
     """k_srf (randomisation method) against the sequential CPU restatement on the same modes; anisotropic 3-D and 2-D."""
