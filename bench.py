@@ -450,8 +450,9 @@ def run_secondary_newmark(args, local_rank):
 # element (once per block that sees it) and 84 in each of the 16 pair lanes
 ASM_FMA_PER_HEXA8 = 8 * (4 * 121 + 16 * 84)
 
-# dram__bytes_read.sum + dram__bytes_write.sum of one k_spmv<2> launch from the committed ncu capture (profiles/), by box size
-TRAFFIC = {255: 41377949000 + 420294000}      # profiles/r1_v4_k_spmv_node_mode2_255cube.txt (k_spmv_node<2,2,2>, 1 GPU)
+# dram__bytes_read.sum + dram__bytes_write.sum of one fused central-difference launch (k_spmv_node<2,2,2> with the column
+# dictionary) from the committed ncu capture, by box size
+TRAFFIC = {255: 35245933000 + 408624640}      # profiles/r1_v5_k_spmv_node_dict_255cube.txt (1 GPU)
 
 
 def main():
