@@ -74,14 +74,6 @@ def gmsh_face_order(points: np.ndarray) -> np.ndarray:
     return np.array(corners)
 
 
-def face_mass(face_type: str, order: int, xy: np.ndarray) -> np.ndarray:
-    """S[a,b] = sum_g N_a N_b detJ w over a 2-D face element (discretisation.py:419-433 with unit density)."""
-    N, dN, w = _lib.shape_table(face_type, order)
-    J = np.einsum("gad,ak->gdk", dN, xy[:, :2])
-    det = J[:, 0, 0] * J[:, 1, 1] - J[:, 0, 1] * J[:, 1, 0]
-    return np.einsum("ga,gb,g->ab", N, N, det * w)
-
-
 def _absorbing_faces(data):
     """(element, direction, node rows[nl]) of every absorbing face, in the reference's element / direction order
     (system_matrix.py:274-316): a face exists where exactly `nb_nodes_lower_elem` nodes of an element absorb in a direction."""
