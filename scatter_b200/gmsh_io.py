@@ -16,48 +16,61 @@ TYPE_TO_GMSH = {v: k for k, v in GMSH_TO_TYPE.items()}
 TYPE_TO_GMSH["quad8"] = 16      # not accepted as a domain element by the reference (mesher.py:181); writer only
 
 
-def _section(lines, start, end):
-    i0 = next(i for i, l in enumerate(lines) if l.startswith(start))
-    i1 = next(i for i, l in enumerate(lines) if l.startswith(end))
-    return i0, i1
+# nodes per gmsh element type (all types gmsh 2.2 can write for points, lines, triangles, quads, tets, hexes, prisms, pyramids)
+_GMSH_NNODES = {1: 2, 2: 3, 3: 4, 4: 4, 5: 8, 6: 6, 7: 5, 8: 3, 9: 6, 10: 9, 11: 10, 12: 27, 13: 18, 14: 14, 15: 1, 16: 8, 17: 20,
+                18: 15, 19: 13}
+
+
+def _section_text(text: str, start: str, end: str):
+    i0 = text.find(start)
+    i1 = text.find(end)
+    if i0 < 0 or i1 < 0:
+        return None
+    return text[text.index("\n", i0) + 1:i1]
 
 
 def read_msh(path: str) -> dict:
+    """Whole-array reader: every section is tokenised in one call and the (ragged) element records are decoded block by
+    block -- a run of records of the same type and tag count is one reshape -- so a 16 M-element file costs seconds, not
+    the minute a per-line loop takes."""
     with open(path, "r") as f:
-        lines = f.readlines()
+        text = f.read()
     # physical names: [dim(float), tag(int), name(str)] like utils.search_idx + mesher.py:146-147
     names = []
-    try:
-        i0, i1 = _section(lines, "$PhysicalNames", "$EndPhysicalNames")
-        for l in lines[i0 + 2:i1]:
+    sec = _section_text(text, "$PhysicalNames", "$EndPhysicalNames")
+    if sec is not None:
+        for l in sec.splitlines()[1:]:
             t = l.split()
-            names.append([float(t[0]), int(float(t[1])), " ".join(t[2:]).replace('"', "")])
-    except StopIteration:
-        pass
-    i0, i1 = _section(lines, "$Nodes", "$EndNodes")
-    nodes = np.array(" ".join(lines[i0 + 2:i1]).split(), dtype=float).reshape(-1, 4)
-    i0, i1 = _section(lines, "$Elements", "$EndElements")
-    rows = [np.array(l.split(), dtype=np.int64) for l in lines[i0 + 2:i1] if l.strip()]
-    # consecutive rows of the same gmsh type form one block (file order is kept)
-    blocks = []
-    k = 0
-    while k < len(rows):
-        j = k
-        while j < len(rows) and rows[j][1] == rows[k][1] and len(rows[j]) == len(rows[k]):
-            j += 1
-        blk = np.vstack(rows[k:j])
-        ntags = int(blk[0, 2])
+            if t:
+                names.append([float(t[0]), int(float(t[1])), " ".join(t[2:]).replace('"', "")])
+    sec = _section_text(text, "$Nodes", "$EndNodes")
+    if sec is None:
+        raise SystemExit("ERROR: the mesh file has no $Nodes section")
+    flat = np.fromstring(sec, sep=" ")
+    nodes = flat[1:].reshape(-1, 4)
+    sec = _section_text(text, "$Elements", "$EndElements")
+    if sec is None:
+        raise SystemExit("ERROR: the mesh file has no $Elements section")
+    flat = np.fromstring(sec, sep=" ", dtype=np.int64)[1:]        # records: id type ntags tags... node ids...
+    merged = []
+    p, n = 0, len(flat)
+    while p < n:
+        et, ntags = int(flat[p + 1]), int(flat[p + 2])
         if ntags != 2:
             raise SystemExit("ERROR: gmsh elements must carry exactly 2 tags")
-        blocks.append((int(blk[0, 1]), blk[:, 3].copy(), blk[:, 3 + ntags:].copy()))
-        k = j
-    # merge blocks of equal type (ids are irrelevant for the reference, order is)
-    merged = []
-    for b in blocks:
-        if merged and merged[-1][0] == b[0]:
-            merged[-1] = (b[0], np.concatenate([merged[-1][1], b[1]]), np.vstack([merged[-1][2], b[2]]))
+        if et not in _GMSH_NNODES:
+            raise SystemExit(f"ERROR: gmsh element type {et} not supported")
+        L = 3 + ntags + _GMSH_NNODES[et]
+        rows = flat[p:p + ((n - p) // L) * L].reshape(-1, L)
+        same = (rows[:, 1] == et) & (rows[:, 2] == ntags)
+        k = len(rows) if same.all() else int(np.argmin(same))     # records up to the first one of another kind
+        blk = rows[:k]
+        # consecutive blocks of equal type are one block (ids are irrelevant for the reference, order is)
+        if merged and merged[-1][0] == et:
+            merged[-1] = (et, np.concatenate([merged[-1][1], blk[:, 3]]), np.vstack([merged[-1][2], blk[:, 3 + ntags:]]))
         else:
-            merged.append(b)
+            merged.append((et, blk[:, 3].copy(), blk[:, 3 + ntags:].copy()))
+        p += k * L
     return {"physical_names": names, "nodes": nodes, "elements": merged}
 
 

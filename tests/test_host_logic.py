@@ -84,6 +84,26 @@ def test_reader_skips_lower_dimensional_elements(golden_meshes, tmp_path):
     assert np.array_equal(a.nodes, b.nodes)
 
 
+def test_reader_rejects_records_it_cannot_decode(golden_meshes, tmp_path):
+    from scatter_b200 import gmsh_io
+    src = open(golden_meshes["column_2D.msh"]).read().splitlines()
+    i0 = src.index("$Elements")
+    bad = list(src)
+    t = bad[i0 + 2].split()
+    bad[i0 + 2] = " ".join(t[:2] + ["3"] + t[3:5] + ["9"] + t[5:])           # three tags instead of two
+    p = os.path.join(tmp_path, "tags.msh")
+    open(p, "w").write("\n".join(bad) + "\n")
+    with pytest.raises(SystemExit, match="exactly 2 tags"):
+        gmsh_io.read_msh(p)
+    bad = list(src)
+    t = bad[i0 + 2].split()
+    bad[i0 + 2] = " ".join([t[0], "93"] + t[2:])                              # unknown element type
+    p = os.path.join(tmp_path, "type.msh")
+    open(p, "w").write("\n".join(bad) + "\n")
+    with pytest.raises(SystemExit, match="not supported"):
+        gmsh_io.read_msh(p)
+
+
 def test_mesher_errors(tmp_path):
     from scatter_b200 import mesher
     with pytest.raises(SystemExit, match="Mesh file does not exit"):
