@@ -372,3 +372,80 @@ def test_bench_reference_arm_runs_without_gpu():
     assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1 and "sample" in line["cpu_baseline"]
     assert line["e2e"] == {"value": line["value"], "unit": "DOF*steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "workload" in line["config"]
+
+
+# ---- property tests (hypothesis) ----------------------------------------------------------------------------------
+from hypothesis import given, settings as hsettings, strategies as st  # noqa: E402
+
+
+@hsettings(max_examples=25, deadline=None)
+@given(et=st.sampled_from(["tri3", "tri6", "quad4", "tetra4", "tetra10", "hexa8", "hexa20"]), nn=st.integers(30, 80),
+       ne=st.integers(1, 40), nline=st.integers(0, 6), seed=st.integers(0, 2 ** 31 - 1))
+def test_gmsh_write_read_round_trip(et, nn, ne, nline, seed, tmp_path_factory):
+    """Any (nodes, connectivity, tags) written by the repo's writer comes back unchanged, with or without leading
+    lower-dimensional records, and node coordinates survive to the last bit."""
+    from scatter_b200 import _lib, gmsh_io
+    rng = np.random.default_rng(seed)
+    nne = _lib.ELEM_NNE[et]
+    nodes = np.c_[np.arange(1, nn + 1), rng.normal(size=(nn, 3)) * 10.0 ** rng.integers(-3, 4)]
+    elem = np.array([rng.choice(nn, nne, replace=False) + 1 for _ in range(ne)])
+    tags = rng.integers(1, 4, ne)
+    phys = [[float(_lib.ELEM_DIM[et]), 1, "a b"], [float(_lib.ELEM_DIM[et]), 2, "soil"], [float(_lib.ELEM_DIM[et]), 3, "c"]]
+    path = os.path.join(tmp_path_factory.mktemp("rt"), "m.msh")
+    gmsh_io.write_msh(path, nodes, elem, tags, phys, et)
+    if nline:
+        src = open(path).read().splitlines()
+        i0 = src.index("$Elements")
+        lines = [f"{k + 1} 1 2 9 9 {k + 1} {k + 2}" for k in range(nline)]
+        body = [" ".join([str(k + 1 + nline)] + l.split()[1:]) for k, l in enumerate(src[i0 + 2:i0 + 2 + ne])]
+        open(path, "w").write("\n".join(src[:i0 + 1] + [str(ne + nline)] + lines + body + src[i0 + 2 + ne:]) + "\n")
+    r = gmsh_io.read_msh(path)
+    assert np.array_equal(r["nodes"], nodes)
+    code = gmsh_io.TYPE_TO_GMSH[et]
+    blocks = {b[0]: b for b in r["elements"]}
+    assert np.array_equal(blocks[code][2], elem) and np.array_equal(blocks[code][1], tags)
+    assert (1 in blocks) == (nline > 0) and [p[2] for p in r["physical_names"]] == ["a b", "soil", "c"]
+
+
+@hsettings(max_examples=30, deadline=None)
+@given(nn=st.integers(1, 400), world=st.integers(1, 9), seed=st.integers(0, 2 ** 31 - 1), dup=st.booleans())
+def test_rcb_properties(nn, world, seed, dup):
+    """Recursive coordinate bisection: every node gets a rank, the parts differ by at most one node per bisection level,
+    and coincident points (ties) do not break the balance."""
+    import types
+    from scatter_b200 import partition
+    rng = np.random.default_rng(seed)
+    xyz = rng.normal(size=(nn, 3))
+    if dup:
+        xyz[:, 0] = np.round(xyz[:, 0])                         # many ties along x
+        xyz[:, 1:] = 0.0
+    model = types.SimpleNamespace(nodes=np.c_[np.arange(1, nn + 1), xyz])
+    owner = partition.owner_by_rcb(model, world)
+    counts = np.bincount(owner, minlength=world)
+    assert owner.min() >= 0 and owner.max() < world and counts.sum() == nn
+    assert counts.max() - counts.min() <= int(np.ceil(np.log2(max(world, 2)))) + 1
+    assert np.array_equal(owner, partition.owner_by_rcb(model, world))
+
+
+@hsettings(max_examples=30, deadline=None)
+@given(n_eq=st.integers(1, 60), steps=st.integers(1, 12), world=st.integers(1, 4), seed=st.integers(0, 2 ** 31 - 1))
+def test_localised_schedules_partition_the_global_one(n_eq, steps, world, seed):
+    import types
+    from scatter_b200 import partition
+    rng = np.random.default_rng(seed)
+    counts = rng.integers(0, 5, steps)
+    ptr = np.concatenate([[0], np.cumsum(counts)])
+    dof = rng.integers(0, n_eq, ptr[-1]); val = rng.normal(size=ptr[-1])
+    owner_of_eq = rng.integers(0, world, n_eq)
+    seen = []
+    for r in range(world):
+        geq = np.where(owner_of_eq == r)[0]
+        loc = rng.permutation(len(geq) + 3)[:len(geq)]          # arbitrary local numbering (ghost dofs in between)
+        dom = types.SimpleNamespace(n_global_eq=n_eq, global_eq_of_owned=geq, owned_eq=loc)
+        lp, ld, lv = partition.localise_schedule(dom, ptr, dof, val)
+        assert lp[0] == 0 and len(lp) == steps + 1 and lp[-1] == len(ld) == len(lv)
+        back = {int(l): int(g) for l, g in zip(loc, geq)}
+        for t in range(steps):
+            seen += [(t, back[int(d)], float(v)) for d, v in zip(ld[lp[t]:lp[t + 1]], lv[lp[t]:lp[t + 1]])]
+    want = [(t, int(d), float(v)) for t in range(steps) for d, v in zip(dof[ptr[t]:ptr[t + 1]], val[ptr[t]:ptr[t + 1]])]
+    assert sorted(seen) == sorted(want)
