@@ -449,3 +449,20 @@ def test_localised_schedules_partition_the_global_one(n_eq, steps, world, seed):
             seen += [(t, back[int(d)], float(v)) for d, v in zip(ld[lp[t]:lp[t + 1]], lv[lp[t]:lp[t + 1]])]
     want = [(t, int(d), float(v)) for t in range(steps) for d, v in zip(dof[ptr[t]:ptr[t + 1]], val[ptr[t]:ptr[t + 1]])]
     assert sorted(seen) == sorted(want)
+
+
+def test_committed_bench_lines_carry_the_contract_keys():
+    """The JSON lines kept under profiles/ are what `bench.py` printed on the B200: every key of the bench contract is there."""
+    import json
+    for fn, n in (("r1_bench_1gpu_final.json", 1), ("r1_bench_2gpu_final.json", 2)):
+        line = json.loads(open(os.path.join(ROOT, "profiles", fn)).read().strip().splitlines()[-1])
+        for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
+                    "dtype", "data", "config", "roofline", "cpu_baseline", "e2e", "gpu_launches", "clocks"):
+            assert key in line, (fn, key)
+        assert line["n_gpus"] == n and line["dtype"] == "f64" and line["scaling"] == "weak" and "workload" in line["config"]
+        assert set(("bound", "achieved", "peak", "unit", "frac", "traffic")) <= set(line["roofline"])
+        assert abs(line["roofline"]["frac"] - line["roofline"]["achieved"] / line["roofline"]["peak"]) < 1e-12
+        assert set(("value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step")) <= set(line["e2e"])
+        assert line["e2e"]["h2d_bytes_per_step"] > 0 and line["e2e"]["value"] < line["value"] and line["gpu_launches"] > 0
+        if n == 1:
+            assert set(("value", "unit", "cores", "kind", "sample")) <= set(line["cpu_baseline"])
