@@ -379,7 +379,10 @@ def run_ours(args):
                 "roofline": {"bound": "hbm", "kernel": st.get("step_kernel", "?") + ": fused SpMV + central-difference update",
                              "bytes_per_launch_plain_csr": 12 * nnz + 48 * n_owned,
                              "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
-                             "bytes_per_launch": step_bytes, "kernel_ms": 1e3 * kernel_s, "traffic": TRAFFIC.get(s)},
+                             "bytes_per_launch": step_bytes, "kernel_ms": 1e3 * kernel_s, "traffic": TRAFFIC.get(s),
+                             # the same launch time against the plain-CSR byte count BASELINE.md 4 derives its roofline from
+                             # (1 020 B/DOF/step): how close the time loop is to what an ideal plain-CSR SpMV could reach
+                             "frac_plain_csr_equivalent": (12 * nnz + 48 * n_owned) / kernel_s / 1e9 / peak},
                 "assembly": {"seconds": t_asm, "pattern_seconds": t_pattern, "gbs": asm_bytes / t_asm / 1e9,
                              "frac_hbm": asm_bytes / t_asm / 1e9 / peak, "elements_per_s": ne / t_asm, "algorithmic_bytes": asm_bytes,
                              "host_mesh_seconds": t_mesh,
