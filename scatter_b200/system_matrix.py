@@ -83,7 +83,10 @@ def _absorbing_faces(data):
     nl, dim = data.nb_nodes_lower_elem, data.dimension
     touched = np.where(absorb.any(axis=1)[rows].any(axis=1))[0]
     out = []
-    if len(touched) == 0:
+    # 2-D element types have no face element (`nb_nodes_lower_elem == []`, mesher.py:187-198): the reference's test
+    # `len(...) == data.nb_nodes_lower_elem` is then never true, so absorbing codes on 2-D meshes are silently ignored and
+    # its "not implemented for 2D" exit (system_matrix.py:324-326) is unreachable
+    if len(touched) == 0 or not isinstance(nl, (int, np.integer)):
         return out
     fl = absorb[rows[touched]]                                     # (nt, nne, dim)
     cnt = fl.sum(axis=1)                                           # (nt, dim)

@@ -466,3 +466,51 @@ def test_committed_bench_lines_carry_the_contract_keys():
         assert line["e2e"]["h2d_bytes_per_step"] > 0 and line["e2e"]["value"] < line["value"] and line["gpu_launches"] > 0
         if n == 1:
             assert set(("value", "unit", "cores", "kind", "sample")) <= set(line["cpu_baseline"])
+
+
+def test_absorbing_plan_groups_and_restriction(golden_meshes):
+    """Index plan handed to sc_add_absorbing_faces: sorted unique keys, entries grouped in face order, restriction to owned rows."""
+    from scatter_b200 import mesher, system_matrix
+    m = mesher.ReadMesh(golden_meshes["cube.msh"])
+    m.read_gmsh(); m.read_bc(cases.BC_CUBE_ABS); m.mapping(); m.connectivities()
+    plan = system_matrix.absorbing_plan(m)
+    nf, nl = plan.i1.shape
+    assert plan.face_type == "quad4" and nl == 4 and plan.nodes.shape == (nf, 4) and plan.perp.shape == (nf, 4)
+    key = plan.rows * m.number_eq + plan.cols
+    assert (np.diff(key) > 0).all()                                                   # sorted, unique
+    assert plan.grp_ptr[0] == 0 and plan.grp_ptr[-1] == nf * nl * nl == len(plan.grp_entry)
+    assert sorted(plan.grp_entry.tolist()) == list(range(nf * nl * nl))              # every per-face entry exactly once
+    for u in (0, len(plan.rows) // 2, len(plan.rows) - 1):
+        ent = plan.grp_entry[plan.grp_ptr[u]:plan.grp_ptr[u + 1]]
+        assert (np.diff(ent) > 0).all()                                               # face order inside a key
+        f, a, b = ent // (nl * nl), (ent // nl) % nl, ent % nl
+        assert (plan.i1[f, a] == plan.rows[u]).all() and (plan.i1[f, b] == plan.cols[u]).all()
+    n_keys = len(plan.rows)
+    half = np.unique(plan.rows)[::2]
+    plan.restrict_rows(half)
+    assert 0 < len(plan.rows) < n_keys and np.isin(plan.rows, half).all() and plan.grp_ptr[-1] == len(plan.grp_entry)
+    plan.restrict_rows(np.zeros(0, dtype=np.int64))
+    assert len(plan.rows) == 0 and len(plan.grp_entry) == 0 and plan.grp_ptr.tolist() == [0]
+    # no absorbing dofs -> no plan
+    m2 = mesher.ReadMesh(golden_meshes["cube.msh"])
+    m2.read_gmsh(); m2.read_bc(cases.BC_CUBE); m2.mapping(); m2.connectivities()
+    assert system_matrix.absorbing_plan(m2) is None
+
+
+def test_absorbing_codes_on_2d_meshes_are_ignored_like_in_the_reference(golden_meshes, oracle):
+    """2-D element types have no face element (`nb_nodes_lower_elem == []`), so the reference never finds an absorbing
+    face on a 2-D mesh -- its "not implemented for 2D" exit is unreachable -- and the "2" dofs simply stay free."""
+    from scatter_b200 import mesher, system_matrix
+    bc = dict(cases.BC_2D); bc["bottom"] = ["02", bc["bottom"][1]]
+    m = mesher.ReadMesh(golden_meshes["column_2D.msh"])
+    m.read_gmsh(); m.read_bc(bc); m.mapping(); m.connectivities()
+    assert (np.asarray(m.type_BC) == "Absorb").any() and m.nb_nodes_lower_elem == []
+    assert system_matrix.absorbing_plan(m) is None
+    ne = len(m.elem)
+    assert system_matrix.absorbing_entries(m, np.full(ne, 30e6), np.full(ne, 0.2), np.full(ne, 1500.0), 2, [1, 1], 1e3) == ({}, {})
+    om = oracle.build_model(golden_meshes["column_2D.msh"], bc)
+    assert om.number_eq == m.number_eq
+    K, M, C, _ = oracle.system_matrices(om, cases.materials(), cases.settings())     # runs, no absorbing contribution
+    E, nu, rho = oracle.element_properties(om, cases.materials())
+    K0, _ = oracle.assemble_global(om, E, nu, rho, 2)
+    assert abs(K - K0).max() == 0
