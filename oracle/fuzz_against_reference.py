@@ -191,6 +191,51 @@ mx.absorbing_boundaries(a, cases.materials(), [1, 1], 1e3)
 log(f"- absorbing codes on a 2-D mesh: the reference runs through (its 2-D exit is unreachable), |K - K0| = "
     f"{abs(sp.csr_matrix(mx.K) - K0).max():.1f}, C has {sp.csr_matrix(mx.C).nnz} entries -> ignored; scatter_b200 does the same")
 
+# ---- 6. oracle assembly on perturbed, two-material meshes ----------------------------------------------------------------
+import fem_np as orc  # noqa: E402
+
+rng = np.random.default_rng(3)
+worst = 0.0
+n_cases = 0
+MAT2 = {"solid": {"density": 1500, "Young": 30e6, "poisson": 0.2}, "bottom": {"density": 2100, "Young": 170e6, "poisson": 0.33}}
+for fn, bc in ((IT + "cube.msh", cases.BC_CUBE_ABS), (IT + "column_3D_tetra10.msh", cases.BC_B2_3D), (IT + "column_2D_tri6.msh", cases.BC_2D),
+               (IT + "column_2D.msh", cases.BC_2D), (IT + "column_high_order.msh", cases.BC_COLUMN_ABS), (RUN + "embankment_rose2D.msh", cases.MATRIX_CASES["embankment_rose2D"][1])):
+    m = ref.mesher.ReadMesh(fn); m.read_gmsh()
+    corner = {"hexa8": 8, "hexa20": 8, "tetra10": 4, "tetra4": 4, "tri6": 3, "tri3": 3, "quad4": 4}[m.element_type]
+    # move the corner nodes a little (mid-side nodes follow their edge, boundary planes stay planes: interior nodes only)
+    lo, hi = m.nodes[:, 1:].min(0), m.nodes[:, 1:].max(0)
+    interior = np.all((m.nodes[:, 1:1 + m.dimension] > lo[:m.dimension] + 1e-9) & (m.nodes[:, 1:1 + m.dimension] < hi[:m.dimension] - 1e-9), axis=1)
+    if m.element_type in ("hexa8", "tri3", "quad4"):
+        h = np.min(np.linalg.norm(m.nodes[m.elem[:, 0] - 1, 1:] - m.nodes[m.elem[:, 1] - 1, 1:], axis=1))
+        m.nodes[interior, 1:1 + m.dimension] += rng.uniform(-0.15, 0.15, (int(interior.sum()), m.dimension)) * h
+    if "embankment" in fn:
+        mat = cases.materials_embankment()
+    else:
+        mat = MAT2
+        m.materials = [[float(m.dimension), 1, "solid"], [float(m.dimension), 2, "bottom"]]
+        m.materials_index = rng.integers(1, 3, len(m.elem))
+    m.read_bc(bc); m.mapping(); m.connectivities()
+    mx = ref.system_matrix.GenerateMatrix(m.number_eq, 2)
+    mx.generate_stiffness_and_mass(m, mat)
+    Ks, Ms = sp.csr_matrix(mx.K), sp.csr_matrix(mx.M)
+    mx.absorbing_boundaries(m, mat, [1, 1], 1e3)
+    mx.damping_Rayleigh([1, 0.01, 30, 0.01])
+    om = orc.Model(nodes=m.nodes, elem=m.elem, materials_index=m.materials_index, materials=m.materials, element_type=m.element_type,
+                   dimension=m.dimension, BC=m.BC, BC_dir=m.BC_dir, eq_nb_dof=m.eq_nb_dof, type_BC=m.type_BC, number_eq=m.number_eq,
+                   eq_nb_elem=m.eq_nb_elem, nb_nodes_elem=m.elem.shape[1])
+    om.lower_element_type, om.nb_nodes_lower_elem = m.lower_element_type, m.nb_nodes_lower_elem
+    ids = m.nodes[:, 0].astype(np.int64)
+    om.extra["node_rows"] = np.searchsorted(ids, m.elem) if not np.array_equal(ids, np.arange(1, len(ids) + 1)) else m.elem - 1
+    E, nu, rho = orc.element_properties(om, mat)
+    Ko, Mo = orc.assemble_global(om, E, nu, rho, 2)
+    Kf, Mf, Cf, _ = orc.system_matrices(om, mat, {"int_order": 2, "damping": [1, 0.01, 30, 0.01], "absorbing_BC": [1, 1], "absorbing_BC_stiff": 1e3})
+    errs = [abs(Ko - Ks).max() / abs(Ks).max(), abs(Mo - Ms).max() / abs(Ms).max(), abs(Kf - sp.csr_matrix(mx.K)).max() / abs(Ks).max(),
+            abs(Cf - sp.csr_matrix(mx.C)).max() / abs(sp.csr_matrix(mx.C)).max()]
+    worst = max(worst, max(errs))
+    n_cases += 1
+log(f"- oracle assembly (K, M, final K and C incl. absorbing + Rayleigh) on {n_cases} perturbed / randomly two-material meshes "
+    f"(hexa8, hexa20, tetra10, tri6, quad4, tri3): worst difference {worst:.1e} of the matrix max-norm")
+
 with open(os.path.join(HERE, "VALIDATION_FUZZ.md"), "w") as f:
     f.write("# Host-logic fuzzing against the unmodified reference (generated by oracle/fuzz_against_reference.py in the build container)\n\n")
     f.write("\n".join(lines) + "\n")
