@@ -1,0 +1,232 @@
+"""The Python layer of `scatter(...)` end to end on CPU: mesh -> random field -> matrices -> solver -> loads -> integrate ->
+export, for every solver of the `Solver` enum.
+
+There is no GPU here, so `_lib.Context` (the ctypes binding of the CUDA library) is replaced by a stand-in built on the
+oracle -- TEST INFRASTRUCTURE, the product never does this -- which receives exactly the calls the real context gets
+(same methods, same argument layout) and checks them.  What this pins every round, without a GPU: the dict schemas, the
+stage protocol (`update` / `calculate`), the load schedule handed to the device, output-row bookkeeping, pickle / VTK
+files and the returned object.  The CUDA path itself is pinned by the `-m gpu` tests.
+"""
+import os
+import pickle
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+import cases
+from conftest import load_oracle, rel_l2
+
+
+class OracleContext:
+    """Stand-in for scatter_b200._lib.Context (methods used by GenerateMatrix / the solver classes)."""
+
+    def __init__(self, device=0):
+        self.oracle = load_oracle()
+        self.device, self.n_eq, self.nnz, self.closed = device, 0, 0, False
+        self.c0 = self.c1 = 0.0
+        self.Cabs = None
+        self.calls = []
+
+    # ---- mesh / matrices
+    def set_mesh(self, elem_type, xyz, conn, eq, n_eq, active=None):
+        assert xyz.shape[1] == 3 and conn.dtype.kind == "i" and eq.shape == (xyz.shape[0], 2 if elem_type in ("tri3", "tri6", "quad4", "quad8") else 3)
+        assert active is None
+        self.elem_type, self.xyz, self.conn, self.eq, self.n_eq = elem_type, np.asarray(xyz, float), np.asarray(conn), np.asarray(eq), int(n_eq)
+        self.n_elem, self.n_nodes = len(conn), len(xyz)
+        self.calls.append("set_mesh")
+
+    def set_materials(self, E, nu, rho):
+        self.E, self.nu, self.rho = (np.broadcast_to(np.asarray(a, float), (self.n_elem,)).copy() for a in (E, nu, rho))
+        self.calls.append("set_materials")
+
+    def _model(self):
+        o = self.oracle
+        dim = self.eq.shape[1]
+        nodes = np.c_[np.arange(1, self.n_nodes + 1), self.xyz]
+        eqf = np.where(self.eq < 0, np.nan, self.eq.astype(float))
+        m = o.Model(nodes=nodes, elem=self.conn + 1, materials_index=np.ones(self.n_elem, int), materials=[[float(dim), 1, "m"]],
+                    element_type=self.elem_type, dimension=dim, BC=None, BC_dir=None, eq_nb_dof=eqf, type_BC=None, number_eq=self.n_eq,
+                    eq_nb_elem=eqf[self.conn].reshape(self.n_elem, -1), nb_nodes_elem=self.conn.shape[1])
+        m.extra["node_rows"] = self.conn
+        return m
+
+    def build_pattern(self):
+        self.calls.append("build_pattern")
+        return 0
+
+    def assemble(self, order, flags):
+        K, M = self.oracle.assemble_global(self._model(), self.E, self.nu, self.rho, order)
+        self.K, self.M, self.flags = K.tocsr(), M.tocsr(), flags
+        self.nnz = self.K.nnz
+        self.calls.append("assemble")
+        return 0.0
+
+    def add_absorbing_faces(self, plan, order, p0, p1, stiff):
+        # evaluate the plan like k_abs_faces / k_abs_reduce do
+        from scatter_b200 import _lib
+        N, dN, w = _lib.shape_table(plan.face_type, order)
+        nf, nl = plan.i1.shape
+        keep = np.array([[1, 2], [0, 2], [0, 1]])[plan.direction]
+        xy = np.take_along_axis(self.xyz[plan.nodes], keep[:, None, :], axis=2)
+        J = np.einsum("gad,fak->fgdk", dN, xy)
+        det = J[..., 0, 0] * J[..., 1, 1] - J[..., 0, 1] * J[..., 1, 0]
+        S = np.einsum("ga,gb,fg->fab", N, N, det * w[None, :])
+        E, nu, rho = self.E[plan.elem], self.nu[plan.elem], self.rho[plan.elem]
+        Ec = E * (1 - nu) / ((1 + nu) * (1 - 2 * nu)); G = E / (2 * (1 + nu))
+        perp = plan.perp.astype(bool)
+        fct = np.where(perp, (p0 * rho * np.sqrt(Ec / rho))[:, None], (p1 * rho * np.sqrt(G / rho))[:, None])
+        fct2 = np.where(perp, Ec[:, None], G[:, None])
+        cv, kv = (S * fct[:, None, :]).ravel(), (np.abs(S) * fct2[:, None, :]).ravel()
+        grp = np.repeat(np.arange(len(plan.rows)), np.diff(plan.grp_ptr))
+        cs = np.zeros(len(plan.rows)); ks = np.zeros(len(plan.rows))
+        np.add.at(cs, grp, cv[plan.grp_entry]); np.add.at(ks, grp, kv[plan.grp_entry])
+        n = self.n_eq
+        self.Cabs = sp.csr_matrix((cs, (plan.rows, plan.cols)), shape=(n, n))
+        self.K = (self.K + sp.csr_matrix((ks / stiff, (plan.rows, plan.cols)), shape=(n, n))).tocsr()
+        self.calls.append("add_absorbing_faces")
+
+    def set_rayleigh(self, c0, c1):
+        self.c0, self.c1 = c0, c1
+
+    def _C(self):
+        C = self.M * self.c0 + self.K * self.c1
+        return (C + self.Cabs).tocsr() if self.Cabs is not None else C.tocsr()
+
+    # ---- loads / state / time loops
+    def set_load_schedule(self, ptr, dof, val):
+        ptr, dof, val = np.asarray(ptr), np.asarray(dof), np.asarray(val)
+        assert ptr[0] == 0 and ptr[-1] == len(dof) == len(val) and (np.diff(ptr) >= 0).all()
+        assert len(dof) == 0 or (dof.min() >= 0 and dof.max() < self.n_eq)
+        self.sched = (ptr, dof, val)
+
+    def _force(self, t):
+        ptr, dof, val = self.sched
+        f = np.zeros(self.n_eq)
+        if 0 <= t < len(ptr) - 1:
+            f[dof[ptr[t]:ptr[t + 1]]] = val[ptr[t]:ptr[t + 1]]
+        return f
+
+    def set_state(self, u=None, v=None):
+        assert u is None or not np.any(u)            # scatter() starts from rest
+        assert v is None or not np.any(v)
+
+    def _store(self, res, outs):
+        for src, dst in zip(res, outs):
+            if dst is not None:
+                assert dst.shape == src.shape, (dst.shape, src.shape)
+                dst[...] = src
+
+    def run_newmark(self, dt, t_start, n_steps, oi=1, beta=0.25, gamma=0.5, rtol=1e-14, maxit=20000, u_out=None, v_out=None, a_out=None, store=True):
+        assert t_start == 0 and self.flags & 2           # full mass assembled
+        U, V, A, _ = self.oracle.newmark(self.M, self._C(), self.K, self._force, np.arange(n_steps + 1) * dt, oi, beta, gamma)
+        self._store((U, V, A), (u_out, v_out, a_out))
+        return u_out, v_out, a_out, {"pcg_iterations": 0}
+
+    def run_central_difference(self, dt, t_start, n_steps, oi=1, u_out=None, v_out=None, a_out=None, store=True):
+        assert t_start == 0 and self.flags & 4           # lumped mass assembled
+        U, V, A, _ = self.oracle.central_difference(self.M, self._C(), self.K, self._force, np.arange(n_steps + 1) * dt, oi)
+        self._store((U, V, A), (u_out, v_out, a_out))
+        return u_out, v_out, a_out, {}
+
+    def run_bathe(self, dt, t_start, n_steps, oi=1, rtol=1e-14, maxit=20000, u_out=None, v_out=None, a_out=None):
+        assert t_start == 0
+        U, V, A, _ = self.oracle.bathe(self.M, self._C(), self.K, self._force, np.arange(n_steps + 1) * dt, oi)
+        self._store((U, V, A), (u_out, v_out, a_out))
+        return u_out, v_out, a_out, {}
+
+    def run_static(self, t_start, n_steps, oi=1, rtol=1e-12, maxit=100000, u_out=None):
+        assert t_start == 0
+        U, _ = self.oracle.static(self.K, self._force, np.arange(n_steps + 1, dtype=float), oi)
+        self._store((U,), (u_out,))
+        return u_out, {}
+
+    def get_pattern(self):
+        return self.K.indptr.astype(np.int64), self.K.indices.astype(np.int32)
+
+    def get_values(self, which):
+        return {0: self.K, 1: self.M, 2: self._C()}[which].data
+
+    def close(self):
+        self.closed = True
+
+
+@pytest.fixture
+def oracle_device(monkeypatch):
+    from scatter_b200 import _lib, random_fields
+    made = []
+
+    def factory(device=0):
+        made.append(OracleContext(device))
+        return made[-1]
+    monkeypatch.setattr(_lib, "Context", factory)
+
+    def cpu_field(self, pos, lognormal=False, device=0, ctx=None):
+        o = load_oracle()
+        return o.srf_field(self.isometrize(pos), self.k, self.z1, self.z2, np.sqrt(self.var / self.mode_no), self.mean, lognormal)
+    monkeypatch.setattr(random_fields.SpectralField, "__call__", cpu_field)
+    return made
+
+
+SOLVER_OF = {"NEWMARK_EXPLICIT": "newmark", "NEWMARK_IMPLICIT": "newmark", "CENTRAL_DIFFERENCE": "cd", "BATHE": "bathe", "STATIC": "static"}
+
+
+@pytest.mark.parametrize("solver_name", list(SOLVER_OF))
+def test_scatter_entry_point_every_solver(solver_name, oracle_device, golden_meshes, oracle, tmp_path):
+    from scatter_b200 import scatter, Solver
+    mesh, bc = golden_meshes["cube.msh"], cases.BC_CUBE_ABS                       # absorbing bottom and left face
+    dt = 2e-4 if solver_name == "CENTRAL_DIFFERENCE" else 2e-3
+    load = {"force": [0, -1000, 0], "node": [8, 9], "time": 20 * dt, "type": "heaviside"}   # ini_steps defaults to 5
+    sett = cases.settings(damping=[1, 0.01, 30, 0.01], output_interval=4, VTK=True, VTK_binary=(solver_name == "BATHE"), pickle_nodes=[8, 3])
+    mats = cases.materials()
+    res = scatter(mesh, str(tmp_path), mats, bc, sett, load, time_step=dt, solver=getattr(Solver, solver_name))
+    assert load["ini_steps"] == 5                                                  # validator default, written into the caller's dict
+    ctx = oracle_device[-1]
+    assert ctx.calls[:4] == ["set_mesh", "set_materials", "build_pattern", "assemble"] and "add_absorbing_faces" in ctx.calls
+    # the oracle's own end-to-end run of the same case
+    om = oracle.build_model(mesh, bc)
+    K, M, C, _ = oracle.system_matrices(om, cases.materials(), sett)
+    time = oracle.time_array(load["time"], dt)
+    force = oracle.LoadSchedule(om, dict(load, ini_steps=5), time)
+    kind = SOLVER_OF[solver_name]
+    if kind == "static":
+        U, tt = oracle.static(K, force, time, 4)
+        V = A = np.zeros_like(U)
+    else:
+        U, V, A, tt = {"newmark": oracle.newmark, "cd": oracle.central_difference, "bathe": oracle.bathe}[kind](M, C, K, force, time, 4)
+    assert res.dis.shape == U.shape == (6, om.number_eq) and np.abs(U).max() > 0
+    assert rel_l2(res.dis, U) <= 1e-10 and np.allclose(res.time, tt)
+    if kind != "static":
+        assert rel_l2(res.vel, V) <= 1e-10 and rel_l2(res.acc, A) <= 1e-10
+    # files: pickle of the two requested nodes, one VTK file per stored row
+    with open(os.path.join(tmp_path, "data.pickle"), "rb") as f:
+        data = pickle.load(f)
+    assert data["nodes"] == [8, 3] and set(data["displacement"]) == {"8", "3"} and len(data["position"]) == 2
+    row = int(np.where(om.nodes[:, 0] == 8)[0][0])
+    assert np.array_equal(data["displacement"]["8"]["y"], res.dis[:, int(om.eq_nb_dof[row, 1])])
+    vtk = sorted(os.listdir(os.path.join(tmp_path, "VTK")))
+    assert vtk == sorted(f"data_{k}.vtk" for k in range(6))
+    head = open(os.path.join(tmp_path, "VTK", "data_2.vtk"), "rb").read(200).decode("latin1").splitlines()
+    assert head[0] == "# vtk DataFile Version 2.0" and head[2] == ("BINARY" if solver_name == "BATHE" else "ASCII")
+
+
+def test_scatter_entry_point_with_random_field_cpu(oracle_device, golden_meshes, oracle, tmp_path):
+    from scatter_b200 import scatter
+    case = "embankment_rose2D"
+    fn, bc = cases.MATRIX_CASES[case]
+    mats = cases.case_materials(case)
+    sett = cases.settings(damping=[1, 0.005, 20, 0.005])
+    load = {"force": [0, -1e4, 0], "node": [4], "time": 0.02, "type": "pulse", "ini_steps": 7}
+    res = scatter(golden_meshes[fn], str(tmp_path), mats, bc, sett, load, time_step=1e-3, random_props=cases.rf_properties(case, "Exponential"))
+    om = oracle.build_model(golden_meshes[fn], bc)
+    tag = [m[1] for m in om.materials if m[2] == "soil1"][0]
+    n_rf = int((np.asarray(om.materials_index) == tag).sum())
+    young = np.array([mats[f"material_{k + 1}"]["Young"] for k in range(n_rf)])
+    assert len([k for k in mats if k.startswith("material_")]) == n_rf and young.std() > 0
+    base = cases.case_materials(case)
+    E, nu, rho = oracle.element_properties(om, base)
+    E[np.asarray(om.materials_index) == tag] = young
+    _, _, (U, V, A, _) = oracle.run_case(golden_meshes[fn], base, bc, sett, load, 1e-3, elem_props=(E, nu, rho))
+    assert np.abs(U).max() > 0 and rel_l2(res.dis, U) <= 1e-10 and rel_l2(res.vel, V) <= 1e-10
+    assert os.path.isfile(os.path.join(tmp_path, "rf_props.txt")) and os.path.isfile(os.path.join(tmp_path, "data.pickle"))
+    assert res.dis.shape[0] == len(oracle.time_array(0.02, 1e-3))
