@@ -514,3 +514,17 @@ def test_absorbing_codes_on_2d_meshes_are_ignored_like_in_the_reference(golden_m
     E, nu, rho = oracle.element_properties(om, cases.materials())
     K0, _ = oracle.assemble_global(om, E, nu, rho, 2)
     assert abs(K - K0).max() == 0
+
+
+def test_header_is_plain_c():
+    """include/scatter_b200.h is the drop-in boundary: it must compile as C (no C++ types, no torch types in the signatures)."""
+    import shutil
+    import subprocess
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("gcc not available")
+    hdr = os.path.join(ROOT, "include", "scatter_b200.h")
+    r = subprocess.run([gcc, "-fsyntax-only", "-x", "c", "-std=c99", "-Wall", "-Werror", hdr], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    text = open(hdr).read()
+    assert "torch" not in text and "std::" not in text and 'extern "C"' in text
