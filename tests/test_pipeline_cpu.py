@@ -108,8 +108,7 @@ class OracleContext:
         return f
 
     def set_state(self, u=None, v=None):
-        assert u is None or not np.any(u)            # scatter() starts from rest
-        assert v is None or not np.any(v)
+        self.state = (None if u is None else np.array(u), None if v is None else np.array(v))
 
     def _store(self, res, outs):
         for src, dst in zip(res, outs):
@@ -118,9 +117,16 @@ class OracleContext:
                 dst[...] = src
 
     def run_newmark(self, dt, t_start, n_steps, oi=1, beta=0.25, gamma=0.5, rtol=1e-14, maxit=20000, u_out=None, v_out=None, a_out=None, store=True):
-        assert t_start == 0 and self.flags & 2           # full mass assembled
-        U, V, A, _ = self.oracle.newmark(self.M, self._C(), self.K, self._force, np.arange(n_steps + 1) * dt, oi, beta, gamma)
-        self._store((U, V, A), (u_out, v_out, a_out))
+        assert self.flags & 2                            # full mass assembled
+        # a stage is the tail of the run from rest (the device continues from the state of the previous stage)
+        full = self.oracle.newmark(self.M, self._C(), self.K, self._force, np.arange(t_start + n_steps + 1) * dt, 1, beta, gamma)[:3]
+        u0, v0 = getattr(self, "state", (None, None))
+        if t_start > 0 and u0 is not None:               # restart hook: the uploaded state is the stored row of step t_start
+            assert np.allclose(u0, full[0][t_start], rtol=0, atol=1e-12 * np.abs(full[0]).max())
+            assert np.allclose(v0, full[1][t_start], rtol=0, atol=1e-12 * np.abs(full[1]).max())
+        self.state = (None, None)                        # consumed: a following stage without set_state continues on the device
+        steps = [t for t in range(t_start, t_start + n_steps + 1) if t % oi == 0]
+        self._store(tuple(f[steps] for f in full), tuple(None if o is None else o[:len(steps)] for o in (u_out, v_out, a_out)))
         return u_out, v_out, a_out, {"pcg_iterations": 0}
 
     def run_central_difference(self, dt, t_start, n_steps, oi=1, u_out=None, v_out=None, a_out=None, store=True):
@@ -230,3 +236,39 @@ def test_scatter_entry_point_with_random_field_cpu(oracle_device, golden_meshes,
     assert np.abs(U).max() > 0 and rel_l2(res.dis, U) <= 1e-10 and rel_l2(res.vel, V) <= 1e-10
     assert os.path.isfile(os.path.join(tmp_path, "rf_props.txt")) and os.path.isfile(os.path.join(tmp_path, "data.pickle"))
     assert res.dis.shape[0] == len(oracle.time_array(0.02, 1e-3))
+
+
+@pytest.mark.parametrize("with_update", [False, True])
+def test_solver_stages_fill_the_right_output_rows(with_update, oracle_device, golden_meshes, oracle):
+    """Stage protocol of scatter.py:153-159 / rose_utils.py: `calculate(t0, t1)` called stage by stage (optionally with the
+    restart hook `update(t0)` in between) must fill the same rows as one run over the whole time axis."""
+    from scatter_b200 import force_external, mesher, solvers, system_matrix
+    mesh, bc = golden_meshes["column_2D.msh"], cases.BC_2D
+    m = mesher.ReadMesh(mesh)
+    m.read_gmsh(); m.read_bc(bc); m.mapping(); m.connectivities()
+    mx = system_matrix.GenerateMatrix(m.number_eq, 2)
+    mx.generate_stiffness_and_mass(m, cases.materials())
+    mx.absorbing_boundaries(m, cases.materials(), [1, 1], 1e3)
+    mx.damping_Rayleigh([1, 0.005, 20, 0.005])
+    load = {"force": [0, -1e6, 0], "node": [3, 4, 25], "time": 0.135, "type": "heaviside", "ini_steps": 5}
+    time = oracle.time_array(load["time"], 5e-3)                                   # 28 time indices
+    num = solvers.NewmarkExplicit(); num.output_interval = 3
+    num.initialise(m.number_eq, time); num.bind(mx)
+    F = force_external.Force(); F.initialise_load(load, time, m, num)
+    num.update_rhs_at_time_step_func = F.update_load_at_t
+    num.update(0)
+    for t0, t1 in ((0, 7), (7, 9), (9, 20), (20, 27)):                              # stage ends on and off the output grid
+        if with_update and t0 % 3 == 0 and t0 > 0:
+            num.update(t0)
+        num.calculate(None, None, None, F.force_vector, t0, t1)
+    om = oracle.build_model(mesh, bc)
+    K, M, C, _ = oracle.system_matrices(om, cases.materials(), cases.settings(damping=[1, 0.005, 20, 0.005]))
+    U, V, A, tt = oracle.newmark(M, C, K, oracle.LoadSchedule(om, load, time), time, 3)
+    assert num.u.shape == U.shape == (10, m.number_eq) and np.allclose(num.output_time, tt)
+    assert rel_l2(num.u, U) <= 1e-10 and rel_l2(num.v, V) <= 1e-10 and rel_l2(num.a, A) <= 1e-10
+
+
+def test_output_row_count():
+    from scatter_b200 import _lib
+    rows = _lib.Context.n_output_rows
+    assert rows(7, 2, 3) == 1 and rows(10, 1, 3) == 0 and rows(0, 27, 3) == 10 and rows(0, 0, 1) == 1 and rows(5, 0, 5) == 1
