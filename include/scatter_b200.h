@@ -65,6 +65,10 @@ const char* sc_last_error(sc_ctx* ctx);          /* ctx may be NULL: error of a 
 int         sc_version(void);
 int         sc_device_info(sc_ctx* ctx, int* sm_count, int64_t* total_mem, int64_t* free_mem, char* name, int name_len);
 int64_t     sc_kernel_launches(sc_ctx* ctx);     /* running count of kernels launched by this context */
+/* kernel-selection switches for tests and A/B measurements (the defaults are the product path; nothing reads the
+ * environment): "node_spmv", "tma_spmv", "column_dictionary", "small_pcg", "pcg_graph" (default 1), "generic_assembly"
+ * (default 0) */
+int         sc_set_option(sc_ctx* ctx, const char* name, int64_t value);
 
 /* page-locked host buffers for result rows / initial states (faster, asynchronous host<->device copies) */
 int         sc_host_alloc(void** out, int64_t bytes);
@@ -136,6 +140,15 @@ int sc_get_lumped_mass(sc_ctx* ctx, double* diag /*[n_eq]*/);
 /* y = A x with the device SpMV kernel (test hook; A = K, M, C or KHAT) */
 int sc_spmv(sc_ctx* ctx, int which, const double* x, double* y);
 
+/* ---- caller-supplied matrices: the time-loop seam with matrices this library did not assemble
+ *      (solvers.NewmarkExplicit().calculate(matrix.M, matrix.C, matrix.K, F, t0, t1), scatter.py:159, with the scipy
+ *      matrices of the reference's own GenerateMatrix).  One CSR pattern (sorted, unique columns; the union of the three
+ *      patterns), values of K and optionally M and C on it.  Replaces any mesh / pattern / matrices of the context; the
+ *      time loops then run the row-wise SpMV kernels, C enters as given (no Rayleigh split: the central-difference solver
+ *      lumps all of it by row sums). */
+int sc_set_csr(sc_ctx* ctx, int64_t n_eq, const int64_t* rowptr /*[n_eq+1]*/, const int32_t* col /*[nnz]*/,
+               const double* K /*[nnz]*/, const double* M /*[nnz] or NULL*/, const double* C /*[nnz] or NULL*/);
+
 /* ---- loads (replaces the per-step callback Force.update_load_at_t, force_external.py:55-74, scatter.py:151):
  *      total external force of step t = entries step_ptr[t]..step_ptr[t+1] of (dof, val); other dofs zero -------- */
 int sc_set_load_schedule(sc_ctx* ctx, int64_t n_steps, const int64_t* step_ptr, const int64_t* dof, const double* val);
@@ -149,12 +162,25 @@ int sc_get_state(sc_ctx* ctx, double* u, double* v, double* a /*each [n_eq] or N
  *  state at step t_start + r*out_interval ... only steps with (t % out_interval == 0) are stored, the first stored
  *  row is the state at t_start itself when t_start % out_interval == 0.  u_out/v_out/a_out are host buffers of
  *  n_out*n_eq doubles or NULL.  The implicit solve uses Jacobi-preconditioned CG to relative residual pcg_rtol.   */
+/* Output selection (export_results.Write.pickle(nodes=[...]), export_results.py:117-135: only a few nodes are kept): the
+ * output rows of the run functions then hold just these equations, in this order -- u_out/v_out/a_out are n_out*n doubles.
+ * dofs = NULL restores full rows of n_eq doubles. */
+int sc_set_output_dofs(sc_ctx* ctx, int64_t n, const int64_t* dofs);
+
+/* One extra output step: the state at load-schedule step `step` is stored as an output row even when it is not a
+ * multiple of out_interval (the solver objects pass the last index of the time axis, so that the final state of a run is
+ * always kept); -1 switches it off.  n_out of the run functions counts it when it falls inside the stage. */
+int sc_set_final_output_step(sc_ctx* ctx, int64_t step);
+
 int sc_run_newmark(sc_ctx* ctx, double dt, int64_t t_start, int64_t n_steps, int64_t out_interval, double beta,
                    double gamma, double pcg_rtol, int pcg_maxit, int64_t n_out, double* u_out, double* v_out,
                    double* a_out, sc_stats* stats);
 
-/* explicit central difference with row-sum lumped M and C (solvers.CentralDifferenceSolver; scheme documented in
- * DESIGN.md -- the reference ships no fixture for it) */
+/* explicit central difference (solvers.CentralDifferenceSolver; the reference ships no fixture for it and the solver
+ * source is not in its tree, so the scheme is this library's own -- DESIGN.md 3.3):  row-sum lumped mass m; damping
+ * C = C_abs + c0 M + c1 K split into the diagonal c_d = c0 m + rowsum(C_abs), centred in time, and the
+ * stiffness-proportional part c1 K applied to the lagged velocity (u(t) - u(t-dt))/dt through the step's SpMV:
+ *   (m/dt^2 + c_d/2dt) u(t+dt) = F(t) - K [(1 + c1/dt) u(t) - (c1/dt) u(t-dt)] + 2 m/dt^2 u(t) - (m/dt^2 - c_d/2dt) u(t-dt) */
 int sc_run_central_difference(sc_ctx* ctx, double dt, int64_t t_start, int64_t n_steps, int64_t out_interval,
                               int64_t n_out, double* u_out, double* v_out, double* a_out, sc_stats* stats);
 

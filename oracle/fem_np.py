@@ -653,21 +653,29 @@ def lump_rows(M) -> np.ndarray:
     return np.asarray(sp.csr_matrix(M).sum(axis=1)).ravel()
 
 
-def central_difference(M, C, K, force, time: np.ndarray, output_interval: int = 1):
-    """Explicit central difference with row-sum lumped M and C (Bathe, Table 9.1).  PARITY UNPINNED (own scheme).
+def central_difference(M, C, K, force, time: np.ndarray, output_interval: int = 1, c1: float = 0.0):
+    """Explicit central difference with row-sum lumped M (Bathe, Table 9.1).  PARITY UNPINNED: the reference only forwards
+    `Solver.CENTRAL_DIFFERENCE` to the un-vendored PuggleSolvers class (scatter/scatter.py:124-125) and ships no fixture.
 
-        a0 = 1/dt^2, a1 = 1/(2dt), a2 = 2 a0
-        u(-dt) = u0 - dt v0 + dt^2/2 a0_vec,   a0_vec = (F0 - C v0 - K u0) / m
-        (a0 m + a1 c) u(t+dt) = F(t) - K u(t) + a2 m u(t) - (a0 m - a1 c) u(t-dt)
+    The damping C = C_abs + c0 M + c1 K (system_matrix.py:198) is split.  Row sums of K vanish away from supports (a rigid
+    translation produces no force), so lumping c1 K would silently drop the stiffness-proportional damping; instead
+    `c1` names that part, which acts on the lagged velocity (u(t) - u(t-dt))/dt and stays a full matrix, while the rest,
+    c_d = rowsum(C - c1 K) = c0 m + rowsum(C_abs), is diagonal and centred in time:
+
+        a0 = 1/dt^2, a1 = 1/(2dt), g = c1/dt
+        u(-dt) = u0 - dt v0 + dt^2/2 acc0,   acc0 = (F0 - K (u0 + c1 v0) - c_d v0) / m
+        (a0 m + a1 c_d) u(t+dt) = F(t) - K [(1+g) u(t) - g u(t-dt)] + 2 a0 m u(t) - (a0 m - a1 c_d) u(t-dt)
         v(t) = a1 (u(t+dt) - u(t-dt)),   a(t) = a0 (u(t+dt) - 2 u(t) + u(t-dt))
     """
     K = sp.csr_matrix(K)
-    m, c = lump_rows(M), lump_rows(C)
+    m = lump_rows(M)
+    c = lump_rows(C) - c1 * lump_rows(K)
     n = len(m)
     nt = len(time)
     dt = (time[-1] - time[0]) / (nt - 1)
     a0, a1 = 1.0 / dt ** 2, 1.0 / (2 * dt)
     a2 = 2 * a0
+    g = c1 / dt
     inv_d = 1.0 / (a0 * m + a1 * c)
     out_idx = np.arange(0, nt, output_interval)
     U = np.zeros((len(out_idx), n)); V = np.zeros_like(U); A = np.zeros_like(U)
@@ -676,7 +684,8 @@ def central_difference(M, C, K, force, time: np.ndarray, output_interval: int = 
     u_prev = u + 0.5 * dt * dt * acc0
     row = 0
     for t in range(nt):
-        u_next = inv_d * (force(t) - K @ u + a2 * m * u - (a0 * m - a1 * c) * u_prev)
+        w = (1.0 + g) * u - g * u_prev if g != 0.0 else u
+        u_next = inv_d * (force(t) - K @ w + a2 * m * u - (a0 * m - a1 * c) * u_prev)
         if t % output_interval == 0:
             U[row] = u
             V[row] = a1 * (u_next - u_prev)
@@ -704,7 +713,7 @@ def run_case(mesh_file: str, materials: dict, bc: dict, settings: dict, loading:
     if solver == "newmark":
         U, V, A, t_out = newmark(M, C, K, force, time, oi)
     else:
-        U, V, A, t_out = central_difference(M, C, K, force, time, oi)
+        U, V, A, t_out = central_difference(M, C, K, force, time, oi, c1=rayleigh_coefficients(settings["damping"])[1])
     return model, (K, M, C), (U, V, A, t_out)
 
 

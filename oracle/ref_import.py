@@ -1,9 +1,10 @@
 """TEST INFRASTRUCTURE (container-only helper) -- import the *unmodified* reference from /root/reference.
 
-Only usable where /root/reference exists (the build container).  It is used by
-`oracle/make_golden.py` to generate the fixtures under tests/golden/ and by
-`oracle/validate_against_reference.py` to pin the numpy restatement in `oracle/fem_np.py`.
-Nothing in tests/ -m gpu, bench.py or the product imports this file.
+In the build container it imports /root/reference: `oracle/make_golden.py` generates the fixtures under tests/golden/
+with it and `oracle/validate_against_reference.py` pins the numpy restatement in `oracle/fem_np.py`.  On the GPU box the
+same code is available as `baseline/_ref` (an offline `pip install --target` of the reference tree made by
+`__graft_entry__.build()`, git-ignored): only the CPU-baseline legs of `bench.py` (`cpu_baseline`, `--impl reference`)
+import it from there -- to TIME the reference's own assembler.  No test marked gpu, smoke() or product code imports this file.
 
 The reference imports third-party packages that are not installed here
 (SURVEY.md Appendix B): `rose`, `solvers` (PuggleSolvers 1.0.1), `shapely`, `meshio`,
@@ -15,7 +16,12 @@ import sys
 import types
 import warnings
 
+import os
+
+# the reference tree in the build container; on the GPU box only `baseline/_ref` exists (pip install --target of that same
+# tree, git-ignored, made by __graft_entry__.build()) -- bench.py's CPU-baseline legs use whichever is present
 REF_ROOT = "/root/reference"
+_REF_INSTALL = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "baseline", "_ref")
 
 
 def _stub(name, **attrs):
@@ -51,12 +57,12 @@ def install_stubs():
 
 def load_reference():
     """Return the reference modules (mesher, system_matrix, discretisation, element_types, material_models)."""
-    import os
-    if not os.path.isdir(REF_ROOT):
-        raise RuntimeError("reference tree not present: this helper only works in the build container")
+    root = REF_ROOT if os.path.isdir(os.path.join(REF_ROOT, "scatter")) else _REF_INSTALL
+    if not os.path.isdir(os.path.join(root, "scatter")):
+        raise RuntimeError("reference not present (neither /root/reference nor baseline/_ref)")
     install_stubs()
-    if REF_ROOT not in sys.path:
-        sys.path.insert(0, REF_ROOT)
+    if root not in sys.path:
+        sys.path.insert(0, root)
     warnings.filterwarnings("ignore", category=DeprecationWarning)
     from scatter import mesher, system_matrix, discretisation, element_types, material_models, utils
     return types.SimpleNamespace(mesher=mesher, system_matrix=system_matrix, discretisation=discretisation,

@@ -22,11 +22,11 @@ ASM_K, ASM_M_FULL, ASM_M_LUMPED = 1, 2, 4
 
 # every symbol include/scatter_b200.h declares (checked by tests/test_host_logic.py)
 SYMBOLS = [
-    "sc_create", "sc_destroy", "sc_last_error", "sc_version", "sc_device_info", "sc_kernel_launches", "sc_shape_table",
+    "sc_create", "sc_destroy", "sc_last_error", "sc_version", "sc_device_info", "sc_kernel_launches", "sc_set_option", "sc_shape_table",
     "sc_host_alloc", "sc_host_free",
-    "sc_set_mesh", "sc_set_materials", "sc_build_pattern", "sc_get_pattern", "sc_pattern_stats", "sc_assemble", "sc_add_entries",
+    "sc_set_mesh", "sc_set_csr", "sc_set_output_dofs", "sc_set_materials", "sc_build_pattern", "sc_get_pattern", "sc_pattern_stats", "sc_assemble", "sc_add_entries",
     "sc_set_rayleigh", "sc_get_values", "sc_get_lumped_mass", "sc_spmv", "sc_set_load_schedule", "sc_set_state",
-    "sc_get_state", "sc_run_newmark", "sc_run_central_difference", "sc_run_bathe", "sc_run_static", "sc_nccl_unique_id", "sc_dist_init", "sc_set_halo",
+    "sc_get_state", "sc_set_final_output_step", "sc_run_newmark", "sc_run_central_difference", "sc_run_bathe", "sc_run_static", "sc_nccl_unique_id", "sc_dist_init", "sc_set_halo",
     "sc_halo_exchange", "sc_srf_sample", "sc_add_absorbing_faces",
 ]
 
@@ -39,6 +39,7 @@ class Stats(C.Structure):
     def as_dict(self):
         d = {k: getattr(self, k) for k, _ in self._fields_ if k != "reserved"}
         d["step_bytes"] = self.reserved[0]
+        d["pcg_stagnations"] = int(self.reserved[2])
         d["step_kernel"] = {0: "k_spmv (register staged)", 1: "k_spmv_tma (row tiles)", 2: "k_spmv_node (node-blocked, TMA)"}.get(int(self.reserved[1]), "?")
         return d
 
@@ -72,10 +73,13 @@ def load_library():
     lib.sc_device_info.argtypes = [vp, P(i32), P(i64), P(i64), C.c_char_p, i32]
     lib.sc_kernel_launches.argtypes = [vp]
     lib.sc_kernel_launches.restype = i64
+    lib.sc_set_option.argtypes = [vp, C.c_char_p, i64]
     lib.sc_shape_table.argtypes = [i32, i32, P(i32), P(i32), P(i32), vp, vp, vp]
     lib.sc_host_alloc.argtypes = [P(vp), i64]
     lib.sc_host_free.argtypes = [vp]
     lib.sc_set_mesh.argtypes = [vp, i32, i64, vp, i64, vp, vp, i64, vp]
+    lib.sc_set_csr.argtypes = [vp, i64, vp, vp, vp, vp, vp]
+    lib.sc_set_output_dofs.argtypes = [vp, i64, vp]
     lib.sc_set_materials.argtypes = [vp, vp, vp, vp]
     lib.sc_build_pattern.argtypes = [vp, P(i64)]
     lib.sc_get_pattern.argtypes = [vp, vp, vp]
@@ -89,6 +93,7 @@ def load_library():
     lib.sc_set_load_schedule.argtypes = [vp, i64, vp, vp, vp]
     lib.sc_set_state.argtypes = [vp, vp, vp]
     lib.sc_get_state.argtypes = [vp, vp, vp, vp]
+    lib.sc_set_final_output_step.argtypes = [vp, i64]
     lib.sc_run_newmark.argtypes = [vp, dbl, i64, i64, i64, dbl, dbl, dbl, i32, i64, vp, vp, vp, P(Stats)]
     lib.sc_run_central_difference.argtypes = [vp, dbl, i64, i64, i64, i64, vp, vp, vp, P(Stats)]
     lib.sc_run_bathe.argtypes = [vp, dbl, i64, i64, i64, dbl, i32, i64, vp, vp, vp, P(Stats)]
@@ -168,6 +173,10 @@ def nccl_unique_id() -> bytes:
     return buf.raw
 
 
+# options applied to every new Context (`sc_set_option`); empty in production, filled by tests / A-B measurements
+DEFAULT_OPTIONS: dict = {}
+
+
 class Context:
     """One GPU context (`sc_ctx`).  Thin, 1:1 over the C ABI; all arrays are numpy, all heavy work is on the device."""
 
@@ -182,6 +191,11 @@ class Context:
         self.n_eq = 0
         self.nnz = 0
         self.elem_type = None
+        for name, value in DEFAULT_OPTIONS.items():
+            self.set_option(name, value)
+        self.state_epoch = 0            # bumped by everything that changes u, v, a on the device (see solvers._prepare)
+        self.final_output_step = -1
+        self.output_dofs = None
 
     def close(self):
         if getattr(self, "h", None):
@@ -208,6 +222,10 @@ class Context:
     def kernel_launches(self) -> int:
         return int(self.lib.sc_kernel_launches(self.h))
 
+    def set_option(self, name: str, value: int):
+        """Kernel-selection switch (tests / A-B measurements); see `sc_set_option` in include/scatter_b200.h."""
+        self._ck(self.lib.sc_set_option(self.h, name.encode(), int(value)))
+
     # ---- mesh / matrices
     def set_mesh(self, elem_type: str, xyz, conn, eq, n_eq: int, active=None):
         xyz = _arr(xyz, np.float64); conn = _arr(conn, np.int32); eq = _arr(eq, np.int64)
@@ -218,8 +236,44 @@ class Context:
                                       _ptr(eq), int(n_eq), _ptr(active)))
         self.n_eq = int(n_eq)
         self.elem_type = elem_type
+        self.state_epoch += 1
+        self.output_dofs = None
         self.n_elem = conn.shape[0]
         self.n_nodes = xyz.shape[0]
+
+    def set_csr(self, M, C, K):
+        """Upload caller-supplied scipy matrices (any sparse format) on the union of their patterns (`sc_set_csr`)."""
+        import scipy.sparse as sp
+        mats = [None if m is None else sp.csr_matrix(m) for m in (M, C, K)]
+        if mats[2] is None:
+            raise ValueError("K is required")
+        n = mats[2].shape[0]
+        keys = []
+        for m in mats:
+            if m is None:
+                continue
+            if m.shape != (n, n):
+                raise ValueError("M, C, K must be square matrices of equal shape")
+            m.sum_duplicates()
+            rows = np.repeat(np.arange(n, dtype=np.int64), np.diff(m.indptr))
+            keys.append(rows * n + m.indices.astype(np.int64))
+        keys.append(np.arange(n, dtype=np.int64) * (n + 1))             # the diagonal is always stored (Jacobi scaling)
+        union = np.unique(np.concatenate(keys))
+        rowptr = np.zeros(n + 1, dtype=np.int64)
+        np.cumsum(np.bincount(union // n, minlength=n), out=rowptr[1:])
+        col = (union % n).astype(np.int32)
+
+        def values(m):
+            if m is None:
+                return None
+            rows = np.repeat(np.arange(n, dtype=np.int64), np.diff(m.indptr))
+            v = np.zeros(len(union))
+            v[np.searchsorted(union, rows * n + m.indices.astype(np.int64))] = m.data
+            return v
+        vM, vC, vK = (values(m) for m in mats)
+        self._ck(self.lib.sc_set_csr(self.h, n, _ptr(rowptr), _ptr(col), _ptr(vK), _ptr(vM), _ptr(vC)))
+        self.n_eq, self.nnz, self.elem_type = n, int(len(union)), None
+        self.state_epoch += 1
 
     def set_materials(self, young, poisson, density):
         E = _arr(np.broadcast_to(young, (self.n_elem,)), np.float64)
@@ -298,56 +352,85 @@ class Context:
     def set_state(self, u=None, v=None):
         u = _arr(u, np.float64); v = _arr(v, np.float64)
         self._ck(self.lib.sc_set_state(self.h, _ptr(u), _ptr(v)))
+        self.state_epoch += 1
+
+    def set_output_dofs(self, dofs=None):
+        """Only these equations are copied to the host per output row (None: full rows of n_eq values)."""
+        if dofs is None:
+            if self.output_dofs is not None:
+                self._ck(self.lib.sc_set_output_dofs(self.h, 0, None))
+            self.output_dofs = None
+            return
+        if dofs is self.output_dofs:
+            return
+        dofs = _arr(dofs, np.int64)
+        self._ck(self.lib.sc_set_output_dofs(self.h, len(dofs), _ptr(dofs) if len(dofs) else _ptr(np.zeros(1, dtype=np.int64))))
+        self.output_dofs = dofs
+
+    def _row_len(self):
+        return self.n_eq if self.output_dofs is None else len(self.output_dofs)
 
     def get_state(self):
         u = np.empty(self.n_eq); v = np.empty(self.n_eq); a = np.empty(self.n_eq)
         self._ck(self.lib.sc_get_state(self.h, _ptr(u), _ptr(v), _ptr(a)))
         return u, v, a
 
+    def set_final_output_step(self, step: int | None):
+        """Also store the state at this step (None / -1: only multiples of the output interval)."""
+        self.final_output_step = -1 if step is None else int(step)
+        self._ck(self.lib.sc_set_final_output_step(self.h, self.final_output_step))
+
     @staticmethod
-    def n_output_rows(t_start: int, n_steps: int, out_interval: int) -> int:
+    def n_output_rows(t_start: int, n_steps: int, out_interval: int, final_step: int = -1) -> int:
         first = -(-t_start // out_interval) * out_interval
         last = t_start + n_steps
-        return 0 if first > last else (last - first) // out_interval + 1
+        n = 0 if first > last else (last - first) // out_interval + 1
+        if t_start <= final_step <= last and final_step % out_interval != 0:
+            n += 1
+        return n
 
     def run_newmark(self, dt, t_start, n_steps, out_interval=1, beta=0.25, gamma=0.5, rtol=1e-14, maxit=20000,
                     u_out=None, v_out=None, a_out=None, store=True):
-        n_out = self.n_output_rows(t_start, n_steps, out_interval) if store else 0
+        n_out = self.n_output_rows(t_start, n_steps, out_interval, self.final_output_step) if store else 0
         if store:
-            u_out = np.zeros((n_out, self.n_eq)) if u_out is None else u_out
-            v_out = np.zeros((n_out, self.n_eq)) if v_out is None else v_out
-            a_out = np.zeros((n_out, self.n_eq)) if a_out is None else a_out
+            u_out = np.zeros((n_out, self._row_len())) if u_out is None else u_out
+            v_out = np.zeros((n_out, self._row_len())) if v_out is None else v_out
+            a_out = np.zeros((n_out, self._row_len())) if a_out is None else a_out
         st = Stats()
+        self.state_epoch += 1
         self._ck(self.lib.sc_run_newmark(self.h, float(dt), int(t_start), int(n_steps), int(out_interval), float(beta),
                                          float(gamma), float(rtol), int(maxit), n_out, _ptr(u_out), _ptr(v_out), _ptr(a_out),
                                          C.byref(st)))
         return u_out, v_out, a_out, st.as_dict()
 
     def run_central_difference(self, dt, t_start, n_steps, out_interval=1, u_out=None, v_out=None, a_out=None, store=True):
-        n_out = self.n_output_rows(t_start, n_steps, out_interval) if store else 0
+        n_out = self.n_output_rows(t_start, n_steps, out_interval, self.final_output_step) if store else 0
         if store:
-            u_out = np.zeros((n_out, self.n_eq)) if u_out is None else u_out
-            v_out = np.zeros((n_out, self.n_eq)) if v_out is None else v_out
-            a_out = np.zeros((n_out, self.n_eq)) if a_out is None else a_out
+            u_out = np.zeros((n_out, self._row_len())) if u_out is None else u_out
+            v_out = np.zeros((n_out, self._row_len())) if v_out is None else v_out
+            a_out = np.zeros((n_out, self._row_len())) if a_out is None else a_out
         st = Stats()
+        self.state_epoch += 1
         self._ck(self.lib.sc_run_central_difference(self.h, float(dt), int(t_start), int(n_steps), int(out_interval), n_out,
                                                     _ptr(u_out), _ptr(v_out), _ptr(a_out), C.byref(st)))
         return u_out, v_out, a_out, st.as_dict()
 
     def run_bathe(self, dt, t_start, n_steps, out_interval=1, rtol=1e-14, maxit=20000, u_out=None, v_out=None, a_out=None):
-        n_out = self.n_output_rows(t_start, n_steps, out_interval)
-        u_out = np.zeros((n_out, self.n_eq)) if u_out is None else u_out
-        v_out = np.zeros((n_out, self.n_eq)) if v_out is None else v_out
-        a_out = np.zeros((n_out, self.n_eq)) if a_out is None else a_out
+        n_out = self.n_output_rows(t_start, n_steps, out_interval, self.final_output_step)
+        u_out = np.zeros((n_out, self._row_len())) if u_out is None else u_out
+        v_out = np.zeros((n_out, self._row_len())) if v_out is None else v_out
+        a_out = np.zeros((n_out, self._row_len())) if a_out is None else a_out
         st = Stats()
+        self.state_epoch += 1
         self._ck(self.lib.sc_run_bathe(self.h, float(dt), int(t_start), int(n_steps), int(out_interval), float(rtol), int(maxit),
                                        n_out, _ptr(u_out), _ptr(v_out), _ptr(a_out), C.byref(st)))
         return u_out, v_out, a_out, st.as_dict()
 
     def run_static(self, t_start, n_steps, out_interval=1, rtol=1e-12, maxit=100000, u_out=None):
-        n_out = self.n_output_rows(t_start, n_steps, out_interval)
-        u_out = np.zeros((n_out, self.n_eq)) if u_out is None else u_out
+        n_out = self.n_output_rows(t_start, n_steps, out_interval, self.final_output_step)
+        u_out = np.zeros((n_out, self._row_len())) if u_out is None else u_out
         st = Stats()
+        self.state_epoch += 1
         self._ck(self.lib.sc_run_static(self.h, int(t_start), int(n_steps), int(out_interval), float(rtol), int(maxit), n_out,
                                         _ptr(u_out), C.byref(st)))
         return u_out, st.as_dict()

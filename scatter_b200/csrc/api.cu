@@ -41,7 +41,7 @@ void free_pattern(sc_ctx* c) {
     pcg_graph_drop(c);
     sc_free(&c->d_n2e_ptr); sc_free(&c->d_n2e); sc_free(&c->d_nbr_ptr); sc_free(&c->d_nbr); sc_free(&c->d_nbr_off); sc_free(&c->d_nbr_free);
     sc_free(&c->d_node_rl); sc_free(&c->d_node_row0); sc_free(&c->d_rowptr); sc_free(&c->d_col); sc_free(&c->d_nd); sc_free(&c->d_ncol); sc_free(&c->d_dict); c->n_dict = 0; sc_free(&c->d_pair_pos); sc_free(&c->d_pair_al);
-    sc_free(&c->d_K); sc_free(&c->d_M); sc_free(&c->d_Ml); sc_free(&c->d_Khat); sc_free(&c->d_Khat2);
+    sc_free(&c->d_K); sc_free(&c->d_M); sc_free(&c->d_Ml); sc_free(&c->d_Khat); sc_free(&c->d_Khat2); sc_free(&c->d_C); c->csr_only = false;
     sc_free(&c->d_cabs_rowid); sc_free(&c->d_cabs_rptr); sc_free(&c->d_cabs_col); sc_free(&c->d_cabs_slot); sc_free(&c->d_cabs_val);
     c->cabs_n = c->cabs_rows = 0;
     c->have_pattern = c->have_K = c->have_M = c->have_Ml = false;
@@ -54,17 +54,19 @@ void free_vectors(sc_ctx* c) {
     for (auto& w : c->work) sc_free(&w);
     c->work.clear();
     sc_free(&c->d_partial);
-    for (int k = 0; k < 3; ++k) sc_free(&c->d_snap[k]);
+    for (int k = 0; k < 3; ++k) { sc_free(&c->d_snap[k]); sc_free(&c->d_selbuf[k]); }
+    sc_free(&c->d_sel); c->n_sel = -1;
     c->rows_pending = false;
     c->cd_resume_valid = false; c->nm_resume_valid = false; c->cd_coef_dt = -1.0;
 }
 
 // values of C = C_abs + c0 M + c1 K into a fresh device buffer
 int build_C(sc_ctx* ctx, double** out) {
-    if (!ctx->have_K || !ctx->have_M) return sc_fail(ctx, SC_ERR_STATE, "C needs assembled K and full M");
+    if (!ctx->d_C && (!ctx->have_K || !ctx->have_M)) return sc_fail(ctx, SC_ERR_STATE, "C needs assembled K and full M");
     double* tmp = nullptr;
     SC_TRY(sc_alloc(ctx, &tmp, (size_t)ctx->nnz));
-    int rc = la_axpby_vals(ctx, tmp, ctx->c0, ctx->d_M, ctx->c1, ctx->d_K, ctx->nnz);
+    int rc = ctx->d_C ? la_axpby_vals(ctx, tmp, 1.0, ctx->d_C, 0.0, nullptr, ctx->nnz)
+                      : la_axpby_vals(ctx, tmp, ctx->c0, ctx->d_M, ctx->c1, ctx->d_K, ctx->nnz);
     if (rc == SC_OK) rc = la_cabs_add_values(ctx, tmp, 1.0);
     if (rc != SC_OK) { sc_free(&tmp); return rc; }
     *out = tmp;
@@ -109,24 +111,6 @@ int sc_create(int device, sc_ctx** out) {
         return SC_ERR_CUDA;
     }
     cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
-    const char* no_tma = getenv("SCATTER_B200_NO_TMA");
-    ctx->force_no_tma = no_tma && no_tma[0] == '1';
-    const char* no_node = getenv("SCATTER_B200_NO_NODE");
-    ctx->force_no_node = no_node && no_node[0] == '1';
-    // the software-pipelined node kernel measured 2 % slower than the two-nodes-per-warp kernel on the 50 M-dof box
-    // (8.22 vs 8.08 ms): opt-in only
-    const char* pipe = getenv("SCATTER_B200_PIPE");
-    ctx->force_no_pipe = !(pipe && pipe[0] == '1');
-    const char* gen_asm = getenv("SCATTER_B200_GENERIC_ASSEMBLY");
-    ctx->force_generic_assembly = gen_asm && gen_asm[0] == '1';
-    const char* no_small = getenv("SCATTER_B200_NO_SMALL_PCG");
-    ctx->no_small_pcg = no_small && no_small[0] == '1';
-    const char* no_graph = getenv("SCATTER_B200_NO_GRAPH");
-    ctx->no_graph = no_graph && no_graph[0] == '1';
-    const char* no_dict = getenv("SCATTER_B200_NO_DICT");
-    ctx->no_dict = no_dict && no_dict[0] == '1';
-    const char* pair_asm = getenv("SCATTER_B200_PAIR_ASSEMBLY");
-    ctx->force_pair_assembly = pair_asm && pair_asm[0] == '1';
     *out = ctx;
     return SC_OK;
 }
@@ -164,6 +148,23 @@ int sc_device_info(sc_ctx* ctx, int* sm_count, int64_t* total_mem, int64_t* free
 }
 
 int64_t sc_kernel_launches(sc_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+// Kernel-selection switches for tests and A/B measurements; the defaults are the product path.
+int sc_set_option(sc_ctx* ctx, const char* name, int64_t value) {
+    if (!ctx || !name) return SC_ERR_ARG;
+    const std::string k(name);
+    const bool on = value != 0;
+    if (k == "node_spmv") ctx->force_no_node = !on;                 // node-blocked TMA SpMV (default on)
+    else if (k == "tma_spmv") ctx->force_no_tma = !on;              // row-tile TMA SpMV as the second choice (default on)
+    else if (k == "column_dictionary") ctx->no_dict = !on;          // relative column lists in shared memory (default on); takes
+                                                                    // effect at the next sc_build_pattern
+    else if (k == "small_pcg") ctx->no_small_pcg = !on;             // cooperative single-kernel PCG below 250 k equations (default on)
+    else if (k == "pcg_graph") ctx->no_graph = !on;                 // CUDA-graph replay of the PCG iteration (default on)
+    else if (k == "generic_assembly") ctx->force_generic_assembly = on;   // warp-per-node assembly for every element type (default off)
+    else return sc_fail(ctx, SC_ERR_ARG, "unknown option '%s'", name);
+    pcg_graph_drop(ctx);
+    return SC_OK;
+}
 
 int sc_host_alloc(void** out, int64_t bytes) {
     if (!out || bytes < 0) return SC_ERR_ARG;
@@ -379,6 +380,7 @@ int sc_add_absorbing_faces(sc_ctx* ctx, int face_type, int gauss_order, int64_t 
 
 int sc_set_rayleigh(sc_ctx* ctx, double c0, double c1) {
     if (!ctx) return SC_ERR_ARG;
+    if (ctx->d_C && (c0 != 0.0 || c1 != 0.0)) return sc_fail(ctx, SC_ERR_UNSUPPORTED, "sc_set_csr supplied C explicitly; add Rayleigh terms to it before the upload");
     ctx->c0 = c0; ctx->c1 = c1;
     ctx->cd_resume_valid = false; ctx->nm_resume_valid = false; ctx->khat_a1 = ctx->khat_a4 = -1.0; ctx->cd_coef_dt = -1.0;
     return SC_OK;
@@ -433,7 +435,7 @@ int sc_spmv(sc_ctx* ctx, int which, const double* x, double* y) {
 }
 
 int sc_set_load_schedule(sc_ctx* ctx, int64_t n_steps, const int64_t* step_ptr, const int64_t* dof, const double* val) {
-    if (!ctx || !ctx->have_mesh) return sc_fail(ctx, SC_ERR_STATE, "sc_set_mesh must be called first");
+    if (!ctx || !(ctx->have_mesh || ctx->csr_only)) return sc_fail(ctx, SC_ERR_STATE, "sc_set_mesh (or sc_set_csr) must be called first");
     if (n_steps < 0 || (n_steps > 0 && !step_ptr)) return sc_fail(ctx, SC_ERR_ARG, "bad load schedule");
     SC_CUDA(ctx, cudaSetDevice(ctx->device));
     ctx->load_steps = n_steps;
@@ -450,7 +452,7 @@ int sc_set_load_schedule(sc_ctx* ctx, int64_t n_steps, const int64_t* step_ptr, 
 }
 
 int sc_set_state(sc_ctx* ctx, const double* u, const double* v) {
-    if (!ctx || !ctx->have_mesh) return sc_fail(ctx, SC_ERR_STATE, "sc_set_mesh must be called first");
+    if (!ctx || !(ctx->have_mesh || ctx->csr_only)) return sc_fail(ctx, SC_ERR_STATE, "sc_set_mesh (or sc_set_csr) must be called first");
     SC_CUDA(ctx, cudaSetDevice(ctx->device));
     const size_t n = (size_t)ctx->n_eq;
     for (int k = 0; k < 3; ++k) {
@@ -461,6 +463,78 @@ int sc_set_state(sc_ctx* ctx, const double* u, const double* v) {
         else SC_CUDA(ctx, cudaMemset(*d, 0, n * sizeof(double)));
     }
     ctx->cd_resume_valid = false; ctx->nm_resume_valid = false;
+    return SC_OK;
+}
+
+// Caller-supplied matrices (seam B2 of SURVEY.md 8b: solvers.*.calculate(M, C, K, F, t0, t1) with scipy matrices that were
+// not assembled by this library, scatter/scatter.py:159).  One CSR pattern, three value arrays.
+int sc_set_csr(sc_ctx* ctx, int64_t n_eq, const int64_t* rowptr, const int32_t* col, const double* K, const double* M, const double* C) {
+    if (!ctx || n_eq <= 0 || !rowptr || !col || !K) return sc_fail(ctx, SC_ERR_ARG, "sc_set_csr needs n_eq > 0, a pattern and K");
+    if (n_eq >= (int64_t)1 << 31) return sc_fail(ctx, SC_ERR_UNSUPPORTED, "more than 2^31 equations per rank");
+    if (rowptr[0] != 0) return sc_fail(ctx, SC_ERR_ARG, "rowptr[0] must be 0");
+    int max_rl = 0;
+    for (int64_t i = 0; i < n_eq; ++i) {
+        const int64_t len = rowptr[i + 1] - rowptr[i];
+        if (len < 0 || len > 65535) return sc_fail(ctx, SC_ERR_ARG, "row %lld has a bad length %lld", (long long)i, (long long)len);
+        max_rl = std::max(max_rl, (int)len);
+        for (int64_t k = rowptr[i]; k < rowptr[i + 1]; ++k) {
+            if (col[k] < 0 || col[k] >= n_eq) return sc_fail(ctx, SC_ERR_ARG, "column index out of range in row %lld", (long long)i);
+            if (k > rowptr[i] && col[k] <= col[k - 1]) return sc_fail(ctx, SC_ERR_ARG, "columns of row %lld are not sorted / unique", (long long)i);
+        }
+    }
+    SC_CUDA(ctx, cudaSetDevice(ctx->device));
+    free_pattern(ctx);
+    free_vectors(ctx);
+    sc_free(&ctx->d_xyz); sc_free(&ctx->d_conn); sc_free(&ctx->d_eq); sc_free(&ctx->d_active);
+    ctx->have_mesh = false; ctx->have_mat = false;
+    ctx->elem_type = -1; ctx->nne = 0; ctx->dim = 0; ctx->n_nodes = 0; ctx->n_elem = 0;
+    ctx->n_eq = n_eq; ctx->nnz = rowptr[n_eq]; ctx->max_rl = max_rl;
+    ctx->c0 = ctx->c1 = 0.0;
+    SC_TRY(upload(ctx, &ctx->d_rowptr, rowptr, (size_t)n_eq + 1));
+    SC_TRY(upload(ctx, &ctx->d_col, col, (size_t)ctx->nnz));
+    SC_TRY(upload(ctx, &ctx->d_K, K, (size_t)ctx->nnz));
+    ctx->have_pattern = true; ctx->have_K = true; ctx->csr_only = true;
+    if (M) {
+        SC_TRY(upload(ctx, &ctx->d_M, M, (size_t)ctx->nnz));
+        ctx->have_M = true;
+        // row sums of M = lumped mass of the explicit scheme
+        double* ones = nullptr;
+        SC_TRY(sc_alloc(ctx, &ones, (size_t)n_eq));
+        SC_TRY(sc_alloc(ctx, &ctx->d_Ml, (size_t)n_eq));
+        int rc = la_fill(ctx, ones, 1.0, n_eq);
+        if (rc == SC_OK) rc = la_spmv(ctx, ctx->d_M, ones, ctx->d_Ml);
+        if (rc == SC_OK && cudaStreamSynchronize(ctx->stream) != cudaSuccess) rc = sc_fail(ctx, SC_ERR_CUDA, "lumping M failed");
+        sc_free(&ones);
+        SC_TRY(rc);
+        ctx->have_Ml = true;
+    }
+    if (C) SC_TRY(upload(ctx, &ctx->d_C, C, (size_t)ctx->nnz));
+    return SC_OK;
+}
+
+// Only these equations are copied to the host per output row (n = 0 .. n_eq, sorted or not; NULL restores full rows).
+int sc_set_output_dofs(sc_ctx* ctx, int64_t n, const int64_t* dofs) {
+    if (!ctx) return SC_ERR_ARG;
+    SC_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (ctx->rows_pending) { cudaStreamSynchronize(ctx->copy_stream); ctx->rows_pending = false; }
+    sc_free(&ctx->d_sel);
+    for (int k = 0; k < 3; ++k) sc_free(&ctx->d_selbuf[k]);
+    ctx->n_sel = -1;
+    if (!dofs) return SC_OK;
+    if (n < 0) return sc_fail(ctx, SC_ERR_ARG, "negative count");
+    std::vector<int32_t> d32((size_t)n);
+    for (int64_t i = 0; i < n; ++i) {
+        if (dofs[i] < 0 || dofs[i] >= ctx->n_eq) return sc_fail(ctx, SC_ERR_ARG, "output dof %lld out of range", (long long)dofs[i]);
+        d32[i] = (int32_t)dofs[i];
+    }
+    SC_TRY(upload(ctx, &ctx->d_sel, d32.data(), (size_t)n));
+    ctx->n_sel = n;
+    return SC_OK;
+}
+
+int sc_set_final_output_step(sc_ctx* ctx, int64_t step) {
+    if (!ctx) return SC_ERR_ARG;
+    ctx->extra_out_step = step < 0 ? -1 : step;
     return SC_OK;
 }
 

@@ -9,10 +9,9 @@
 // the elements touching its node.  A block of consecutive nodes therefore produces its CSR rows alone: it walks the
 // elements of each node in ascending element id -- the order in which the reference adds them to a slot -- evaluates
 // only the DIM x (NNE*DIM) row block of Ke that belongs to the node, and sums per slot in that order.  Nobody else
-// writes those rows, so the result is reproducible bit for bit.  Three kernels implement it: `k_assemble_blk` (default:
+// writes those rows, so the result is reproducible bit for bit.  Two kernels implement it: `k_assemble_blk` (default:
 // row block in registers, one, two or five lanes per (node, element) pair, Jacobian set-up shared by the pairs of a
-// block), `k_assemble_pairs` (its predecessor for tri3..hexa8: set-up repeated per lane; kept as a cross-check behind
-// SCATTER_B200_PAIR_ASSEMBLY=1) and `k_assemble` (one warp per node, shared-memory staging; very high node valences).
+// block) and `k_assemble` (one warp per node, shared-memory staging; very high node valences).
 //
 // Isotropic elasticity lets the row block be formed without B or D:
 //   K[(a,i),(b,j)] = sum_g w_g detJ_g ( lam dNa_i dNb_j + mu dNa_j dNb_i + delta_ij mu dNa.dNb )
@@ -242,227 +241,15 @@ __constant__ double c_tabN[SC_MAX_GP * SC_MAX_NNE];
 __constant__ double c_tabdN[SC_MAX_GP * SC_MAX_NNE * 3];
 __constant__ double c_tabw[SC_MAX_GP];
 
-// LPP lanes share one (node, element) pair: every lane evaluates the Jacobians (redundantly) and NNE/LPP of the NNE
-// node blocks of the row block.  LPP = 2 halves the register-resident accumulators of hexa8 (72 -> 36 doubles), which
-// doubles the resident warps per SM; the extra Jacobian work costs less than the latency it hides.
-template <int NNE, int DIM, int NGP, int TPB, int LPP, int MINB, int UG>
-__global__ void __launch_bounds__(TPB, MINB) k_assemble_pairs(AsmParams p, int npb) {
-    constexpr int DD = DIM * DIM, ND = NNE * DIM;
-    constexpr int NBB = NNE / LPP;                       // node blocks per lane
-    constexpr int PPB = TPB / LPP;                       // pairs per block
-    constexpr int SST = DIM * ND + 1;                    // stride of one pair's row block in the staging area (odd: no bank conflicts)
-    static_assert(NNE % LPP == 0, "lanes per pair must divide the node count");
-    extern __shared__ double smem[];
-    // region A is used twice: coordinates + detJ*w during the integration, the staged row blocks afterwards
-    double* xs = smem;                                   // [ND][TPB]   coordinates, one column per thread
-    double* swj = xs + ND * TPB;                         // [NGP][TPB]  detJ*w per Gauss point
-    double* stage = smem;                                // [PPB][SST]  row block of every pair
-    double* stage_m = stage + (size_t)PPB * SST;         // [PPB][NNE]  rho * sum_g detJ w N_a N_b of every pair
-    constexpr size_t SZ_STAGE = (size_t)PPB * SST + (size_t)PPB * NNE, SZ_INT = (size_t)(ND + NGP) * TPB;
-    constexpr size_t REGION_A = SZ_STAGE > SZ_INT ? SZ_STAGE : SZ_INT;
-    double* sdN = smem + REGION_A;                       // [NGP*NNE*DIM] table copy for lane-dependent rows
-    double* sN = sdN + NGP * NNE * DIM;                  // [NGP*NNE]
-    double* s_mitem = sN + NGP * NNE;                    // [npb*max_nbr] mass of every (node, neighbour) item
-    long long* s_rowbase = reinterpret_cast<long long*>(s_mitem + (size_t)npb * p.max_nbr);   // [npb*DIM] first slot of row (a,i) or -1
-    int* s_ptr = reinterpret_cast<int*>(s_rowbase + (size_t)npb * DIM);   // [npb+1] pair offsets of the block's nodes
-    int* s_nptr = s_ptr + npb + 1;                       // [npb+1] neighbour-list offsets
-    unsigned char* s_inv = reinterpret_cast<unsigned char*>(s_nptr + npb + 1);   // [PPB][max_nbr] neighbour position -> local node
-
-    const int tid = threadIdx.x;
-    const int64_t a0 = (int64_t)blockIdx.x * npb;
-    const int64_t a1 = min(a0 + npb, p.n_nodes);
-    const int nbn = (int)(a1 - a0);
-    const int64_t P0 = p.n2e_ptr[a0];
-    const int64_t nbr0 = p.nbr_ptr[a0];
-    for (int t = tid; t <= nbn; t += TPB) {
-        s_ptr[t] = (int)(p.n2e_ptr[a0 + t] - P0);
-        s_nptr[t] = (int)(p.nbr_ptr[a0 + t] - nbr0);
-    }
-    for (int t = tid; t < NGP * NNE * DIM; t += TPB) sdN[t] = p.tabdN[t];
-    for (int t = tid; t < NGP * NNE; t += TPB) sN[t] = p.tabN[t];
-    for (int t = tid; t < PPB * p.max_nbr; t += TPB) s_inv[t] = 0xff;
-    for (int t = tid; t < nbn * DIM; t += TPB) {
-        const int rr = p.eq[(a0 + t / DIM) * DIM + t % DIM];
-        s_rowbase[t] = (rr >= 0 && p.node_rl[a0 + t / DIM] > 0) ? (long long)p.rowptr[rr] : -1;
-    }
-    __syncthreads();
-    const int npairs = s_ptr[nbn];                       // <= PPB by construction of npb
-    const int n_items = s_nptr[nbn];
-
-    // ---- phase 1: LPP lanes per (node, element) pair, their part of the row block in registers -----------------------
-    const int k = tid / LPP, half = tid % LPP;
-    bool valid = k < npairs;
-    double acc[DIM][NBB * DIM];
-    double mab[NBB];
-#pragma unroll
-    for (int i = 0; i < DIM; ++i)
-#pragma unroll
-        for (int c = 0; c < NBB * DIM; ++c) acc[i][c] = 0.0;
-#pragma unroll
-    for (int b = 0; b < NBB; ++b) mab[b] = 0.0;
-    if (valid) {
-        int lo = 0, hi = nbn;
-        while (hi - lo > 1) {
-            const int mid = (lo + hi) >> 1;
-            if (s_ptr[mid] <= k) lo = mid; else hi = mid;
-        }
-        valid = p.node_rl[a0 + lo] > 0;                  // ghost nodes of a domain decomposition own no rows
-        if (valid) {
-            const int e = p.n2e[P0 + k];
-            const int al = p.pair_al[P0 + k];
-#pragma unroll
-            for (int b = 0; b < NNE; ++b) {
-                const int c = p.conn[(int64_t)e * NNE + b];
-#pragma unroll
-                for (int d = 0; d < DIM; ++d) xs[(b * DIM + d) * TPB + tid] = p.xyz[(int64_t)c * 3 + d];
-            }
-            if (half == 0) {
-#pragma unroll
-                for (int b = 0; b < NNE; ++b) s_inv[k * p.max_nbr + p.pair_pos[(P0 + k) * NNE + b]] = (unsigned char)b;
-            }
-            const double E = p.E[e], nu = p.nu[e];
-            const double rho = p.rho[e];
-            const double lam = E * nu / ((1.0 + nu) * (1.0 - 2.0 * nu));
-            const double mu = E / (2.0 * (1.0 + nu));
-#pragma unroll UG
-            for (int g = 0; g < NGP; ++g) {
-                double J[DD], inv[DD], det;
-#pragma unroll
-                for (int r = 0; r < DD; ++r) J[r] = 0.0;
-#pragma unroll
-                for (int b = 0; b < NNE; ++b)
-#pragma unroll
-                    for (int d = 0; d < DIM; ++d) {
-                        const double dn = c_tabdN[(g * NNE + b) * DIM + d];
-#pragma unroll
-                        for (int kk = 0; kk < DIM; ++kk) J[d * DIM + kk] += dn * xs[(b * DIM + kk) * TPB + tid];
-                    }
-                invert<DIM>(J, inv, det);
-                const double wj = det * c_tabw[g];
-                swj[g * TPB + tid] = wj;
-                double lga[DIM], mga[DIM];
-#pragma unroll
-                for (int kk = 0; kk < DIM; ++kk) {
-                    double s = 0.0;
-#pragma unroll
-                    for (int d = 0; d < DIM; ++d) s += sdN[(g * NNE + al) * DIM + d] * inv[kk * DIM + d];
-                    lga[kk] = lam * wj * s;
-                    mga[kk] = mu * wj * s;
-                }
-#pragma unroll
-                for (int bb = 0; bb < NBB; ++bb) {
-                    // node block b = half * NBB + bb: the table row is lane dependent for LPP > 1 -> shared-memory copy
-                    const double* dnb = (LPP > 1) ? (sdN + (g * NNE + half * NBB + bb) * DIM) : (c_tabdN + (g * NNE + bb) * DIM);
-                    double gb[DIM];
-#pragma unroll
-                    for (int kk = 0; kk < DIM; ++kk) {
-                        double s = 0.0;
-#pragma unroll
-                        for (int d = 0; d < DIM; ++d) s += dnb[d] * inv[kk * DIM + d];
-                        gb[kk] = s;
-                    }
-                    double sdot = 0.0;
-#pragma unroll
-                    for (int d = 0; d < DIM; ++d) sdot += mga[d] * gb[d];
-#pragma unroll
-                    for (int i = 0; i < DIM; ++i)
-#pragma unroll
-                        for (int j = 0; j < DIM; ++j) {
-                            double t = lga[i] * gb[j] + mga[j] * gb[i];
-                            if (i == j) t += sdot;
-                            acc[i][bb * DIM + j] += t;
-                        }
-                }
-            }
-            // consistent mass of the node pairs: rho * sum_g detJ w N_a N_b   (discretisation.py:213-214)
-#pragma unroll
-            for (int bb = 0; bb < NBB; ++bb) {
-                double m = 0.0;
-#pragma unroll
-                for (int g = 0; g < NGP; ++g) m += swj[g * TPB + tid] * sN[g * NNE + al] * sN[g * NNE + half * NBB + bb];
-                mab[bb] = rho * m;
-            }
-        }
-    }
-    __syncthreads();                                     // everybody is done with xs / swj: region A becomes the staging area
-    if (valid) {
-#pragma unroll
-        for (int i = 0; i < DIM; ++i)
-#pragma unroll
-            for (int c = 0; c < NBB * DIM; ++c) stage[(size_t)k * SST + i * ND + half * NBB * DIM + c] = acc[i][c];
-#pragma unroll
-        for (int bb = 0; bb < NBB; ++bb) stage_m[k * NNE + half * NBB + bb] = mab[bb];
-    }
-    __syncthreads();
-
-    // ---- phase 2: one thread per (node, neighbour) item = one DIM x DIM block of the global matrix; it adds the staged
-    //      contributions of the node's elements in ascending element id (the reference's summation order) -------------
-    for (int q = tid; q < n_items; q += TPB) {
-        int lo = 0, hi = nbn;
-        while (hi - lo > 1) {
-            const int mid = (lo + hi) >> 1;
-            if (s_nptr[mid] <= q) lo = mid; else hi = mid;
-        }
-        const int n = lo, pidx = q - s_nptr[n];
-        const int64_t a = a0 + n;
-        double blk[DIM][DIM];
-#pragma unroll
-        for (int i = 0; i < DIM; ++i)
-#pragma unroll
-            for (int j = 0; j < DIM; ++j) blk[i][j] = 0.0;
-        double m = 0.0;
-        for (int pr = s_ptr[n]; pr < s_ptr[n + 1]; ++pr) {
-            const int b = s_inv[pr * p.max_nbr + pidx];
-            if (b == 0xff) continue;
-            const double* sp = stage + (size_t)pr * SST + b * DIM;
-#pragma unroll
-            for (int i = 0; i < DIM; ++i)
-#pragma unroll
-                for (int j = 0; j < DIM; ++j) blk[i][j] += sp[i * ND + j];
-            m += stage_m[pr * NNE + b];
-        }
-        s_mitem[q] = m;
-        const int off = p.nbr_off[nbr0 + q];
-        const int fmask = p.nbr_free[nbr0 + q];
-#pragma unroll
-        for (int i = 0; i < DIM; ++i) {
-            const long long rb = s_rowbase[n * DIM + i];
-            if (rb < 0) continue;
-            int64_t o = rb + off;
-#pragma unroll
-            for (int j = 0; j < DIM; ++j) {
-                if (!(fmask & (1 << j))) continue;
-                if (p.K) p.K[o] = blk[i][j];
-                if (p.M) p.M[o] = (i == j) ? m : 0.0;
-                ++o;
-            }
-        }
-    }
-    if (p.Ml) {
-        __syncthreads();
-        // row sums of the consistent mass: columns (b,i) that exist, neighbour order
-        for (int t = tid; t < nbn * DIM; t += TPB) {
-            const int n = t / DIM, i = t % DIM;
-            if (s_rowbase[t] < 0) continue;
-            double s = 0.0;
-            for (int q = s_nptr[n]; q < s_nptr[n + 1]; ++q)
-                if (p.nbr_free[nbr0 + q] & (1 << i)) s += s_mitem[q];
-            p.Ml[p.eq[(a0 + n) * DIM + i]] = s;
-        }
-    }
-}
-
-
-// ---------------------------------------------------------------------------------------------------------------------
-// Block-level element sharing (default for tri3 .. hexa8).  `k_assemble_pairs` repeats the Jacobian set-up in every
-// lane of every (node, element) pair: for hexa8 that is 16 evaluations per element and Gauss point inside one block
-// alone.  Here a block first lists the *distinct* elements of its pairs (consecutive nodes share most of theirs),
+// Block-level element sharing (default for every element type).  Repeating the Jacobian set-up in every lane of every
+// (node, element) pair costs 16 evaluations per hexa8 element and Gauss point inside one block alone (the previous
+// generation of this kernel did).  Here a block first lists the *distinct* elements of its pairs (consecutive nodes share most of theirs),
 // evaluates J^-1 and detJ*w once per (element, Gauss point) -- a few threads per element, coordinates in registers --
 // and parks the 10 numbers in shared memory.  The pair lanes then only accumulate the gradient products
 //     G_ab[i][j] = sum_g detJ w  dNa_i dNb_j          (9 FMA per node block and Gauss point, tables from __constant__)
 // and apply the material law once at the end:  K_ab[i][j] = lam G[i][j] + mu G[j][i] + delta_ij mu tr G.
-// Staging and the ordered gather (phase 2) are the same as in `k_assemble_pairs`, so the summation order -- and the
-// bit pattern of repeated runs -- is unchanged.  FP64 instructions per block: 2.1x fewer for hexa8.
+// All pairs park their row blocks in a shared-memory staging area and one thread per (node, neighbour) block adds the
+// staged contributions in ascending element id (the reference's accumulation order), so repeated runs are bit-identical.
 template <int NNE, int DIM, int NGP, int TPB, int LPP, int MINB>
 __global__ void __launch_bounds__(TPB, MINB) k_assemble_blk(AsmParams p, int npb) {
     constexpr int DD = DIM * DIM, ND = NNE * DIM;
@@ -805,34 +592,6 @@ int launch_blk(sc_ctx* ctx, const AsmParams& p, const ShapeTable& t, bool* handl
 }
 
 template <int NNE, int DIM, int NGP>
-int launch_pairs(sc_ctx* ctx, const AsmParams& p, const ShapeTable& t, bool* handled) {
-    constexpr int TPB = 128;
-    constexpr int LPP = (DIM * NNE * DIM > 36 && NNE % 2 == 0) ? 2 : 1;       // two lanes per pair for hexa8 / quad8
-    constexpr int PPB = TPB / LPP;
-    constexpr int ND = NNE * DIM, SST = DIM * ND + 1;
-    *handled = false;
-    if (!p.pair_pos || ctx->max_valence <= 0 || ctx->max_valence > PPB || p.max_nbr > 255) return SC_OK;
-    const int npb = std::max(1, PPB / ctx->max_valence);
-    const size_t region_a = std::max((size_t)PPB * SST + (size_t)PPB * NNE, (size_t)(ND + NGP) * TPB);
-    const size_t bytes = (region_a + (size_t)NGP * NNE * DIM + (size_t)NGP * NNE + (size_t)npb * p.max_nbr + (size_t)npb * DIM) * sizeof(double) +
-                         2 * (size_t)(npb + 1) * sizeof(int) + (size_t)PPB * p.max_nbr + 16;
-    if (bytes > 110 * 1024) return SC_OK;
-    SC_CUDA(ctx, cudaMemcpyToSymbolAsync(c_tabN, t.N.data(), t.N.size() * sizeof(double), 0, cudaMemcpyHostToDevice, ctx->stream));
-    SC_CUDA(ctx, cudaMemcpyToSymbolAsync(c_tabdN, t.dN.data(), t.dN.size() * sizeof(double), 0, cudaMemcpyHostToDevice, ctx->stream));
-    SC_CUDA(ctx, cudaMemcpyToSymbolAsync(c_tabw, t.w.data(), t.w.size() * sizeof(double), 0, cudaMemcpyHostToDevice, ctx->stream));
-    const unsigned grid = (unsigned)((p.n_nodes + npb - 1) / npb);
-    // (measured on B200, hexa8: 4 blocks/SM with a 128-register cap spills and is 1.45x slower; unrolling the Gauss-point
-    //  loop x2 is 1.09x slower -- instruction cache)
-    constexpr int MINB = LPP > 1 ? 3 : 2;
-    auto kern = k_assemble_pairs<NNE, DIM, NGP, TPB, LPP, MINB, 1>;
-    SC_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
-    kern<<<grid, TPB, bytes, ctx->stream>>>(p, npb);
-    SC_CHECK_LAUNCH(ctx);
-    *handled = true;
-    return SC_OK;
-}
-
-template <int NNE, int DIM, int NGP>
 int launch(sc_ctx* ctx, const AsmParams& p) {
     constexpr int JS = DIM * DIM + 1;
     const size_t tables = (size_t)NGP * NNE + (size_t)NGP * NNE * DIM + NGP;
@@ -895,10 +654,7 @@ int sc_assemble_run(sc_ctx* ctx, int order, int flags, double* seconds) {
         {                                                                                \
             bool done = false;                                                           \
             rc = SC_OK;                                                                  \
-            if (!ctx->force_generic_assembly && !ctx->force_pair_assembly)                                   \
-                rc = launch_blk<NNE, DIM, NGP>(ctx, p, t, &done);                        \
-            if (rc == SC_OK && !done && DIM * NNE * DIM <= 72 && !ctx->force_generic_assembly)               \
-                rc = launch_pairs<NNE, DIM, NGP>(ctx, p, t, &done);                      \
+            if (!ctx->force_generic_assembly) rc = launch_blk<NNE, DIM, NGP>(ctx, p, t, &done); \
             if (rc == SC_OK && !done) rc = launch<NNE, DIM, NGP>(ctx, p);                \
         }                                                                                \
         break;

@@ -66,7 +66,7 @@ struct sc_ctx {
     int64_t ncol_total = 0;
     int32_t* d_dict = nullptr;      // [n_dict*dict_stride] most frequent relative column lists (node_dict.cu); nodes with one of
     int n_dict = 0, dict_stride = 0;   // them carry its id in their descriptor and have no explicit list in d_ncol
-    bool no_dict = false;           // SCATTER_B200_NO_DICT=1: keep every explicit node column list
+    bool no_dict = false;           // sc_set_option("column_dictionary", 0): keep every explicit node column list
     int max_nbr = 0, max_rl = 0, max_valence = 0;   // max neighbours / row length / elements per node
 
     // dof-level CSR
@@ -81,6 +81,8 @@ struct sc_ctx {
     double* d_Ml = nullptr;         // [n_eq] lumped mass (optional)
     double* d_Khat = nullptr;       // [nnz] effective matrix (Newmark / Bathe sub-step 1)
     double* d_Khat2 = nullptr;      // [nnz] effective matrix of Bathe sub-step 2
+    double* d_C = nullptr;          // [nnz] explicit damping matrix of sc_set_csr (null: C = C_abs + c0 M + c1 K, never stored)
+    bool csr_only = false;          // matrices came from sc_set_csr: no mesh, no node structure, row-wise kernels only
     bool have_K = false, have_M = false, have_Ml = false;
     double c0 = 0.0, c1 = 0.0;
 
@@ -98,6 +100,9 @@ struct sc_ctx {
     int32_t* d_load_dof = nullptr;
     double* d_load_val = nullptr;
 
+    int64_t pcg_stagnations = 0;    // solves accepted at a stagnated residual below 1e-9 (see timeloop.cu: pcg)
+    int64_t extra_out_step = -1;    // sc_set_final_output_step: this step is stored even if it is no multiple of the interval
+
     // state
     double *d_u = nullptr, *d_v = nullptr, *d_a = nullptr;   // [n_eq]
     std::vector<double*> work;      // work vectors [n_eq], allocated on demand
@@ -107,18 +112,19 @@ struct sc_ctx {
     cudaEvent_t ev_rows_ready = nullptr, ev_rows_done = nullptr;   // output rows: snapshot ready / D2H finished
     bool rows_pending = false;
     double* d_snap[3] = {nullptr, nullptr, nullptr};               // snapshots of u, v, a while their D2H copy is in flight
-    bool force_no_pipe = true;             // env SCATTER_B200_PIPE=1 selects the software-pipelined node kernel (experimental)
-    bool force_no_node = false;            // env SCATTER_B200_NO_NODE: row-wise kernels instead of the node-blocked one
-    bool force_no_tma = false;             // test hook / env SCATTER_B200_NO_TMA: register-staged SpMV instead of the TMA ring
-    bool no_small_pcg = false;             // SCATTER_B200_NO_SMALL_PCG=1: never use the cooperative single-kernel PCG
+    int32_t* d_sel = nullptr;                                      // sc_set_output_dofs: equations copied out per output row
+    int64_t n_sel = -1;                                            // -1: full rows
+    double* d_selbuf[3] = {nullptr, nullptr, nullptr};             // gathered u, v, a of the current output row
+    bool force_no_node = false;            // sc_set_option("node_spmv", 0): row-wise kernels instead of the node-blocked one
+    bool force_no_tma = false;             // sc_set_option("tma_spmv", 0): register-staged SpMV instead of the TMA ring
+    bool no_small_pcg = false;             // sc_set_option("small_pcg", 0): never use the cooperative single-kernel PCG
     int small_pcg_grid = 0;                // co-resident grid limit of k_pcg_small (0: not queried yet)
-    bool no_graph = false;                 // SCATTER_B200_NO_GRAPH=1: launch the PCG iteration kernel by kernel
+    bool no_graph = false;                 // sc_set_option("pcg_graph", 0): launch the PCG iteration kernel by kernel
     cudaGraphExec_t pcg_graph = nullptr;   // captured PCG iteration (single-GPU), valid for the pointers in pcg_graph_key
     const void* pcg_graph_key[8] = {};
     int64_t pcg_graph_n = 0;
     int pcg_graph_launches = 0;
-    bool force_pair_assembly = false;      // test hook: previous generation (set-up repeated per pair lane)
-    bool force_generic_assembly = false;   // test hook: use the warp-per-node kernel for every element type
+    bool force_generic_assembly = false;   // sc_set_option("generic_assembly", 1): warp-per-node kernel for every element type
     bool nm_resume_valid = false;   // d_a holds the Newmark acceleration of step nm_resume_t (stage continuation)
     int64_t nm_resume_t = 0;
     double khat_a1 = -1.0, khat_a4 = -1.0;   // parameters d_Khat was built with (-1: invalid)
@@ -215,18 +221,21 @@ bool pcg_small_usable(sc_ctx* ctx);
 int pcg_small(sc_ctx* ctx, const double* vals, const double* dinv, const double* b, double* x, double* r, double* p, double* q,
               double rtol, int maxit, int* iters, double* relres, double ref_norm2);
 void pcg_graph_drop(sc_ctx* ctx);                                        // timeloop.cu: forget the captured PCG iteration
-int la_cd_step(sc_ctx* ctx, const double* K, const double* u, double* uprev_next, const double* inv_d, const double* alpha);
+int la_cd_step(sc_ctx* ctx, const double* K, const double* w, const double* u, double* uprev_next, const double* inv_d,
+               const double* alpha, double g, double* w_next);
 int la_spmv_dot(sc_ctx* ctx, const double* vals, const double* p, double* q, double* d_out);
 // spmv_tma.cu
 bool la_tma_usable(sc_ctx* ctx);
 // spmv_node.cu
 bool la_node_usable(sc_ctx* ctx);
 int la_node_spmv(sc_ctx* ctx, const double* vals, const double* x, double* y);
-int la_node_cd_step(sc_ctx* ctx, const double* K, const double* u, double* uprev_next, const double* inv_d, const double* alpha);
+int la_node_cd_step(sc_ctx* ctx, const double* K, const double* w, const double* u, double* uprev_next, const double* inv_d,
+                    const double* alpha, double g, double* w_next);
 int la_node_spmv_dot(sc_ctx* ctx, const double* vals, const double* p, double* q, double* partial, unsigned* nblocks);
-int64_t la_node_step_bytes(sc_ctx* ctx);
+int64_t la_node_step_bytes(sc_ctx* ctx, bool lagged);
 int la_tma_spmv(sc_ctx* ctx, const double* vals, const double* x, double* y);
-int la_tma_cd_step(sc_ctx* ctx, const double* K, const double* u, double* uprev_next, const double* inv_d, const double* alpha);
+int la_tma_cd_step(sc_ctx* ctx, const double* K, const double* w, const double* u, double* uprev_next, const double* inv_d,
+                   const double* alpha, double g, double* w_next);
 int la_tma_spmv_dot(sc_ctx* ctx, const double* vals, const double* p, double* q, double* partial, unsigned* nblocks);
 // timeloop.cu
 int tl_newmark(sc_ctx* ctx, double dt, int64_t t0, int64_t n_steps, int64_t oi, double beta, double gamma, double rtol,

@@ -20,14 +20,16 @@ constexpr int SPMV_WARPS = SPMV_THREADS / 32;
 // products staged in shared memory, one thread per row adding them -- showed 51 long-scoreboard stalls per issue and
 // 40 % DRAM throughput).  Lane partials are added in entry order, then a fixed xor butterfly: deterministic.
 // MODE 0: y = A xa            MODE 1: y = A xa + B xb
-// MODE 2: central-difference step  un[i] = inv_d[i]*(-sum) + alpha[i]*xa[i] - (alpha[i]-1)*un[i]   (un holds u_prev)
+// MODE 2: central-difference step  un[i] = inv_d[i]*(-sum) + alpha[i]*xe[i] - (alpha[i]-1)*un[i]   (un holds u_prev; xa is the
+//         gathered vector w = (1+g) u - g u_prev that carries the lagged stiffness-proportional damping, xe = u; with
+//         y2 != null the next gather vector y2[i] = (1+g) un[i] - g xe[i] is written by the same epilogue)
 // MODE 3: PCG product  y = A xa  and per-block partial of xa.y  (partial[blockIdx])
 template <int MODE, int RPW, int U>
 __global__ void __launch_bounds__(SPMV_THREADS)
 k_spmv(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col, const double* __restrict__ va,
        const double* __restrict__ xa, const double* __restrict__ vb, const double* __restrict__ xb,
        double* __restrict__ y, const double* __restrict__ inv_d, const double* __restrict__ alpha,
-       double* __restrict__ partial, int64_t n_rows) {
+       double* __restrict__ partial, int64_t n_rows, const double* __restrict__ xe, double* __restrict__ y2, double g) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t row0 = ((int64_t)blockIdx.x * SPMV_WARPS + warp) * RPW;
     // row pointers of the warp's rows: lanes 0..RPW load, everybody reads them through shuffles
@@ -47,7 +49,7 @@ k_spmv(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col, cons
     const bool owner = lane < RPW && myrow < n_rows;
     double e_al = 0.0, e_id = 0.0, e_x = 0.0, e_y = 0.0;
     if (owner) {
-        if (MODE == 2) { e_al = alpha[myrow]; e_id = inv_d[myrow]; e_x = xa[myrow]; e_y = y[myrow]; }
+        if (MODE == 2) { e_al = alpha[myrow]; e_id = inv_d[myrow]; e_x = xe[myrow]; e_y = y[myrow]; }
         if (MODE == 3) e_x = xa[myrow];
     }
     double sum[RPW];
@@ -102,7 +104,11 @@ k_spmv(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col, cons
     const int64_t rp_next = __shfl_down_sync(0xffffffffu, rp, 1);
     if (owner) {
         if (MODE == 2) {
-            if (rp_next > rp) y[myrow] = e_id * (-mine) + e_al * e_x - (e_al - 1.0) * e_y;
+            if (rp_next > rp) {
+                const double un = e_id * (-mine) + e_al * e_x - (e_al - 1.0) * e_y;
+                y[myrow] = un;
+                if (y2) y2[myrow] = (1.0 + g) * un - g * e_x;
+            }
         } else {
             y[myrow] = mine;
             if (MODE == 3) dotv = e_x * mine;
@@ -166,7 +172,7 @@ __global__ void k_fill(double* __restrict__ x, double v, int64_t n) {
     int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (i < n) x[i] = v;
 }
-__global__ void k_axpby(double* __restrict__ out, double a, const double* __restrict__ x, double b, const double* __restrict__ y, int64_t n) {
+__global__ void k_axpby(double* out, double a, const double* x, double b, const double* __restrict__ y, int64_t n) {   // out may alias x
     int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (i < n) out[i] = a * x[i] + (y ? b * y[i] : 0.0);
 }
@@ -205,7 +211,8 @@ inline unsigned nblk(int64_t n, int t) { return (unsigned)((n + t - 1) / t); }
 // launch configuration from the average row length: U chunks of 32 entries per pass, RPW rows per warp
 template <int MODE>
 int spmv_launch(sc_ctx* ctx, const double* va, const double* xa, const double* vb, const double* xb, double* y,
-                const double* inv_d, const double* alpha, double* partial, unsigned* nblocks_out) {
+                const double* inv_d, const double* alpha, double* partial, unsigned* nblocks_out,
+                const double* xe = nullptr, double* y2 = nullptr, double g = 0.0) {
     const double avg = ctx->n_eq > 0 ? (double)ctx->nnz / (double)ctx->n_eq : 1.0;
     const int64_t n = ctx->n_eq;
     cudaStream_t st = ctx->stream;
@@ -214,7 +221,7 @@ int spmv_launch(sc_ctx* ctx, const double* va, const double* xa, const double* v
         const unsigned nb = (unsigned)((n + (int64_t)SPMV_WARPS * RPW - 1) / ((int64_t)SPMV_WARPS * RPW));             \
         if (nblocks_out) *nblocks_out = nb;                                                                             \
         k_spmv<MODE, RPW, U><<<nb, SPMV_THREADS, 0, st>>>(ctx->d_rowptr, ctx->d_col, va, xa, vb, xb, y, inv_d, alpha,   \
-                                                           partial, n);                                                 \
+                                                           partial, n, xe, y2, g);                                      \
     }
     if (avg <= 32.0) SC_SPMV_GO(4, 1)
     else if (avg <= 64.0) SC_SPMV_GO(2, 2)
@@ -257,11 +264,13 @@ int la_spmv2(sc_ctx* ctx, const double* va, const double* xa, const double* vb, 
     return spmv_launch<1>(ctx, va, xa, vb, xb, y, nullptr, nullptr, nullptr, nullptr);
 }
 
-// u_next (in place over u_prev) = inv_d*(-K u) + alpha*u - (alpha-1)*u_prev
-int la_cd_step(sc_ctx* ctx, const double* K, const double* u, double* uprev_next, const double* inv_d, const double* alpha) {
-    if (la_node_usable(ctx)) return la_node_cd_step(ctx, K, u, uprev_next, inv_d, alpha);
-    if (la_tma_usable(ctx)) return la_tma_cd_step(ctx, K, u, uprev_next, inv_d, alpha);
-    return spmv_launch<2>(ctx, K, u, nullptr, nullptr, uprev_next, inv_d, alpha, nullptr, nullptr);
+// u_next (in place over u_prev) = inv_d*(-K w) + alpha*u - (alpha-1)*u_prev;  w_next = (1+g) u_next - g u when w_next != null
+// (g = c1/dt: lagged stiffness-proportional damping; with g = 0 the caller passes w = u and w_next = null)
+int la_cd_step(sc_ctx* ctx, const double* K, const double* w, const double* u, double* uprev_next, const double* inv_d,
+               const double* alpha, double g, double* w_next) {
+    if (la_node_usable(ctx)) return la_node_cd_step(ctx, K, w, u, uprev_next, inv_d, alpha, g, w_next);
+    if (la_tma_usable(ctx)) return la_tma_cd_step(ctx, K, w, u, uprev_next, inv_d, alpha, g, w_next);
+    return spmv_launch<2>(ctx, K, w, nullptr, nullptr, uprev_next, inv_d, alpha, nullptr, nullptr, u, w_next, g);
 }
 
 // q = A p and d_out[0] = p.q (device scalar)

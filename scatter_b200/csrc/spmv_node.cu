@@ -52,13 +52,17 @@ __device__ __forceinline__ void tma_load_1d(void* dst_smem, const void* src_gmem
                  : "memory");
 }
 
-// MODE 0: y = A xa   MODE 2: central-difference step   MODE 3: y = A xa, partial[blockIdx] = xa.y
+// MODE 0: y = A xa   MODE 3: y = A xa, partial[blockIdx] = xa.y
+// MODE 2: central-difference step  y <- inv_d (-A xa) + alpha xe - (alpha - 1) y  with xe = u(t), y = u(t-dt) on entry and
+//         xa = w(t) = (1+g) u(t) - g u(t-dt) the gathered vector (lagged stiffness-proportional damping, g = c1/dt);
+//         y2 != null: the next gather vector w(t+dt) = (1+g) y - g xe is written by the same epilogue (g = 0: xa = xe, y2 = null)
 template <int MODE, int STAGES, int NB_NPW>
 __global__ void __launch_bounds__(NB_THREADS, 2)
 k_spmv_node(const NodeDesc* __restrict__ nd, const int32_t* __restrict__ ncol, const double* __restrict__ va,
             const double* __restrict__ xa, double* __restrict__ y, const double* __restrict__ inv_d,
             const double* __restrict__ alpha, double* __restrict__ partial, int64_t n_nodes, int64_t n_rows, int64_t n_tiles,
-            int cap_v, int cap_c, const int32_t* __restrict__ dict, int n_dict, int dict_stride) {
+            int cap_v, int cap_c, const int32_t* __restrict__ dict, int n_dict, int dict_stride,
+            const double* __restrict__ xe, double* __restrict__ y2, double g) {
     constexpr int NB_NODES = NB_WARPS * NB_NPW;      // nodes per tile; NB_NPW nodes per consumer warp (gathers in flight together)
     constexpr int NB_VT = 3 * NB_NODES + 8;          // vector slots per tile (rows + alignment), multiple of 2
     constexpr int NVEC = (MODE == 2) ? 4 : (MODE == 3 ? 1 : 0);
@@ -127,7 +131,7 @@ k_spmv_node(const NodeDesc* __restrict__ nd, const int32_t* __restrict__ ncol, c
                         if (MODE == 2) {
                             tma_load_1d(sv, alpha + rs, rb, &bar_full[stage]);
                             tma_load_1d(sv + NB_VT, inv_d + rs, rb, &bar_full[stage]);
-                            tma_load_1d(sv + 2 * NB_VT, xa + rs, rb, &bar_full[stage]);
+                            tma_load_1d(sv + 2 * NB_VT, xe + rs, rb, &bar_full[stage]);
                             tma_load_1d(sv + 3 * NB_VT, y + rs, rb, &bar_full[stage]);
                         }
                         if (MODE == 3) tma_load_1d(sv, xa + rs, rb, &bar_full[stage]);
@@ -230,7 +234,9 @@ k_spmv_node(const NodeDesc* __restrict__ nd, const int32_t* __restrict__ ncol, c
                 if (owner[q]) {
                     const int64_t row = (int64_t)row0[q] + myr;
                     if (MODE == 2) {
-                        y[row] = e_id[q] * (-mine) + e_al[q] * e_x[q] - (e_al[q] - 1.0) * e_y[q];
+                        const double un = e_id[q] * (-mine) + e_al[q] * e_x[q] - (e_al[q] - 1.0) * e_y[q];
+                        y[row] = un;
+                        if (y2) y2[row] = (1.0 + g) * un - g * e_x[q];
                     } else {
                         y[row] = mine;
                         if (MODE == 3) dot_acc += e_x[q] * mine;
@@ -254,206 +260,12 @@ k_spmv_node(const NodeDesc* __restrict__ nd, const int32_t* __restrict__ ncol, c
     }
 }
 
-// Software-pipelined variant for short rows (<= 96 entries per row, e.g. hexa8 / tetra4 / 2-D meshes): one node per
-// consumer warp and tile (8-node tiles, deep ring), and every warp issues the x gathers of its node TWO tiles ahead of
-// the tile it is reducing.  ncu on k_spmv_node showed 30 % of the samples on the first FMA waiting for the gathers
-// (L2 latency under load); here that latency overlaps the shared-memory reads, FMAs, butterfly and epilogue of the two
-// tiles in between.
-template <int MODE, int STAGES>
-__global__ void __launch_bounds__(NB_THREADS, 2)
-k_spmv_node_pipe(const NodeDesc* __restrict__ nd, const int32_t* __restrict__ ncol, const double* __restrict__ va,
-                 const double* __restrict__ xa, double* __restrict__ y, const double* __restrict__ inv_d,
-                 const double* __restrict__ alpha, double* __restrict__ partial, int64_t n_nodes, int64_t n_rows, int64_t n_tiles,
-                 int cap_v, int cap_c) {
-    constexpr int NB_NODES = NB_WARPS;
-    constexpr int NB_VT = 3 * NB_NODES + 8;
-    constexpr int NVEC = (MODE == 2) ? 4 : (MODE == 3 ? 1 : 0);
-    constexpr int NV1 = NVEC > 0 ? NVEC : 1;
-    constexpr int U = 3;
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    double* s_val = reinterpret_cast<double*>(smem_raw);
-    double* s_vec = s_val + (size_t)STAGES * cap_v;
-    NodeDesc* s_nd = reinterpret_cast<NodeDesc*>(s_vec + (size_t)STAGES * NV1 * NB_VT);
-    int* s_col = reinterpret_cast<int*>(s_nd + (size_t)STAGES * NB_NODES);
-    uint64_t* bar_full = reinterpret_cast<uint64_t*>(s_col + (size_t)STAGES * cap_c);
-    uint64_t* bar_empty = bar_full + STAGES;
-    __shared__ double red[NB_WARPS];
-
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    if (threadIdx.x == 0) {
-        for (int s = 0; s < STAGES; ++s) {
-            mbar_init(&bar_full[s], 1);
-            mbar_init(&bar_empty[s], NB_WARPS);
-        }
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
-    const int64_t G = gridDim.x;
-    double dot_acc = 0.0;
-
-    if (warp == NB_WARPS) {
-        // producer warp: identical to k_spmv_node
-        int stage = 0;
-        uint32_t phase = 0;
-        for (int64_t ib = 0;; ib += 32) {
-            const int64_t t_first = blockIdx.x + ib * G;
-            if (t_first >= n_tiles) break;
-            const int64_t t = blockIdx.x + (ib + lane) * G;
-            int64_t v0 = 0, v1 = 0, c0 = 0, c1 = 0;
-            int r0 = 0, r1 = 0;
-            if (t < n_tiles) {
-                const NodeDesc d0 = nd[t * NB_NODES];
-                const NodeDesc d1 = nd[t * NB_NODES + NB_NODES];
-                v0 = d0.val_off; v1 = d1.val_off; c0 = d0.col_off; c1 = d1.col_off; r0 = d0.row0; r1 = d1.row0;
-            }
-            for (int j = 0; j < 32; ++j) {
-                const int64_t tj = blockIdx.x + (ib + j) * G;
-                if (tj >= n_tiles) break;
-                const int64_t a_v0 = __shfl_sync(0xffffffffu, v0, j), a_v1 = __shfl_sync(0xffffffffu, v1, j);
-                const int64_t a_c0 = __shfl_sync(0xffffffffu, c0, j), a_c1 = __shfl_sync(0xffffffffu, c1, j);
-                const int a_r0 = __shfl_sync(0xffffffffu, r0, j), a_r1 = __shfl_sync(0xffffffffu, r1, j);
-                if (lane == 0) {
-                    mbar_wait(&bar_empty[stage], phase ^ 1u);
-                    const int64_t vs = a_v0 & ~(int64_t)1, cs = a_c0 & ~(int64_t)3;
-                    const int rs = a_r0 & ~1;
-                    const uint32_t vb = (uint32_t)(((a_v1 - vs + 1) & ~(int64_t)1) * 8);
-                    const uint32_t cb = (uint32_t)(((a_c1 - cs + 3) & ~(int64_t)3) * 4);
-                    const uint32_t rb = (uint32_t)(((a_r1 - rs + 1) & ~1) * 8);
-                    const uint32_t db = NB_NODES * (uint32_t)sizeof(NodeDesc);
-                    const bool has = a_v1 > a_v0;
-                    mbar_expect_tx(&bar_full[stage], db + (has ? vb + cb + NVEC * rb : 0u));
-                    tma_load_1d(s_nd + (size_t)stage * NB_NODES, nd + tj * NB_NODES, db, &bar_full[stage]);
-                    if (has) {
-                        tma_load_1d(s_val + (size_t)stage * cap_v, va + vs, vb, &bar_full[stage]);
-                        tma_load_1d(s_col + (size_t)stage * cap_c, ncol + cs, cb, &bar_full[stage]);
-                        double* sv = s_vec + (size_t)stage * NV1 * NB_VT;
-                        if (MODE == 2) {
-                            tma_load_1d(sv, alpha + rs, rb, &bar_full[stage]);
-                            tma_load_1d(sv + NB_VT, inv_d + rs, rb, &bar_full[stage]);
-                            tma_load_1d(sv + 2 * NB_VT, xa + rs, rb, &bar_full[stage]);
-                            tma_load_1d(sv + 3 * NB_VT, y + rs, rb, &bar_full[stage]);
-                        }
-                        if (MODE == 3) tma_load_1d(sv, xa + rs, rb, &bar_full[stage]);
-                    }
-                }
-                if (++stage == STAGES) { stage = 0; phase ^= 1u; }
-            }
-        }
-    } else {
-        // consumer warps.  Tile sequence of this CTA: i = 0, 1, 2, ... (global tile blockIdx.x + i*G); stage = i % STAGES.
-        const int64_t my_tiles = (n_tiles - blockIdx.x + G - 1) / G;
-        const int myr = lane >> 3;
-        const bool h16 = (lane & 16) != 0, h8 = (lane & 8) != 0;
-
-        // gathers of tile i into xg (needs the stage's columns: waits for the "full" barrier)
-        auto prefetch = [&](int64_t i, double (&xg)[U]) {
-            if (i >= my_tiles) return;
-            const int stage = (int)(i % STAGES);
-            mbar_wait(&bar_full[stage], (uint32_t)((i / STAGES) & 1));
-            const NodeDesc* snd = s_nd + (size_t)stage * NB_NODES;
-            const NodeDesc d0 = snd[0], d = snd[warp];
-            const int nfree = d.len_nfree >> 24;
-            const int L = nfree > 0 ? (d.len_nfree & 0xffff) : 0;
-            const int* sc = s_col + (size_t)stage * cap_c + (int)(d.col_off - (d0.col_off & ~(int64_t)3)) + lane;
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-                int c = 0;
-                if (32 * u + lane < L) c = sc[32 * u];
-                xg[u] = __ldg(xa + c);
-            }
-        };
-        // reduction of tile i with the gathers issued earlier
-        auto process = [&](int64_t i, const double (&xg)[U]) {
-            if (i >= my_tiles) return;
-            const int stage = (int)(i % STAGES);
-            const NodeDesc* snd = s_nd + (size_t)stage * NB_NODES;
-            const NodeDesc d0 = snd[0], d = snd[warp];
-            const int nfree = d.len_nfree >> 24;
-            const int L = nfree > 0 ? (d.len_nfree & 0xffff) : 0;
-            const double* sv = s_val + (size_t)stage * cap_v + (int)(d.val_off - (d0.val_off & ~(int64_t)1)) + lane;
-            const bool owner = (lane & 7) == 0 && myr < nfree && (L > 0 || MODE != 2);
-            double e_al = 0.0, e_id = 0.0, e_x = 0.0, e_y = 0.0;
-            if (NVEC > 0 && owner) {
-                const double* svec = s_vec + (size_t)stage * NV1 * NB_VT + (d.row0 - (d0.row0 & ~1)) + myr;
-                if (MODE == 2) { e_al = svec[0]; e_id = svec[NB_VT]; e_x = svec[2 * NB_VT]; e_y = svec[3 * NB_VT]; }
-                if (MODE == 3) e_x = svec[0];
-            }
-            double s0 = 0.0, s1 = 0.0, s2 = 0.0;
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-                if (32 * u + lane < L) {
-                    s0 += sv[32 * u] * xg[u];
-                    if (nfree > 1) s1 += sv[L + 32 * u] * xg[u];
-                    if (nfree > 2) s2 += sv[2 * L + 32 * u] * xg[u];
-                }
-            }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&bar_empty[stage]);
-            double k0 = h16 ? s2 : s0, k1 = h16 ? 0.0 : s1;
-            const double g0 = h16 ? s0 : s2, g1 = h16 ? s1 : 0.0;
-            k0 += __shfl_xor_sync(0xffffffffu, g0, 16);
-            k1 += __shfl_xor_sync(0xffffffffu, g1, 16);
-            double mine = h8 ? k1 : k0;
-            const double g = h8 ? k0 : k1;
-            mine += __shfl_xor_sync(0xffffffffu, g, 8);
-            mine += __shfl_xor_sync(0xffffffffu, mine, 4);
-            mine += __shfl_xor_sync(0xffffffffu, mine, 2);
-            mine += __shfl_xor_sync(0xffffffffu, mine, 1);
-            if (owner) {
-                const int64_t row = (int64_t)d.row0 + myr;
-                if (MODE == 2) {
-                    y[row] = e_id * (-mine) + e_al * e_x - (e_al - 1.0) * e_y;
-                } else {
-                    y[row] = mine;
-                    if (MODE == 3) dot_acc += e_x * mine;
-                }
-            }
-        };
-        double xa0[U], xa1[U], xa2[U];
-        prefetch(0, xa0);
-        prefetch(1, xa1);
-        for (int64_t i = 0; i < my_tiles; i += 3) {
-            prefetch(i + 2, xa2);
-            process(i, xa0);
-            prefetch(i + 3, xa0);
-            process(i + 1, xa1);
-            prefetch(i + 4, xa1);
-            process(i + 2, xa2);
-        }
-    }
-    if (MODE == 3) {
-        if (warp < NB_WARPS) {
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) dot_acc += __shfl_down_sync(0xffffffffu, dot_acc, o);
-            if (lane == 0) red[warp] = dot_acc;
-        }
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            double s = 0.0;
-            for (int w = 0; w < NB_WARPS; ++w) s += red[w];
-            partial[blockIdx.x] = s;
-        }
-    }
-}
-
-struct NodeCfg { int cap_v, cap_c, stages, npw; size_t bytes; bool pipe; };
+struct NodeCfg { int cap_v, cap_c, stages, npw; size_t bytes; };
 constexpr size_t NODE_SMEM_MAX = 112 * 1024;       // two CTAs per SM
 
 // ring configuration (dictionary not counted: `node_dict_room` sizes the dictionary into what is left)
 bool node_cfg(sc_ctx* ctx, NodeCfg& c) {
     if (ctx->force_no_node || !ctx->d_nd || ctx->max_rl <= 0 || ctx->dim > 3) return false;
-    c.pipe = false;
-    if (ctx->max_rl <= 96 && !ctx->force_no_pipe && ctx->n_dict == 0) {
-        // software-pipelined kernel: one node per warp, 8-node tiles, as many stages as fit (needs >= 4 for the look-ahead of 2)
-        const int nodes = NB_WARPS, vt = 3 * nodes + 8;
-        c.cap_v = (nodes * 3 * ctx->max_rl + 2 + 15) & ~15;
-        c.cap_c = (nodes * ctx->max_rl + 4 + 31) & ~31;
-        const size_t per_stage = (size_t)c.cap_v * 8 + (size_t)c.cap_c * 4 + 4 * (size_t)vt * 8 + nodes * sizeof(NodeDesc);
-        for (int st = 5; st >= 4; --st) {
-            const size_t bytes = st * per_stage + 2 * st * sizeof(uint64_t) + 64;
-            if (bytes <= 104 * 1024) { c.stages = st; c.npw = 1; c.bytes = bytes; c.pipe = true; return true; }
-        }
-    }
     // two nodes per consumer warp when the stages fit (short rows), one node per warp for long rows (hexa20, tetra10)
     for (int npw = 2; npw >= 1; --npw) {
         const int nodes = NB_WARPS * npw, vt = 3 * nodes + 8;
@@ -471,7 +283,7 @@ bool node_cfg(sc_ctx* ctx, NodeCfg& c) {
 
 template <int MODE, int STAGES, int NPW>
 int launch_node(sc_ctx* ctx, const NodeCfg& c, const double* va, const double* xa, double* y, const double* inv_d, const double* alpha,
-                double* partial, unsigned* nblocks_out) {
+                double* partial, unsigned* nblocks_out, const double* xe, double* y2, double g) {
     constexpr int NODES = NB_WARPS * NPW;
     const int64_t n_tiles = (ctx->n_nodes + NODES - 1) / NODES;
     auto kern = k_spmv_node<MODE, STAGES, NPW>;
@@ -481,43 +293,24 @@ int launch_node(sc_ctx* ctx, const NodeCfg& c, const double* va, const double* x
     if (grid == 0) grid = 1;
     if (nblocks_out) *nblocks_out = grid;
     kern<<<grid, NB_THREADS, bytes, ctx->stream>>>(ctx->d_nd, ctx->d_ncol, va, xa, y, inv_d, alpha, partial, ctx->n_nodes, ctx->n_eq,
-                                                   n_tiles, c.cap_v, c.cap_c, ctx->d_dict, ctx->n_dict, ctx->dict_stride);
+                                                   n_tiles, c.cap_v, c.cap_c, ctx->d_dict, ctx->n_dict, ctx->dict_stride, xe, y2, g);
     SC_CHECK_LAUNCH(ctx);
     return SC_OK;
 }
 
 template <int MODE>
 int launch_mode(sc_ctx* ctx, const double* va, const double* xa, double* y, const double* inv_d, const double* alpha, double* partial,
-                unsigned* nblocks_out) {
+                unsigned* nblocks_out, const double* xe = nullptr, double* y2 = nullptr, double g = 0.0) {
     NodeCfg c;
     if (!node_cfg(ctx, c)) return sc_fail(ctx, SC_ERR_UNSUPPORTED, "node-blocked SpMV not usable for this pattern");
-    if (c.pipe) {
-        const int64_t n_tiles = (ctx->n_nodes + NB_WARPS - 1) / NB_WARPS;
-        unsigned grid = (unsigned)std::min<int64_t>(n_tiles, (int64_t)ctx->sm_count * 2);
-        if (grid == 0) grid = 1;
-        if (nblocks_out) *nblocks_out = grid;
-        if (c.stages == 5) {
-            auto kern = k_spmv_node_pipe<MODE, 5>;
-            SC_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.bytes));
-            kern<<<grid, NB_THREADS, c.bytes, ctx->stream>>>(ctx->d_nd, ctx->d_ncol, va, xa, y, inv_d, alpha, partial, ctx->n_nodes,
-                                                             ctx->n_eq, n_tiles, c.cap_v, c.cap_c);
-        } else {
-            auto kern = k_spmv_node_pipe<MODE, 4>;
-            SC_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.bytes));
-            kern<<<grid, NB_THREADS, c.bytes, ctx->stream>>>(ctx->d_nd, ctx->d_ncol, va, xa, y, inv_d, alpha, partial, ctx->n_nodes,
-                                                             ctx->n_eq, n_tiles, c.cap_v, c.cap_c);
-        }
-        SC_CHECK_LAUNCH(ctx);
-        return SC_OK;
-    }
     if (c.npw == 2) {
-        if (c.stages == 4) return launch_node<MODE, 4, 2>(ctx, c, va, xa, y, inv_d, alpha, partial, nblocks_out);
-        if (c.stages == 3) return launch_node<MODE, 3, 2>(ctx, c, va, xa, y, inv_d, alpha, partial, nblocks_out);
-        return launch_node<MODE, 2, 2>(ctx, c, va, xa, y, inv_d, alpha, partial, nblocks_out);
+        if (c.stages == 4) return launch_node<MODE, 4, 2>(ctx, c, va, xa, y, inv_d, alpha, partial, nblocks_out, xe, y2, g);
+        if (c.stages == 3) return launch_node<MODE, 3, 2>(ctx, c, va, xa, y, inv_d, alpha, partial, nblocks_out, xe, y2, g);
+        return launch_node<MODE, 2, 2>(ctx, c, va, xa, y, inv_d, alpha, partial, nblocks_out, xe, y2, g);
     }
-    if (c.stages == 4) return launch_node<MODE, 4, 1>(ctx, c, va, xa, y, inv_d, alpha, partial, nblocks_out);
-    if (c.stages == 3) return launch_node<MODE, 3, 1>(ctx, c, va, xa, y, inv_d, alpha, partial, nblocks_out);
-    return launch_node<MODE, 2, 1>(ctx, c, va, xa, y, inv_d, alpha, partial, nblocks_out);
+    if (c.stages == 4) return launch_node<MODE, 4, 1>(ctx, c, va, xa, y, inv_d, alpha, partial, nblocks_out, xe, y2, g);
+    if (c.stages == 3) return launch_node<MODE, 3, 1>(ctx, c, va, xa, y, inv_d, alpha, partial, nblocks_out, xe, y2, g);
+    return launch_node<MODE, 2, 1>(ctx, c, va, xa, y, inv_d, alpha, partial, nblocks_out, xe, y2, g);
 }
 
 }  // namespace
@@ -531,7 +324,7 @@ int64_t node_dict_room(sc_ctx* ctx) {
     NodeCfg c;
     const int keep = ctx->n_dict;
     ctx->n_dict = 0;
-    const bool ok = node_cfg(ctx, c) && !c.pipe;
+    const bool ok = node_cfg(ctx, c);
     ctx->n_dict = keep;
     if (!ok || c.bytes + 64 >= NODE_SMEM_MAX) return 0;
     return (int64_t)(NODE_SMEM_MAX - c.bytes - 64);
@@ -539,14 +332,16 @@ int64_t node_dict_room(sc_ctx* ctx) {
 int la_node_spmv(sc_ctx* ctx, const double* vals, const double* x, double* y) {
     return launch_mode<0>(ctx, vals, x, y, nullptr, nullptr, nullptr, nullptr);
 }
-int la_node_cd_step(sc_ctx* ctx, const double* K, const double* u, double* uprev_next, const double* inv_d, const double* alpha) {
-    return launch_mode<2>(ctx, K, u, uprev_next, inv_d, alpha, nullptr, nullptr);
+int la_node_cd_step(sc_ctx* ctx, const double* K, const double* w, const double* u, double* uprev_next, const double* inv_d,
+                    const double* alpha, double g, double* w_next) {
+    return launch_mode<2>(ctx, K, w, uprev_next, inv_d, alpha, nullptr, nullptr, u, w_next, g);
 }
 int la_node_spmv_dot(sc_ctx* ctx, const double* vals, const double* p, double* q, double* partial, unsigned* nblocks) {
     return launch_mode<3>(ctx, vals, p, q, nullptr, nullptr, partial, nblocks);
 }
 // bytes one fused central-difference launch has to move with this format: values, node column lists, node descriptors,
-// and five vector passes (alpha, inv_d, u gathered once, u_prev read, u_next written)
-int64_t la_node_step_bytes(sc_ctx* ctx) {
-    return ctx->nnz * 8 + ctx->ncol_total * 4 + ctx->n_nodes * (int64_t)sizeof(NodeDesc) + ctx->n_eq * 40;
+// and five vector passes (alpha, inv_d, u gathered once, u_prev read, u_next written); with stiffness-proportional
+// damping (g != 0) two more: the gather vector w is a separate read and w_next is written
+int64_t la_node_step_bytes(sc_ctx* ctx, bool lagged) {
+    return ctx->nnz * 8 + ctx->ncol_total * 4 + ctx->n_nodes * (int64_t)sizeof(NodeDesc) + ctx->n_eq * (lagged ? 56 : 40);
 }

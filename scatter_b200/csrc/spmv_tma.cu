@@ -62,7 +62,8 @@ template <int MODE, int TR>
 __global__ void __launch_bounds__(TMA_THREADS, 2)
 k_spmv_tma(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col, const double* __restrict__ va,
            const double* __restrict__ xa, double* __restrict__ y, const double* __restrict__ inv_d,
-           const double* __restrict__ alpha, double* __restrict__ partial, int64_t n_rows, int64_t n_tiles, int cap) {
+           const double* __restrict__ alpha, double* __restrict__ partial, int64_t n_rows, int64_t n_tiles, int cap,
+           const double* __restrict__ xe, double* __restrict__ y2, double g) {
     constexpr int RW = TR / TMA_CONSUMER_WARPS;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     // layout: [STAGES][cap] doubles | [STAGES][cap] ints | barriers
@@ -126,7 +127,7 @@ k_spmv_tma(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col, 
                         if (MODE == 2) {
                             tma_load_1d(sv, alpha + r0, rb, &bar_full[stage]);
                             tma_load_1d(sv + TR, inv_d + r0, rb, &bar_full[stage]);
-                            tma_load_1d(sv + 2 * TR, xa + r0, rb, &bar_full[stage]);
+                            tma_load_1d(sv + 2 * TR, xe + r0, rb, &bar_full[stage]);
                             tma_load_1d(sv + 3 * TR, y + r0, rb, &bar_full[stage]);
                         }
                         if (MODE == 3) tma_load_1d(sv, xa + r0, rb, &bar_full[stage]);
@@ -245,7 +246,11 @@ k_spmv_tma(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col, 
             for (int r = 1; r < RW; ++r) mylen = (myr == r) ? len[r] : mylen;
             if (owner) {
                 if (MODE == 2) {
-                    if (mylen > 0) y[myrow] = e_id * (-mine) + e_al * e_x - (e_al - 1.0) * e_y;
+                    if (mylen > 0) {
+                        const double un = e_id * (-mine) + e_al * e_x - (e_al - 1.0) * e_y;
+                        y[myrow] = un;
+                        if (y2) y2[myrow] = (1.0 + g) * un - g * e_x;
+                    }
                 } else {
                     y[myrow] = mine;
                     if (MODE == 3 && mylen > 0) dot_acc += e_x * mine;
@@ -270,7 +275,7 @@ k_spmv_tma(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col, 
 
 template <int MODE, int TR>
 int launch_tr(sc_ctx* ctx, const double* va, const double* xa, double* y, const double* inv_d, const double* alpha,
-              double* partial, unsigned* nblocks_out) {
+              double* partial, unsigned* nblocks_out, const double* xe, double* y2, double g) {
     const int64_t n = ctx->n_eq;
     const int64_t n_tiles = (n + TR - 1) / TR;
     int cap = TR * ctx->max_rl + 8;
@@ -282,7 +287,7 @@ int launch_tr(sc_ctx* ctx, const double* va, const double* xa, double* y, const 
     unsigned grid = (unsigned)std::min<int64_t>(n_tiles, (int64_t)ctx->sm_count * 2);
     if (grid == 0) grid = 1;
     if (nblocks_out) *nblocks_out = grid;
-    kern<<<grid, TMA_THREADS, bytes, ctx->stream>>>(ctx->d_rowptr, ctx->d_col, va, xa, y, inv_d, alpha, partial, n, n_tiles, cap);
+    kern<<<grid, TMA_THREADS, bytes, ctx->stream>>>(ctx->d_rowptr, ctx->d_col, va, xa, y, inv_d, alpha, partial, n, n_tiles, cap, xe, y2, g);
     SC_CHECK_LAUNCH(ctx);
     return SC_OK;
 }
@@ -299,20 +304,21 @@ bool la_tma_usable(sc_ctx* ctx) {
 
 template <int MODE>
 static int launch_mode(sc_ctx* ctx, const double* va, const double* xa, double* y, const double* inv_d, const double* alpha,
-                       double* partial, unsigned* nblocks_out) {
+                       double* partial, unsigned* nblocks_out, const double* xe = nullptr, double* y2 = nullptr, double g = 0.0) {
     const size_t per_entry = sizeof(double) + sizeof(int);
     const size_t budget = 100 * 1024;
     auto fits = [&](int tr) { return (size_t)TMA_STAGES * ((size_t)tr * ctx->max_rl + 40) * per_entry + (size_t)TMA_STAGES * 32 * tr <= budget; };
-    if (fits(32)) return launch_tr<MODE, 32>(ctx, va, xa, y, inv_d, alpha, partial, nblocks_out);
-    if (fits(16)) return launch_tr<MODE, 16>(ctx, va, xa, y, inv_d, alpha, partial, nblocks_out);
-    return launch_tr<MODE, 8>(ctx, va, xa, y, inv_d, alpha, partial, nblocks_out);
+    if (fits(32)) return launch_tr<MODE, 32>(ctx, va, xa, y, inv_d, alpha, partial, nblocks_out, xe, y2, g);
+    if (fits(16)) return launch_tr<MODE, 16>(ctx, va, xa, y, inv_d, alpha, partial, nblocks_out, xe, y2, g);
+    return launch_tr<MODE, 8>(ctx, va, xa, y, inv_d, alpha, partial, nblocks_out, xe, y2, g);
 }
 
 int la_tma_spmv(sc_ctx* ctx, const double* vals, const double* x, double* y) {
     return launch_mode<0>(ctx, vals, x, y, nullptr, nullptr, nullptr, nullptr);
 }
-int la_tma_cd_step(sc_ctx* ctx, const double* K, const double* u, double* uprev_next, const double* inv_d, const double* alpha) {
-    return launch_mode<2>(ctx, K, u, uprev_next, inv_d, alpha, nullptr, nullptr);
+int la_tma_cd_step(sc_ctx* ctx, const double* K, const double* w, const double* u, double* uprev_next, const double* inv_d,
+                   const double* alpha, double g, double* w_next) {
+    return launch_mode<2>(ctx, K, w, uprev_next, inv_d, alpha, nullptr, nullptr, u, w_next, g);
 }
 int la_tma_spmv_dot(sc_ctx* ctx, const double* vals, const double* p, double* q, double* partial, unsigned* nblocks) {
     return launch_mode<3>(ctx, vals, p, q, nullptr, nullptr, partial, nblocks);

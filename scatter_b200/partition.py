@@ -134,15 +134,24 @@ def partition_model(model: ReadMesh, owner: np.ndarray, rank: int) -> LocalDomai
                        owned_eq=leq[owned_mask], global_eq_of_owned=geq[owned_mask], n_global_eq=int(model.number_eq))
 
 
-def slab_partition(nx: int, ny: int, nz_per_rank: int, rank: int, world: int, h: float = 0.5, element_type: str = "hexa8",
-                   bottom: str = "111") -> LocalDomain:
-    """z-slab of the global box nx x ny x (nz_per_rank*world): rank r owns node planes [r*nz_per_rank, (r+1)*nz_per_rank)
-    (the last rank also the final plane) and holds one ghost element layer towards each neighbour (hexa8 only)."""
+def slab_planes(nz: int, rank: int, world: int):
+    """Owned node planes [p0, p1) of `rank` when the nz + 1 node planes of a box are cut into `world` slabs of (nearly) equal
+    thickness: plane bounds at round(r * nz / world); the last rank also owns the final plane."""
+    b0, b1 = (rank * nz) // world, ((rank + 1) * nz) // world
+    return b0, b1 + (1 if rank == world - 1 else 0)
+
+
+def slab_partition(nx: int, ny: int, nz_per_rank, rank: int, world: int, h: float = 0.5, element_type: str = "hexa8",
+                   bottom: str = "111", nz_total: int | None = None) -> LocalDomain:
+    """z-slab of the global box nx x ny x nz, nz = nz_per_rank*world (weak scaling) or `nz_total` (a fixed box; the layer
+    count need not divide by the rank count): rank r owns the node planes `slab_planes(nz, r, world)` and holds one ghost
+    element layer towards each neighbour (hexa8 only)."""
     if element_type != "hexa8":
         raise NotImplementedError("slab_partition builds hexa8 boxes; use partition_model for other element types")
-    nz = nz_per_rank * world
-    p0 = rank * nz_per_rank
-    p1 = (rank + 1) * nz_per_rank + (1 if rank == world - 1 else 0)      # owned planes [p0, p1)
+    nz = int(nz_total) if nz_total is not None else nz_per_rank * world
+    if nz < world:
+        raise ValueError("fewer element layers than ranks")
+    p0, p1 = slab_planes(nz, rank, world)                                  # owned planes [p0, p1)
     z0, z1 = max(p0 - 1, 0), min(p1, nz)                                   # local element layers [z0, z1)
     nodes, elem = boxmesh.box_arrays(nx, ny, nz, h, element_type, z_range=(z0, z1))
     m = ReadMesh.from_arrays(nodes, elem, np.ones(len(elem), dtype=np.int64), [[3.0, 1, "solid"]], element_type)

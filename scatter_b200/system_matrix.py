@@ -216,14 +216,22 @@ class GenerateMatrix:
         """system_matrix.py:35-121 -- element integration + assembly, on the device."""
         E, nu, rho = resolve_element_properties(data, material) if elem_props is None else elem_props
         self._props = (np.asarray(E, float), np.asarray(nu, float), np.asarray(rho, float))
+        import time
+        t0 = time.perf_counter()
         rows = data.node_rows()
         eq = data.equation_table_int()
+        t1 = time.perf_counter()
         self.ctx.set_mesh(data.element_type, data.nodes[:, 1:], rows, eq, data.number_eq, active)
         self.ctx.set_materials(*self._props)
+        t2 = time.perf_counter()
         self.ctx.build_pattern()
+        t3 = time.perf_counter()
         flags = _lib.ASM_K | (_lib.ASM_M_FULL if self.want_full_mass else 0) | (_lib.ASM_M_LUMPED if self.want_lumped_mass else 0)
         self.assembly_seconds = self.ctx.assemble(self.order, flags)
         self._pattern = None
+        # host wall-clock split of this call (bench.py reports it for the whole-pipeline run)
+        self.timings = {"host_tables_seconds": t1 - t0, "h2d_seconds": t2 - t1, "pattern_seconds": t3 - t2,
+                        "assembly_kernel_seconds": self.assembly_seconds, "assembly_call_seconds": time.perf_counter() - t3}
 
     def absorbing_boundaries(self, data, material: dict, parameters_viscous: list, parameters_stiff: float, owned_rows=None) -> None:
         """system_matrix.py:256-376 -- Lysmer-Kuhlemeyer dashpots into C, springs into K.  The host only plans (which faces,

@@ -109,7 +109,7 @@ def test_two_gpu_time_loops_match_single_domain_oracle(golden_meshes, tmp_path):
         f = np.zeros(n)
         f[d] = -1000.0 * (min(t, 4) / 4.0)
         return f
-    Ucd, Vcd, _, _ = oracle.central_difference(M, C, K, force, np.arange(61) * 2e-4, 10)
+    Ucd, Vcd, _, _ = oracle.central_difference(M, C, K, force, np.arange(61) * 2e-4, 10, c1=c1)
     Unm, Vnm, Anm, _ = oracle.newmark(M, C, K, force, np.arange(21) * 5e-3, 5)
     got = {k: np.full(ref.shape, np.nan) for k, ref in (("cd_u", Ucd), ("cd_v", Vcd), ("nm_u", Unm), ("nm_v", Vnm), ("nm_a", Anm))}
     for r in range(world):

@@ -259,21 +259,22 @@ def test_assembly_is_bit_reproducible(golden_meshes):
 @pytest.mark.parametrize("case", ["cube", "column_3D_tetra4", "column_2D", "column_2D_tri6", "column_high_order", "column_3D_tetra10",
                                   "rose_2D_side"])
 def test_assembly_kernel_generations_agree(case, golden_meshes, monkeypatch):
-    """k_assemble_blk (default), k_assemble_pairs and the warp-per-node k_assemble sum the same contributions in the same
-    order; they differ only in how a single element contribution is rounded (material law per Gauss point vs once)."""
+    """k_assemble_blk (default) and the warp-per-node k_assemble sum the same contributions in the same order; they differ
+    only in how a single element contribution is rounded (material law per Gauss point vs once)."""
     if case not in cases.MATRIX_CASES:
         pytest.skip("case not in the fixture set")
     fn, bc = cases.MATRIX_CASES[case]
     vals = {}
-    for name, env in (("blk", None), ("pairs", "SCATTER_B200_PAIR_ASSEMBLY"), ("generic", "SCATTER_B200_GENERIC_ASSEMBLY")):
-        if env:
-            monkeypatch.setenv(env, "1")
+    from scatter_b200 import _lib
+    for name, opt in (("blk", None), ("generic", "generic_assembly")):
+        if opt:
+            monkeypatch.setitem(_lib.DEFAULT_OPTIONS, opt, 1)
         _, mx = build(golden_meshes[fn], bc, cases.case_materials(case), cases.settings())
         vals[name] = (mx.ctx.get_values(0), mx.ctx.get_values(1), mx.ctx.get_lumped_mass())
         mx.ctx.close()
-        if env:
-            monkeypatch.delenv(env)
-    for other in ("pairs", "generic"):
+        if opt:
+            monkeypatch.delitem(_lib.DEFAULT_OPTIONS, opt)
+    for other in ("generic",):
         for a, b in zip(vals["blk"], vals[other]):
             assert a.shape == b.shape
             assert np.abs(a - b).max() <= 1e-13 * np.abs(b).max()
@@ -306,11 +307,11 @@ def test_box_mesh_random_field(oracle, tmp_path):
 def test_column_dictionary_is_bitwise_neutral(case, golden_meshes, monkeypatch, tmp_path):
     """node_dict.cu replaces the explicit column lists of nodes with a frequent relative list by a dictionary id: SpMV, the
     fused central-difference step and a Newmark stage must give bit-identical results with and without it."""
-    from scatter_b200 import boxmesh, solvers, system_matrix
+    from scatter_b200 import _lib, boxmesh, solvers, system_matrix
     out = {}
     for mode in ("dict", "explicit"):
         if mode == "explicit":
-            monkeypatch.setenv("SCATTER_B200_NO_DICT", "1")
+            monkeypatch.setitem(_lib.DEFAULT_OPTIONS, "column_dictionary", 0)
         if case == "box":
             model = boxmesh.box_model(14, 9, 11, 0.5, "hexa8")
             model.connectivities()
@@ -336,7 +337,7 @@ def test_column_dictionary_is_bitwise_neutral(case, golden_meshes, monkeypatch, 
         out[mode] = (st, y, ucd, vcd, unm, anm)
         ctx.close()
         if mode == "explicit":
-            monkeypatch.delenv("SCATTER_B200_NO_DICT")
+            monkeypatch.delitem(_lib.DEFAULT_OPTIONS, "column_dictionary")
     sd, se = out["dict"][0], out["explicit"][0]
     assert se["dict_patterns"] == 0 and sd["nnz"] == se["nnz"]
     if case in ("cube", "cube_abs", "box"):
@@ -440,10 +441,11 @@ def test_newmark_hexa8_pulse_vs_reference_golden(golden_meshes, golden_histories
 def test_newmark_quad4_heaviside_vs_reference_golden(pcg_path, golden_meshes, golden_histories, monkeypatch):
     # the three PCG drivers (one cooperative kernel for small systems; stream-ordered iterations replayed from a CUDA
     # graph, or launched one by one as on multi-GPU runs) must all reproduce the reference history
+    from scatter_b200 import _lib
     if pcg_path != "cooperative":
-        monkeypatch.setenv("SCATTER_B200_NO_SMALL_PCG", "1")
+        monkeypatch.setitem(_lib.DEFAULT_OPTIONS, "small_pcg", 0)
     if pcg_path == "eager":
-        monkeypatch.setenv("SCATTER_B200_NO_GRAPH", "1")
+        monkeypatch.setitem(_lib.DEFAULT_OPTIONS, "pcg_graph", 0)
     H = golden_histories
     m, mx, num = run_history("quad4_heaviside", golden_meshes)
     ids = list(m.nodes[:, 0].astype(int))

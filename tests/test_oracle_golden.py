@@ -111,3 +111,57 @@ def test_oracle_central_difference_converges_to_newmark(oracle, golden_meshes):
     _, (K, M, C), (U2, V2, A2, t2) = oracle.run_case(golden_meshes[c["mesh"]], c["materials"], c["bc"], sett, load, dt, solver="cd")
     # lumped vs consistent mass differ at O(h^2): agreement to a few percent of the peak is what the schemes allow
     assert np.abs(U1 - U2).max() <= 0.02 * np.abs(U1).max()
+
+
+def _lumped_newmark_reference(oracle, golden_meshes, damping, dt, t_end, ini_steps_time=0.01):
+    """Column case integrated two ways on the same lumped-mass system: Newmark with the *full* Rayleigh matrix
+    C = c0 diag(m) + c1 K (what the reference builds, system_matrix.py:198, on a lumped mass) and the explicit scheme."""
+    import scipy.sparse as sp
+    c = cases.history_case("hexa8_pulse")
+    model = oracle.build_model(golden_meshes[c["mesh"]], c["bc"])
+    sett = dict(c["settings"], damping=damping)
+    K, M, C, _ = oracle.system_matrices(model, c["materials"], sett)
+    c0, c1 = oracle.rayleigh_coefficients(damping)
+    m = oracle.lump_rows(M)
+    Ml = sp.diags(m).tocsr()
+    Cl = (Ml * c0 + sp.csr_matrix(K) * c1).tocsr()
+    time = oracle.time_array(t_end, dt)
+    load = dict(c["loading"], time=t_end, type="heaviside", ini_steps=max(int(round(ini_steps_time / dt)), 2))
+    force = oracle.LoadSchedule(model, load, time)
+    U1 = oracle.newmark(Ml, Cl, K, force, time)[0]
+    U2 = oracle.central_difference(Ml, Cl, K, force, time, 1, c1=c1)[0]
+    U3 = oracle.central_difference(Ml, Ml * c0, K, force, time, 1, c1=0.0)[0]     # stiffness-proportional part dropped
+    return U1, U2, U3
+
+
+def test_oracle_central_difference_keeps_stiffness_proportional_damping(oracle, golden_meshes):
+    """Central difference vs Newmark on the same lumped-mass system WITH Rayleigh damping [1, 0.01, 30, 0.01] (the bench
+    setting).  The lagged c1 K term makes the scheme first-order consistent in the damping force, so the gap closes with
+    dt; a scheme that drops c1 K (row-sum lumping of C: rowsum(K) = 0 away from supports) keeps a dt-independent gap."""
+    damping = [1, 0.05, 30, 0.05]
+    errs, errs_dropped = [], []
+    for dt in (4e-5, 2e-5):
+        U1, U2, U3 = _lumped_newmark_reference(oracle, golden_meshes, damping, dt, 0.03)
+        errs.append(rel_l2(U2, U1)); errs_dropped.append(rel_l2(U3, U1))
+    assert errs[0] <= 2e-3 and errs[1] <= 0.6 * errs[0], errs            # converges (between first and second order)
+    assert errs_dropped[1] >= 10 * errs[1] and errs_dropped[1] >= 0.8 * errs_dropped[0], (errs, errs_dropped)
+
+
+def test_oracle_central_difference_vs_analytical_column(oracle, golden_meshes):
+    """1-D wave in a finite column under a suddenly applied pressure (Churchill; the reference's
+    integration_tests/analytical_solutions/analytical_wave_prop.py:50-81, only ever plotted there): top displacement
+    u(L, t) = p0/K (L + 8L/pi^2 sum_k (-1)^k/(2k-1)^2 sin(lam_k L) cos(lam_k c t)), lam_k = (2k-1) pi / (2L)."""
+    c = cases.history_case("hexa8_pulse")                # 0.1 x 20 x 0.1 m column, 200 hexa8 over the height, roller sides
+    mat, load = c["materials"], dict(c["loading"], time=0.3, type="heaviside", ini_steps=2)
+    sett = dict(c["settings"], damping=[1, 0.0, 30, 0.0], output_interval=1)
+    dt = 5e-5
+    model, _, (U, V, A, tt) = oracle.run_case(golden_meshes[c["mesh"]], mat, c["bc"], sett, load, dt, solver="cd")
+    E, nu, rho = mat["solid"]["Young"], mat["solid"]["poisson"], mat["solid"]["density"]
+    L, Kb = 20.0, E * (1 - nu) / ((1 + nu) * (1 - 2 * nu))                 # laterally confined column: constrained modulus
+    p0 = -1000.0 * len(load["node"]) / (0.1 * 0.1)
+    cw = np.sqrt(Kb / rho)
+    k = np.arange(1, 400)[:, None]
+    lam = (2 * k - 1) * np.pi / (2 * L)
+    u_top = p0 / Kb * (L + 8 * L / np.pi ** 2 * ((-1.0) ** k / (2 * k - 1) ** 2 * np.sin(lam * L) * np.cos(lam * cw * tt[None, :])).sum(axis=0))
+    top = int(model.eq_nb_dof[int(np.where(model.nodes[:, 0] == load["node"][0])[0][0]), 1])
+    assert rel_l2(U[:, top], u_top) <= 0.01 and np.abs(U[:, top] - u_top).max() <= 0.01 * np.abs(u_top).max()

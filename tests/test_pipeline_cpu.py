@@ -27,6 +27,15 @@ class OracleContext:
         self.c0 = self.c1 = 0.0
         self.Cabs = None
         self.calls = []
+        self.state_epoch = 0
+        self.final_output_step = -1
+        self.output_dofs = None
+
+    def set_final_output_step(self, step):
+        self.final_output_step = -1 if step is None else int(step)
+
+    def set_output_dofs(self, dofs=None):
+        assert dofs is None
 
     # ---- mesh / matrices
     def set_mesh(self, elem_type, xyz, conn, eq, n_eq, active=None):
@@ -109,6 +118,7 @@ class OracleContext:
 
     def set_state(self, u=None, v=None):
         self.state = (None if u is None else np.array(u), None if v is None else np.array(v))
+        self.state_epoch += 1
 
     def _store(self, res, outs):
         for src, dst in zip(res, outs):
@@ -125,13 +135,14 @@ class OracleContext:
             assert np.allclose(u0, full[0][t_start], rtol=0, atol=1e-12 * np.abs(full[0]).max())
             assert np.allclose(v0, full[1][t_start], rtol=0, atol=1e-12 * np.abs(full[1]).max())
         self.state = (None, None)                        # consumed: a following stage without set_state continues on the device
-        steps = [t for t in range(t_start, t_start + n_steps + 1) if t % oi == 0]
+        self.state_epoch += 1
+        steps = [t for t in range(t_start, t_start + n_steps + 1) if t % oi == 0 or t == self.final_output_step]
         self._store(tuple(f[steps] for f in full), tuple(None if o is None else o[:len(steps)] for o in (u_out, v_out, a_out)))
         return u_out, v_out, a_out, {"pcg_iterations": 0}
 
     def run_central_difference(self, dt, t_start, n_steps, oi=1, u_out=None, v_out=None, a_out=None, store=True):
         assert t_start == 0 and self.flags & 4           # lumped mass assembled
-        U, V, A, _ = self.oracle.central_difference(self.M, self._C(), self.K, self._force, np.arange(n_steps + 1) * dt, oi)
+        U, V, A, _ = self.oracle.central_difference(self.M, self._C(), self.K, self._force, np.arange(n_steps + 1) * dt, oi, c1=self.c1)
         self._store((U, V, A), (u_out, v_out, a_out))
         return u_out, v_out, a_out, {}
 
@@ -199,7 +210,8 @@ def test_scatter_entry_point_every_solver(solver_name, oracle_device, golden_mes
         U, tt = oracle.static(K, force, time, 4)
         V = A = np.zeros_like(U)
     else:
-        U, V, A, tt = {"newmark": oracle.newmark, "cd": oracle.central_difference, "bathe": oracle.bathe}[kind](M, C, K, force, time, 4)
+        kw = {"c1": oracle.rayleigh_coefficients(sett["damping"])[1]} if kind == "cd" else {}
+        U, V, A, tt = {"newmark": oracle.newmark, "cd": oracle.central_difference, "bathe": oracle.bathe}[kind](M, C, K, force, time, 4, **kw)
     assert res.dis.shape == U.shape == (6, om.number_eq) and np.abs(U).max() > 0
     assert rel_l2(res.dis, U) <= 1e-10 and np.allclose(res.time, tt)
     if kind != "static":
@@ -268,7 +280,52 @@ def test_solver_stages_fill_the_right_output_rows(with_update, oracle_device, go
     assert rel_l2(num.u, U) <= 1e-10 and rel_l2(num.v, V) <= 1e-10 and rel_l2(num.a, A) <= 1e-10
 
 
+def test_last_step_is_stored_and_rerun_restarts_from_u0(oracle_device, golden_meshes, oracle):
+    """(i) An output interval that does not divide the number of steps still keeps the final state (extra last row);
+    (ii) calling `calculate(0, n)` a second time starts again from u0 / v0 (the reference protocol), not from the state the
+    first run left on the device: the initial state is uploaded again and the histories are identical."""
+    from scatter_b200 import force_external, mesher, solvers, system_matrix
+    mesh, bc = golden_meshes["column_2D.msh"], cases.BC_2D
+    m = mesher.ReadMesh(mesh)
+    m.read_gmsh(); m.read_bc(bc); m.mapping(); m.connectivities()
+    mx = system_matrix.GenerateMatrix(m.number_eq, 2)
+    mx.generate_stiffness_and_mass(m, cases.materials())
+    mx.absorbing_boundaries(m, cases.materials(), [1, 1], 1e3)
+    mx.damping_Rayleigh([1, 0.005, 20, 0.005])
+    load = {"force": [0, -1e6, 0], "node": [3, 4, 25], "time": 0.14, "type": "heaviside", "ini_steps": 5}
+    time = np.linspace(0, 0.14, 29)                                                # 29 time indices, 28 steps
+    num = solvers.NewmarkExplicit(); num.output_interval = 3
+    num.initialise(m.number_eq, time); num.bind(mx)
+    assert list(num.output_time_indices) == [0, 3, 6, 9, 12, 15, 18, 21, 24, 27, 28] and num.u.shape[0] == 11
+    F = force_external.Force(); F.initialise_load(load, time, m, num)
+    num.update_rhs_at_time_step_func = F.update_load_at_t
+    num.update(0)
+    num.calculate(None, None, None, F.force_vector, 0, 28)
+    om = oracle.build_model(mesh, bc)
+    K, M, C, _ = oracle.system_matrices(om, cases.materials(), cases.settings(damping=[1, 0.005, 20, 0.005]))
+    U = oracle.newmark(M, C, K, oracle.LoadSchedule(om, load, time), time, 1)[0]
+    assert rel_l2(num.u, U[num.output_time_indices]) <= 1e-10
+    first = num.u.copy()
+    ctx = mx.ctx
+    e0 = ctx.state_epoch
+    num.update(0)
+    num.calculate(None, None, None, F.force_vector, 0, 28)
+    assert ctx.state_epoch == e0 + 2                     # set_state + run: the stale device state was not reused
+    assert np.array_equal(num.u, first)
+    # a stage that continues exactly where the previous one ended does not upload anything
+    num2 = solvers.NewmarkExplicit(); num2.output_interval = 3
+    num2.initialise(m.number_eq, time); num2.bind(mx)
+    num2.update_rhs_at_time_step_func = F.update_load_at_t
+    num2.update(0)
+    num2.calculate(None, None, None, F.force_vector, 0, 10)
+    e1 = ctx.state_epoch
+    num2.calculate(None, None, None, F.force_vector, 10, 28)
+    assert ctx.state_epoch == e1 + 1 and rel_l2(num2.u, first) <= 1e-12
+
+
 def test_output_row_count():
     from scatter_b200 import _lib
     rows = _lib.Context.n_output_rows
     assert rows(7, 2, 3) == 1 and rows(10, 1, 3) == 0 and rows(0, 27, 3) == 10 and rows(0, 0, 1) == 1 and rows(5, 0, 5) == 1
+    # the last step of the time axis is always stored (sc_set_final_output_step)
+    assert rows(0, 28, 3, 28) == 11 and rows(0, 27, 3, 27) == 10 and rows(9, 10, 3, 28) == 4 and rows(27, 1, 3, 28) == 2
