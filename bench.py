@@ -567,8 +567,8 @@ def run_ours(args):
         if idx[-1] != len(time_arr) - 1:
             idx = np.append(idx, len(time_arr) - 1)
         num.output_time_indices, num.output_time = idx, time_arr[idx]
-        assert len(idx) <= pool_rows
         ncol = n_eq if output_dofs is None else len(output_dofs)
+        assert len(idx) * ncol <= pool[0].size
         num.u, num.v, num.a = (p.reshape(-1)[:len(idx) * ncol].reshape(len(idx), ncol) for p in pool)
         num.u0 = pool[0][0] if output_dofs is None else np.zeros(n_eq)
         num.v0 = pool[1][0] if output_dofs is None else np.zeros(n_eq)
@@ -613,8 +613,7 @@ def run_ours(args):
         # output selection: the y-displacements of the 1000 free nodes nearest to the load leave the GPU at EVERY time step
         sel = np.unique(eq[:, 1][eq[:, 1] >= 0])[-1000:].astype(np.int64)
         num = make_solver(1, 3 * 100, output_dofs=sel)
-        pool_ok = len(num.output_time_indices) * len(sel) <= pool[0].size
-        if pool_ok:
+        if True:
             wsec = time_stages(num, 100, 1, 2)
             e2e_by["1_selected_dofs"] = {"dof_steps_per_s": total_dof * 200 / wsec, "ms_per_time_step": 1e3 * wsec / 200,
                                          "selected_dofs": int(len(sel)), "d2h_bytes_per_time_step": 3 * 8 * len(sel)}

@@ -92,8 +92,10 @@ def box_model(nx: int, ny: int, nz: int, h: float = 0.5, element_type: str = "he
               z_range=None) -> ReadMesh:
     nodes, elem = box_arrays(nx, ny, nz, h, element_type, z_range)
     m = ReadMesh.from_arrays(nodes, elem, np.ones(len(elem), dtype=np.int64), [[3.0, 1, "solid"]], element_type)
-    m.read_bc(box_boundaries(nx, ny, nz, h, bottom))
+    bc = box_boundaries(nx, ny, nz, h, bottom)
+    m.read_bc(bc)
     m.mapping()
+    m.prepared_bc = bc              # `Pipeline.mesh` skips its own read_bc / mapping when handed the same boundaries
     return m
 
 

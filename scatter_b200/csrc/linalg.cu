@@ -29,7 +29,7 @@ __global__ void __launch_bounds__(SPMV_THREADS)
 k_spmv(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col, const double* __restrict__ va,
        const double* __restrict__ xa, const double* __restrict__ vb, const double* __restrict__ xb,
        double* __restrict__ y, const double* __restrict__ inv_d, const double* __restrict__ alpha,
-       double* __restrict__ partial, int64_t n_rows, const double* __restrict__ xe, double* __restrict__ y2, double g) {
+       double* __restrict__ partial, int64_t n_rows, const double* __restrict__ xe, double* __restrict__ y2, double lag) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t row0 = ((int64_t)blockIdx.x * SPMV_WARPS + warp) * RPW;
     // row pointers of the warp's rows: lanes 0..RPW load, everybody reads them through shuffles
@@ -107,7 +107,7 @@ k_spmv(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col, cons
             if (rp_next > rp) {
                 const double un = e_id * (-mine) + e_al * e_x - (e_al - 1.0) * e_y;
                 y[myrow] = un;
-                if (y2) y2[myrow] = (1.0 + g) * un - g * e_x;
+                if (y2) y2[myrow] = (1.0 + lag) * un - lag * e_x;
             }
         } else {
             y[myrow] = mine;

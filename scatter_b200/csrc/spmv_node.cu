@@ -62,7 +62,7 @@ k_spmv_node(const NodeDesc* __restrict__ nd, const int32_t* __restrict__ ncol, c
             const double* __restrict__ xa, double* __restrict__ y, const double* __restrict__ inv_d,
             const double* __restrict__ alpha, double* __restrict__ partial, int64_t n_nodes, int64_t n_rows, int64_t n_tiles,
             int cap_v, int cap_c, const int32_t* __restrict__ dict, int n_dict, int dict_stride,
-            const double* __restrict__ xe, double* __restrict__ y2, double g) {
+            const double* __restrict__ xe, double* __restrict__ y2, double lag) {
     constexpr int NB_NODES = NB_WARPS * NB_NPW;      // nodes per tile; NB_NPW nodes per consumer warp (gathers in flight together)
     constexpr int NB_VT = 3 * NB_NODES + 8;          // vector slots per tile (rows + alignment), multiple of 2
     constexpr int NVEC = (MODE == 2) ? 4 : (MODE == 3 ? 1 : 0);
@@ -236,7 +236,7 @@ k_spmv_node(const NodeDesc* __restrict__ nd, const int32_t* __restrict__ ncol, c
                     if (MODE == 2) {
                         const double un = e_id[q] * (-mine) + e_al[q] * e_x[q] - (e_al[q] - 1.0) * e_y[q];
                         y[row] = un;
-                        if (y2) y2[row] = (1.0 + g) * un - g * e_x[q];
+                        if (y2) y2[row] = (1.0 + lag) * un - lag * e_x[q];
                     } else {
                         y[row] = mine;
                         if (MODE == 3) dot_acc += e_x[q] * mine;

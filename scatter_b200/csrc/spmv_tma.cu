@@ -63,7 +63,7 @@ __global__ void __launch_bounds__(TMA_THREADS, 2)
 k_spmv_tma(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col, const double* __restrict__ va,
            const double* __restrict__ xa, double* __restrict__ y, const double* __restrict__ inv_d,
            const double* __restrict__ alpha, double* __restrict__ partial, int64_t n_rows, int64_t n_tiles, int cap,
-           const double* __restrict__ xe, double* __restrict__ y2, double g) {
+           const double* __restrict__ xe, double* __restrict__ y2, double lag) {
     constexpr int RW = TR / TMA_CONSUMER_WARPS;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     // layout: [STAGES][cap] doubles | [STAGES][cap] ints | barriers
@@ -249,7 +249,7 @@ k_spmv_tma(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col, 
                     if (mylen > 0) {
                         const double un = e_id * (-mine) + e_al * e_x - (e_al - 1.0) * e_y;
                         y[myrow] = un;
-                        if (y2) y2[myrow] = (1.0 + g) * un - g * e_x;
+                        if (y2) y2[myrow] = (1.0 + lag) * un - lag * e_x;
                     }
                 } else {
                     y[myrow] = mine;

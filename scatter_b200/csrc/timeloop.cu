@@ -570,7 +570,8 @@ int tl_central_difference(sc_ctx* ctx, double dt, int64_t t0, int64_t n_steps, i
             // keep u(t-dt): the step overwrites it
             SC_CUDA(ctx, cudaMemcpyAsync(uc, prev, sizeof(double) * n, cudaMemcpyDeviceToDevice, st));
         }
-        // prev <- u(t+dt), w_nxt <- w(t+dt)
+        // prev <- u(t+dt), w_nxt <- w(t+dt)   (without stiffness-proportional damping the gathered vector is u(t) itself)
+        if (!lagged) w_cur = cur;
         SC_TRY(la_cd_step(ctx, ctx->d_K, w_cur, cur, prev, inv_d, alpha, g, w_nxt));
         SC_TRY(apply_load(ctx, t, 1.0, inv_d, prev));
         if (lagged) SC_TRY(apply_load(ctx, t, 1.0 + g, inv_d, w_nxt));

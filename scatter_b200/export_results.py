@@ -1,8 +1,8 @@
 """Result export -- same output layout as the reference's `scatter/export_results.py:10-213`.
 
 * `Write.data` = {"time", "nodes", "position", "displacement"|"velocity"|"acceleration": {str(node): {"x","y"[,"z"]}}}
-  with zeros for fixed dofs (`export_results.py:68-103`); built lazily (the reference builds O(Nn*dim) Python objects
-  eagerly, which is unusable beyond ~1e6 nodes).
+  with zeros for fixed dofs (`export_results.py:68-103`).  The three per-node dictionaries are lazy mappings
+  (`NodalHistories`): an entry is built when it is read, the reference builds O(Nn*dim) Python objects eagerly.
 * `pickle()` writes `<folder>/data.pickle` (all nodes or a subset, `:105-141`).
 * `vtk()` writes legacy-VTK unstructured grids `<folder>/VTK/data_<k>.vtk` (`:143-213`).  The reference delegates the
   file format to the un-vendored `vtk_tools` package; the writer below reproduces the byte layout of the reference's
@@ -14,7 +14,7 @@ from __future__ import annotations
 
 import os
 import pickle
-from collections import defaultdict
+from collections.abc import Mapping
 
 import numpy as np
 
@@ -22,6 +22,40 @@ _VTK_PERM = {"hexa8": list(range(8)), "hexa20": list(range(20)), "quad4": list(r
              "tri6": list(range(6)), "tetra4": list(range(4)), "tetra10": [0, 1, 2, 3, 4, 5, 6, 7, 9, 8],
              "quad8": list(range(8))}
 _VTK_CELL = {"hexa8": 12, "hexa20": 25, "quad4": 9, "quad8": 23, "tri3": 5, "tri6": 22, "tetra4": 10, "tetra10": 24}
+
+
+class NodalHistories(Mapping):
+    """`data["displacement"]` & co. of the reference's result dictionary -- {str(node id): {"x": history, "y": ..., ["z": ...]}}
+    (export_results.py:74-102) -- as a read-only mapping over the (n_out, n_eq) result array: an entry is built when it is
+    asked for, so a 10^7-node run does not create 10^8 Python objects it never reads.  `to_dict()` gives the plain dict."""
+
+    def __init__(self, write, field):
+        self._w, self._field = write, field
+
+    def __len__(self):
+        return len(self._w.nodes)
+
+    def __iter__(self):
+        return (str(int(n)) for n in self._w.nodes)
+
+    def __contains__(self, key):
+        try:
+            self._w.node_row(int(key))
+            return True
+        except (ValueError, TypeError):
+            return False
+
+    def __getitem__(self, key):
+        try:
+            row = self._w.node_row(int(key))
+        except (ValueError, TypeError):
+            raise KeyError(key) from None
+        return self._w.node_entry(self._field, row)
+
+    def to_dict(self, rows=None) -> dict:
+        w = self._w
+        rows = range(len(w.nodes)) if rows is None else rows
+        return {str(int(w.nodes[r])): w.node_entry(self._field, r) for r in rows}
 
 
 class Write:
@@ -34,19 +68,70 @@ class Write:
         self.nodes = model.nodes[:, 0].astype(int)
         self.eq_nb_dof = model.eq_nb_dof
         self.coordinates = model.nodes[:, 1:]
-        self.elements = model.elem[:, self.idx_vtk] - 1
+        self._model_elem = model.elem
+        self._elements = None
         self.time = numerical.output_time
         self.dis = numerical.u
         self.vel = numerical.v
         self.acc = numerical.a
+        # the solver may have kept only some equations (`output_dofs`): column of every equation in the stored rows, or -1
+        sel = getattr(numerical, "output_dofs", None)
+        self._col_of = None
+        if sel is not None:
+            self._col_of = -np.ones(int(model.number_eq), dtype=np.int64)
+            self._col_of[np.asarray(sel, dtype=np.int64)] = np.arange(len(sel))
         self.mat = model.materials
         self.mat_idx = model.materials_index
         self.materials = materials
         self.bc = model.BC
         self.n_dim = model.dimension
         self._data = None
+        self._row_lookup = None
+        self._zeros = None
+
+    @property
+    def elements(self):
+        """0-based element table in VTK node order (export_results.py:51) -- only the VTK writer needs it."""
+        if self._elements is None:
+            self._elements = np.asarray(self._model_elem)[:, self.idx_vtk] - 1
+        return self._elements
 
     # ------------------------------------------------------------------------------------------------------------
+    def node_row(self, node_id: int) -> int:
+        """Row of a node id (first occurrence, like `list.index`); raises ValueError for an unknown id."""
+        ids = self.nodes
+        if self._row_lookup is None:
+            if len(ids) and ids[0] == 1 and ids[-1] == len(ids) and np.array_equal(ids, np.arange(1, len(ids) + 1)):
+                self._row_lookup = "identity"
+            else:
+                order = np.argsort(ids, kind="stable")
+                self._row_lookup = (order, ids[order])
+        if isinstance(self._row_lookup, str):
+            if not 1 <= node_id <= len(ids):
+                raise ValueError(f"{node_id} is not in list")
+            return node_id - 1
+        order, sorted_ids = self._row_lookup
+        k = int(np.searchsorted(sorted_ids, node_id, side="left"))
+        if k >= len(sorted_ids) or sorted_ids[k] != node_id:
+            raise ValueError(f"{node_id} is not in list")
+        return int(order[k])
+
+    def node_entry(self, field: np.ndarray, row: int) -> dict:
+        """{"x": history, ...} of one node: zeros for fixed dofs (export_results.py:89-102)."""
+        if self._zeros is None:
+            self._zeros = np.zeros(len(self.time))
+        out = {}
+        for j, lab in enumerate(("x", "y", "z")[:self.n_dim]):
+            dof = self.eq_nb_dof[row][j]
+            if np.isnan(dof):
+                out[lab] = self._zeros
+                continue
+            col = int(dof) if self._col_of is None else int(self._col_of[int(dof)])
+            if col < 0:
+                raise KeyError(f"the history of node row {row} was not stored (output_dofs does not include equation {int(dof)})")
+            out[lab] = field[:, col]
+        return out
+
     @property
     def data(self) -> dict:
         if self._data is None:
@@ -54,40 +139,42 @@ class Write:
             self.parse_data()
         return self._data
 
-    def nodal_field(self, field: np.ndarray) -> np.ndarray:
-        """(n_out, Nn, dim) array of a result field with zeros at fixed dofs."""
+    def nodal_field(self, field: np.ndarray, rows=None) -> np.ndarray:
+        """(n_out, Nn, dim) array of a result field with zeros at fixed dofs; `rows`: only these output rows."""
         eq = self.eq_nb_dof
         free = ~np.isnan(eq)
-        out = np.zeros((field.shape[0],) + eq.shape)
-        out[:, free] = field[:, eq[free].astype(np.int64)]
+        cols = eq[free].astype(np.int64)
+        if self._col_of is not None:
+            cols = self._col_of[cols]
+            if (cols < 0).any():
+                raise KeyError("whole-mesh fields need full output rows (output_dofs is set)")
+        src = field if rows is None else field[rows]
+        out = np.zeros((src.shape[0],) + eq.shape)
+        out[:, free] = src[:, cols]
         return out
 
     def parse_data(self) -> None:
-        labels = ["x", "y", "z"][:self.n_dim]
-        d = {"time": self.time, "nodes": list(map(int, self.nodes)), "position": self.coordinates,
-             "displacement": defaultdict(dict), "velocity": defaultdict(dict), "acceleration": defaultdict(dict)}
-        zeros = np.zeros(len(self.time))
-        for name, field in (("displacement", self.dis), ("velocity", self.vel), ("acceleration", self.acc)):
-            target = d[name]
-            for i, nid in enumerate(self.nodes):
-                key = str(int(nid))
-                for j, lab in enumerate(labels):
-                    dof = self.eq_nb_dof[i][j]
-                    target[key][lab] = zeros if np.isnan(dof) else field[:, int(dof)]
-        self._data.update(d)
+        """The reference's result dictionary (export_results.py:68-103), with the three per-node dictionaries as lazy
+        mappings (`NodalHistories`)."""
+        self._data.update({"time": self.time, "nodes": self.nodes.tolist(), "position": self.coordinates,
+                           "displacement": NodalHistories(self, self.dis), "velocity": NodalHistories(self, self.vel),
+                           "acceleration": NodalHistories(self, self.acc)})
 
     def pickle(self, name="data", write=True, nodes="all") -> None:
+        """`<folder>/<name>.pickle` with plain dictionaries, all nodes or a subset (export_results.py:105-141).  The subset
+        path touches only the requested nodes."""
         if not write:
             return
-        if nodes != "all":
-            idx = [self.data["nodes"].index(int(i)) for i in nodes]
-            data = {"time": self.data["time"], "nodes": nodes, "position": [self.data["position"][i] for i in idx],
-                    "displacement": defaultdict(dict), "velocity": defaultdict(dict), "acceleration": defaultdict(dict)}
-            for n in nodes:
-                for key in ("displacement", "velocity", "acceleration"):
-                    data[key].update({str(n): self.data[key][str(n)]})
+        fields = (("displacement", self.dis), ("velocity", self.vel), ("acceleration", self.acc))
+        if isinstance(nodes, str) and nodes == "all":
+            data = {"time": self.time, "nodes": self.nodes.tolist(), "position": self.coordinates}
+            for key, field in fields:
+                data[key] = NodalHistories(self, field).to_dict()
         else:
-            data = self.data
+            idx = [self.node_row(int(i)) for i in nodes]
+            data = {"time": self.time, "nodes": nodes, "position": [self.coordinates[i] for i in idx]}
+            for key, field in fields:
+                data[key] = {str(n): self.node_entry(field, i) for n, i in zip(nodes, idx)}
         with open(os.path.join(self.output_folder, f"{name}.pickle"), "wb") as f:
             pickle.dump(data, f)
 
@@ -108,15 +195,13 @@ class Write:
             bc[:, :2] = self.bc
         else:
             bc = self.bc
-        dis = self.nodal_field(self.dis)
-        vel = self.nodal_field(self.vel)
         folder = os.path.join(self.output_folder, "VTK")
         os.makedirs(folder, exist_ok=True)
         for output_t in range(int(len(self.time) / output_interval)):
             t = int(output_t * output_interval)
             d3 = np.zeros((len(self.nodes), 3)); v3 = np.zeros((len(self.nodes), 3))
-            d3[:, :self.n_dim] = dis[t]
-            v3[:, :self.n_dim] = vel[t]
+            d3[:, :self.n_dim] = self.nodal_field(self.dis, [t])[0]        # one frame at a time: no (n_out, Nn, dim) copy
+            v3[:, :self.n_dim] = self.nodal_field(self.vel, [t])[0]
             w = LegacyVtk(os.path.join(folder, f"{name}_{output_t}.vtk"), f"{name}_{output_t}", binary)
             w.mesh(self.coordinates, self.elements, self.element_type)
             w.point_vectors([("displacement", d3), ("velocity", v3), ("boundary_conditions", bc)])

@@ -57,11 +57,25 @@ class Force:
         self.force_vector = self.update_load_at_t(0)
 
     def _node_row(self, node_id: int) -> int:
+        """Row of a node id in the node table; first occurrence wins, like the reference's `list(...).index(n)`
+        (force_external.py:262,275,341)."""
+        ids = self._ids
         if self._row_of is None:
-            self._row_of = {}
-            for i, n in enumerate(self._ids):          # first occurrence wins, like list.index
-                self._row_of.setdefault(int(n), i)
-        return self._row_of[int(node_id)]
+            if len(ids) and ids[0] == 1 and ids[-1] == len(ids) and np.array_equal(ids, np.arange(1, len(ids) + 1)):
+                self._row_of = "identity"
+            else:
+                order = np.argsort(ids, kind="stable")
+                self._row_of = (order, ids[order])
+        if isinstance(self._row_of, str):
+            row = int(node_id) - 1
+            if not 0 <= row < len(ids):
+                raise ValueError(f"{node_id} is not in list")
+            return row
+        order, sorted_ids = self._row_of
+        k = int(np.searchsorted(sorted_ids, int(node_id), side="left"))
+        if k >= len(sorted_ids) or sorted_ids[k] != int(node_id):
+            raise ValueError(f"{node_id} is not in list")
+        return int(order[k])
 
     def _init_moving(self, load_speed):
         nd = self.model_nodes

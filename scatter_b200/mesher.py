@@ -39,24 +39,82 @@ class ReadMesh:
         self.elem = []
         self.rose_elem = []
         self.rose_nodes = []
-        self.boundary_elem = []
         self.nb_nodes_elem = []
         self.materials = []
         self.BC = []
         self.BC_dir = []
         self.number_eq = []
-        self.type_BC = []
         self.eq_nb_dof = []
-        self.eq_nb_elem = []
         self.eq_nb_dof_rose_nodes = []
         self.rose_eq_nb = []
-        self.type_BC_elem = []
+        # the reference's string / per-element tables (type_BC, eq_nb_elem, type_BC_elem, boundary_elem) are derived data that
+        # cost 1-10 GB on a 50 M-dof mesh: they are built on first access (the hot path itself consumes BC and eq_nb_dof)
+        self._type_BC = self._eq_nb_elem = self._type_BC_elem = self._boundary_elem = None
+        self._connected = False
         self.element_type = []
         self.lower_element_type = []
         self.nb_nodes_lower_elem = []
         self.materials_index = []
         self.dimension = 3
         self._node_rows = None          # (Ne, nne) 0-based rows into self.nodes
+
+    # ---- lazily derived attributes of the reference's data model ---------------------------------------------------
+    @property
+    def type_BC(self):
+        """"Normal" / "Fixed" / "Absorb" per (node, dof) -- mesher.py:293-305."""
+        if self._type_BC is None:
+            if len(self.BC) == 0 or len(self.eq_nb_dof) == 0:
+                return []
+            bc = np.asarray(self.BC)
+            t = np.full(bc.shape, "Normal")
+            t[bc == 1] = "Fixed"
+            t[bc == 2] = "Absorb"
+            self._type_BC = t
+        return self._type_BC
+
+    @type_BC.setter
+    def type_BC(self, value):
+        self._type_BC = value
+
+    @property
+    def eq_nb_elem(self):
+        """Equation numbers per element, node-major (NaN = fixed) -- mesher.py:312-326."""
+        if self._eq_nb_elem is None:
+            if not self._connected:
+                return []
+            rows = self.node_rows()
+            self._eq_nb_elem = self.eq_nb_dof[rows].reshape(rows.shape[0], -1)
+        return self._eq_nb_elem
+
+    @eq_nb_elem.setter
+    def eq_nb_elem(self, value):
+        self._eq_nb_elem = value
+
+    @property
+    def type_BC_elem(self):
+        if self._type_BC_elem is None:
+            if not self._connected:
+                return []
+            rows = self.node_rows()
+            self._type_BC_elem = self.type_BC[rows].reshape(rows.shape[0], -1)
+        return self._type_BC_elem
+
+    @type_BC_elem.setter
+    def type_BC_elem(self, value):
+        self._type_BC_elem = value
+
+    @property
+    def boundary_elem(self):
+        """Boundary faces of a hexa8 mesh (mesher.py:328-391); computed by `get_mesh_edges`, on first access at the latest."""
+        if self._boundary_elem is None:
+            if self.element_type != "hexa8":
+                return []
+            self._compute_mesh_edges()
+        return self._boundary_elem
+
+    @boundary_elem.setter
+    def boundary_elem(self, value):
+        self._boundary_elem = value
 
     # ------------------------------------------------------------------------------------------------------------
     @classmethod
@@ -142,9 +200,7 @@ class ReadMesh:
         numbers = np.cumsum(free.ravel()) - 1
         eq = np.where(free.ravel(), numbers, np.nan).reshape(bc.shape).astype(float)
         self.eq_nb_dof = eq
-        self.type_BC = np.full(bc.shape, "Normal")
-        self.type_BC[bc == 1] = "Fixed"
-        self.type_BC[bc == 2] = "Absorb"
+        self._type_BC = self._eq_nb_elem = self._type_BC_elem = None
         self.number_eq = int(free.sum())
 
     def node_rows(self) -> np.ndarray:
@@ -161,10 +217,11 @@ class ReadMesh:
         return self._node_rows
 
     def connectivities(self) -> None:
-        rows = self.node_rows()
-        ne = rows.shape[0]
-        self.eq_nb_elem = self.eq_nb_dof[rows].reshape(ne, -1)
-        self.type_BC_elem = self.type_BC[rows].reshape(ne, -1)
+        """mesher.py:312-326: per-element equation / BC-type tables (`eq_nb_elem`, `type_BC_elem`) -- available from now on,
+        materialised on first access."""
+        self.node_rows()
+        self._connected = True
+        self._eq_nb_elem = self._type_BC_elem = None
 
     def equation_table_int(self) -> np.ndarray:
         """eq_nb_dof as int64 with -1 for fixed dofs (the C ABI's representation)."""
@@ -172,9 +229,11 @@ class ReadMesh:
 
     # ------------------------------------------------------------------------------------------------------------
     def get_mesh_edges(self):
-        """Boundary faces of a hexa8 mesh (node ids), unique rows -- mesher.py:328-391."""
-        if self.element_type != "hexa8":
-            return
+        """Boundary faces of a hexa8 mesh (node ids), unique rows -- mesher.py:328-391.  The faces are only consumed by
+        `get_top_surface` (moving_at_plane loads): they are computed when `boundary_elem` is first read."""
+        self._boundary_elem = None
+
+    def _compute_mesh_edges(self):
         rows = self.node_rows()
         nn = len(self.nodes)
         count = np.bincount(rows.ravel(), minlength=nn)

@@ -12,10 +12,16 @@ with k_j drawn from the spectral density of the covariance model and z1, z2 ~ N(
 host (`sample_modes`) and the O(elements x modes) evaluation runs in the CUDA library (`sc_srf_sample`, csrc/srf.cu).
 Class, method and attribute names follow the reference, so `scatter.scatter(..., random_props=...)` is unchanged.
 
-Parity: **unpinned** against gstools itself -- the package is not available, so its private random stream (seed ->
-modes) cannot be reproduced; a realisation here has the same mean, variance and covariance function as the
-reference's, not the same numbers.  The kernel is checked against the CPU restatement (oracle/fem_np.py:srf_field) on
-the same modes, the mode sampler against the analytical correlation functions (tests/test_host_logic.py).
+Parity.  gstools is not installed, but for the covariance models whose radial spectral density has a closed-form
+inverse (`CovModel.has_ppf`: Exponential and Gaussian in 1-D / 2-D) its seed -> modes path is plain numpy `RandomState`
+arithmetic, restated in `gstools_modes`.  **Pinned**: the 2-D Exponential field -- the reference's own random-field test
+(`integration_tests/integration_test.py:376-421`, golden `results_rf_2d/data.pickle`) is reproduced to 1e-14 relative
+(`tests/golden/history_rf_2d.npz`; CPU test of the sampler, GPU test of `scatter(..., random_props=...)` end to end).  The
+2-D Gaussian model follows the same path with gstools' published formulas but has no reference fixture.  In 3-D (and for
+Matern) gstools samples the radii with an `emcee` MCMC ensemble, which is not restated: there `sample_modes` draws its own
+stream -- **unpinned**: same mean, variance and covariance function as the reference's realisation, not the same numbers.
+The kernel is checked against the CPU restatement (oracle/fem_np.py:srf_field) on the same modes, the own mode sampler
+against the analytical correlation functions (tests/test_host_logic.py).
 """
 from __future__ import annotations
 
@@ -42,6 +48,47 @@ def correlation(model_name: str, h):
     r = np.sqrt(nu) * s * np.maximum(h, 1e-300)
     out = 2.0 ** (1.0 - nu) / gamma(nu) * r ** nu * kv(nu, r)
     return np.where(h == 0, 1.0, out)
+
+
+def gstools_has_ppf(model_name: str, dim: int) -> bool:
+    """Models / dimensions for which gstools 1.7.0 samples the radii by inversion (`CovModel.has_ppf`)."""
+    return model_name in ("Exponential", "Gaussian") and dim in (1, 2)
+
+
+def gstools_modes(model_name: str, dim: int, len_scale: float, seed: int, mode_no: int = MODE_NO):
+    """Restatement of `gstools.field.generator.RandMeth.reset_seed` (gstools 1.7.0) for models with `has_ppf`:
+    -> wave vectors k (mode_no, 3) [1/length] for the main length scale `len_scale`, amplitudes z1, z2 (mode_no,).
+
+    * `gstools.random.rng.MasterRNG(seed)`: `RandomState(seed).randint(1, 2**16 - 1)` hands out one sub-seed per stream;
+      `RNG.random` opens a fresh `RandomState(sub-seed)` at every access.
+    * streams, in this order: z1 ~ normal, z2 ~ normal, directions (`RNG.sample_sphere`: +-1 in 1-D, the angle
+      uniform(0, 2 pi) in 2-D), radii (`RNG.sample_dist` -> scipy `rv_continuous.rvs`: `ppf(RandomState(sub-seed).uniform)`).
+    * radial ppf with f = len_scale / rescale.  Exponential (`gstools/covmodel/models.py`): 1-D tan(pi u / 2) / f, 2-D
+      sqrt(1/u^2 - 1) / f (gstools inverts the survival function there; kept, the golden depends on it).  Gaussian: 1-D
+      2 erfinv(u) / f, 2-D 2 sqrt(-log(1 - u)) / f."""
+    if not gstools_has_ppf(model_name, dim):
+        raise ValueError("gstools samples this model/dimension with an MCMC ensemble; no restatement")
+    master = np.random.RandomState(int(seed))
+
+    def stream():
+        return np.random.RandomState(master.randint(1, 2 ** 16 - 1))
+    z1 = stream().normal(size=mode_no)
+    z2 = stream().normal(size=mode_no)
+    if dim == 1:
+        sphere = stream().choice([-1, 1], size=mode_no)[None, :].astype(float)
+    else:
+        ang = stream().uniform(0.0, 2 * np.pi, mode_no)
+        sphere = np.vstack([np.cos(ang), np.sin(ang)])
+    u = stream().uniform(size=mode_no)
+    f = float(len_scale) / RESCALE[model_name]
+    if model_name == "Exponential":
+        rad = np.tan(np.pi / 2 * u) / f if dim == 1 else np.sqrt(1.0 / u ** 2 - 1.0) / f
+    else:
+        from scipy.special import erfinv
+        rad = 2.0 / f * erfinv(u) if dim == 1 else 2.0 / f * np.sqrt(-np.log(1.0 - u))
+    k3 = np.zeros((mode_no, 3))
+    k3[:, :dim] = (rad * sphere).T
+    return k3, z1, z2
 
 
 def sample_modes(model_name: str, dim: int, seed: int, mode_no: int = MODE_NO):
@@ -79,7 +126,14 @@ class SpectralField:
         self.model_name, self.dim, self.var, self.mean = model_name, dim, float(var), float(mean)
         self.len_scale = np.asarray(len_scale, dtype=float)[:dim]
         self.angles, self.seed, self.mode_no = float(angles), int(seed), int(mode_no)
-        self.k, self.z1, self.z2 = sample_modes(model_name, dim, seed, mode_no)
+        self.gstools_stream = gstools_has_ppf(model_name, dim)
+        if self.gstools_stream:
+            # gstools' own modes for the main length scale; `isometrize` divides every coordinate by its length scale, so the
+            # wave vectors are brought to the unit-length-scale form the kernel expects (same phases k . x)
+            k, self.z1, self.z2 = gstools_modes(model_name, dim, self.len_scale[0], seed, mode_no)
+            self.k = k * self.len_scale[0]
+        else:
+            self.k, self.z1, self.z2 = sample_modes(model_name, dim, seed, mode_no)
         self.seconds_device = 0.0
 
     def isometrize(self, pos):

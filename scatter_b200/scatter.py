@@ -53,8 +53,9 @@ class Pipeline:
         else:
             model = mesher.ReadMesh(mesh_file)
             model.read_gmsh()
-        model.read_bc(self.boundaries)
-        model.mapping()
+        if getattr(model, "prepared_bc", None) != self.boundaries:      # a prepared model already carries these BC / numbers
+            model.read_bc(self.boundaries)
+            model.mapping()
         model.connectivities()
         if self.loading["type"] == "rose":
             raise NotImplementedError("ROSE train-track coupling is outside the scope of the B200 hot path")
@@ -98,6 +99,8 @@ class Pipeline:
             sys.exit(f"Error: {self.solver_kind} not supported")
         num = _SOLVER_CLASSES[self.solver_kind]()
         num.output_interval = self.settings.get("output_interval", 1)
+        if "pcg_rtol" in self.settings and hasattr(num, "pcg_rtol"):     # optional: tolerance of the iterative solve
+            num.pcg_rtol = float(self.settings["pcg_rtol"])
         num.initialise(self.model.number_eq, self.time)
         num.bind(self.matrix)
         self.numerical = num

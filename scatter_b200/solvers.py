@@ -176,10 +176,11 @@ class NewmarkExplicit(_DeviceSolver):
 
     def __init__(self):
         super().__init__()
-        # relative residual of the effective-stiffness solve.  The reference solves exactly (sparse LU); 1e-12 keeps a
-        # 1000-step history within 1e-8 of it.  A solve that stagnates above the target but below 1e-9 is
-        # accepted and counted in stats["pcg_stagnations"] instead of aborting the run.
-        self.pcg_rtol = 1e-12
+        # relative residual of the effective-stiffness solve.  The reference solves exactly (sparse LU); the increments of
+        # the inexact solves accumulate, and 1e-12 already leaves 3e-8 after the 1000 steps of the reference's hexa8 golden,
+        # so the default sits at the round-off floor.  A solve that stagnates above the target but below 1e-9 is accepted
+        # and counted in stats["pcg_stagnations"] instead of aborting the run (a direct solver cannot fail that way).
+        self.pcg_rtol = 1e-14
         self.pcg_maxit = 20000
 
     def calculate(self, M, C, K, F, t_start_idx, t_end_idx):
@@ -213,7 +214,7 @@ class BatheSolver(_DeviceSolver):
 
     def __init__(self):
         super().__init__()
-        self.pcg_rtol = 1e-12
+        self.pcg_rtol = 1e-14
         self.pcg_maxit = 20000
 
     def calculate(self, M, C, K, F, t_start_idx, t_end_idx):

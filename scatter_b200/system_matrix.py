@@ -77,8 +77,8 @@ def gmsh_face_order(points: np.ndarray) -> np.ndarray:
 def _absorbing_faces(data):
     """(element, direction, node rows[nl]) of every absorbing face, in the reference's element / direction order
     (system_matrix.py:274-316): a face exists where exactly `nb_nodes_lower_elem` nodes of an element absorb in a direction."""
-    type_bc = np.asarray(data.type_BC)
-    absorb = type_bc == "Absorb"                                   # (Nn, dim)
+    # "Absorb" <=> BC code 2 (mesher.py:293-305); the integer table avoids the (Nn, dim) string array on large meshes
+    absorb = (np.asarray(data.BC) == 2) if len(data.BC) else (np.asarray(data.type_BC) == "Absorb")   # (Nn, dim)
     rows = data.node_rows()
     nl, dim = data.nb_nodes_lower_elem, data.dimension
     touched = np.where(absorb.any(axis=1)[rows].any(axis=1))[0]

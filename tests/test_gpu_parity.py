@@ -383,7 +383,8 @@ def test_scatter_with_random_field(golden_meshes, oracle, tmp_path):
     out = os.path.join(tmp_path, "rf2d")
     res = scatter(golden_meshes[fn], out, mats, bc, sett, dict(load), time_step=1e-3, random_props=cases.rf_properties(case, "Gaussian"))
     young = np.array([v["Young"] for k, v in mats.items() if k.startswith("material_")])
-    assert len(young) == 602 and abs(young.mean() / 500e5 - 1) < 0.05 and 0.2 < young.std() / 3e6 < 3.0
+    # one realisation over a domain of a few correlation lengths: its mean sits within a couple of field standard deviations (6 %)
+    assert len(young) == 602 and abs(young.mean() / 500e5 - 1) < 0.15 and 0.2 < young.std() / 3e6 < 3.0
     assert os.path.isfile(os.path.join(out, "rf_props.txt"))
     # oracle with the same per-element materials (tags 0..N-1 = field elements, the others shifted)
     om = oracle.build_model(golden_meshes[fn], bc)

@@ -64,7 +64,10 @@ def test_unbound_solver_integrates_caller_matrices(case, oracle, golden_meshes):
     ns.initialise(n, time[:7]); ns.update_rhs_at_time_step_func = force
     ns.calculate(Kc, force(0), 0, 6)
     assert rel_l2(ns.u, Us) <= 1e-7
-    # explicit scheme: with caller matrices all of C is lumped by row sums (no Rayleigh split is known)
+    # explicit scheme: with caller matrices all of C is lumped by row sums (no Rayleigh split is known).  Not for tri6: the
+    # row sums of a quadratic triangle's mass matrix vanish at the corner nodes, no explicit scheme runs on that
+    if case == "column_2D_tri6":
+        return
     dt = 1e-4
     t2 = np.arange(61) * dt
     Ucd = oracle.central_difference(M, C, K, force, t2, 10, c1=0.0)[0]
@@ -197,3 +200,16 @@ def test_mid_size_box_against_oracle(oracle):
     u, v, a, st = ctx.run_central_difference(dt, 0, nt - 1, 10)
     assert np.abs(U).max() > 0 and rel_l2(u, U) <= TOL_HIST and rel_l2(v, V) <= TOL_HIST
     ctx.close()
+
+
+def test_reference_random_field_case_on_device(golden_meshes, tmp_path):
+    """The reference's random-field test (integration_test.py:376-431) end to end on the GPU: gstools-compatible modes
+    (`random_fields.gstools_modes`), field evaluation in `k_srf`, assembly, Newmark -- against the reference's own golden
+    `results_rf_2d/data.pickle` (tests/golden/history_rf_2d.npz)."""
+    from scatter_b200.scatter import scatter
+    from test_pipeline_cpu import RF_2D_PROPS, check_rf_2d_golden
+    sett = cases.settings(damping=[1, 0.005, 20, 0.005])
+    load = {"force": [0, -1e6, 0], "node": [3, 4, 25], "time": 1.0, "type": "heaviside"}
+    res = scatter(golden_meshes["column_2D.msh"], str(tmp_path), cases.materials(), cases.BC_2D, sett, load, time_step=5e-3,
+                  random_props=dict(RF_2D_PROPS))
+    check_rf_2d_golden(res)

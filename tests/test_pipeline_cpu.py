@@ -250,6 +250,34 @@ def test_scatter_entry_point_with_random_field_cpu(oracle_device, golden_meshes,
     assert res.dis.shape[0] == len(oracle.time_array(0.02, 1e-3))
 
 
+RF_2D_PROPS = {"number_realisations": 1, "element_size": 1, "theta": 5, "seed_number": -26021981, "material": "solid",
+               "key_material": "Young", "std_value": 3e6, "aniso_x": 2 / 5, "aniso_z": 1 / 5, "model_name": "Exponential"}
+
+
+def check_rf_2d_golden(res, decimal_tol=1e-8):
+    """The reference's own assertion for this case (integration_test.py:423-431: every array of the result dictionary
+    against results_rf_2d/data.pickle, 5 decimals), tightened to a relative L2 tolerance."""
+    G = np.load(os.path.join(os.path.dirname(__file__), "golden", "history_rf_2d.npz"))
+    data = res.data
+    assert [int(n) for n in data["nodes"]] == [int(n) for n in G["nodes"]] and np.allclose(data["time"], G["time"])
+    for name in ("displacement", "velocity", "acceleration"):
+        mine = np.array([[data[name][str(int(n))][lab] for lab in "xy"] for n in G["nodes"]])
+        assert rel_l2(mine, G[name]) <= (decimal_tol if name != "acceleration" else 100 * decimal_tol), name
+        np.testing.assert_almost_equal(mine, G[name], decimal=5)
+
+
+def test_reference_random_field_case_reproduces_its_golden(oracle_device, golden_meshes, tmp_path):
+    """Test1DWavePropagation_2D.test_2 of the reference (integration_test.py:376-431): quad4 column whose Young's modulus is a
+    gstools Exponential random field.  Pins `random_fields.gstools_modes` (the restated RandMeth seed -> modes path): the
+    golden history only comes out if every element receives the modulus gstools 1.7.0 gave it."""
+    from scatter_b200.scatter import scatter
+    sett = cases.settings(damping=[1, 0.005, 20, 0.005])
+    load = {"force": [0, -1e6, 0], "node": [3, 4, 25], "time": 1.0, "type": "heaviside"}
+    res = scatter(golden_meshes["column_2D.msh"], str(tmp_path), cases.materials(), cases.BC_2D, sett, load, time_step=5e-3,
+                  random_props=dict(RF_2D_PROPS))
+    check_rf_2d_golden(res)
+
+
 @pytest.mark.parametrize("with_update", [False, True])
 def test_solver_stages_fill_the_right_output_rows(with_update, oracle_device, golden_meshes, oracle):
     """Stage protocol of scatter.py:153-159 / rose_utils.py: `calculate(t0, t1)` called stage by stage (optionally with the
