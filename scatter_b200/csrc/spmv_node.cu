@@ -142,105 +142,92 @@ k_spmv_node(const NodeDesc* __restrict__ nd, const int32_t* __restrict__ ncol, c
         }
     } else {
         // ------------------------------------------------ consumer warps: NB_NPW nodes each per tile -----------------
+        // The warp's NB_NPW nodes are processed side by side: LPN = 32 / NB_NPW lanes per node, every lane belongs to one
+        // node, so one instruction stream serves all of them (round 1 looped over the nodes with all 32 lanes: 3x the
+        // instructions per node, per-node arrays that spilled, a butterfly per node).  Lane l of a node takes entries
+        // l, l + LPN, ... of each of the node's rows; U entries per lane are in flight together.
+        constexpr int LPN = 32 / NB_NPW;                 // lanes per node
+        constexpr int U = NB_NPW == 1 ? 3 : 6;           // entries per lane and pass (96 entries per node and pass)
+        const int grp = lane / LPN, l = lane % LPN;
+        const int myr = l / (LPN / 4);                   // row of the node this lane owns after the reduction (3 = none)
         int stage = 0;
         uint32_t phase = 0;
         for (int64_t t = blockIdx.x; t < n_tiles; t += G) {
             mbar_wait(&bar_full[stage], phase);
             const NodeDesc* snd = s_nd + (size_t)stage * NB_NODES;
             const NodeDesc d0 = snd[0];
-            const int myr = lane >> 3;                       // lanes 0, 8, 16 own rows 0, 1, 2 of a node after the reduction
-            int L[NB_NPW], nfree[NB_NPW], row0[NB_NPW], cadd[NB_NPW];
-            const double* sv[NB_NPW];
-            const int* sc[NB_NPW];
-            double e_al[NB_NPW], e_id[NB_NPW], e_x[NB_NPW], e_y[NB_NPW];
-            bool owner[NB_NPW];
-            int maxL = 0;
-#pragma unroll
-            for (int q = 0; q < NB_NPW; ++q) {
-                const NodeDesc d = snd[warp * NB_NPW + q];
-                nfree[q] = d.len_nfree >> 24;
-                L[q] = nfree[q] > 0 ? (d.len_nfree & 0xffff) : 0;
-                row0[q] = d.row0;
-                maxL = max(maxL, L[q]);
-                sv[q] = s_val + (size_t)stage * cap_v + (int)(d.val_off - (d0.val_off & ~(int64_t)1)) + lane;
-                // columns: the node's explicit list in the ring, or row0 + a relative list of the dictionary (bits 16..23: pattern id)
-                const int pid = (d.len_nfree >> 16) & 0xff;
-                sc[q] = pid ? s_dict + (pid - 1) * dict_stride + lane
-                            : s_col + (size_t)stage * cap_c + (int)(d.col_off - (d0.col_off & ~(int64_t)3)) + lane;
-                cadd[q] = pid ? d.row0 : 0;
-                // rows without entries (ghost nodes of a domain decomposition) still get y = 0: PCG reads q on every local
-                // row; the fused central-difference step leaves them alone (their u comes from the halo exchange)
-                owner[q] = (lane & 7) == 0 && myr < nfree[q] && (L[q] > 0 || MODE != 2);
-                e_al[q] = e_id[q] = e_x[q] = e_y[q] = 0.0;
-                if (NVEC > 0 && owner[q]) {
-                    const double* svec = s_vec + (size_t)stage * NV1 * NB_VT + (d.row0 - (d0.row0 & ~1)) + myr;
-                    if (MODE == 2) { e_al[q] = svec[0]; e_id[q] = svec[NB_VT]; e_x[q] = svec[2 * NB_VT]; e_y[q] = svec[3 * NB_VT]; }
-                    if (MODE == 3) e_x[q] = svec[0];
-                }
+            const NodeDesc d = snd[warp * NB_NPW + grp];
+            const int nfree = d.len_nfree >> 24;
+            const int L = nfree > 0 ? (d.len_nfree & 0xffff) : 0;
+            int maxL = L;
+            if (NB_NPW == 2) maxL = max(maxL, __shfl_xor_sync(0xffffffffu, maxL, 16));
+            const double* sv = s_val + (size_t)stage * cap_v + (int)(d.val_off - (d0.val_off & ~(int64_t)1)) + l;
+            // columns: the node's explicit list in the ring, or row0 + a relative list of the dictionary (bits 16..23: pattern id)
+            const int pid = (d.len_nfree >> 16) & 0xff;
+            const int* sc = pid ? s_dict + (pid - 1) * dict_stride + l
+                                : s_col + (size_t)stage * cap_c + (int)(d.col_off - (d0.col_off & ~(int64_t)3)) + l;
+            const int cadd = pid ? d.row0 : 0;
+            const int L1 = nfree > 1 ? L : -1, L2 = nfree > 2 ? 2 * L : -1;     // offsets of rows 1, 2 in the value slice (-1: no such row)
+            // rows without entries (ghost nodes of a domain decomposition) still get y = 0: PCG reads q on every local
+            // row; the fused central-difference step leaves them alone (their u comes from the halo exchange)
+            const bool owner = (l % (LPN / 4)) == 0 && myr < nfree && (L > 0 || MODE != 2);
+            double e_al = 0.0, e_id = 0.0, e_x = 0.0, e_y = 0.0;
+            if (NVEC > 0 && owner) {
+                const double* svec = s_vec + (size_t)stage * NV1 * NB_VT + (d.row0 - (d0.row0 & ~1)) + myr;
+                if (MODE == 2) { e_al = svec[0]; e_id = svec[NB_VT]; e_x = svec[2 * NB_VT]; e_y = svec[3 * NB_VT]; }
+                if (MODE == 3) e_x = svec[0];
             }
-            double s0[NB_NPW], s1[NB_NPW], s2[NB_NPW];
+            double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+            for (int kb = 0; kb < maxL; kb += LPN * U) {
+                int c[U];
+                double xg[U], v0[U], v1[U], v2[U];
 #pragma unroll
-            for (int q = 0; q < NB_NPW; ++q) { s0[q] = 0.0; s1[q] = 0.0; s2[q] = 0.0; }
-            constexpr int U = 3;
-            for (int kb = 0; kb < maxL; kb += 32 * U) {
-                int c[NB_NPW][U];
-                double xg[NB_NPW][U], v0[NB_NPW][U], v1[NB_NPW][U], v2[NB_NPW][U];
-#pragma unroll
-                for (int q = 0; q < NB_NPW; ++q)
-#pragma unroll
-                    for (int u = 0; u < U; ++u) {
-                        const int k = kb + 32 * u;
-                        const bool ok = k + lane < L[q];
-                        c[q][u] = 0; v0[q][u] = 0.0; v1[q][u] = 0.0; v2[q][u] = 0.0;
-                        if (ok) {
-                            c[q][u] = sc[q][k] + cadd[q];
-                            v0[q][u] = sv[q][k];
-                            if (nfree[q] > 1) v1[q][u] = sv[q][L[q] + k];
-                            if (nfree[q] > 2) v2[q][u] = sv[q][2 * L[q] + k];
-                        }
+                for (int u = 0; u < U; ++u) {
+                    const int k = kb + LPN * u;
+                    const bool ok = k + l < L;
+                    c[u] = 0; v0[u] = 0.0; v1[u] = 0.0; v2[u] = 0.0;
+                    if (ok) {
+                        c[u] = sc[k] + cadd;
+                        v0[u] = sv[k];
+                        if (L1 >= 0) v1[u] = sv[L1 + k];
+                        if (L2 >= 0) v2[u] = sv[L2 + k];
                     }
+                }
 #pragma unroll
-                for (int q = 0; q < NB_NPW; ++q)
-#pragma unroll
-                    for (int u = 0; u < U; ++u) xg[q][u] = __ldg(xa + c[q][u]);
+                for (int u = 0; u < U; ++u) xg[u] = __ldg(xa + c[u]);
                 __syncwarp();      // scheduling fence: all gathers of the pass are issued before the first FMA
 #pragma unroll
-                for (int q = 0; q < NB_NPW; ++q)
-#pragma unroll
-                    for (int u = 0; u < U; ++u) {
-                        s0[q] += v0[q][u] * xg[q][u];
-                        s1[q] += v1[q][u] * xg[q][u];
-                        s2[q] += v2[q][u] * xg[q][u];
-                    }
+                for (int u = 0; u < U; ++u) {
+                    s0 += v0[u] * xg[u];
+                    s1 += v1[u] * xg[u];
+                    s2 += v2[u] * xg[u];
+                }
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&bar_empty[stage]);
             if (++stage == STAGES) { stage = 0; phase ^= 1u; }
 
-            // three-row butterfly per node (a fourth, empty row keeps the 4-row pattern): row r ends up in lanes [8r, 8r+8)
-            const bool h16 = (lane & 16) != 0, h8 = (lane & 8) != 0;
+            // three-row butterfly inside the node's LPN lanes (a fourth, empty row keeps the 4-row pattern): two steps halve the
+            // live rows per lane, the rest adds up one row per quarter; row r ends up in lanes [r LPN/4, (r+1) LPN/4) of the node
+            const bool hi = (l & (LPN / 2)) != 0, hb = (l & (LPN / 4)) != 0;
+            double k0 = hi ? s2 : s0, k1 = hi ? 0.0 : s1;
+            const double g0 = hi ? s0 : s2, g1 = hi ? s1 : 0.0;
+            k0 += __shfl_xor_sync(0xffffffffu, g0, LPN / 2);
+            k1 += __shfl_xor_sync(0xffffffffu, g1, LPN / 2);
+            double mine = hb ? k1 : k0;
+            const double gq = hb ? k0 : k1;
+            mine += __shfl_xor_sync(0xffffffffu, gq, LPN / 4);
 #pragma unroll
-            for (int q = 0; q < NB_NPW; ++q) {
-                double k0 = h16 ? s2[q] : s0[q], k1 = h16 ? 0.0 : s1[q];
-                const double g0 = h16 ? s0[q] : s2[q], g1 = h16 ? s1[q] : 0.0;
-                k0 += __shfl_xor_sync(0xffffffffu, g0, 16);
-                k1 += __shfl_xor_sync(0xffffffffu, g1, 16);
-                double mine = h8 ? k1 : k0;
-                const double g = h8 ? k0 : k1;
-                mine += __shfl_xor_sync(0xffffffffu, g, 8);
-                mine += __shfl_xor_sync(0xffffffffu, mine, 4);
-                mine += __shfl_xor_sync(0xffffffffu, mine, 2);
-                mine += __shfl_xor_sync(0xffffffffu, mine, 1);
-                if (owner[q]) {
-                    const int64_t row = (int64_t)row0[q] + myr;
-                    if (MODE == 2) {
-                        const double un = e_id[q] * (-mine) + e_al[q] * e_x[q] - (e_al[q] - 1.0) * e_y[q];
-                        y[row] = un;
-                        if (y2) y2[row] = (1.0 + lag) * un - lag * e_x[q];
-                    } else {
-                        y[row] = mine;
-                        if (MODE == 3) dot_acc += e_x[q] * mine;
-                    }
+            for (int o = LPN / 8; o > 0; o >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, o);
+            if (owner) {
+                const int64_t row = (int64_t)d.row0 + myr;
+                if (MODE == 2) {
+                    const double un = e_id * (-mine) + e_al * e_x - (e_al - 1.0) * e_y;
+                    y[row] = un;
+                    if (y2) y2[row] = (1.0 + lag) * un - lag * e_x;
+                } else {
+                    y[row] = mine;
+                    if (MODE == 3) dot_acc += e_x * mine;
                 }
             }
         }

@@ -1,6 +1,8 @@
 """GPU tests of the boundary seams added in round 2: caller-supplied matrices (`sc_set_csr`), output selections
 (`sc_set_output_dofs`), the always-stored last step, the re-run protocol, and the explicit scheme against the analytical
 column solution.  Everything goes through the C ABI; the oracle is only the checker."""
+import os
+
 import numpy as np
 import pytest
 import scipy.sparse as sp
@@ -213,3 +215,38 @@ def test_reference_random_field_case_on_device(golden_meshes, tmp_path):
     res = scatter(golden_meshes["column_2D.msh"], str(tmp_path), cases.materials(), cases.BC_2D, sett, load, time_step=5e-3,
                   random_props=dict(RF_2D_PROPS))
     check_rf_2d_golden(res)
+
+
+def test_layered_box_with_moving_plane_load(oracle, tmp_path):
+    """Substitute for BASELINE config 3 (`mesh/embankment_rose.msh` is a missing blob and its load needs the un-vendored ROSE
+    package): a layered 3-D box with the three materials of run_scatter_rose_3D.py:35-43 (embankment over
+    soil1 over soil2), absorbing bottom, and the in-tree moving load on the top surface (`moving_at_plane`,
+    force_external.py:151-212,281-318; settings of integration_test.py:551-602), through `scatter(...)` against the oracle."""
+    from scatter_b200 import boxmesh, gmsh_io
+    from scatter_b200.scatter import scatter
+    nx, ny, nz, h = 8, 6, 7, 1.0
+    nodes, elem = boxmesh.box_arrays(nx, ny, nz, h, "hexa8")
+    layer = (np.arange(len(elem)) // nx) % ny                       # element layer along y (x fastest, then y, then z)
+    tags = np.where(layer >= 4, 1, np.where(layer >= 2, 2, 3))
+    phys = [[3, 1, "embankment"], [3, 2, "soil1"], [3, 3, "soil2"]]
+    path = os.path.join(tmp_path, "layers.msh")
+    gmsh_io.write_msh(path, nodes, elem, tags, phys, "hexa8")
+    mats = {"embankment": {"density": 2000, "Young": 100e6, "poisson": 0.2}, "soil1": {"density": 1700, "Young": 40e6, "poisson": 0.2},
+            "soil2": {"density": 2000, "Young": 10e6, "poisson": 0.2}}
+    bc = boxmesh.box_boundaries(nx, ny, nz, h, bottom="020")
+    sett = cases.settings(damping=[1, 0.01, 30, 0.01], pickle_nodes=[int(boxmesh.top_centre_node(nx, ny, nz))], output_interval=5)
+    load = {"force": [0, -1000, 0], "start_coord": [1.5, 1.5], "time": 0.1, "type": "moving_at_plane", "direction": [1, 0.5],
+            "speed": 30, "ini_steps": 10}
+    dt = 1e-3
+    res = scatter(path, os.path.join(tmp_path, "out"), mats, bc, sett, dict(load), time_step=dt)
+    om = oracle.build_model(path, bc)
+    K, M, C, _ = oracle.system_matrices(om, mats, sett)
+    time = oracle.time_array(load["time"], dt)
+    top = oracle.top_surface_faces(om, oracle.boundary_faces_hexa8(om))
+    force = oracle.MovingAtPlaneLoad(om, dict(load), time, top)
+    U, V, A, tt = oracle.newmark(M, C, K, force, time, 5)
+    assert len(set(tags)) == 3 and np.abs(U).max() > 0 and (np.asarray(om.type_BC) == "Absorb").any()
+    assert rel_l2(res.dis, U) <= TOL_HIST and rel_l2(res.vel, V) <= TOL_HIST and np.allclose(res.time, tt)
+    # the load really travels: the loaded dofs at the first and last loaded step differ
+    f0, f1 = force(12), force(len(time) - 1)
+    assert set(np.nonzero(f0)[0]) != set(np.nonzero(f1)[0])
