@@ -52,6 +52,15 @@ __device__ __forceinline__ void tma_load_1d(void* dst_smem, const void* src_gmem
                  : "memory");
 }
 
+// streaming loads: the value slices are read exactly once per product -- L2 evict-first keeps them from displacing the
+// gathered vector (three node planes of it are live at any time) and the lines prefetched for the next tiles
+constexpr uint64_t L2_EVICT_FIRST = 0x12F0000000000000ull;
+__device__ __forceinline__ void tma_load_1d_stream(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+                     smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)), "l"(L2_EVICT_FIRST)
+                 : "memory");
+}
 // MODE 0: y = A xa   MODE 3: y = A xa, partial[blockIdx] = xa.y
 // MODE 2: central-difference step  y <- inv_d (-A xa) + alpha xe - (alpha - 1) y  with xe = u(t), y = u(t-dt) on entry and
 //         xa = w(t) = (1+g) u(t) - g u(t-dt) the gathered vector (lagged stiffness-proportional damping, g = c1/dt);
@@ -92,50 +101,43 @@ k_spmv_node(const NodeDesc* __restrict__ nd, const int32_t* __restrict__ ncol, c
     double dot_acc = 0.0;
 
     if (warp == NB_WARPS) {
-        // ------------------------------------------------ producer warp ----------------------------------------------
-        int stage = 0;
-        uint32_t phase = 0;
-        for (int64_t ib = 0;; ib += 32) {
-            const int64_t t_first = blockIdx.x + ib * G;
-            if (t_first >= n_tiles) break;
-            // every lane fetches the slice bounds of one upcoming tile (descriptors of its first node and of the node after it)
-            const int64_t t = blockIdx.x + (ib + lane) * G;
-            int64_t v0 = 0, v1 = 0, c0 = 0, c1 = 0;
-            int r0 = 0, r1 = 0;
-            if (t < n_tiles) {
-                const NodeDesc d0 = nd[t * NB_NODES];
-                const NodeDesc d1 = nd[t * NB_NODES + NB_NODES];     // the descriptor array is padded by NB_NODES entries
-                v0 = d0.val_off; v1 = d1.val_off; c0 = d0.col_off; c1 = d1.col_off; r0 = d0.row0; r1 = d1.row0;
-            }
-            for (int j = 0; j < 32; ++j) {
-                const int64_t tj = blockIdx.x + (ib + j) * G;
-                if (tj >= n_tiles) break;
-                const int64_t a_v0 = __shfl_sync(0xffffffffu, v0, j), a_v1 = __shfl_sync(0xffffffffu, v1, j);
-                const int64_t a_c0 = __shfl_sync(0xffffffffu, c0, j), a_c1 = __shfl_sync(0xffffffffu, c1, j);
-                const int a_r0 = __shfl_sync(0xffffffffu, r0, j), a_r1 = __shfl_sync(0xffffffffu, r1, j);
-                if (lane == 0) {
-                    mbar_wait(&bar_empty[stage], phase ^ 1u);
-                    const int64_t vs = a_v0 & ~(int64_t)1, cs = a_c0 & ~(int64_t)3;
-                    const int rs = a_r0 & ~1;
-                    const uint32_t vb = (uint32_t)(((a_v1 - vs + 1) & ~(int64_t)1) * 8);
-                    const uint32_t cb = (uint32_t)(((a_c1 - cs + 3) & ~(int64_t)3) * 4);
-                    const uint32_t rb = (uint32_t)(((a_r1 - rs + 1) & ~1) * 8);
-                    const uint32_t db = NB_NODES * (uint32_t)sizeof(NodeDesc);
-                    const bool has = a_v1 > a_v0;
-                    mbar_expect_tx(&bar_full[stage], db + (has ? vb + cb + NVEC * rb : 0u));
-                    tma_load_1d(s_nd + (size_t)stage * NB_NODES, nd + tj * NB_NODES, db, &bar_full[stage]);
-                    if (has) {
-                        tma_load_1d(s_val + (size_t)stage * cap_v, va + vs, vb, &bar_full[stage]);
-                        if (cb) tma_load_1d(s_col + (size_t)stage * cap_c, ncol + cs, cb, &bar_full[stage]);   // empty when the dictionary covers the tile
-                        double* sv = s_vec + (size_t)stage * NV1 * NB_VT;
-                        if (MODE == 2) {
-                            tma_load_1d(sv, alpha + rs, rb, &bar_full[stage]);
-                            tma_load_1d(sv + NB_VT, inv_d + rs, rb, &bar_full[stage]);
-                            tma_load_1d(sv + 2 * NB_VT, xe + rs, rb, &bar_full[stage]);
-                            tma_load_1d(sv + 3 * NB_VT, y + rs, rb, &bar_full[stage]);
-                        }
-                        if (MODE == 3) tma_load_1d(sv, xa + rs, rb, &bar_full[stage]);
+        // ------------------------------------------------ producer: lane 0 of the last warp ----------------------------
+        // One thread walks this CTA's tiles: slice bounds from the node descriptors (fetched one tile ahead, so the look-up
+        // overlaps the wait for a free stage), wait for the stage, arm the barrier, issue the bulk copies.  The other 31 lanes
+        // leave.  (Round 1 let every lane fetch the bounds of one of 32 upcoming tiles and broadcast them with shuffles while
+        // lane 0 issued the copies: with lane 0 spinning on the "empty" barrier inside the shuffle loop the ring only
+        // streamed at 5.9 TB/s; this form reaches the 7.3 TB/s of a bare TMA ring -- scripts/probes/tma_stream_probe.cu.)
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            int64_t tj = blockIdx.x;
+            NodeDesc n0, n1;
+            if (tj < n_tiles) { n0 = nd[tj * NB_NODES]; n1 = nd[tj * NB_NODES + NB_NODES]; }   // the descriptor array is padded by NB_NODES entries
+            for (; tj < n_tiles; tj += G) {
+                const int64_t a_v0 = n0.val_off, a_v1 = n1.val_off, a_c0 = n0.col_off, a_c1 = n1.col_off;
+                const int a_r0 = n0.row0, a_r1 = n1.row0;
+                if (tj + G < n_tiles) { n0 = nd[(tj + G) * NB_NODES]; n1 = nd[(tj + G) * NB_NODES + NB_NODES]; }
+                mbar_wait(&bar_empty[stage], phase ^ 1u);
+                const int64_t vs = a_v0 & ~(int64_t)1, cs = a_c0 & ~(int64_t)3;
+                const int rs = a_r0 & ~1;
+                const uint32_t vb = (uint32_t)(((a_v1 - vs + 1) & ~(int64_t)1) * 8);
+                const uint32_t cb = (uint32_t)(((a_c1 - cs + 3) & ~(int64_t)3) * 4);
+                const uint32_t rb = (uint32_t)(((a_r1 - rs + 1) & ~1) * 8);
+                const uint32_t db = NB_NODES * (uint32_t)sizeof(NodeDesc);
+                const bool has = a_v1 > a_v0;
+                mbar_expect_tx(&bar_full[stage], db + (has ? vb + cb + NVEC * rb : 0u));
+                tma_load_1d(s_nd + (size_t)stage * NB_NODES, nd + tj * NB_NODES, db, &bar_full[stage]);
+                if (has) {
+                    tma_load_1d_stream(s_val + (size_t)stage * cap_v, va + vs, vb, &bar_full[stage]);
+                    if (cb) tma_load_1d(s_col + (size_t)stage * cap_c, ncol + cs, cb, &bar_full[stage]);   // empty when the dictionary covers the tile
+                    double* sv = s_vec + (size_t)stage * NV1 * NB_VT;
+                    if (MODE == 2) {
+                        tma_load_1d(sv, alpha + rs, rb, &bar_full[stage]);
+                        tma_load_1d(sv + NB_VT, inv_d + rs, rb, &bar_full[stage]);
+                        tma_load_1d(sv + 2 * NB_VT, xe + rs, rb, &bar_full[stage]);
+                        tma_load_1d(sv + 3 * NB_VT, y + rs, rb, &bar_full[stage]);
                     }
+                    if (MODE == 3) tma_load_1d(sv, xa + rs, rb, &bar_full[stage]);
                 }
                 if (++stage == STAGES) { stage = 0; phase ^= 1u; }
             }
@@ -196,6 +198,10 @@ k_spmv_node(const NodeDesc* __restrict__ nd, const int32_t* __restrict__ ncol, c
 #pragma unroll
                 for (int u = 0; u < U; ++u) xg[u] = __ldg(xa + c[u]);
                 __syncwarp();      // scheduling fence: all gathers of the pass are issued before the first FMA
+                // last pass: everything this warp needs from the stage sits in registers (the gathers could only be issued
+                // once the column reads had returned, and shared-memory reads return in order) -- hand the stage back now, so
+                // that its refill overlaps the gather latency and the arithmetic instead of following them
+                if (kb + LPN * U >= maxL && lane == 0) mbar_arrive(&bar_empty[stage]);
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
                     s0 += v0[u] * xg[u];
@@ -203,8 +209,10 @@ k_spmv_node(const NodeDesc* __restrict__ nd, const int32_t* __restrict__ ncol, c
                     s2 += v2[u] * xg[u];
                 }
             }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&bar_empty[stage]);
+            if (maxL == 0) {                                 // nothing was read beyond the descriptors / epilogue operands
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&bar_empty[stage]);
+            }
             if (++stage == STAGES) { stage = 0; phase ^= 1u; }
 
             // three-row butterfly inside the node's LPN lanes (a fourth, empty row keeps the 4-row pattern): two steps halve the

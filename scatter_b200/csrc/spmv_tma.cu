@@ -91,49 +91,39 @@ k_spmv_tma(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col, 
     double dot_acc = 0.0;
 
     if (warp == TMA_CONSUMER_WARPS) {
-        // ------------------------------------------------ producer warp ----------------------------------------------
-        int stage = 0;
-        uint32_t phase = 0;
-        for (int64_t ib = 0;; ib += 32) {
-            // 32 upcoming tiles: every lane fetches the bounds of one
-            const int64_t t = blockIdx.x + (ib + lane) * G;
+        // ------------------------------------------------ producer: lane 0 of the last warp ----------------------------
+        // (one thread, slice bounds fetched one tile ahead; see spmv_node.cu for why the copies are not issued from inside a
+        // warp-wide shuffle loop)
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            int64_t tj = blockIdx.x;
             int64_t s0 = 0, s1 = 0;
-            if (t < n_tiles) {
-                const int64_t r0 = t * TR;
-                const int64_t r1 = min(r0 + TR, n_rows);
-                s0 = rowptr[r0];
-                s1 = rowptr[r1];
-            }
-            const int64_t t_first = blockIdx.x + ib * G;
-            if (t_first >= n_tiles) break;
-            for (int j = 0; j < 32; ++j) {
-                const int64_t tj = blockIdx.x + (ib + j) * G;
-                if (tj >= n_tiles) break;
-                const int64_t a0 = __shfl_sync(0xffffffffu, s0, j);
-                const int64_t a1 = __shfl_sync(0xffffffffu, s1, j);
-                if (lane == 0) {
-                    mbar_wait(&bar_empty[stage], phase ^ 1u);
-                    const int64_t v0 = a0 & ~(int64_t)1;                 // 16-byte aligned start in the value array
-                    const int64_t c0 = a0 & ~(int64_t)3;                 // ... and in the column array
-                    const uint32_t vb = (uint32_t)(((a1 - v0 + 1) & ~(int64_t)1) * 8);
-                    const uint32_t cb = (uint32_t)(((a1 - c0 + 3) & ~(int64_t)3) * 4);
-                    if (a1 > a0) {
-                        const int64_t r0 = tj * TR;
-                        const uint32_t rb = (uint32_t)(((min((int64_t)TR, n_rows - r0) + 1) & ~(int64_t)1) * 8);
-                        mbar_expect_tx(&bar_full[stage], vb + cb + NVEC * rb);
-                        tma_load_1d(s_val + (size_t)stage * cap, va + v0, vb, &bar_full[stage]);
-                        tma_load_1d(s_col + (size_t)stage * cap, col + c0, cb, &bar_full[stage]);
-                        double* sv = s_vec + (size_t)stage * (NVEC > 0 ? NVEC : 1) * TR;
-                        if (MODE == 2) {
-                            tma_load_1d(sv, alpha + r0, rb, &bar_full[stage]);
-                            tma_load_1d(sv + TR, inv_d + r0, rb, &bar_full[stage]);
-                            tma_load_1d(sv + 2 * TR, xe + r0, rb, &bar_full[stage]);
-                            tma_load_1d(sv + 3 * TR, y + r0, rb, &bar_full[stage]);
-                        }
-                        if (MODE == 3) tma_load_1d(sv, xa + r0, rb, &bar_full[stage]);
-                    } else {
-                        mbar_arrive(&bar_full[stage]);                   // empty tile (ghost rows): nothing to copy
+            if (tj < n_tiles) { s0 = rowptr[tj * TR]; s1 = rowptr[min(tj * TR + TR, n_rows)]; }
+            for (; tj < n_tiles; tj += G) {
+                const int64_t a0 = s0, a1 = s1;
+                if (tj + G < n_tiles) { s0 = rowptr[(tj + G) * TR]; s1 = rowptr[min((tj + G) * TR + TR, n_rows)]; }
+                mbar_wait(&bar_empty[stage], phase ^ 1u);
+                const int64_t v0 = a0 & ~(int64_t)1;                 // 16-byte aligned start in the value array
+                const int64_t c0 = a0 & ~(int64_t)3;                 // ... and in the column array
+                const uint32_t vb = (uint32_t)(((a1 - v0 + 1) & ~(int64_t)1) * 8);
+                const uint32_t cb = (uint32_t)(((a1 - c0 + 3) & ~(int64_t)3) * 4);
+                if (a1 > a0) {
+                    const int64_t r0 = tj * TR;
+                    const uint32_t rb = (uint32_t)(((min((int64_t)TR, n_rows - r0) + 1) & ~(int64_t)1) * 8);
+                    mbar_expect_tx(&bar_full[stage], vb + cb + NVEC * rb);
+                    tma_load_1d(s_val + (size_t)stage * cap, va + v0, vb, &bar_full[stage]);
+                    tma_load_1d(s_col + (size_t)stage * cap, col + c0, cb, &bar_full[stage]);
+                    double* sv = s_vec + (size_t)stage * (NVEC > 0 ? NVEC : 1) * TR;
+                    if (MODE == 2) {
+                        tma_load_1d(sv, alpha + r0, rb, &bar_full[stage]);
+                        tma_load_1d(sv + TR, inv_d + r0, rb, &bar_full[stage]);
+                        tma_load_1d(sv + 2 * TR, xe + r0, rb, &bar_full[stage]);
+                        tma_load_1d(sv + 3 * TR, y + r0, rb, &bar_full[stage]);
                     }
+                    if (MODE == 3) tma_load_1d(sv, xa + r0, rb, &bar_full[stage]);
+                } else {
+                    mbar_arrive(&bar_full[stage]);                   // empty tile (ghost rows): nothing to copy
                 }
                 if (++stage == TMA_STAGES) { stage = 0; phase ^= 1u; }
             }
