@@ -160,6 +160,7 @@ int sc_set_option(sc_ctx* ctx, const char* name, int64_t value) {
                                                                     // effect at the next sc_build_pattern
     else if (k == "small_pcg") ctx->no_small_pcg = !on;             // cooperative single-kernel PCG below 250 k equations (default on)
     else if (k == "pcg_graph") ctx->no_graph = !on;                 // CUDA-graph replay of the PCG iteration (default on)
+    else if (k == "spmv_groups") ctx->force_one_group = value == 1;      // 1: one consumer group per CTA, two CTAs per SM; default 2
     else if (k == "generic_assembly") ctx->force_generic_assembly = on;   // warp-per-node assembly for every element type (default off)
     else return sc_fail(ctx, SC_ERR_ARG, "unknown option '%s'", name);
     pcg_graph_drop(ctx);

@@ -115,6 +115,7 @@ struct sc_ctx {
     int32_t* d_sel = nullptr;                                      // sc_set_output_dofs: equations copied out per output row
     int64_t n_sel = -1;                                            // -1: full rows
     double* d_selbuf[3] = {nullptr, nullptr, nullptr};             // gathered u, v, a of the current output row
+    bool force_one_group = false;          // sc_set_option("spmv_groups", 1): two CTAs per SM with their own short rings (round-1 layout)
     bool force_no_node = false;            // sc_set_option("node_spmv", 0): row-wise kernels instead of the node-blocked one
     bool force_no_tma = false;             // sc_set_option("tma_spmv", 0): register-staged SpMV instead of the TMA ring
     bool no_small_pcg = false;             // sc_set_option("small_pcg", 0): never use the cooperative single-kernel PCG

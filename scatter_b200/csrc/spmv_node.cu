@@ -18,7 +18,6 @@
 namespace {
 
 constexpr int NB_WARPS = 8;                       // consumer warps
-constexpr int NB_THREADS = 32 * (NB_WARPS + 1);
 using NodeDesc = sc_ctx::NodeDesc;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -65,8 +64,11 @@ __device__ __forceinline__ void tma_load_1d_stream(void* dst_smem, const void* s
 // MODE 2: central-difference step  y <- inv_d (-A xa) + alpha xe - (alpha - 1) y  with xe = u(t), y = u(t-dt) on entry and
 //         xa = w(t) = (1+g) u(t) - g u(t-dt) the gathered vector (lagged stiffness-proportional damping, g = c1/dt);
 //         y2 != null: the next gather vector w(t+dt) = (1+g) y - g xe is written by the same epilogue (g = 0: xa = xe, y2 = null)
-template <int MODE, int STAGES, int NB_NPW>
-__global__ void __launch_bounds__(NB_THREADS, 2)
+// NG consumer groups of NB_WARPS warps share one ring: group g takes the CTA's tiles g, g + NG, ... -- with NG = 2 (one CTA
+// per SM, a ring of 4-6 stages) two tiles are being reduced while the others load, which hides the per-tile latency of a
+// consumer warp (gather -> FMA -> butterfly -> store) that a two-stage ring per CTA exposes.
+template <int MODE, int STAGES, int NB_NPW, int NG>
+__global__ void __launch_bounds__(32 * (NG * NB_WARPS + 1), NG == 1 ? 2 : 1)
 k_spmv_node(const NodeDesc* __restrict__ nd, const int32_t* __restrict__ ncol, const double* __restrict__ va,
             const double* __restrict__ xa, double* __restrict__ y, const double* __restrict__ inv_d,
             const double* __restrict__ alpha, double* __restrict__ partial, int64_t n_nodes, int64_t n_rows, int64_t n_tiles,
@@ -84,7 +86,8 @@ k_spmv_node(const NodeDesc* __restrict__ nd, const int32_t* __restrict__ ncol, c
     uint64_t* bar_full = reinterpret_cast<uint64_t*>(s_col + (size_t)STAGES * cap_c);
     uint64_t* bar_empty = bar_full + STAGES;
     int* s_dict = reinterpret_cast<int*>(bar_empty + STAGES);                     // [n_dict][dict_stride] relative column lists (node_dict.cu)
-    __shared__ double red[NB_WARPS];
+    __shared__ double red[NG * NB_WARPS];
+    constexpr int NTHREADS = 32 * (NG * NB_WARPS + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
@@ -94,13 +97,13 @@ k_spmv_node(const NodeDesc* __restrict__ nd, const int32_t* __restrict__ ncol, c
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    for (int t = threadIdx.x; t < n_dict * dict_stride; t += NB_THREADS) s_dict[t] = dict[t];
+    for (int t = threadIdx.x; t < n_dict * dict_stride; t += NTHREADS) s_dict[t] = dict[t];
     __syncthreads();
 
     const int64_t G = gridDim.x;
     double dot_acc = 0.0;
 
-    if (warp == NB_WARPS) {
+    if (warp == NG * NB_WARPS) {
         // ------------------------------------------------ producer: lane 0 of the last warp ----------------------------
         // One thread walks this CTA's tiles: slice bounds from the node descriptors (fetched one tile ahead, so the look-up
         // overlaps the wait for a free stage), wait for the stage, arm the barrier, issue the bulk copies.  The other 31 lanes
@@ -152,13 +155,14 @@ k_spmv_node(const NodeDesc* __restrict__ nd, const int32_t* __restrict__ ncol, c
         constexpr int U = NB_NPW == 1 ? 3 : 6;           // entries per lane and pass (96 entries per node and pass)
         const int grp = lane / LPN, l = lane % LPN;
         const int myr = l / (LPN / 4);                   // row of the node this lane owns after the reduction (3 = none)
-        int stage = 0;
-        uint32_t phase = 0;
-        for (int64_t t = blockIdx.x; t < n_tiles; t += G) {
+        const int wl = warp % NB_WARPS;                  // warp inside its consumer group
+        for (int64_t i = warp / NB_WARPS; blockIdx.x + i * G < n_tiles; i += NG) {     // i: position in this CTA's tile sequence
+            const int stage = (int)(i % STAGES);
+            const uint32_t phase = (uint32_t)((i / STAGES) & 1);
             mbar_wait(&bar_full[stage], phase);
             const NodeDesc* snd = s_nd + (size_t)stage * NB_NODES;
             const NodeDesc d0 = snd[0];
-            const NodeDesc d = snd[warp * NB_NPW + grp];
+            const NodeDesc d = snd[wl * NB_NPW + grp];
             const int nfree = d.len_nfree >> 24;
             const int L = nfree > 0 ? (d.len_nfree & 0xffff) : 0;
             int maxL = L;
@@ -213,7 +217,6 @@ k_spmv_node(const NodeDesc* __restrict__ nd, const int32_t* __restrict__ ncol, c
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&bar_empty[stage]);
             }
-            if (++stage == STAGES) { stage = 0; phase ^= 1u; }
 
             // three-row butterfly inside the node's LPN lanes (a fourth, empty row keeps the 4-row pattern): two steps halve the
             // live rows per lane, the rest adds up one row per quarter; row r ends up in lanes [r LPN/4, (r+1) LPN/4) of the node
@@ -241,7 +244,7 @@ k_spmv_node(const NodeDesc* __restrict__ nd, const int32_t* __restrict__ ncol, c
         }
     }
     if (MODE == 3) {
-        if (warp < NB_WARPS) {
+        if (warp < NG * NB_WARPS) {
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) dot_acc += __shfl_down_sync(0xffffffffu, dot_acc, o);
             if (lane == 0) red[warp] = dot_acc;
@@ -249,14 +252,15 @@ k_spmv_node(const NodeDesc* __restrict__ nd, const int32_t* __restrict__ ncol, c
         __syncthreads();
         if (threadIdx.x == 0) {
             double s = 0.0;
-            for (int w = 0; w < NB_WARPS; ++w) s += red[w];
+            for (int w = 0; w < NG * NB_WARPS; ++w) s += red[w];
             partial[blockIdx.x] = s;
         }
     }
 }
 
-struct NodeCfg { int cap_v, cap_c, stages, npw; size_t bytes; };
+struct NodeCfg { int cap_v, cap_c, stages, npw, ng; size_t bytes, max_bytes; };
 constexpr size_t NODE_SMEM_MAX = 112 * 1024;       // two CTAs per SM
+constexpr size_t NODE_SMEM_MAX_1CTA = 224 * 1024;  // one CTA per SM (two consumer groups)
 
 // ring configuration (dictionary not counted: `node_dict_room` sizes the dictionary into what is left)
 bool node_cfg(sc_ctx* ctx, NodeCfg& c) {
@@ -267,28 +271,38 @@ bool node_cfg(sc_ctx* ctx, NodeCfg& c) {
         c.cap_v = (nodes * 3 * ctx->max_rl + 2 + 15) & ~15;
         c.cap_c = (nodes * ctx->max_rl + 4 + 31) & ~31;
         const size_t per_stage = (size_t)c.cap_v * 8 + (size_t)c.cap_c * 4 + 4 * (size_t)vt * 8 + nodes * sizeof(NodeDesc);
+        // preferred: one CTA per SM, two consumer groups on a ring of 3-6 stages that still leaves room for a full dictionary
+        const size_t dict_full = (size_t)SC_DICT_MAX * ctx->max_rl * sizeof(int32_t);
+        for (int st = 6; st >= 3 && !ctx->force_one_group; --st) {
+            const size_t bytes = st * per_stage + 2 * st * sizeof(uint64_t) + 64;
+            if (bytes + dict_full + 64 <= NODE_SMEM_MAX_1CTA) {
+                c.stages = st; c.npw = npw; c.ng = 2; c.bytes = bytes; c.max_bytes = NODE_SMEM_MAX_1CTA;
+                return true;
+            }
+        }
         const size_t budget = (npw == 2 ? 104 : 112) * 1024;
         for (int st = 4; st >= 2; --st) {
             const size_t bytes = st * per_stage + 2 * st * sizeof(uint64_t) + 64;
-            if (bytes <= budget) { c.stages = st; c.npw = npw; c.bytes = bytes; return true; }
+            if (bytes <= budget) { c.stages = st; c.npw = npw; c.ng = 1; c.bytes = bytes; c.max_bytes = NODE_SMEM_MAX; return true; }
         }
     }
     return false;
 }
 
-template <int MODE, int STAGES, int NPW>
+template <int MODE, int STAGES, int NPW, int NG>
 int launch_node(sc_ctx* ctx, const NodeCfg& c, const double* va, const double* xa, double* y, const double* inv_d, const double* alpha,
                 double* partial, unsigned* nblocks_out, const double* xe, double* y2, double g) {
     constexpr int NODES = NB_WARPS * NPW;
     const int64_t n_tiles = (ctx->n_nodes + NODES - 1) / NODES;
-    auto kern = k_spmv_node<MODE, STAGES, NPW>;
+    auto kern = k_spmv_node<MODE, STAGES, NPW, NG>;
     const size_t bytes = c.bytes + (size_t)ctx->n_dict * ctx->dict_stride * sizeof(int32_t);
     SC_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
-    unsigned grid = (unsigned)std::min<int64_t>(n_tiles, (int64_t)ctx->sm_count * 2);
+    unsigned grid = (unsigned)std::min<int64_t>(n_tiles, (int64_t)ctx->sm_count * (NG == 1 ? 2 : 1));
     if (grid == 0) grid = 1;
     if (nblocks_out) *nblocks_out = grid;
-    kern<<<grid, NB_THREADS, bytes, ctx->stream>>>(ctx->d_nd, ctx->d_ncol, va, xa, y, inv_d, alpha, partial, ctx->n_nodes, ctx->n_eq,
-                                                   n_tiles, c.cap_v, c.cap_c, ctx->d_dict, ctx->n_dict, ctx->dict_stride, xe, y2, g);
+    kern<<<grid, 32 * (NG * NB_WARPS + 1), bytes, ctx->stream>>>(ctx->d_nd, ctx->d_ncol, va, xa, y, inv_d, alpha, partial, ctx->n_nodes,
+                                                                  ctx->n_eq, n_tiles, c.cap_v, c.cap_c, ctx->d_dict, ctx->n_dict,
+                                                                  ctx->dict_stride, xe, y2, g);
     SC_CHECK_LAUNCH(ctx);
     return SC_OK;
 }
@@ -298,14 +312,14 @@ int launch_mode(sc_ctx* ctx, const double* va, const double* xa, double* y, cons
                 unsigned* nblocks_out, const double* xe = nullptr, double* y2 = nullptr, double g = 0.0) {
     NodeCfg c;
     if (!node_cfg(ctx, c)) return sc_fail(ctx, SC_ERR_UNSUPPORTED, "node-blocked SpMV not usable for this pattern");
-    if (c.npw == 2) {
-        if (c.stages == 4) return launch_node<MODE, 4, 2>(ctx, c, va, xa, y, inv_d, alpha, partial, nblocks_out, xe, y2, g);
-        if (c.stages == 3) return launch_node<MODE, 3, 2>(ctx, c, va, xa, y, inv_d, alpha, partial, nblocks_out, xe, y2, g);
-        return launch_node<MODE, 2, 2>(ctx, c, va, xa, y, inv_d, alpha, partial, nblocks_out, xe, y2, g);
+#define SC_NODE_GO(ST, NPW, NG) return launch_node<MODE, ST, NPW, NG>(ctx, c, va, xa, y, inv_d, alpha, partial, nblocks_out, xe, y2, g)
+    if (c.ng == 2) {
+        if (c.npw == 2) { if (c.stages == 6) SC_NODE_GO(6, 2, 2); if (c.stages == 5) SC_NODE_GO(5, 2, 2); if (c.stages == 4) SC_NODE_GO(4, 2, 2); SC_NODE_GO(3, 2, 2); }
+        if (c.stages == 6) SC_NODE_GO(6, 1, 2); if (c.stages == 5) SC_NODE_GO(5, 1, 2); if (c.stages == 4) SC_NODE_GO(4, 1, 2); SC_NODE_GO(3, 1, 2);
     }
-    if (c.stages == 4) return launch_node<MODE, 4, 1>(ctx, c, va, xa, y, inv_d, alpha, partial, nblocks_out, xe, y2, g);
-    if (c.stages == 3) return launch_node<MODE, 3, 1>(ctx, c, va, xa, y, inv_d, alpha, partial, nblocks_out, xe, y2, g);
-    return launch_node<MODE, 2, 1>(ctx, c, va, xa, y, inv_d, alpha, partial, nblocks_out, xe, y2, g);
+    if (c.npw == 2) { if (c.stages == 4) SC_NODE_GO(4, 2, 1); if (c.stages == 3) SC_NODE_GO(3, 2, 1); SC_NODE_GO(2, 2, 1); }
+    if (c.stages == 4) SC_NODE_GO(4, 1, 1); if (c.stages == 3) SC_NODE_GO(3, 1, 1); SC_NODE_GO(2, 1, 1);
+#undef SC_NODE_GO
 }
 
 }  // namespace
@@ -321,8 +335,8 @@ int64_t node_dict_room(sc_ctx* ctx) {
     ctx->n_dict = 0;
     const bool ok = node_cfg(ctx, c);
     ctx->n_dict = keep;
-    if (!ok || c.bytes + 64 >= NODE_SMEM_MAX) return 0;
-    return (int64_t)(NODE_SMEM_MAX - c.bytes - 64);
+    if (!ok || c.bytes + 64 >= c.max_bytes) return 0;
+    return (int64_t)(c.max_bytes - c.bytes - 64);
 }
 int la_node_spmv(sc_ctx* ctx, const double* vals, const double* x, double* y) {
     return launch_mode<0>(ctx, vals, x, y, nullptr, nullptr, nullptr, nullptr);
