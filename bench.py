@@ -886,21 +886,28 @@ def run_secondary_newmark(args, local_rank):
     ramp = np.ones(total); ramp[:5] = np.linspace(0, 1, 5)
     ctx.set_load_schedule(np.arange(total + 1, dtype=np.int64), np.full(total, d, dtype=np.int64), -1000.0 * ramp)
     ctx.set_state(None, None)
-    ctx.run_newmark(dt, 0, 2, 1, rtol=rtol, store=False)                       # warm-up (also builds Khat)
+    _, _, _, st0 = ctx.run_newmark(dt, 0, 2, 1, rtol=rtol, store=False)        # warm-up (also builds Khat and its FSAI factor)
     _, _, _, st = ctx.run_newmark(dt, 2, nsteps, 1, rtol=rtol, store=False)
     its = st["pcg_iterations"] / max(nsteps, 1)
+    pre = ctx.precond_info()
     # bytes per step: rhs two-matrix SpMV (values of M and K, CSR columns once) + per PCG iteration one SpMV (node-blocked
-    # index: one column list per node) + 14 vector passes (SpMV x/y, fused update, direction update)
+    # index: one column list per node), the two FSAI factor products (8 bytes per entry of G and of G^T, row pointers) and
+    # 16 vector passes (SpMV x/y, fused update, preconditioner in/out, direction update)
     ps = ctx.pattern_stats()
     idx_bytes = ps["node_col_entries"] * 4 + ps["n_nodes"] * 24 if ps["node_blocked"] else nnz * 4 + n * 8
     rhs_bytes = nnz * 20 + n * 8 * 12
-    it_bytes = nnz * 8 + idx_bytes + n * 8 * 14
+    fsai_bytes = 2 * (pre["fsai_nnz"] * 8 + n * 8) if pre["fsai_nnz"] else 0
+    it_bytes = nnz * 8 + idx_bytes + fsai_bytes + n * 8 * (16 if pre["fsai_nnz"] else 14)
     step_bytes = rhs_bytes + its * it_bytes
     sec = st["seconds_device"] / nsteps
     peak, _ = measured_peak()
     out = {"workload": f"hexa20 soil box {s}^3 elements, Newmark + PCG (rtol {rtol:g}), dt {dt}", "dof": n, "nnz": nnz,
            "dof_timesteps_per_s": n / sec, "ms_per_time_step": 1e3 * sec, "pcg_iterations_per_step": its, "pcg_rtol": rtol,
            "pcg_stagnations": st.get("pcg_stagnations", 0),
+           "preconditioner": ({"kind": "FSAI (G^T G, FP32 factor on a filtered lower pattern) + projection onto previous solutions",
+                               "fsai_entries": pre["fsai_nnz"], "fsai_entries_per_matrix_entry": pre["fsai_nnz"] / nnz,
+                               "fsai_setup_seconds": st0.get("fsai_setup_seconds", 0.0), "projection_vectors": pre["projection_vectors"]}
+                              if pre["fsai_nnz"] else {"kind": "Jacobi"}),
            "roofline": {"bound": "hbm", "achieved": step_bytes / sec / 1e9, "peak": peak, "unit": "GB/s",
                         "frac": step_bytes / sec / 1e9 / peak, "bytes_per_step": step_bytes},
            "assembly": {"seconds": t_asm, "elements_per_s": ne / t_asm, "pattern_seconds": t_pat, "host_mesh_seconds": t_mesh},

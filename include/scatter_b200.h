@@ -65,9 +65,15 @@ const char* sc_last_error(sc_ctx* ctx);          /* ctx may be NULL: error of a 
 int         sc_version(void);
 int         sc_device_info(sc_ctx* ctx, int* sm_count, int64_t* total_mem, int64_t* free_mem, char* name, int name_len);
 int64_t     sc_kernel_launches(sc_ctx* ctx);     /* running count of kernels launched by this context */
+/* preconditioner currently held for the effective matrix (slot 0: Newmark / static / Bathe sub-step 1, slot 1: Bathe
+ * sub-step 2): entries of the FSAI factor G (0: none, Jacobi in use), its set-up time, vectors in the projection basis */
+int         sc_precond_info(sc_ctx* ctx, int slot, int64_t* fsai_nnz, double* fsai_seconds, int* projection_vectors);
 /* kernel-selection switches for tests and A/B measurements (the defaults are the product path; nothing reads the
  * environment): "node_spmv", "tma_spmv", "column_dictionary", "small_pcg", "pcg_graph" (default 1), "generic_assembly"
- * (default 0) */
+ * (default 0), "spmv_groups" (consumer groups per CTA of the node-blocked SpMV: 2, or 1 for the two-CTA layout);
+ * solver options of the implicit integrators: "fsai" (default 1: factorised sparse approximate inverse preconditioner
+ * for systems beyond the cooperative small-system kernel; 0: Jacobi), "fsai_tau_permille" (pattern filter, default 50),
+ * "pcg_projection" (previous solutions the right-hand side is projected on before PCG, default 16, 0: off) */
 int         sc_set_option(sc_ctx* ctx, const char* name, int64_t value);
 
 /* page-locked host buffers for result rows / initial states (faster, asynchronous host<->device copies) */

@@ -22,7 +22,7 @@ ASM_K, ASM_M_FULL, ASM_M_LUMPED = 1, 2, 4
 
 # every symbol include/scatter_b200.h declares (checked by tests/test_host_logic.py)
 SYMBOLS = [
-    "sc_create", "sc_destroy", "sc_last_error", "sc_version", "sc_device_info", "sc_kernel_launches", "sc_set_option", "sc_shape_table",
+    "sc_create", "sc_destroy", "sc_last_error", "sc_version", "sc_device_info", "sc_kernel_launches", "sc_precond_info", "sc_set_option", "sc_shape_table",
     "sc_host_alloc", "sc_host_free",
     "sc_set_mesh", "sc_set_csr", "sc_set_output_dofs", "sc_set_materials", "sc_build_pattern", "sc_get_pattern", "sc_pattern_stats", "sc_assemble", "sc_add_entries",
     "sc_set_rayleigh", "sc_get_values", "sc_get_lumped_mass", "sc_spmv", "sc_set_load_schedule", "sc_set_state",
@@ -40,6 +40,7 @@ class Stats(C.Structure):
         d = {k: getattr(self, k) for k, _ in self._fields_ if k != "reserved"}
         d["step_bytes"] = self.reserved[0]
         d["pcg_stagnations"] = int(self.reserved[2])
+        d["fsai_setup_seconds"] = self.reserved[3]
         d["step_kernel"] = {0: "k_spmv (register staged)", 1: "k_spmv_tma (row tiles)", 2: "k_spmv_node (node-blocked, TMA)"}.get(int(self.reserved[1]), "?")
         return d
 
@@ -73,6 +74,7 @@ def load_library():
     lib.sc_device_info.argtypes = [vp, P(i32), P(i64), P(i64), C.c_char_p, i32]
     lib.sc_kernel_launches.argtypes = [vp]
     lib.sc_kernel_launches.restype = i64
+    lib.sc_precond_info.argtypes = [vp, i32, P(i64), P(dbl), P(i32)]
     lib.sc_set_option.argtypes = [vp, C.c_char_p, i64]
     lib.sc_shape_table.argtypes = [i32, i32, P(i32), P(i32), P(i32), vp, vp, vp]
     lib.sc_host_alloc.argtypes = [P(vp), i64]
@@ -221,6 +223,12 @@ class Context:
 
     def kernel_launches(self) -> int:
         return int(self.lib.sc_kernel_launches(self.h))
+
+    def precond_info(self, slot: int = 0):
+        """FSAI factor / projection basis currently held for the effective matrix (`sc_precond_info`)."""
+        nnz, sec, nv = C.c_int64(), C.c_double(), C.c_int()
+        self._ck(self.lib.sc_precond_info(self.h, slot, C.byref(nnz), C.byref(sec), C.byref(nv)))
+        return {"fsai_nnz": nnz.value, "fsai_seconds": sec.value, "projection_vectors": nv.value}
 
     def set_option(self, name: str, value: int):
         """Kernel-selection switch (tests / A-B measurements); see `sc_set_option` in include/scatter_b200.h."""

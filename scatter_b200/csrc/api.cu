@@ -39,6 +39,7 @@ int upload(sc_ctx* ctx, T** dst, const T* src, size_t n) {
 
 void free_pattern(sc_ctx* c) {
     pcg_graph_drop(c);
+    precond_destroy(c);
     sc_free(&c->d_n2e_ptr); sc_free(&c->d_n2e); sc_free(&c->d_nbr_ptr); sc_free(&c->d_nbr); sc_free(&c->d_nbr_off); sc_free(&c->d_nbr_free);
     sc_free(&c->d_node_rl); sc_free(&c->d_node_row0); sc_free(&c->d_rowptr); sc_free(&c->d_col); sc_free(&c->d_nd); sc_free(&c->d_ncol); sc_free(&c->d_dict); c->n_dict = 0; sc_free(&c->d_pair_pos); sc_free(&c->d_pair_al);
     sc_free(&c->d_K); sc_free(&c->d_M); sc_free(&c->d_Ml); sc_free(&c->d_Khat); sc_free(&c->d_Khat2); sc_free(&c->d_C); c->csr_only = false;
@@ -50,6 +51,7 @@ void free_pattern(sc_ctx* c) {
 }
 void free_vectors(sc_ctx* c) {
     pcg_graph_drop(c);
+    precond_destroy(c);
     sc_free(&c->d_u); sc_free(&c->d_v); sc_free(&c->d_a);
     for (auto& w : c->work) sc_free(&w);
     c->work.clear();
@@ -149,6 +151,15 @@ int sc_device_info(sc_ctx* ctx, int* sm_count, int64_t* total_mem, int64_t* free
 
 int64_t sc_kernel_launches(sc_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
+int sc_precond_info(sc_ctx* ctx, int slot, int64_t* fsai_nnz, double* fsai_seconds, int* projection_vectors) {
+    if (!ctx || slot < 0 || slot > 1) return SC_ERR_ARG;
+    const sc_fsai& f = ctx->fsai[slot];
+    if (fsai_nnz) *fsai_nnz = f.for_vals ? f.nnz : 0;
+    if (fsai_seconds) *fsai_seconds = f.for_vals ? f.seconds : 0.0;
+    if (projection_vectors) *projection_vectors = ctx->proj_n;
+    return SC_OK;
+}
+
 // Kernel-selection switches for tests and A/B measurements; the defaults are the product path.
 int sc_set_option(sc_ctx* ctx, const char* name, int64_t value) {
     if (!ctx || !name) return SC_ERR_ARG;
@@ -161,6 +172,15 @@ int sc_set_option(sc_ctx* ctx, const char* name, int64_t value) {
     else if (k == "small_pcg") ctx->no_small_pcg = !on;             // cooperative single-kernel PCG below 250 k equations (default on)
     else if (k == "pcg_graph") ctx->no_graph = !on;                 // CUDA-graph replay of the PCG iteration (default on)
     else if (k == "spmv_groups") ctx->force_one_group = value == 1;      // 1: one consumer group per CTA, two CTAs per SM; default 2
+    else if (k == "fsai") { ctx->no_fsai = !on; precond_drop(ctx); }   // FSAI preconditioner of the stream-ordered PCG (default on; 0: Jacobi)
+    else if (k == "fsai_tau_permille") {                              // FSAI pattern filter tau in 1/1000 (default 50)
+        if (value < 0 || value > 1000) return sc_fail(ctx, SC_ERR_ARG, "fsai_tau_permille must lie in [0, 1000]");
+        ctx->fsai_tau = (double)value / 1000.0; precond_drop(ctx);
+    }
+    else if (k == "pcg_projection") {                                 // previous solutions the right-hand side is projected on (default 16; 0: off)
+        if (value < 0 || value > 32) return sc_fail(ctx, SC_ERR_ARG, "pcg_projection must lie in [0, 32]");
+        ctx->proj_k = (int)value; precond_drop(ctx);
+    }
     else if (k == "generic_assembly") ctx->force_generic_assembly = on;   // warp-per-node assembly for every element type (default off)
     else return sc_fail(ctx, SC_ERR_ARG, "unknown option '%s'", name);
     pcg_graph_drop(ctx);
@@ -268,7 +288,7 @@ int sc_assemble(sc_ctx* ctx, int gauss_order, int flags, double* seconds_device)
     if (!ctx->have_mat) return sc_fail(ctx, SC_ERR_STATE, "sc_set_materials must be called first");
     if (!(flags & (SC_ASM_K | SC_ASM_M_FULL | SC_ASM_M_LUMPED))) return sc_fail(ctx, SC_ERR_ARG, "nothing to assemble");
     SC_CUDA(ctx, cudaSetDevice(ctx->device));
-    ctx->cd_resume_valid = false; ctx->nm_resume_valid = false; ctx->khat_a1 = ctx->khat_a4 = -1.0; ctx->cd_coef_dt = -1.0;
+    ctx->cd_resume_valid = false; ctx->nm_resume_valid = false; ctx->khat_a1 = ctx->khat_a4 = -1.0; ctx->cd_coef_dt = -1.0; precond_drop(ctx);
     return sc_assemble_run(ctx, gauss_order, flags, seconds_device);
 }
 
@@ -317,7 +337,7 @@ static int add_sorted_entries(sc_ctx* ctx, int which, int64_t n, const std::vect
     };
     rc = body();
     sc_free(&d_r); sc_free(&d_c); sc_free(&d_slot); sc_free(&d_flag);
-    ctx->cd_resume_valid = false; ctx->nm_resume_valid = false; ctx->khat_a1 = ctx->khat_a4 = -1.0; ctx->cd_coef_dt = -1.0;
+    ctx->cd_resume_valid = false; ctx->nm_resume_valid = false; ctx->khat_a1 = ctx->khat_a4 = -1.0; ctx->cd_coef_dt = -1.0; precond_drop(ctx);
     return rc;
 }
 
@@ -383,7 +403,7 @@ int sc_set_rayleigh(sc_ctx* ctx, double c0, double c1) {
     if (!ctx) return SC_ERR_ARG;
     if (ctx->d_C && (c0 != 0.0 || c1 != 0.0)) return sc_fail(ctx, SC_ERR_UNSUPPORTED, "sc_set_csr supplied C explicitly; add Rayleigh terms to it before the upload");
     ctx->c0 = c0; ctx->c1 = c1;
-    ctx->cd_resume_valid = false; ctx->nm_resume_valid = false; ctx->khat_a1 = ctx->khat_a4 = -1.0; ctx->cd_coef_dt = -1.0;
+    ctx->cd_resume_valid = false; ctx->nm_resume_valid = false; ctx->khat_a1 = ctx->khat_a4 = -1.0; ctx->cd_coef_dt = -1.0; precond_drop(ctx);
     return SC_OK;
 }
 
@@ -557,7 +577,7 @@ int sc_run_newmark(sc_ctx* ctx, double dt, int64_t t_start, int64_t n_steps, int
     SC_CUDA(ctx, cudaSetDevice(ctx->device));
     if (stats) std::memset(stats, 0, sizeof(*stats));
     ctx->cd_resume_valid = false; ctx->cd_coef_dt = -1.0;   // Newmark reuses the work vectors of the cached coefficients
-    if (beta != 0.25 || gamma != 0.5) ctx->khat_a1 = -1.0;   // (a1, a4) identify the matrix only together with beta, gamma
+    if (beta != 0.25 || gamma != 0.5) { ctx->khat_a1 = -1.0; precond_drop(ctx); }   // (a1, a4) identify the matrix only together with beta, gamma
     return tl_newmark(ctx, dt, t_start, n_steps, out_interval, beta, gamma, pcg_rtol, pcg_maxit, n_out, u_out, v_out, a_out, stats);
 }
 
@@ -577,7 +597,7 @@ int sc_run_bathe(sc_ctx* ctx, double dt, int64_t t_start, int64_t n_steps, int64
     if (dt <= 0 || n_steps < 0 || out_interval < 1) return sc_fail(ctx, SC_ERR_ARG, "bad time-integration arguments");
     SC_CUDA(ctx, cudaSetDevice(ctx->device));
     if (stats) std::memset(stats, 0, sizeof(*stats));
-    ctx->cd_resume_valid = false; ctx->nm_resume_valid = false; ctx->khat_a1 = ctx->khat_a4 = -1.0; ctx->cd_coef_dt = -1.0;
+    ctx->cd_resume_valid = false; ctx->nm_resume_valid = false; ctx->khat_a1 = ctx->khat_a4 = -1.0; ctx->cd_coef_dt = -1.0; precond_drop(ctx);
     return tl_bathe(ctx, dt, t_start, n_steps, out_interval, pcg_rtol, pcg_maxit, n_out, u_out, v_out, a_out, stats);
 }
 

@@ -30,6 +30,18 @@ struct DevBuf {
 
 struct NcclApi;   // dist.cu
 
+// Factorised sparse approximate inverse of an SPD matrix A in the CSR pattern of the context:  A^-1 ~ G^T G  with G lower
+// triangular on a filtered subset of A's lower pattern (fsai.cu).  Both factors are kept row-wise (gather form, FP32 values:
+// a preconditioner only has to be symmetric positive definite, the residuals stay FP64).
+struct sc_fsai {
+    const double* for_vals = nullptr;   // values array the factor was computed from (null: empty slot)
+    int64_t nnz = 0;
+    int64_t* rowptr = nullptr;   int2* cv = nullptr;      // G: (column, FP32 value bits) pairs, rows ascending in column, diagonal last
+    int64_t* t_rowptr = nullptr; int2* t_cv = nullptr;    // G^T, diagonal first
+    int lanes = 8;                      // lanes per row of the apply kernels
+    double seconds = 0.0;               // set-up time (device)
+};
+
 struct sc_ctx {
     int device = 0;
     int sm_count = 0;
@@ -99,6 +111,17 @@ struct sc_ctx {
     std::vector<int64_t> h_load_ptr;
     int32_t* d_load_dof = nullptr;
     double* d_load_val = nullptr;
+
+    // PCG preconditioner and initial guess (timeloop.cu, fsai.cu)
+    sc_fsai fsai[2];                // factors of d_Khat / d_Khat2 (or d_K for the static solver)
+    bool no_fsai = false;           // sc_set_option("fsai", 0): Jacobi preconditioner
+    double fsai_tau = 0.05;         // pattern filter: |a_ij| >= tau sqrt(a_ii a_jj)   (sc_set_option("fsai_tau_permille", ..))
+    int proj_k = 16;                // sc_set_option("pcg_projection", k): A-orthonormal basis of up to k previous solutions (0: off)
+    int proj_n = 0;                 // vectors currently in the basis
+    const double* proj_for = nullptr;   // matrix values the basis belongs to
+    std::vector<double*> proj_x, proj_ax;   // [proj_k] basis vectors and their products with the matrix
+    double** d_proj_ptr = nullptr;  // device copy of the 2 proj_k pointers (x first, then ax)
+    double* d_proj_coef = nullptr;  // [proj_k + 2] projection coefficients / norms
 
     int64_t pcg_stagnations = 0;    // solves accepted at a stagnated residual below 1e-9 (see timeloop.cu: pcg)
     int64_t extra_out_step = -1;    // sc_set_final_output_step: this step is stored even if it is no multiple of the interval
@@ -222,9 +245,16 @@ bool pcg_small_usable(sc_ctx* ctx);
 int pcg_small(sc_ctx* ctx, const double* vals, const double* dinv, const double* b, double* x, double* r, double* p, double* q,
               double rtol, int maxit, int* iters, double* relres, double ref_norm2);
 void pcg_graph_drop(sc_ctx* ctx);                                        // timeloop.cu: forget the captured PCG iteration
+void precond_drop(sc_ctx* ctx);                                          // timeloop.cu: forget FSAI factors / projection basis (matrix values changed)
+void precond_destroy(sc_ctx* ctx);                                       // ... and release their buffers (equation count changes)
 int la_cd_step(sc_ctx* ctx, const double* K, const double* w, const double* u, double* uprev_next, const double* inv_d,
                const double* alpha, double g, double* w_next);
 int la_spmv_dot(sc_ctx* ctx, const double* vals, const double* p, double* q, double* d_out);
+// fsai.cu
+int fsai_build(sc_ctx* ctx, sc_fsai* f, const double* vals);            // factor for the matrix `vals` (replaces the slot's content)
+void fsai_free(sc_fsai* f);
+int fsai_apply(sc_ctx* ctx, const sc_fsai* f, const double* r, double* t, double* z, double* partial, int nb);   // z = G^T G r,
+                                                                        // partial[0..nb) = per-block sums of r.z (nb blocks launched)
 // spmv_tma.cu
 bool la_tma_usable(sc_ctx* ctx);
 // spmv_node.cu

@@ -159,6 +159,12 @@ k_spmv_node(const NodeDesc* __restrict__ nd, const int32_t* __restrict__ ncol, c
         for (int64_t i = warp / NB_WARPS; blockIdx.x + i * G < n_tiles; i += NG) {     // i: position in this CTA's tile sequence
             const int stage = (int)(i % STAGES);
             const uint32_t phase = (uint32_t)((i / STAGES) & 1);
+            // With an odd number of stages the groups alternate on a stage, and a parity wait only tells phases apart that
+            // are at most one step from the barrier's current one: a group that runs ahead would take the completed phase of
+            // tile i - 2 STAGES for its own while tile i - STAGES is still loading.  Waiting for the release of tile
+            // i - STAGES first (by the other group; never more than one phase away) pins the "full" barrier to the phase of
+            // tile i or the one after.
+            if (NG > 1 && (STAGES & 1) && i >= STAGES) mbar_wait(&bar_empty[stage], phase ^ 1u);
             mbar_wait(&bar_full[stage], phase);
             const NodeDesc* snd = s_nd + (size_t)stage * NB_NODES;
             const NodeDesc d0 = snd[0];

@@ -438,15 +438,20 @@ def test_newmark_hexa8_pulse_vs_reference_golden(golden_meshes, golden_histories
     assert num.stats[0]["pcg_iterations"] > 0
 
 
-@pytest.mark.parametrize("pcg_path", ["cooperative", "graph", "eager"])
+@pytest.mark.parametrize("pcg_path", ["cooperative", "graph", "eager", "graph_jacobi", "graph_fsai_no_projection", "eager_jacobi_projection"])
 def test_newmark_quad4_heaviside_vs_reference_golden(pcg_path, golden_meshes, golden_histories, monkeypatch):
     # the three PCG drivers (one cooperative kernel for small systems; stream-ordered iterations replayed from a CUDA
-    # graph, or launched one by one as on multi-GPU runs) must all reproduce the reference history
+    # graph, or launched one by one as on multi-GPU runs) must all reproduce the reference history -- the stream-ordered
+    # ones with the FSAI preconditioner and the projection onto previous solutions (the defaults), and with either switched off
     from scatter_b200 import _lib
     if pcg_path != "cooperative":
         monkeypatch.setitem(_lib.DEFAULT_OPTIONS, "small_pcg", 0)
-    if pcg_path == "eager":
+    if pcg_path.startswith("eager"):
         monkeypatch.setitem(_lib.DEFAULT_OPTIONS, "pcg_graph", 0)
+    if "jacobi" in pcg_path:
+        monkeypatch.setitem(_lib.DEFAULT_OPTIONS, "fsai", 0)
+    if pcg_path in ("graph_jacobi", "graph_fsai_no_projection"):
+        monkeypatch.setitem(_lib.DEFAULT_OPTIONS, "pcg_projection", 0)
     H = golden_histories
     m, mx, num = run_history("quad4_heaviside", golden_meshes)
     ids = list(m.nodes[:, 0].astype(int))
@@ -464,7 +469,11 @@ def test_newmark_quad4_heaviside_vs_reference_golden(pcg_path, golden_meshes, go
 
 
 @pytest.mark.parametrize("etype", ["tri3", "tri6", "tetra4", "tetra10"])
-def test_newmark_benchmark_set_2_vs_reference_golden(etype, golden_meshes, golden_histories):
+@pytest.mark.parametrize("stream_pcg", [False, True])
+def test_newmark_benchmark_set_2_vs_reference_golden(etype, stream_pcg, golden_meshes, golden_histories, monkeypatch):
+    if stream_pcg:        # FSAI-preconditioned, projected PCG (what large systems run) instead of the cooperative kernel
+        from scatter_b200 import _lib
+        monkeypatch.setitem(_lib.DEFAULT_OPTIONS, "small_pcg", 0)
     H = golden_histories
     m, mx, num = run_history(etype, golden_meshes)
     assert num.u.shape[0] == 201
@@ -552,11 +561,15 @@ def test_central_difference_reports_divergence(golden_meshes):
         num.calculate(None, None, None, F.force_vector, 0, len(time) - 1)
 
 
-def test_rows_without_entries_do_not_disturb_pcg(golden_meshes, oracle):
+@pytest.mark.parametrize("stream_pcg", [False, True])
+def test_rows_without_entries_do_not_disturb_pcg(stream_pcg, golden_meshes, oracle, monkeypatch):
     """Rank 0's sub-domain of a two-way decomposition, run alone on one GPU with no halo exchange: ghost nodes own equation
     numbers but empty rows, so the system reduces to the owned block with the ghost dofs held at zero.  Regression test:
-    the SpMV must write q = 0 on the empty rows, otherwise stale values leak into the PCG residual norms."""
-    from scatter_b200 import mesher, partition, system_matrix
+    the SpMV must write q = 0 on the empty rows, otherwise stale values leak into the PCG residual norms.  With the
+    stream-ordered driver the FSAI factor leaves the ghost rows / columns out (block preconditioner per rank)."""
+    from scatter_b200 import _lib, mesher, partition, system_matrix
+    if stream_pcg:
+        monkeypatch.setitem(_lib.DEFAULT_OPTIONS, "small_pcg", 0)
     m = mesher.ReadMesh(golden_meshes["cube.msh"])
     m.read_gmsh(); m.read_bc(cases.BC_CUBE); m.mapping(); m.connectivities()
     owner = partition.owner_by_slabs(m, 2, axis=2)
@@ -599,10 +612,13 @@ def test_rows_without_entries_do_not_disturb_pcg(golden_meshes, oracle):
     ctx.close()
 
 
-def test_bathe_and_static_vs_oracle(golden_meshes, oracle):
+@pytest.mark.parametrize("stream_pcg", [False, True])
+def test_bathe_and_static_vs_oracle(stream_pcg, golden_meshes, oracle, monkeypatch):
     """Solver.BATHE / Solver.STATIC have no reference fixture: compare the device loops with the oracle's textbook
     restatement, and Bathe with the pinned Newmark oracle (both second order)."""
-    from scatter_b200 import force_external, solvers
+    from scatter_b200 import _lib, force_external, solvers
+    if stream_pcg:        # FSAI-preconditioned stream-ordered PCG (two factors for Bathe's two effective matrices)
+        monkeypatch.setitem(_lib.DEFAULT_OPTIONS, "small_pcg", 0)
     mesh, bc = "column.msh", cases.BC_COLUMN
     mat, sett = cases.materials(), cases.settings()
     load = {"force": [0, -1000, 0], "node": [3, 4, 7, 8], "time": 0.05, "type": "heaviside", "ini_steps": 20}
@@ -631,6 +647,45 @@ def test_bathe_and_static_vs_oracle(golden_meshes, oracle):
             num.update(0)
             num.calculate(None, None, None, F.force_vector, 0, len(tt) - 1)
             assert rel_l2(num.u, ref[0]) <= TOL_HIST and rel_l2(num.v, ref[1]) <= TOL_HIST and rel_l2(num.a, ref[2]) <= 1e-7
+
+
+def test_hexa20_box_stream_pcg_vs_oracle(oracle, monkeypatch):
+    """10^3 hexa20 box (12 k dofs) through the kernels a large box runs: node-blocked SpMV with two consumer groups on a ring
+    with an odd number of stages (regression: a group running ahead took the other group's completed phase for its own),
+    FSAI + projection PCG.  Products against scipy, 40 Newmark steps against the oracle's direct solve."""
+    from scatter_b200 import _lib, boxmesh, system_matrix
+    monkeypatch.setitem(_lib.DEFAULT_OPTIONS, "small_pcg", 0)
+    s, h, dt, nst = 10, 0.5, 5e-4, 40
+    pm = boxmesh.box_model(s, s, s, h, "hexa20"); pm.connectivities()
+    ne, n = len(pm.elem), pm.number_eq
+    E = boxmesh.lognormal_young(ne, 30e6, 1e6, seed=3)
+    Ko, Mo = oracle.assemble_global(oracle.model_from_readmesh(pm), E, np.full(ne, 0.2), np.full(ne, 1500.0), 2)
+    c0, c1 = oracle.rayleigh_coefficients([1, 0.01, 30, 0.01])
+    d = int(pm.eq_nb_dof[boxmesh.top_centre_node(s, s, s) - 1, 1])
+
+    def force(t):
+        f = np.zeros(n); f[d] = -1000.0 * min(1.0, t / 4.0)
+        return f
+    Uo, Vo, _, _ = oracle.newmark(Mo, Mo * c0 + Ko * c1, Ko, force, np.arange(nst + 1) * dt, 5)
+    mx = system_matrix.GenerateMatrix(n, 2)
+    ctx = mx.ctx
+    ctx.set_mesh("hexa20", pm.nodes[:, 1:], pm.node_rows(), pm.equation_table_int(), n, None)
+    ctx.set_materials(E, np.full(ne, 0.2), np.full(ne, 1500.0))
+    ctx.build_pattern(); ctx.assemble(2, _lib.ASM_K | _lib.ASM_M_FULL)
+    mx.damping_Rayleigh([1, 0.01, 30, 0.01])
+    Ks = sp.csr_matrix(Ko)
+    x = np.sin(0.37 * np.arange(n) + 0.11)
+    ref = Ks @ x
+    for _ in range(30):                                    # the race was timing dependent
+        assert np.abs(ctx.spmv(_lib.MAT_K, x) - ref).max() <= 1e-12 * np.abs(ref).max()
+    ctx.set_load_schedule(np.arange(nst + 2, dtype=np.int64), np.full(nst + 1, d, dtype=np.int64), -1000.0 * np.minimum(1.0, np.arange(nst + 1) / 4.0))
+    ctx.set_state(None, None)
+    u, v, _, st = ctx.run_newmark(dt, 0, nst, 5, rtol=1e-13)
+    assert rel_l2(u, Uo) <= TOL_HIST and rel_l2(v, Vo) <= TOL_HIST
+    info = ctx.precond_info()
+    assert info["fsai_nnz"] > n and info["projection_vectors"] > 0
+    assert st["pcg_iterations"] / nst < 150               # Jacobi needs ~330 per step on this matrix
+    ctx.close()
 
 
 def test_scatter_entry_point_writes_reference_layout(golden_meshes, golden_histories, tmp_path):
