@@ -706,6 +706,7 @@ def run_ours(args):
                              # (1 020 B/DOF/step): how close the time loop is to what an ideal plain-CSR SpMV could reach
                              "frac_plain_csr_equivalent": (12 * nnz + 48 * n_owned) / kernel_s / 1e9 / peak},
                 "halo_seconds_per_step": halo_s / max(args.stage, 1),
+                "halo_overlapped_with_interior_tiles": bool(st.get("halo_overlapped", False)) if world > 1 else None,
                 "assembly": {"seconds": t_asm, "pattern_seconds": t_pattern, "gbs": asm_bytes / t_asm / 1e9,
                              "frac_hbm": asm_bytes / t_asm / 1e9 / peak, "elements_per_s": ne / t_asm, "algorithmic_bytes": asm_bytes,
                              "host_mesh_seconds": t_mesh, "h2d_seconds": t_h2d,
@@ -922,7 +923,7 @@ ASM_FMA_PER_HEXA8 = 8 * (4 * 121 + 16 * 84)
 
 # dram__bytes_read.sum + dram__bytes_write.sum of one fused central-difference launch (k_spmv_node<2,..> with the column
 # dictionary) from the committed ncu capture, by box size
-TRAFFIC = {255: 35245933000 + 408624640}      # profiles/r1_v5_k_spmv_node_dict_255cube.txt (1 GPU)
+TRAFFIC = {255: 34492233000 + 788973056}      # profiles/r2_v7_k_spmv_node_ng2_255cube.txt (1 GPU; lagged damping: two more vector passes)
 
 
 def main():
@@ -945,7 +946,7 @@ def main():
     ap.add_argument("--total", type=int, default=405, help="box edge of config 5 (405^3 elements = 200.8 M DOF)")
     ap.add_argument("--random-field", type=int, default=1, help="also time the random-field sampler on this rank's elements")
     ap.add_argument("--size20", type=int, default=94, help="hexa20 box edge (elements) of the secondary workload")
-    ap.add_argument("--steps20", type=int, default=5)
+    ap.add_argument("--steps20", type=int, default=30)
     ap.add_argument("--rtol20", type=float, default=1e-12, help="PCG tolerance of the hexa20 workload (the product default)")
     args = ap.parse_args()
     if args.impl == "reference":

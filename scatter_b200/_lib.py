@@ -40,7 +40,8 @@ class Stats(C.Structure):
         d = {k: getattr(self, k) for k, _ in self._fields_ if k != "reserved"}
         d["step_bytes"] = self.reserved[0]
         d["pcg_stagnations"] = int(self.reserved[2])
-        d["fsai_setup_seconds"] = self.reserved[3]
+        d["fsai_setup_seconds"] = self.reserved[3]         # implicit loops
+        d["halo_overlapped"] = bool(self.reserved[3])      # central difference on several GPUs: exchange ran beside the interior tiles
         d["step_kernel"] = {0: "k_spmv (register staged)", 1: "k_spmv_tma (row tiles)", 2: "k_spmv_node (node-blocked, TMA)"}.get(int(self.reserved[1]), "?")
         return d
 

@@ -40,6 +40,7 @@ int upload(sc_ctx* ctx, T** dst, const T* src, size_t n) {
 void free_pattern(sc_ctx* c) {
     pcg_graph_drop(c);
     precond_destroy(c);
+    c->ov_planned = c->ov_ok = false;
     sc_free(&c->d_n2e_ptr); sc_free(&c->d_n2e); sc_free(&c->d_nbr_ptr); sc_free(&c->d_nbr); sc_free(&c->d_nbr_off); sc_free(&c->d_nbr_free);
     sc_free(&c->d_node_rl); sc_free(&c->d_node_row0); sc_free(&c->d_rowptr); sc_free(&c->d_col); sc_free(&c->d_nd); sc_free(&c->d_ncol); sc_free(&c->d_dict); c->n_dict = 0; sc_free(&c->d_pair_pos); sc_free(&c->d_pair_al);
     sc_free(&c->d_K); sc_free(&c->d_M); sc_free(&c->d_Ml); sc_free(&c->d_Khat); sc_free(&c->d_Khat2); sc_free(&c->d_C); c->csr_only = false;
@@ -130,6 +131,9 @@ void sc_destroy(sc_ctx* ctx) {
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
     if (ctx->ev_rows_ready) cudaEventDestroy(ctx->ev_rows_ready);
     if (ctx->ev_rows_done) cudaEventDestroy(ctx->ev_rows_done);
+    if (ctx->ev_bnd) cudaEventDestroy(ctx->ev_bnd);
+    if (ctx->ev_halo) cudaEventDestroy(ctx->ev_halo);
+    if (ctx->comm_stream) cudaStreamDestroy(ctx->comm_stream);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     delete ctx;
@@ -173,6 +177,7 @@ int sc_set_option(sc_ctx* ctx, const char* name, int64_t value) {
     else if (k == "pcg_graph") ctx->no_graph = !on;                 // CUDA-graph replay of the PCG iteration (default on)
     else if (k == "spmv_groups") ctx->force_one_group = value == 1;      // 1: one consumer group per CTA, two CTAs per SM; default 2
     else if (k == "fsai") { ctx->no_fsai = !on; precond_drop(ctx); }   // FSAI preconditioner of the stream-ordered PCG (default on; 0: Jacobi)
+    else if (k == "fsai_component_major") { ctx->fsai_no_perm = !on; precond_drop(ctx); }   // factors stored x-, y-, z-equations first (default on)
     else if (k == "fsai_tau_permille") {                              // FSAI pattern filter tau in 1/1000 (default 50)
         if (value < 0 || value > 1000) return sc_fail(ctx, SC_ERR_ARG, "fsai_tau_permille must lie in [0, 1000]");
         ctx->fsai_tau = (double)value / 1000.0; precond_drop(ctx);
@@ -181,6 +186,7 @@ int sc_set_option(sc_ctx* ctx, const char* name, int64_t value) {
         if (value < 0 || value > 32) return sc_fail(ctx, SC_ERR_ARG, "pcg_projection must lie in [0, 32]");
         ctx->proj_k = (int)value; precond_drop(ctx);
     }
+    else if (k == "halo_overlap") { ctx->no_overlap = !on; ctx->ov_planned = false; }   // interior tiles step beside the halo exchange (default on)
     else if (k == "generic_assembly") ctx->force_generic_assembly = on;   // warp-per-node assembly for every element type (default off)
     else return sc_fail(ctx, SC_ERR_ARG, "unknown option '%s'", name);
     pcg_graph_drop(ctx);
@@ -634,6 +640,7 @@ int sc_set_halo(sc_ctx* ctx, int n_neighbors, const int32_t* neighbor_rank, cons
     if (!ctx || !ctx->have_mesh) return sc_fail(ctx, SC_ERR_STATE, "sc_set_mesh must be called first");
     SC_CUDA(ctx, cudaSetDevice(ctx->device));
     ctx->n_nbr_ranks = n_neighbors;
+    ctx->ov_planned = ctx->ov_ok = false;
     ctx->nbr_rank.assign(neighbor_rank, neighbor_rank + n_neighbors);
     ctx->send_ptr.assign(send_ptr, send_ptr + n_neighbors + 1);
     ctx->recv_ptr.assign(recv_ptr, recv_ptr + n_neighbors + 1);

@@ -38,7 +38,12 @@ struct sc_fsai {
     int64_t nnz = 0;
     int64_t* rowptr = nullptr;   int2* cv = nullptr;      // G: (column, FP32 value bits) pairs, rows ascending in column, diagonal last
     int64_t* t_rowptr = nullptr; int2* t_cv = nullptr;    // G^T, diagonal first
+    int32_t* perm = nullptr;            // [n_eq] component-major number of every equation; rows and columns of both factors
+                                        // are stored in that numbering (null: the context's own numbering)
     int lanes = 8;                      // lanes per row of the apply kernels
+    int max_row = 0, t_max_row = 0;     // longest row of G / G^T
+    int tile_max = 0, t_tile_max = 0;   // most entries in one tile of rows of G / G^T (ring stage size of the TMA-fed products)
+    int jacobi_rows = 0;                // rows whose local system was not positive definite (diagonal scaling instead)
     double seconds = 0.0;               // set-up time (device)
 };
 
@@ -115,6 +120,7 @@ struct sc_ctx {
     // PCG preconditioner and initial guess (timeloop.cu, fsai.cu)
     sc_fsai fsai[2];                // factors of d_Khat / d_Khat2 (or d_K for the static solver)
     bool no_fsai = false;           // sc_set_option("fsai", 0): Jacobi preconditioner
+    bool fsai_no_perm = false;      // sc_set_option("fsai_component_major", 0): factors in the context's interleaved numbering
     double fsai_tau = 0.05;         // pattern filter: |a_ij| >= tau sqrt(a_ii a_jj)   (sc_set_option("fsai_tau_permille", ..))
     int proj_k = 16;                // sc_set_option("pcg_projection", k): A-orthonormal basis of up to k previous solutions (0: off)
     int proj_n = 0;                 // vectors currently in the basis
@@ -158,6 +164,12 @@ struct sc_ctx {
     double cd_resume_dt = 0.0;
 
     // multi-GPU
+    // halo overlap of the explicit step (spmv_node.cu: la_node_overlap_plan): tiles [ov_tile_lo, ov_tile_hi) = rows
+    // [ov_row_lo, ov_row_hi) neither send nor read halo values; they run while the exchange of the other tiles is in flight
+    bool ov_planned = false, ov_ok = false, no_overlap = false;   // sc_set_option("halo_overlap", 0) keeps step and exchange serial
+    int64_t ov_tile_lo = 0, ov_tile_hi = 0, ov_row_lo = 0, ov_row_hi = 0;
+    cudaStream_t comm_stream = nullptr;
+    cudaEvent_t ev_bnd = nullptr, ev_halo = nullptr;
     int rank = 0, world = 1;
     NcclApi* nccl = nullptr;
     void* comm = nullptr;
@@ -253,15 +265,18 @@ int la_spmv_dot(sc_ctx* ctx, const double* vals, const double* p, double* q, dou
 // fsai.cu
 int fsai_build(sc_ctx* ctx, sc_fsai* f, const double* vals);            // factor for the matrix `vals` (replaces the slot's content)
 void fsai_free(sc_fsai* f);
-int fsai_apply(sc_ctx* ctx, const sc_fsai* f, const double* r, double* t, double* z, double* partial, int nb);   // z = G^T G r,
-                                                                        // partial[0..nb) = per-block sums of r.z (nb blocks launched)
+int fsai_apply(sc_ctx* ctx, const sc_fsai* f, const double* r, double* t, double* z, double* partial, int nb, double* rp);
+                                                                        // z = G^T G r in the factor's numbering (f->perm), partial[0..nb) =
+                                                                        // per-block sums of r.z; rp: scratch vector (renumbered r)
+int fsai_unpermute(sc_ctx* ctx, const sc_fsai* f, const double* zp, double* z);   // z[i] = zp[f->perm[i]]
 // spmv_tma.cu
 bool la_tma_usable(sc_ctx* ctx);
 // spmv_node.cu
 bool la_node_usable(sc_ctx* ctx);
 int la_node_spmv(sc_ctx* ctx, const double* vals, const double* x, double* y);
 int la_node_cd_step(sc_ctx* ctx, const double* K, const double* w, const double* u, double* uprev_next, const double* inv_d,
-                    const double* alpha, double g, double* w_next);
+                    const double* alpha, double g, double* w_next, int part = 0);
+int la_node_overlap_plan(sc_ctx* ctx);
 int la_node_spmv_dot(sc_ctx* ctx, const double* vals, const double* p, double* q, double* partial, unsigned* nblocks);
 int64_t la_node_step_bytes(sc_ctx* ctx, bool lagged);
 int la_tma_spmv(sc_ctx* ctx, const double* vals, const double* x, double* y);

@@ -13,6 +13,7 @@
 // mbarrier full/empty handshakes, eight consumer warps (one node each per tile).  Deterministic: fixed lane partials
 // and a fixed butterfly, no atomics.
 #include <algorithm>
+#include <vector>
 #include "common.h"
 
 namespace {
@@ -73,7 +74,9 @@ k_spmv_node(const NodeDesc* __restrict__ nd, const int32_t* __restrict__ ncol, c
             const double* __restrict__ xa, double* __restrict__ y, const double* __restrict__ inv_d,
             const double* __restrict__ alpha, double* __restrict__ partial, int64_t n_nodes, int64_t n_rows, int64_t n_tiles,
             int cap_v, int cap_c, const int32_t* __restrict__ dict, int n_dict, int dict_stride,
-            const double* __restrict__ xe, double* __restrict__ y2, double lag) {
+            const double* __restrict__ xe, double* __restrict__ y2, double lag, int64_t t_lo1, int64_t t_n1, int64_t t_lo2) {
+    // `n_tiles` counts the tiles of this launch: positions v < t_n1 map to tile t_lo1 + v, the others to t_lo2 + (v - t_n1)
+    // (whole matrix: t_lo1 = 0, t_n1 = n_tiles; the halo overlap launches the two ends and the interior separately)
     constexpr int NB_NODES = NB_WARPS * NB_NPW;      // nodes per tile; NB_NPW nodes per consumer warp (gathers in flight together)
     constexpr int NB_VT = 3 * NB_NODES + 8;          // vector slots per tile (rows + alignment), multiple of 2
     constexpr int NVEC = (MODE == 2) ? 4 : (MODE == 3 ? 1 : 0);
@@ -113,13 +116,15 @@ k_spmv_node(const NodeDesc* __restrict__ nd, const int32_t* __restrict__ ncol, c
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            int64_t tj = blockIdx.x;
+            int64_t vj = blockIdx.x;
+            auto tile_of = [&](int64_t v) { return v < t_n1 ? t_lo1 + v : t_lo2 + (v - t_n1); };
             NodeDesc n0, n1;
-            if (tj < n_tiles) { n0 = nd[tj * NB_NODES]; n1 = nd[tj * NB_NODES + NB_NODES]; }   // the descriptor array is padded by NB_NODES entries
-            for (; tj < n_tiles; tj += G) {
+            if (vj < n_tiles) { const int64_t t = tile_of(vj); n0 = nd[t * NB_NODES]; n1 = nd[t * NB_NODES + NB_NODES]; }   // the descriptor array is padded by NB_NODES entries
+            for (; vj < n_tiles; vj += G) {
+                const int64_t tj = tile_of(vj);
                 const int64_t a_v0 = n0.val_off, a_v1 = n1.val_off, a_c0 = n0.col_off, a_c1 = n1.col_off;
                 const int a_r0 = n0.row0, a_r1 = n1.row0;
-                if (tj + G < n_tiles) { n0 = nd[(tj + G) * NB_NODES]; n1 = nd[(tj + G) * NB_NODES + NB_NODES]; }
+                if (vj + G < n_tiles) { const int64_t t = tile_of(vj + G); n0 = nd[t * NB_NODES]; n1 = nd[t * NB_NODES + NB_NODES]; }
                 mbar_wait(&bar_empty[stage], phase ^ 1u);
                 const int64_t vs = a_v0 & ~(int64_t)1, cs = a_c0 & ~(int64_t)3;
                 const int rs = a_r0 & ~1;
@@ -297,9 +302,15 @@ bool node_cfg(sc_ctx* ctx, NodeCfg& c) {
 
 template <int MODE, int STAGES, int NPW, int NG>
 int launch_node(sc_ctx* ctx, const NodeCfg& c, const double* va, const double* xa, double* y, const double* inv_d, const double* alpha,
-                double* partial, unsigned* nblocks_out, const double* xe, double* y2, double g) {
+                double* partial, unsigned* nblocks_out, const double* xe, double* y2, double g, int part) {
     constexpr int NODES = NB_WARPS * NPW;
-    const int64_t n_tiles = (ctx->n_nodes + NODES - 1) / NODES;
+    const int64_t all_tiles = (ctx->n_nodes + NODES - 1) / NODES;
+    // part 0: every tile; 1: the tiles outside [ov_tile_lo, ov_tile_hi) (they hold every row the halo exchange sends);
+    // 2: the interior tiles
+    int64_t n_tiles = all_tiles, lo1 = 0, n1 = all_tiles, lo2 = 0;
+    if (part == 1) { lo1 = 0; n1 = ctx->ov_tile_lo; lo2 = ctx->ov_tile_hi; n_tiles = n1 + (all_tiles - lo2); }
+    if (part == 2) { lo1 = ctx->ov_tile_lo; n1 = ctx->ov_tile_hi - ctx->ov_tile_lo; n_tiles = n1; }
+    if (n_tiles <= 0) return SC_OK;
     auto kern = k_spmv_node<MODE, STAGES, NPW, NG>;
     const size_t bytes = c.bytes + (size_t)ctx->n_dict * ctx->dict_stride * sizeof(int32_t);
     SC_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
@@ -308,17 +319,17 @@ int launch_node(sc_ctx* ctx, const NodeCfg& c, const double* va, const double* x
     if (nblocks_out) *nblocks_out = grid;
     kern<<<grid, 32 * (NG * NB_WARPS + 1), bytes, ctx->stream>>>(ctx->d_nd, ctx->d_ncol, va, xa, y, inv_d, alpha, partial, ctx->n_nodes,
                                                                   ctx->n_eq, n_tiles, c.cap_v, c.cap_c, ctx->d_dict, ctx->n_dict,
-                                                                  ctx->dict_stride, xe, y2, g);
+                                                                  ctx->dict_stride, xe, y2, g, lo1, n1, lo2);
     SC_CHECK_LAUNCH(ctx);
     return SC_OK;
 }
 
 template <int MODE>
 int launch_mode(sc_ctx* ctx, const double* va, const double* xa, double* y, const double* inv_d, const double* alpha, double* partial,
-                unsigned* nblocks_out, const double* xe = nullptr, double* y2 = nullptr, double g = 0.0) {
+                unsigned* nblocks_out, const double* xe = nullptr, double* y2 = nullptr, double g = 0.0, int part = 0) {
     NodeCfg c;
     if (!node_cfg(ctx, c)) return sc_fail(ctx, SC_ERR_UNSUPPORTED, "node-blocked SpMV not usable for this pattern");
-#define SC_NODE_GO(ST, NPW, NG) return launch_node<MODE, ST, NPW, NG>(ctx, c, va, xa, y, inv_d, alpha, partial, nblocks_out, xe, y2, g)
+#define SC_NODE_GO(ST, NPW, NG) return launch_node<MODE, ST, NPW, NG>(ctx, c, va, xa, y, inv_d, alpha, partial, nblocks_out, xe, y2, g, part)
     if (c.ng == 2) {
         if (c.npw == 2) { if (c.stages == 6) SC_NODE_GO(6, 2, 2); if (c.stages == 5) SC_NODE_GO(5, 2, 2); if (c.stages == 4) SC_NODE_GO(4, 2, 2); SC_NODE_GO(3, 2, 2); }
         if (c.stages == 6) SC_NODE_GO(6, 1, 2); if (c.stages == 5) SC_NODE_GO(5, 1, 2); if (c.stages == 4) SC_NODE_GO(4, 1, 2); SC_NODE_GO(3, 1, 2);
@@ -348,8 +359,75 @@ int la_node_spmv(sc_ctx* ctx, const double* vals, const double* x, double* y) {
     return launch_mode<0>(ctx, vals, x, y, nullptr, nullptr, nullptr, nullptr);
 }
 int la_node_cd_step(sc_ctx* ctx, const double* K, const double* w, const double* u, double* uprev_next, const double* inv_d,
-                    const double* alpha, double g, double* w_next) {
-    return launch_mode<2>(ctx, K, w, uprev_next, inv_d, alpha, nullptr, nullptr, u, w_next, g);
+                    const double* alpha, double g, double* w_next, int part) {
+    return launch_mode<2>(ctx, K, w, uprev_next, inv_d, alpha, nullptr, nullptr, u, w_next, g, part);
+}
+
+namespace {
+// tile of every row the halo exchange sends (rows -> node by bisection of the node row offsets)
+__global__ void k_flag_send_tiles(const int64_t* __restrict__ send_idx, int64_t ns, const int64_t* __restrict__ node_row0,
+                                  int64_t n_nodes, int nodes_per_tile, unsigned char* __restrict__ flag) {
+    int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (t >= ns) return;
+    const int64_t row = send_idx[t];
+    int64_t lo = 0, hi = n_nodes;                      // last node with node_row0 <= row
+    while (hi - lo > 1) {
+        const int64_t mid = (lo + hi) >> 1;
+        if (node_row0[mid] <= row) lo = mid; else hi = mid;
+    }
+    flag[lo / nodes_per_tile] = 1;                     // every writer stores the same byte
+}
+}  // namespace
+
+// Interior of the halo overlap: the longest run of tiles [lo, hi) that holds no row of the send lists (for slab / RCB
+// partitions of a sorted mesh the interface rows sit at the two ends of the numbering).  Nodes of those tiles are not
+// adjacent to ghost nodes either (adjacency is symmetric: a node next to a ghost is needed by the ghost's owner), so their
+// products neither produce values the exchange sends nor read values it delivers.  Returns false when the run covers less
+// than half of the tiles (then the step and the exchange stay serial).
+int la_node_overlap_plan(sc_ctx* ctx) {
+    if (ctx->ov_planned) return SC_OK;
+    ctx->ov_planned = true;
+    ctx->ov_ok = false;
+    NodeCfg c;
+    if (ctx->world <= 1 || ctx->no_overlap || !node_cfg(ctx, c) || !ctx->d_node_row0) return SC_OK;
+    const int nodes = NB_WARPS * c.npw;
+    const int64_t n_tiles = (ctx->n_nodes + nodes - 1) / nodes;
+    const int64_t ns = ctx->send_ptr.empty() ? 0 : ctx->send_ptr.back();
+    if (n_tiles < 64 || ns == 0) return SC_OK;
+    unsigned char* d_flag = nullptr;
+    SC_TRY(sc_alloc(ctx, &d_flag, (size_t)n_tiles));
+    std::vector<unsigned char> flag((size_t)n_tiles);
+    int rc = SC_OK;
+    auto body = [&]() -> int {
+        SC_CUDA(ctx, cudaMemsetAsync(d_flag, 0, (size_t)n_tiles, ctx->stream));
+        k_flag_send_tiles<<<(unsigned)((ns + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_send_idx, ns, ctx->d_node_row0, ctx->n_nodes, nodes, d_flag);
+        SC_CHECK_LAUNCH(ctx);
+        SC_CUDA(ctx, cudaMemcpyAsync(flag.data(), d_flag, (size_t)n_tiles, cudaMemcpyDeviceToHost, ctx->stream));
+        SC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        return SC_OK;
+    };
+    rc = body();
+    sc_free(&d_flag);
+    SC_TRY(rc);
+    int64_t best_lo = 0, best_hi = 0, run = -1;
+    for (int64_t t = 0; t <= n_tiles; ++t) {
+        const bool set = t == n_tiles || flag[(size_t)t] != 0;
+        if (!set && run < 0) run = t;
+        if (set && run >= 0) {
+            if (t - run > best_hi - best_lo) { best_lo = run; best_hi = t; }
+            run = -1;
+        }
+    }
+    if (best_hi - best_lo < n_tiles / 2) return SC_OK;
+    ctx->ov_tile_lo = best_lo; ctx->ov_tile_hi = best_hi;
+    // first rows of the two cut tiles (for the range filter of the sparse load kernel)
+    int64_t h[2] = {0, 0};
+    const int64_t n_lo = std::min<int64_t>(best_lo * nodes, ctx->n_nodes), n_hi = std::min<int64_t>(best_hi * nodes, ctx->n_nodes);
+    SC_CUDA(ctx, cudaMemcpy(&h[0], ctx->d_node_row0 + n_lo, sizeof(int64_t), cudaMemcpyDeviceToHost));
+    SC_CUDA(ctx, cudaMemcpy(&h[1], ctx->d_node_row0 + n_hi, sizeof(int64_t), cudaMemcpyDeviceToHost));
+    ctx->ov_row_lo = h[0]; ctx->ov_row_hi = h[1];
+    ctx->ov_ok = true;
+    return SC_OK;
 }
 int la_node_spmv_dot(sc_ctx* ctx, const double* vals, const double* p, double* q, double* partial, unsigned* nblocks) {
     return launch_mode<3>(ctx, vals, p, q, nullptr, nullptr, partial, nblocks);

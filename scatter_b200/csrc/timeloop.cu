@@ -142,12 +142,13 @@ __global__ void k_pcg_update_np(const double* __restrict__ scal, const double* _
         partial[nb + blockIdx.x] = c;
     }
 }
-// p = z + beta p, beta = scal[2]/scal[0]
-__global__ void k_pcg_pz(const double* __restrict__ scal, const double* __restrict__ z, double* __restrict__ p, int64_t n) {
+// p = z + beta p, beta = scal[2]/scal[0]; z is read through the factor's renumbering when there is one
+__global__ void k_pcg_pz(const double* __restrict__ scal, const double* __restrict__ z, const int32_t* __restrict__ perm,
+                         double* __restrict__ p, int64_t n) {
     int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (i >= n) return;
     const double beta = scal[0] != 0.0 ? scal[2] / scal[0] : 0.0;
-    p[i] = z[i] + beta * p[i];
+    p[i] = z[perm ? perm[i] : i] + beta * p[i];
 }
 
 // ---- projection onto previous solutions (Fischer 1998): dots with / combinations of up to proj_k vectors ---------------
@@ -225,11 +226,14 @@ __global__ void k_nm_update(const double* __restrict__ du, double* __restrict__ 
     u[i] += d; v[i] = vi + dv; a[i] = ai + da;
 }
 // sparse load entries: y[dof] += scale * val   (dofs are unique within a step)
+// sel 0: every entry; 1: dofs outside [lo, hi); 2: dofs inside (the two launches of a step split for the halo overlap)
 __global__ void k_load_add(const int32_t* __restrict__ dof, const double* __restrict__ val, int64_t n, double scale,
-                           const double* __restrict__ mult, double* __restrict__ y) {
+                           const double* __restrict__ mult, double* __restrict__ y, int sel, int64_t lo, int64_t hi) {
     int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (t >= n) return;
     const int d = dof[t];
+    const bool inside = d >= lo && d < hi;
+    if ((sel == 1 && inside) || (sel == 2 && !inside)) return;
     y[d] += scale * val[t] * (mult ? mult[d] : 1.0);
 }
 __global__ void k_cd_coeffs(const double* __restrict__ m, const double* __restrict__ c, double a0, double a1, double* __restrict__ inv_d,
@@ -322,7 +326,8 @@ int pcg(sc_ctx* ctx, const double* vals, const double* dinv, const double* b, do
     if (F) {
         k_pcg_init_np<<<PCG_NB, 256, 0, st>>>(b, x, r, n, ctx->d_partial, PCG_NB);
         SC_CHECK_LAUNCH(ctx);
-        SC_TRY(fsai_apply(ctx, F, r, tv, p, ctx->d_partial, PCG_NB));       // p = z = G^T G r, partials of r.z
+        SC_TRY(fsai_apply(ctx, F, r, tv, z, ctx->d_partial, PCG_NB, q));       // z = G^T G r (factor numbering), partials of r.z; q: scratch here
+        SC_TRY(fsai_unpermute(ctx, F, z, p));
     } else {
         k_pcg_init<<<PCG_NB, 256, 0, st>>>(b, dinv, x, r, p, n, ctx->d_partial, PCG_NB);
         SC_CHECK_LAUNCH(ctx);
@@ -353,7 +358,7 @@ int pcg(sc_ctx* ctx, const double* vals, const double* dinv, const double* b, do
         if (F) {
             k_pcg_update_np<<<PCG_NB, 256, 0, st>>>(sc, p, q, x, r, n, ctx->d_partial, PCG_NB);
             SC_CHECK_LAUNCH(ctx);
-            SC_TRY(fsai_apply(ctx, F, r, tv, z, ctx->d_partial, PCG_NB));
+            SC_TRY(fsai_apply(ctx, F, r, tv, z, ctx->d_partial, PCG_NB, q));    // q is free between the update and the next product
         } else {
             k_pcg_update<<<PCG_NB, 256, 0, st>>>(sc, p, q, dinv, x, r, n, ctx->d_partial, PCG_NB);
             SC_CHECK_LAUNCH(ctx);
@@ -362,7 +367,7 @@ int pcg(sc_ctx* ctx, const double* vals, const double* dinv, const double* b, do
         SC_CHECK_LAUNCH(ctx);
         if (ctx->world > 1) SC_TRY(dist_allreduce_sum(ctx, sc + 2, 2, st));
         SC_CUDA(ctx, cudaMemcpyAsync(ctx->h_pinned, sc, 5 * sizeof(double), cudaMemcpyDeviceToHost, st));
-        if (F) k_pcg_pz<<<nblk(n, 256), 256, 0, st>>>(sc, z, p, n);
+        if (F) k_pcg_pz<<<nblk(n, 256), 256, 0, st>>>(sc, z, F->perm, p, n);
         else k_pcg_p<<<nblk(n, 256), 256, 0, st>>>(sc, r, dinv, p, n);
         SC_CHECK_LAUNCH(ctx);
         k_shift<<<1, 1, 0, st>>>(sc);
@@ -582,11 +587,12 @@ int proj_solve(sc_ctx* ctx, const double* vals, const double* dinv, const sc_fsa
     return SC_OK;
 }
 
-int apply_load(sc_ctx* ctx, int64_t t, double scale, const double* mult, double* y) {
+int apply_load(sc_ctx* ctx, int64_t t, double scale, const double* mult, double* y, int sel = 0) {
     if (t < 0 || t >= ctx->load_steps) return SC_OK;   // outside the schedule: zero force
     const int64_t s = ctx->h_load_ptr[t], e = ctx->h_load_ptr[t + 1];
     if (e == s) return SC_OK;
-    k_load_add<<<nblk(e - s, 128), 128, 0, ctx->stream>>>(ctx->d_load_dof + s, ctx->d_load_val + s, e - s, scale, mult, y);
+    k_load_add<<<nblk(e - s, 128), 128, 0, ctx->stream>>>(ctx->d_load_dof + s, ctx->d_load_val + s, e - s, scale, mult, y, sel,
+                                                          ctx->ov_row_lo, ctx->ov_row_hi);
     SC_CHECK_LAUNCH(ctx);
     return SC_OK;
 }
@@ -845,6 +851,22 @@ int tl_central_difference(sc_ctx* ctx, double dt, int64_t t0, int64_t n_steps, i
 
     const bool want_out = (u_out || v_out || a_out) && n_out > 0;
     if (want_out) { SC_TRY(sc_work(ctx, 6, &vv)); SC_TRY(sc_work(ctx, 7, &aa)); }
+    // Several GPUs: the tiles that hold the interface rows step first, their values leave on the communication stream, and
+    // the interior tiles (no row sent, no ghost column read) step while the exchange is in flight.
+    bool overlap = false;
+    if (ctx->world > 1 && la_node_usable(ctx)) {
+        SC_TRY(la_node_overlap_plan(ctx));
+        overlap = ctx->ov_ok;
+        if (overlap && !ctx->comm_stream) {
+            SC_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->comm_stream, cudaStreamNonBlocking));
+            SC_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_bnd, cudaEventDisableTiming));
+            SC_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_halo, cudaEventDisableTiming));
+        }
+    }
+    // device time of the exchange itself, sampled on the first steps of the stage (pack, NCCL send/recv, unpack)
+    constexpr int HALO_SAMPLES = 16;
+    cudaEvent_t hs[HALO_SAMPLES][2];
+    int n_hs = 0;
     int64_t row = 0;
     sc_gpu_timer timer(st);
     timer.start();
@@ -859,11 +881,36 @@ int tl_central_difference(sc_ctx* ctx, double dt, int64_t t0, int64_t n_steps, i
         }
         // prev <- u(t+dt), w_nxt <- w(t+dt)   (without stiffness-proportional damping the gathered vector is u(t) itself)
         if (!lagged) w_cur = cur;
-        SC_TRY(la_cd_step(ctx, ctx->d_K, w_cur, cur, prev, inv_d, alpha, g, w_nxt));
-        SC_TRY(apply_load(ctx, t, 1.0, inv_d, prev));
-        if (lagged) SC_TRY(apply_load(ctx, t, 1.0 + g, inv_d, w_nxt));
         // ghost values: only the gathered vector needs them (u itself is read on owned rows only)
-        if (ctx->world > 1) SC_TRY(dist_halo(ctx, lagged ? w_nxt : prev, st));
+        double* hx = lagged ? w_nxt : prev;
+        const bool sample = ctx->world > 1 && n_hs < HALO_SAMPLES;
+        if (sample) { cudaEventCreate(&hs[n_hs][0]); cudaEventCreate(&hs[n_hs][1]); }
+        if (overlap) {
+            cudaStream_t cs = ctx->comm_stream;
+            SC_TRY(la_node_cd_step(ctx, ctx->d_K, w_cur, cur, prev, inv_d, alpha, g, w_nxt, 1));
+            SC_TRY(apply_load(ctx, t, 1.0, inv_d, prev, 1));
+            if (lagged) SC_TRY(apply_load(ctx, t, 1.0 + g, inv_d, w_nxt, 1));
+            SC_CUDA(ctx, cudaEventRecord(ctx->ev_bnd, st));
+            SC_CUDA(ctx, cudaStreamWaitEvent(cs, ctx->ev_bnd, 0));
+            if (sample) cudaEventRecord(hs[n_hs][0], cs);
+            SC_TRY(dist_halo(ctx, hx, cs));
+            if (sample) cudaEventRecord(hs[n_hs][1], cs);
+            SC_CUDA(ctx, cudaEventRecord(ctx->ev_halo, cs));
+            SC_TRY(la_node_cd_step(ctx, ctx->d_K, w_cur, cur, prev, inv_d, alpha, g, w_nxt, 2));
+            SC_TRY(apply_load(ctx, t, 1.0, inv_d, prev, 2));
+            if (lagged) SC_TRY(apply_load(ctx, t, 1.0 + g, inv_d, w_nxt, 2));
+            SC_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev_halo, 0));
+        } else {
+            SC_TRY(la_cd_step(ctx, ctx->d_K, w_cur, cur, prev, inv_d, alpha, g, w_nxt));
+            SC_TRY(apply_load(ctx, t, 1.0, inv_d, prev));
+            if (lagged) SC_TRY(apply_load(ctx, t, 1.0 + g, inv_d, w_nxt));
+            if (ctx->world > 1) {
+                if (sample) cudaEventRecord(hs[n_hs][0], st);
+                SC_TRY(dist_halo(ctx, hx, st));
+                if (sample) cudaEventRecord(hs[n_hs][1], st);
+            }
+        }
+        if (sample) ++n_hs;
         if (out_now) {
             if (ctx->rows_pending) SC_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev_rows_done, 0));   // vv / aa are still being copied
             k_cd_va<<<nblk(n, 256), 256, 0, st>>>(prev, cur, uc, a0, a1, vv, aa, n);
@@ -901,6 +948,13 @@ int tl_central_difference(sc_ctx* ctx, double dt, int64_t t0, int64_t n_steps, i
     SC_TRY(finish_rows(ctx));
     SC_CUDA(ctx, cudaStreamSynchronize(st));
     const float ms = timer.ms();
+    double halo_ms = 0.0;
+    for (int k = 0; k < n_hs; ++k) {
+        float v = 0.f;
+        if (cudaEventElapsedTime(&v, hs[k][0], hs[k][1]) == cudaSuccess) halo_ms += v;
+        cudaEventDestroy(hs[k][0]); cudaEventDestroy(hs[k][1]);
+    }
+    const double halo_per_step = n_hs > 0 ? halo_ms * 1e-3 / n_hs : 0.0;
     double diverged = ctx->h_pinned[9];
     if (ctx->world > 1) {                                // every rank must take the same exit
         SC_TRY(dist_allreduce_sum(ctx, ctx->d_scal + 9, 1, st));
@@ -924,7 +978,10 @@ int tl_central_difference(sc_ctx* ctx, double dt, int64_t t0, int64_t n_steps, i
         stats->pcg_iterations = 0;
         stats->kernel_launches = ctx->launches - launches0;
         stats->last_residual = 0.0;
-        stats->seconds_halo = 0.0;
+        // exchange time extrapolated from the sampled steps; with the overlap it runs beside the interior tiles and is
+        // not part of seconds_device any more (reserved[3] = 1 says so)
+        stats->seconds_halo = halo_per_step * (double)steps_done;
+        stats->reserved[3] = overlap ? 1.0 : 0.0;
     }
     return SC_OK;
 }
