@@ -346,6 +346,14 @@ def parity_check(rank, world, local_rank, dist):
         ctx.set_state(None, None)
         u, v, _, _ = ctx.run_central_difference(dt_cd, 0, n_cd, 10)
         res = [u[:, dom.owned_eq], v[:, dom.owned_eq]]
+        if world > 1:
+            # the optional overlap of the halo exchange with the interior tiles must give the same history bit for bit
+            ctx.set_option("halo_overlap", 1)
+            ctx.set_state(None, None)
+            u2, v2, _, st2 = ctx.run_central_difference(dt_cd, 0, n_cd, 10)
+            if not (np.array_equal(u2, u) and np.array_equal(v2, v)):
+                raise RuntimeError("halo overlap changed the central-difference history")
+            ctx.set_option("halo_overlap", 0)
         if newmark:
             ctx.set_state(None, None)
             u, v, _, _ = ctx.run_newmark(dt_nm, 0, n_nm, 5, rtol=1e-12)
@@ -720,6 +728,7 @@ def run_ours(args):
                         "ms_per_step": 1e3 * e2e_wall / args.steps, "output_interval": args.stage},
                 "e2e_by_output_interval": e2e_by,
                 "parity_check": parity,
+                "options": dict(a.split("=") for a in args.option) or None,
                 "gpu_launches": int(launches), "clocks": clocks, "device": info["name"], "secondary": secondary,
                 "scatter_e2e": scatter_e2e, "config5": config5}
         print(json.dumps(line))
@@ -948,10 +957,17 @@ def main():
     ap.add_argument("--size20", type=int, default=94, help="hexa20 box edge (elements) of the secondary workload")
     ap.add_argument("--steps20", type=int, default=30)
     ap.add_argument("--rtol20", type=float, default=1e-12, help="PCG tolerance of the hexa20 workload (the product default)")
+    ap.add_argument("--option", action="append", default=[], metavar="NAME=VALUE",
+                    help="library option for A/B runs (sc_set_option), e.g. halo_overlap=0; the defaults are the product path")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
     else:
+        if args.option:
+            from scatter_b200 import _lib
+            for kv in args.option:
+                k, v = kv.split("=")
+                _lib.DEFAULT_OPTIONS[k] = int(v)
         run_ours(args)
 
 

@@ -40,9 +40,8 @@ def box_arrays(nx: int, ny: int, nz: int, h: float = 0.5, element_type: str = "h
     ek, ej, ei = (a.ravel() for a in np.meshgrid(np.arange(nzl), np.arange(ny), np.arange(nx), indexing="ij"))
     ne = nx * ny * nzl
     first = (ek * NY + ej) * NX + ei
-    corner = np.empty((ne, 8), dtype=np.int64)
-    for a, (di, dj, dk) in enumerate(_CORNER_OFF):
-        corner[:, a] = first + ((dk * NY + dj) * NX + di)
+    off8 = np.array([(dk * NY + dj) * NX + di for di, dj, dk in _CORNER_OFF], dtype=np.int64)
+    corner = first[:, None] + off8[None, :]              # one contiguous pass (column-wise fills are strided)
     if element_type == "hexa8":
         nodes = np.empty((n_corner, 4))
         nodes[:, 0] = np.arange(1, n_corner + 1)

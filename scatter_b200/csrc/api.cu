@@ -186,7 +186,11 @@ int sc_set_option(sc_ctx* ctx, const char* name, int64_t value) {
         if (value < 0 || value > 32) return sc_fail(ctx, SC_ERR_ARG, "pcg_projection must lie in [0, 32]");
         ctx->proj_k = (int)value; precond_drop(ctx);
     }
-    else if (k == "halo_overlap") { ctx->no_overlap = !on; ctx->ov_planned = false; }   // interior tiles step beside the halo exchange (default on)
+    else if (k == "halo_spare_sms") {
+        if (value < 0 || value > 64) return sc_fail(ctx, SC_ERR_ARG, "halo_spare_sms must lie in [0, 64]");
+        ctx->ov_spare_sms = (int)value;
+    }
+    else if (k == "halo_overlap") { ctx->no_overlap = !on; ctx->ov_planned = false; }   // interior tiles step beside the halo exchange (default off: measured, no gain -- DESIGN.md 3.5)
     else if (k == "generic_assembly") ctx->force_generic_assembly = on;   // warp-per-node assembly for every element type (default off)
     else return sc_fail(ctx, SC_ERR_ARG, "unknown option '%s'", name);
     pcg_graph_drop(ctx);

@@ -150,10 +150,11 @@ struct sc_ctx {
     bool no_small_pcg = false;             // sc_set_option("small_pcg", 0): never use the cooperative single-kernel PCG
     int small_pcg_grid = 0;                // co-resident grid limit of k_pcg_small (0: not queried yet)
     bool no_graph = false;                 // sc_set_option("pcg_graph", 0): launch the PCG iteration kernel by kernel
-    cudaGraphExec_t pcg_graph = nullptr;   // captured PCG iteration (single-GPU), valid for the pointers in pcg_graph_key
-    const void* pcg_graph_key[8] = {};
-    int64_t pcg_graph_n = 0;
-    int pcg_graph_launches = 0;
+    // captured PCG iterations (single-GPU), each valid for the pointers in its key; two slots, because Bathe alternates
+    // between two effective matrices / preconditioners every step
+    struct PcgGraph { cudaGraphExec_t exec = nullptr; const void* key[8] = {}; int64_t n = 0; int launches = 0; uint64_t used = 0; };
+    PcgGraph pcg_graphs[2];
+    uint64_t pcg_graph_clock = 0;
     bool force_generic_assembly = false;   // sc_set_option("generic_assembly", 1): warp-per-node kernel for every element type
     bool nm_resume_valid = false;   // d_a holds the Newmark acceleration of step nm_resume_t (stage continuation)
     int64_t nm_resume_t = 0;
@@ -166,8 +167,9 @@ struct sc_ctx {
     // multi-GPU
     // halo overlap of the explicit step (spmv_node.cu: la_node_overlap_plan): tiles [ov_tile_lo, ov_tile_hi) = rows
     // [ov_row_lo, ov_row_hi) neither send nor read halo values; they run while the exchange of the other tiles is in flight
-    bool ov_planned = false, ov_ok = false, no_overlap = false;   // sc_set_option("halo_overlap", 0) keeps step and exchange serial
+    bool ov_planned = false, ov_ok = false, no_overlap = true;    // sc_set_option("halo_overlap", 1) enables it (default: serial)
     int64_t ov_tile_lo = 0, ov_tile_hi = 0, ov_row_lo = 0, ov_row_hi = 0;
+    int ov_spare_sms = 4;           // SMs the interior launch leaves to NCCL (sc_set_option("halo_spare_sms", k))
     cudaStream_t comm_stream = nullptr;
     cudaEvent_t ev_bnd = nullptr, ev_halo = nullptr;
     int rank = 0, world = 1;

@@ -315,6 +315,9 @@ int launch_node(sc_ctx* ctx, const NodeCfg& c, const double* va, const double* x
     const size_t bytes = c.bytes + (size_t)ctx->n_dict * ctx->dict_stride * sizeof(int32_t);
     SC_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
     unsigned grid = (unsigned)std::min<int64_t>(n_tiles, (int64_t)ctx->sm_count * (NG == 1 ? 2 : 1));
+    // the interior launch of the halo overlap leaves a few SMs to the NCCL send / receive kernels: a persistent CTA per SM
+    // with ~200 KB of shared memory would otherwise keep them waiting until the step is over
+    if (part == 2 && NG == 2 && grid > 16u) grid -= (unsigned)ctx->ov_spare_sms;
     if (grid == 0) grid = 1;
     if (nblocks_out) *nblocks_out = grid;
     kern<<<grid, 32 * (NG * NB_WARPS + 1), bytes, ctx->stream>>>(ctx->d_nd, ctx->d_ncol, va, xa, y, inv_d, alpha, partial, ctx->n_nodes,

@@ -308,8 +308,10 @@ __global__ void k_flag_nonfinite(const double* __restrict__ u, int64_t n, double
 }  // namespace
 
 void pcg_graph_drop(sc_ctx* ctx) {
-    if (ctx->pcg_graph) cudaGraphExecDestroy(ctx->pcg_graph);
-    ctx->pcg_graph = nullptr;
+    for (auto& g : ctx->pcg_graphs) {
+        if (g.exec) cudaGraphExecDestroy(g.exec);
+        g.exec = nullptr;
+    }
 }
 
 namespace {
@@ -375,12 +377,17 @@ int pcg(sc_ctx* ctx, const double* vals, const double* dinv, const double* b, do
         return SC_OK;
     };
     const bool use_graph = ctx->world == 1 && !ctx->no_graph;
+    sc_ctx::PcgGraph* gr = nullptr;
     if (use_graph) {
         const void* key[8] = {vals, F ? (const void*)F->cv : (const void*)dinv, x, r, p, q, ctx->d_nd, ctx->d_partial};
-        bool same = ctx->pcg_graph != nullptr && ctx->pcg_graph_n == n;
-        for (int k = 0; k < 8 && same; ++k) same = ctx->pcg_graph_key[k] == key[k];
-        if (!same) {
-            pcg_graph_drop(ctx);
+        for (auto& g : ctx->pcg_graphs) {
+            bool same = g.exec != nullptr && g.n == n;
+            for (int k = 0; k < 8 && same; ++k) same = g.key[k] == key[k];
+            if (same) gr = &g;
+        }
+        if (!gr) {
+            gr = ctx->pcg_graphs[0].used <= ctx->pcg_graphs[1].used ? &ctx->pcg_graphs[0] : &ctx->pcg_graphs[1];   // least recently used
+            if (gr->exec) { cudaGraphExecDestroy(gr->exec); gr->exec = nullptr; }
             const int64_t l0 = ctx->launches;
             cudaGraph_t graph = nullptr;
             SC_CUDA(ctx, cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
@@ -388,14 +395,15 @@ int pcg(sc_ctx* ctx, const double* vals, const double* dinv, const double* b, do
             const cudaError_t ce = cudaStreamEndCapture(st, &graph);
             if (rc != SC_OK) { if (graph) cudaGraphDestroy(graph); return rc; }
             SC_CUDA(ctx, ce);
-            const cudaError_t ie = cudaGraphInstantiate(&ctx->pcg_graph, graph, 0);
+            const cudaError_t ie = cudaGraphInstantiate(&gr->exec, graph, 0);
             cudaGraphDestroy(graph);
             SC_CUDA(ctx, ie);
-            ctx->pcg_graph_launches = (int)(ctx->launches - l0);
+            gr->launches = (int)(ctx->launches - l0);
             ctx->launches = l0;
-            ctx->pcg_graph_n = n;
-            for (int k = 0; k < 8; ++k) ctx->pcg_graph_key[k] = key[k];
+            gr->n = n;
+            for (int k = 0; k < 8; ++k) gr->key[k] = key[k];
         }
+        gr->used = ++ctx->pcg_graph_clock;
     }
     // The stopping test needs a stream synchronisation.  Small systems (graph replay): every fourth iteration, the up to
     // three extra iterations only tighten the solution (alpha, beta are guarded against r = 0).  Otherwise the next test is
@@ -408,8 +416,8 @@ int pcg(sc_ctx* ctx, const double* vals, const double* dinv, const double* b, do
     int best_it = 0;
     for (int it = 1; it <= maxit; ++it) {
         if (use_graph) {
-            SC_CUDA(ctx, cudaGraphLaunch(ctx->pcg_graph, st));
-            ctx->launches += ctx->pcg_graph_launches;
+            SC_CUDA(ctx, cudaGraphLaunch(gr->exec, st));
+            ctx->launches += gr->launches;
         } else {
             SC_TRY(iteration());
         }

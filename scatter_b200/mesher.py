@@ -174,7 +174,10 @@ class ReadMesh:
                 p1, p2, p3 = (np.array(p, dtype=float) for p in pts[:3])
                 cp = np.cross(p3 - p1, p2 - p1)
                 direction = np.abs(cp / np.linalg.norm(cp))
-                residual = xyz[:, 0] * cp[0] + xyz[:, 1] * cp[1] + xyz[:, 2] * cp[2] - np.dot(cp, p3)
+                residual = np.full(nn, -np.dot(cp, p3))     # plane equation; axis-aligned planes touch one coordinate only
+                for k in range(3):
+                    if cp[k] != 0.0:
+                        residual += xyz[:, k] * cp[k]
             elif dim == 2:
                 p1, p2 = np.array(pts[0], dtype=float), np.array(pts[1], dtype=float)
                 vector = p2 - p1
@@ -183,7 +186,8 @@ class ReadMesh:
                             - np.linalg.norm(p1 - p2))
             else:
                 sys.exit(f"ERROR: dimension: {dim}, is  not supported")
-            idx = np.where(np.isclose(residual, 0.0, atol=1.0e-5))[0]
+            np.abs(residual, out=residual)
+            idx = np.flatnonzero(residual <= 1.0e-5)       # == np.isclose(residual, 0.0, atol=1e-5), without its temporaries
             for j, val in enumerate(typ):
                 if j >= dim:
                     break
