@@ -910,6 +910,18 @@ def run_secondary_newmark(args, local_rank):
     it_bytes = nnz * 8 + idx_bytes + fsai_bytes + n * 8 * (16 if pre["fsai_nnz"] else 14)
     step_bytes = rhs_bytes + its * it_bytes
     sec = st["seconds_device"] / nsteps
+    # second line: the loosest tolerance that still keeps a 12^3 hexa20 history within 1e-8 of the direct solve over 1000
+    # steps (4.3e-9 at 1e-11, 3.2e-8 at 1e-10: profiles/r2_hexa20_rtol_probe_12cube_1000steps.txt); same matrix and factor
+    loose = None
+    if rtol < 1e-11:
+        try:
+            ctx.set_state(None, None)
+            ctx.run_newmark(dt, 0, 2, 1, rtol=1e-11, store=False)
+            _, _, _, stl = ctx.run_newmark(dt, 2, nsteps, 1, rtol=1e-11, store=False)
+            loose = {"pcg_rtol": 1e-11, "ms_per_time_step": 1e3 * stl["seconds_device"] / nsteps,
+                     "dof_timesteps_per_s": n * nsteps / stl["seconds_device"], "pcg_iterations_per_step": stl["pcg_iterations"] / nsteps}
+        except Exception as exc:
+            loose = {"error": repr(exc)}
     peak, _ = measured_peak()
     out = {"workload": f"hexa20 soil box {s}^3 elements, Newmark + PCG (rtol {rtol:g}), dt {dt}", "dof": n, "nnz": nnz,
            "dof_timesteps_per_s": n / sec, "ms_per_time_step": 1e3 * sec, "pcg_iterations_per_step": its, "pcg_rtol": rtol,
@@ -921,7 +933,7 @@ def run_secondary_newmark(args, local_rank):
            "roofline": {"bound": "hbm", "achieved": step_bytes / sec / 1e9, "peak": peak, "unit": "GB/s",
                         "frac": step_bytes / sec / 1e9 / peak, "bytes_per_step": step_bytes},
            "assembly": {"seconds": t_asm, "elements_per_s": ne / t_asm, "pattern_seconds": t_pat, "host_mesh_seconds": t_mesh},
-           "last_residual": st["last_residual"], "parity_check": parity}
+           "last_residual": st["last_residual"], "parity_check": parity, "at_loosest_parity_tolerance": loose}
     ctx.close()
     return out
 

@@ -186,6 +186,7 @@ int sc_set_option(sc_ctx* ctx, const char* name, int64_t value) {
         if (value < 0 || value > 32) return sc_fail(ctx, SC_ERR_ARG, "pcg_projection must lie in [0, 32]");
         ctx->proj_k = (int)value; precond_drop(ctx);
     }
+    else if (k == "peer_halo") { ctx->no_peer_halo = !on; dist_peer_release(ctx); }   // halo values stored straight into the neighbours' HBM (default on; 0: NCCL send / recv)
     else if (k == "halo_spare_sms") {
         if (value < 0 || value > 64) return sc_fail(ctx, SC_ERR_ARG, "halo_spare_sms must lie in [0, 64]");
         ctx->ov_spare_sms = (int)value;
@@ -643,6 +644,7 @@ int sc_set_halo(sc_ctx* ctx, int n_neighbors, const int32_t* neighbor_rank, cons
                 const int64_t* recv_ptr, const int64_t* recv_idx) {
     if (!ctx || !ctx->have_mesh) return sc_fail(ctx, SC_ERR_STATE, "sc_set_mesh must be called first");
     SC_CUDA(ctx, cudaSetDevice(ctx->device));
+    dist_peer_release(ctx);
     ctx->n_nbr_ranks = n_neighbors;
     ctx->ov_planned = ctx->ov_ok = false;
     ctx->nbr_rank.assign(neighbor_rank, neighbor_rank + n_neighbors);

@@ -172,6 +172,16 @@ struct sc_ctx {
     int ov_spare_sms = 4;           // SMs the interior launch leaves to NCCL (sc_set_option("halo_spare_sms", k))
     cudaStream_t comm_stream = nullptr;
     cudaEvent_t ev_bnd = nullptr, ev_halo = nullptr;
+    // peer-memory halo exchange (dist.cu): receive window + flags in this rank's HBM, mapped neighbours' windows / flags
+    bool peer_tried = false, peer_ok = false, no_peer_halo = false;   // sc_set_option("peer_halo", 0): NCCL send / recv instead
+    double* d_peer_win = nullptr;                   // [2][n_recv]
+    unsigned long long* d_peer_flags = nullptr;     // [n_nbr] exchange counters raised by the neighbours, + counter, + time-out mark
+    double** d_peer_win_ptr = nullptr;              // [n_nbr] neighbours' windows
+    unsigned long long** d_peer_flag_ptr = nullptr; // [n_nbr] this rank's flag in every neighbour's flag array
+    int64_t* d_peer_off = nullptr;                  // [2 n_nbr] offset of this rank's values in the neighbour's window; its n_recv
+    int64_t* d_send_ptr = nullptr;                  // [n_nbr + 1]
+    std::vector<void*> peer_maps;                   // IPC mappings to close
+    unsigned long long peer_epoch = 0;
     int rank = 0, world = 1;
     NcclApi* nccl = nullptr;
     void* comm = nullptr;
@@ -310,3 +320,5 @@ int dist_unique_id(void* out);
 int dist_halo(sc_ctx* ctx, double* d_x, cudaStream_t s);      // exchange ghost values of device vector x (in place)
 int dist_allreduce_sum(sc_ctx* ctx, double* d_vals, int n, cudaStream_t s);
 void dist_destroy(sc_ctx* ctx);
+void dist_peer_release(sc_ctx* ctx);                          // drop the peer-memory windows (halo plan changed)
+int dist_peer_check(sc_ctx* ctx);                             // after a stream synchronisation: did a wait on a neighbour time out?

@@ -782,6 +782,7 @@ int tl_newmark(sc_ctx* ctx, double dt, int64_t t0, int64_t n_steps, int64_t oi, 
     timer.stop();
     SC_CUDA(ctx, cudaStreamSynchronize(st));
     SC_TRY(finish_rows(ctx));
+    if (ctx->world > 1) SC_TRY(dist_peer_check(ctx));
     const float ms = timer.ms();
     if (stats) {
         stats->seconds_device = ms * 1e-3;
@@ -955,6 +956,7 @@ int tl_central_difference(sc_ctx* ctx, double dt, int64_t t0, int64_t n_steps, i
     SC_CUDA(ctx, cudaMemcpyAsync(ctx->h_pinned + 9, ctx->d_scal + 9, sizeof(double), cudaMemcpyDeviceToHost, st));
     SC_TRY(finish_rows(ctx));
     SC_CUDA(ctx, cudaStreamSynchronize(st));
+    if (ctx->world > 1) SC_TRY(dist_peer_check(ctx));
     const float ms = timer.ms();
     double halo_ms = 0.0;
     for (int k = 0; k < n_hs; ++k) {

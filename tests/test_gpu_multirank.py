@@ -21,7 +21,7 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, mesh_path, out_dir):
+def _worker(rank, world, port, mesh_path, out_dir, transport):
     import torch
     import torch.distributed as dist
     sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -30,6 +30,8 @@ def _worker(rank, world, port, mesh_path, out_dir):
     torch.cuda.set_device(rank)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     from scatter_b200 import _lib, mesher, partition, system_matrix
+    if transport == "nccl":                    # default: halo values stored straight into the neighbour's HBM (CUDA IPC windows)
+        _lib.DEFAULT_OPTIONS["peer_halo"] = 0
     m = mesher.ReadMesh(mesh_path)
     m.read_gmsh(); m.read_bc(cases.BC_CUBE); m.mapping(); m.connectivities()
     owner = partition.owner_by_slabs(m, world, axis=2)
@@ -85,7 +87,8 @@ def _worker(rank, world, port, mesh_path, out_dir):
     dist.destroy_process_group()
 
 
-def test_two_gpu_time_loops_match_single_domain_oracle(golden_meshes, tmp_path):
+@pytest.mark.parametrize("transport", ["peer_memory", "nccl"])
+def test_two_gpu_time_loops_match_single_domain_oracle(transport, golden_meshes, tmp_path):
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
@@ -93,7 +96,7 @@ def test_two_gpu_time_loops_match_single_domain_oracle(golden_meshes, tmp_path):
     oracle = load_oracle()
     world = 2
     mesh_path = golden_meshes["cube.msh"]
-    mp.spawn(_worker, args=(world, _free_port(), mesh_path, str(tmp_path)), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, _free_port(), mesh_path, str(tmp_path), transport), nprocs=world, join=True)
     from scatter_b200 import mesher
     m = mesher.ReadMesh(mesh_path)
     m.read_gmsh(); m.read_bc(cases.BC_CUBE); m.mapping(); m.connectivities()
