@@ -679,8 +679,8 @@ def run_ours(args):
             rf = {"error": repr(exc)}
 
     info0 = ctx.device_info()
-    secondary = scatter_e2e = config5 = None
-    extra = (rank == 0 and world == 1 and (args.secondary or args.scatter_e2e)) or (world > 1 and args.config5)
+    secondary = scatter_e2e = config5 = newmark_multi = None
+    extra = (rank == 0 and world == 1 and (args.secondary or args.scatter_e2e)) or (world > 1 and (args.config5 or args.nm_size))
     if extra:
         del pool
         ctx.close()
@@ -699,6 +699,11 @@ def run_ours(args):
             config5 = run_config5(args, rank, world, local_rank, dist, barrier, max_over_ranks, sum_over_ranks)
         except Exception as exc:
             config5 = {"error": repr(exc)}
+    if world > 1 and args.nm_size:
+        try:
+            newmark_multi = run_newmark_multi(args, rank, world, local_rank, dist, barrier, max_over_ranks, sum_over_ranks)
+        except Exception as exc:
+            newmark_multi = {"error": repr(exc)}
     if rank == 0:
         info = info0
         sm_max_hz = 1e6 * float(clocks.get("sm_max_mhz") or 1965.0)
@@ -730,7 +735,7 @@ def run_ours(args):
                 "parity_check": parity,
                 "options": dict(a.split("=") for a in args.option) or None,
                 "gpu_launches": int(launches), "clocks": clocks, "device": info["name"], "secondary": secondary,
-                "scatter_e2e": scatter_e2e, "config5": config5}
+                "scatter_e2e": scatter_e2e, "config5": config5, "newmark_weak_scaling": newmark_multi}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -829,6 +834,52 @@ def run_config5(args, rank, world, local_rank, dist, barrier, max_over_ranks, su
             "dof_timesteps_per_s": total_dof * n_st * stage / wall, "ms_per_time_step": 1e3 * wall / (n_st * stage),
             "device_ms_per_time_step": 1e3 * dev / (n_st * stage), "halo_seconds_per_step": halo / stage,
             "assembly_seconds": t_asm, "host_mesh_seconds": t_mesh, "checksum_abs_u": u_norm}
+
+
+def run_newmark_multi(args, rank, world, local_rank, dist, barrier, max_over_ranks, sum_over_ranks):
+    """Implicit path on several GPUs (weak scaling): hexa8 box of --nm-size^3 elements per GPU cut into z-slabs, Newmark + PCG
+    (FSAI built per rank on its own rows, projection, true-residual check; one halo exchange per product, one all-reduce
+    per pair of dots) at rtol 1e-12 -- the tolerance the N-rank parity check of this run uses."""
+    from scatter_b200 import _lib, boxmesh, partition, system_matrix
+    s = args.nm_size
+    dom = partition.slab_partition(s, s, s, rank, world, H, "hexa8")
+    model = dom.model
+    ne = len(model.elem)
+    E = boxmesh.lognormal_young(ne, E_MEAN, E_STD, seed=77 + rank)
+    mx = system_matrix.GenerateMatrix(model.number_eq, 2, device=local_rank)
+    ctx = mx.ctx
+    uid = [_lib.nccl_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(uid, src=0)
+    ctx.dist_init(rank, world, uid[0])
+    ctx.set_mesh("hexa8", model.nodes[:, 1:], model.node_rows(), model.equation_table_int(), model.number_eq, dom.active)
+    ctx.set_materials(E, np.full(ne, NU), np.full(ne, RHO))
+    ctx.build_pattern()
+    ctx.assemble(2, _lib.ASM_K | _lib.ASM_M_FULL)
+    mx.damping_Rayleigh(DAMPING)
+    ctx.set_halo(dom.neighbor_rank, dom.send_ptr, dom.send_idx, dom.recv_ptr, dom.recv_idx)
+    n_owned = int(len(dom.owned_eq))
+    nst, dt = 10, 5e-4
+    total = nst + 8
+    ptr = np.zeros(total + 1, dtype=np.int64); dofs = np.zeros(0, dtype=np.int64); vals = np.zeros(0)
+    if rank == world // 2:
+        d = int(dom.owned_eq[len(dom.owned_eq) // 2])
+        ptr = np.arange(total + 1, dtype=np.int64); dofs = np.full(total, d, dtype=np.int64)
+        vals = -1000.0 * np.minimum(1.0, np.arange(total) / 4.0)
+    ctx.set_load_schedule(ptr, dofs, vals)
+    ctx.set_state(None, None)
+    ctx.run_newmark(dt, 0, 2, 1, rtol=1e-12, store=False)
+    barrier()
+    w0 = time.perf_counter()
+    _, _, _, st = ctx.run_newmark(dt, 2, nst, 1, rtol=1e-12, store=False)
+    barrier()
+    wall = max_over_ranks(time.perf_counter() - w0)
+    total_dof = sum_over_ranks(float(n_owned))
+    pre = ctx.precond_info()
+    ctx.close()
+    return {"workload": f"hexa8 box {s}x{s}x{s * world} elements ({int(total_dof)} DOF) over {world} z-slabs, Newmark + PCG (rtol 1e-12), dt {dt}",
+            "scaling": "weak", "dof_total": total_dof, "dof_timesteps_per_s": total_dof * nst / wall, "ms_per_time_step": 1e3 * wall / nst,
+            "pcg_iterations_per_step": st["pcg_iterations"] / nst, "last_residual": st["last_residual"],
+            "fsai_entries_rank0": pre["fsai_nnz"], "projection_vectors": pre["projection_vectors"]}
 
 
 def run_secondary_newmark(args, local_rank):
@@ -964,6 +1015,7 @@ def main():
     ap.add_argument("--scatter-e2e", type=int, default=1, help="time the whole scatter(...) call at --size (N = 1 only)")
     ap.add_argument("--secondary", type=int, default=1, help="also run the hexa20 Newmark/PCG workload (N = 1 only)")
     ap.add_argument("--config5", type=int, default=1, help="N > 1: also run BASELINE config 5 as named (--total^3 box, fixed size)")
+    ap.add_argument("--nm-size", type=int, default=128, help="N > 1: hexa8 elements per box edge per GPU of the Newmark weak-scaling block (0: skip)")
     ap.add_argument("--total", type=int, default=405, help="box edge of config 5 (405^3 elements = 200.8 M DOF)")
     ap.add_argument("--random-field", type=int, default=1, help="also time the random-field sampler on this rank's elements")
     ap.add_argument("--size20", type=int, default=94, help="hexa20 box edge (elements) of the secondary workload")

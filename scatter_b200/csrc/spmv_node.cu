@@ -157,7 +157,7 @@ k_spmv_node(const NodeDesc* __restrict__ nd, const int32_t* __restrict__ ncol, c
         // instructions per node, per-node arrays that spilled, a butterfly per node).  Lane l of a node takes entries
         // l, l + LPN, ... of each of the node's rows; U entries per lane are in flight together.
         constexpr int LPN = 32 / NB_NPW;                 // lanes per node
-        constexpr int U = NB_NPW == 1 ? 3 : 6;           // entries per lane and pass (96 entries per node and pass)
+        constexpr int U = NB_NPW == 1 ? 4 : 6;           // entries per lane and pass (128 / 96 entries per node and pass)
         const int grp = lane / LPN, l = lane % LPN;
         const int myr = l / (LPN / 4);                   // row of the node this lane owns after the reduction (3 = none)
         const int wl = warp % NB_WARPS;                  // warp inside its consumer group
@@ -192,7 +192,8 @@ k_spmv_node(const NodeDesc* __restrict__ nd, const int32_t* __restrict__ ncol, c
             if (NVEC > 0 && owner) {
                 const double* svec = s_vec + (size_t)stage * NV1 * NB_VT + (d.row0 - (d0.row0 & ~1)) + myr;
                 if (MODE == 2) { e_al = svec[0]; e_id = svec[NB_VT]; e_x = svec[2 * NB_VT]; e_y = svec[3 * NB_VT]; }
-                if (MODE == 3) e_x = svec[0];
+                if (MODE == 3 && L > 0) e_x = svec[0];      // a tile of ghost nodes only loads its descriptors: nothing to read, and
+                                                            // 0 * (stale shared memory) would poison the dot product with a NaN
             }
             double s0 = 0.0, s1 = 0.0, s2 = 0.0;
             for (int kb = 0; kb < maxL; kb += LPN * U) {

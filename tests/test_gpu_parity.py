@@ -484,9 +484,13 @@ def test_newmark_benchmark_set_2_vs_reference_golden(etype, stream_pcg, golden_m
     np.testing.assert_array_almost_equal(num.v[:, 0], H[etype + "__vy"][0::10])
 
 
-def test_newmark_absorbing_and_hexa20_vs_oracle(golden_meshes, oracle):
-    """Cases whose reference goldens are missing blobs: compare with the (pinned) oracle instead."""
-    from scatter_b200 import force_external, solvers
+@pytest.mark.parametrize("stream_pcg", [False, True])
+def test_newmark_absorbing_and_hexa20_vs_oracle(stream_pcg, golden_meshes, oracle, monkeypatch):
+    """Cases whose reference goldens are missing blobs: compare with the (pinned) oracle instead.  stream_pcg: the FSAI +
+    projection driver of large systems on the effective matrix with absorbing dashpots / springs and on hexa20."""
+    from scatter_b200 import _lib, force_external, solvers
+    if stream_pcg:
+        monkeypatch.setitem(_lib.DEFAULT_OPTIONS, "small_pcg", 0)
     for mesh, bc, kind in (("column.msh", cases.BC_COLUMN_ABS, "heaviside"), ("column_high_order.msh", cases.BC_COLUMN, "pulse")):
         load = {"force": [0, -1000, 0], "node": [3, 4, 7, 8], "time": 0.1, "type": kind, "ini_steps": 5}
         sett = cases.settings()
@@ -647,6 +651,37 @@ def test_bathe_and_static_vs_oracle(stream_pcg, golden_meshes, oracle, monkeypat
             num.update(0)
             num.calculate(None, None, None, F.force_vector, 0, len(tt) - 1)
             assert rel_l2(num.u, ref[0]) <= TOL_HIST and rel_l2(num.v, ref[1]) <= TOL_HIST and rel_l2(num.a, ref[2]) <= 1e-7
+
+
+def test_thin_slab_with_tiles_of_ghost_nodes(monkeypatch):
+    """Rank 1 of an 8-slab partition of a 24^3 box, run alone: three owned element layers between two ghost planes, so whole
+    tiles of the node-blocked SpMV hold ghost nodes only (their stage carries descriptors and nothing else).  Regression:
+    the PCG product read its dot-product operand from the unloaded stage and 0 * stale shared memory turned the solve into
+    NaN (first seen in the 8-GPU parity check of bench.py).  The row-wise kernels are the reference."""
+    from scatter_b200 import _lib, partition, system_matrix
+    hist = {}
+    for name, opts in (("node", {}), ("rowwise", {"node_spmv": 0, "tma_spmv": 0})):
+        monkeypatch.setitem(_lib.DEFAULT_OPTIONS, "small_pcg", 0)
+        for k, v in opts.items():
+            monkeypatch.setitem(_lib.DEFAULT_OPTIONS, k, v)
+        dom = partition.slab_partition(24, 24, 3, 1, 8, 0.5, "hexa8")
+        model = dom.model
+        ne = len(model.elem)
+        mx = system_matrix.GenerateMatrix(model.number_eq, 2)
+        ctx = mx.ctx
+        ctx.set_mesh("hexa8", model.nodes[:, 1:], model.node_rows(), model.equation_table_int(), model.number_eq, dom.active)
+        ctx.set_materials(np.full(ne, 30e6), np.full(ne, 0.2), np.full(ne, 1500.0))
+        ctx.build_pattern(); ctx.assemble(2, _lib.ASM_K | _lib.ASM_M_FULL)
+        mx.damping_Rayleigh([1, 0.01, 30, 0.01])
+        nt = 12
+        d = int(dom.owned_eq[len(dom.owned_eq) // 2])
+        ctx.set_load_schedule(np.arange(nt + 1, dtype=np.int64), np.full(nt, d, dtype=np.int64), -1000.0 * np.minimum(1.0, np.arange(nt) / 4.0))
+        ctx.set_state(None, None)
+        u, v, a, st = ctx.run_newmark(5e-4, 0, 10, 5, rtol=1e-13)
+        assert np.isfinite(u).all() and np.abs(u).max() > 0
+        hist[name] = u
+        ctx.close()
+    assert rel_l2(hist["node"], hist["rowwise"]) <= 1e-9
 
 
 def test_hexa20_box_stream_pcg_vs_oracle(oracle, monkeypatch):
