@@ -894,13 +894,13 @@ def run_secondary_newmark(args, local_rank):
         import scipy.sparse as sp
         oracle = _oracle()
         sp_ = 12
-        pm = boxmesh.box_model(sp_, sp_, sp_, H, "hexa20"); pm.connectivities()
+        pm = boxmesh.box_model(sp_, sp_, sp_, H, "hexa20", hexa20_order=args.order20); pm.connectivities()
         pne = len(pm.elem)
         pE = boxmesh.lognormal_young(pne, E_MEAN, E_STD, seed=20)
         Ko, Mo = oracle.assemble_global(oracle.model_from_readmesh(pm), pE, np.full(pne, NU), np.full(pne, RHO), 2)
         c0, c1 = oracle.rayleigh_coefficients(DAMPING)
         pn = pm.number_eq
-        pd = int(pm.eq_nb_dof[boxmesh.top_centre_node(sp_, sp_, sp_) - 1, 1])
+        pd = int(pm.eq_nb_dof[boxmesh.top_centre_node(sp_, sp_, sp_, model=pm, h=H) - 1, 1])
         nst = 20
 
         def force(t):
@@ -927,7 +927,7 @@ def run_secondary_newmark(args, local_rank):
         parity = {"error": repr(exc)}
     s = args.size20
     t0 = time.perf_counter()
-    model = boxmesh.box_model(s, s, s, H, "hexa20")
+    model = boxmesh.box_model(s, s, s, H, "hexa20", hexa20_order=args.order20)
     ne = len(model.elem)
     E = boxmesh.lognormal_young(ne, E_MEAN, E_STD)
     t_mesh = time.perf_counter() - t0
@@ -943,7 +943,7 @@ def run_secondary_newmark(args, local_rank):
     n = model.number_eq
     nsteps = args.steps20
     total = nsteps * 3 + 8
-    d = int(model.eq_nb_dof[boxmesh.top_centre_node(s, s, s) - 1, 1])
+    d = int(model.eq_nb_dof[boxmesh.top_centre_node(s, s, s, model=model, h=H) - 1, 1])
     ramp = np.ones(total); ramp[:5] = np.linspace(0, 1, 5)
     ctx.set_load_schedule(np.arange(total + 1, dtype=np.int64), np.full(total, d, dtype=np.int64), -1000.0 * ramp)
     ctx.set_state(None, None)
@@ -974,7 +974,8 @@ def run_secondary_newmark(args, local_rank):
         except Exception as exc:
             loose = {"error": repr(exc)}
     peak, _ = measured_peak()
-    out = {"workload": f"hexa20 soil box {s}^3 elements, Newmark + PCG (rtol {rtol:g}), dt {dt}", "dof": n, "nnz": nnz,
+    out = {"workload": f"hexa20 soil box {s}^3 elements ({args.order20} node numbering), Newmark + PCG (rtol {rtol:g}), dt {dt}", "dof": n, "nnz": nnz,
+           "node_numbering": args.order20, "column_dictionary_patterns": ps.get("dict_patterns"),
            "dof_timesteps_per_s": n / sec, "ms_per_time_step": 1e3 * sec, "pcg_iterations_per_step": its, "pcg_rtol": rtol,
            "pcg_stagnations": st.get("pcg_stagnations", 0),
            "preconditioner": ({"kind": "FSAI (G^T G, FP32 factor on a filtered lower pattern) + projection onto previous solutions",
@@ -1020,6 +1021,9 @@ def main():
     ap.add_argument("--random-field", type=int, default=1, help="also time the random-field sampler on this rank's elements")
     ap.add_argument("--size20", type=int, default=94, help="hexa20 box edge (elements) of the secondary workload")
     ap.add_argument("--steps20", type=int, default=30)
+    ap.add_argument("--order20", default="interleaved", choices=["interleaved", "grouped"],
+                    help="node numbering of the synthetic hexa20 box: cell by cell (translation invariant, like the hexa8 lattice) or "
+                         "corner lattice followed by the three edge lattices (round 1)")
     ap.add_argument("--rtol20", type=float, default=1e-12, help="PCG tolerance of the hexa20 workload (the product default)")
     ap.add_argument("--option", action="append", default=[], metavar="NAME=VALUE",
                     help="library option for A/B runs (sc_set_option), e.g. halo_overlap=0; the defaults are the product path")

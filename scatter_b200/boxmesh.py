@@ -19,10 +19,14 @@ _HEX20_EDGES = [(0, 1), (0, 3), (0, 4), (1, 2), (1, 5), (2, 3), (2, 6), (3, 7), 
 _CORNER_OFF = np.array([[0, 0, 0], [1, 0, 0], [1, 1, 0], [0, 1, 0], [0, 0, 1], [1, 0, 1], [1, 1, 1], [0, 1, 1]])
 
 
-def box_arrays(nx: int, ny: int, nz: int, h: float = 0.5, element_type: str = "hexa8", z_range=None):
+def box_arrays(nx: int, ny: int, nz: int, h: float = 0.5, element_type: str = "hexa8", z_range=None, hexa20_order: str = "grouped"):
     """-> nodes (Nn,4) [id,x,y,z], elem (Ne,nne) 1-based ids, with ids local to the slab `z_range` = (k0, k1).
 
-    Everything is generated in (k, j, i) C order, which is the id order (x fastest), so no scatter is needed."""
+    Everything is generated in (k, j, i) C order, which is the id order (x fastest), so no scatter is needed.
+    `hexa20_order`: "grouped" numbers the corner lattice first and the x-, y-, z-edge nodes after it (three more lattices with
+    their own strides); "interleaved" numbers cell by cell -- corner, then the x-, y-, z-edge node the cell owns -- which
+    makes the numbering translation invariant in the interior (what the hexa8 lattice is by construction): neighbours
+    stay close in memory and the relative column lists of the node-blocked SpMV repeat (column dictionary)."""
     k0, k1 = (0, nz) if z_range is None else z_range
     nzl = k1 - k0
     NX, NY, NZ = nx + 1, ny + 1, nzl + 1
@@ -74,6 +78,25 @@ def box_arrays(nx: int, ny: int, nz: int, h: float = 0.5, element_type: str = "h
         axis = int(np.nonzero(ob - oa)[0][0])
         lo = np.minimum(oa, ob)
         elem[:, 8 + m] = edge_id(axis, ei + lo[0], ej + lo[1], ek + lo[2])
+    if hexa20_order == "interleaved":
+        # sort key: owner cell (x fastest) * 4 + slot (0 corner, 1..3 edge along x, y, z); the edge lattices are in cell order already
+        key = np.empty(n_total, dtype=np.int64)
+        kk, jj, ii = (a.ravel() for a in np.meshgrid(np.arange(NZ), np.arange(NY), np.arange(NX), indexing="ij"))
+        key[:n_corner] = ((kk * NY + jj) * NX + ii) * 4
+        kk, jj, ii = (a.ravel() for a in np.meshgrid(np.arange(NZ), np.arange(NY), np.arange(nx), indexing="ij"))
+        key[base[0]:base[1]] = ((kk * NY + jj) * NX + ii) * 4 + 1
+        kk, jj, ii = (a.ravel() for a in np.meshgrid(np.arange(NZ), np.arange(ny), np.arange(NX), indexing="ij"))
+        key[base[1]:base[2]] = ((kk * NY + jj) * NX + ii) * 4 + 2
+        kk, jj, ii = (a.ravel() for a in np.meshgrid(np.arange(nzl), np.arange(NY), np.arange(NX), indexing="ij"))
+        key[base[2]:] = ((kk * NY + jj) * NX + ii) * 4 + 3
+        order = np.argsort(key, kind="stable")           # new position -> old row
+        new_of_old = np.empty(n_total, dtype=np.int64)
+        new_of_old[order] = np.arange(n_total)
+        nodes = nodes[order]
+        nodes[:, 0] = np.arange(1, n_total + 1)
+        elem = new_of_old[elem]
+    elif hexa20_order != "grouped":
+        raise ValueError("hexa20_order is 'grouped' or 'interleaved'")
     return nodes, elem + 1
 
 
@@ -88,8 +111,8 @@ def box_boundaries(nx: int, ny: int, nz: int, h: float = 0.5, bottom: str = "111
 
 
 def box_model(nx: int, ny: int, nz: int, h: float = 0.5, element_type: str = "hexa8", bottom: str = "111",
-              z_range=None) -> ReadMesh:
-    nodes, elem = box_arrays(nx, ny, nz, h, element_type, z_range)
+              z_range=None, hexa20_order: str = "grouped") -> ReadMesh:
+    nodes, elem = box_arrays(nx, ny, nz, h, element_type, z_range, hexa20_order)
     m = ReadMesh.from_arrays(nodes, elem, np.ones(len(elem), dtype=np.int64), [[3.0, 1, "solid"]], element_type)
     bc = box_boundaries(nx, ny, nz, h, bottom)
     m.read_bc(bc)
@@ -98,8 +121,13 @@ def box_model(nx: int, ny: int, nz: int, h: float = 0.5, element_type: str = "he
     return m
 
 
-def top_centre_node(nx: int, ny: int, nz: int) -> int:
-    """1-based id of the corner-lattice node at the centre of the free top surface (y = ny*h)."""
+def top_centre_node(nx: int, ny: int, nz: int, model=None, h: float = 0.5) -> int:
+    """1-based id of the corner-lattice node at the centre of the free top surface (y = ny*h).  With a `model` whose node
+    numbering is not the grouped lattice order (hexa20_order="interleaved") the node is located by its coordinates."""
+    if model is not None:
+        target = np.array([(nx // 2) * h, ny * h, (nz // 2) * h])
+        hit = np.flatnonzero(np.abs(model.nodes[:, 1:] - target).max(axis=1) < 1e-9 * max(h, 1.0))
+        return int(model.nodes[hit[0], 0])
     return 1 + nx // 2 + (nx + 1) * (ny + (ny + 1) * (nz // 2))
 
 

@@ -178,6 +178,7 @@ int sc_set_option(sc_ctx* ctx, const char* name, int64_t value) {
     else if (k == "spmv_groups") ctx->force_one_group = value == 1;      // 1: one consumer group per CTA, two CTAs per SM; default 2
     else if (k == "fsai") { ctx->no_fsai = !on; precond_drop(ctx); }   // FSAI preconditioner of the stream-ordered PCG (default on; 0: Jacobi)
     else if (k == "fsai_component_major") { ctx->fsai_no_perm = !on; precond_drop(ctx); }   // factors stored x-, y-, z-equations first (default on)
+    else if (k == "fsai_vertex_first") { ctx->fsai_no_vertex_first = !on; precond_drop(ctx); }   // quadratic meshes: vertex equations precede mid-side ones in the FSAI triangle (default on)
     else if (k == "fsai_tau_permille") {                              // FSAI pattern filter tau in 1/1000 (default 50)
         if (value < 0 || value > 1000) return sc_fail(ctx, SC_ERR_ARG, "fsai_tau_permille must lie in [0, 1000]");
         ctx->fsai_tau = (double)value / 1000.0; precond_drop(ctx);

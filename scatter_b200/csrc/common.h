@@ -121,6 +121,7 @@ struct sc_ctx {
     sc_fsai fsai[2];                // factors of d_Khat / d_Khat2 (or d_K for the static solver)
     bool no_fsai = false;           // sc_set_option("fsai", 0): Jacobi preconditioner
     bool fsai_no_perm = false;      // sc_set_option("fsai_component_major", 0): factors in the context's interleaved numbering
+    bool fsai_no_vertex_first = false;   // sc_set_option("fsai_vertex_first", 0): eliminate in plain equation order (quadratic meshes)
     double fsai_tau = 0.05;         // pattern filter: |a_ij| >= tau sqrt(a_ii a_jj)   (sc_set_option("fsai_tau_permille", ..))
     int proj_k = 16;                // sc_set_option("pcg_projection", k): A-orthonormal basis of up to k previous solutions (0: off)
     int proj_n = 0;                 // vectors currently in the basis

@@ -37,11 +37,23 @@ __device__ __forceinline__ bool fsai_keep(double v, double dinv_i, double dinv_c
     return fabs(v) * sqrt(dinv_i * dinv_c) >= tau;
 }
 
-// entries of row i that pass the filter (strictly lower part, non-ghost columns); the row's own tau is raised until they fit
+// Elimination order of the triangle.  "Lower" means "earlier in the order", and the order lists the vertex equations of a
+// quadratic mesh (class 0) before its mid-side equations (class 1), each class by equation number: for the serendipity
+// elements the vertex block is the badly conditioned one (negative lumped vertex mass), and a mid-side row that sees all
+// its vertex neighbours in its pattern acts like a two-level factorisation -- hexa20 94^3: 104 PCG iterations per step
+// with this order on either node numbering of the box, 250 with plain equation order on the cell-by-cell numbering
+// (gpurun_out/r2_precond9.log).  cls == nullptr (linear elements, caller-supplied CSR): plain equation order.
+__device__ __forceinline__ bool fsai_before(const unsigned char* __restrict__ cls, int j, int64_t i) {
+    if (!cls) return j < i;
+    const unsigned char cj = cls[j], ci = cls[i];
+    return cj < ci || (cj == ci && j < i);
+}
+
+// entries of row i that pass the filter (strictly earlier equations, non-ghost columns); the row's own tau is raised until they fit
 __global__ void __launch_bounds__(32 * FSAI_WARPS)
 k_fsai_count(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col, const double* __restrict__ vals,
-             const double* __restrict__ dinv, double tau0, int64_t n, int64_t* __restrict__ cnt, double* __restrict__ row_tau,
-             int* __restrict__ max_row) {
+             const double* __restrict__ dinv, const unsigned char* __restrict__ cls, double tau0, int64_t n,
+             int64_t* __restrict__ cnt, double* __restrict__ row_tau, int* __restrict__ max_row) {
     const int lane = threadIdx.x & 31;
     const int64_t i = (int64_t)blockIdx.x * FSAI_WARPS + (threadIdx.x >> 5);
     if (i >= n) return;
@@ -57,7 +69,7 @@ k_fsai_count(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col
         c = 0;
         for (int64_t k = k0 + lane; k < k1; k += 32) {
             const int j = col[k];
-            if (j < i && dinv[j] > 0.0 && fsai_keep(vals[k], di, dinv[j], tau)) ++c;
+            if (fsai_before(cls, j, i) && dinv[j] > 0.0 && fsai_keep(vals[k], di, dinv[j], tau)) ++c;
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(FULL, c, o);
@@ -72,8 +84,9 @@ __device__ __forceinline__ int tri(int a, int b) { return a * (a + 1) / 2 + b; }
 // one warp per row: gather A[P,P], Cholesky, back substitution, write the row of G
 __global__ void __launch_bounds__(32 * FSAI_WARPS)
 k_fsai_fill(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col, const double* __restrict__ vals,
-            const double* __restrict__ dinv, int64_t n, const int64_t* __restrict__ g_rowptr,
-            const double* __restrict__ row_tau, int2* __restrict__ g_cv, int* __restrict__ n_fail) {
+            const double* __restrict__ dinv, const unsigned char* __restrict__ cls, int64_t n,
+            const int64_t* __restrict__ g_rowptr, const double* __restrict__ row_tau, int2* __restrict__ g_cv,
+            int* __restrict__ n_fail) {
     __shared__ double sL[FSAI_WARPS][FSAI_TRI];
     __shared__ int sP[FSAI_WARPS][FSAI_CAP];
     __shared__ double sg[FSAI_WARPS][FSAI_CAP];
@@ -97,7 +110,7 @@ k_fsai_fill(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col,
         int j = 0;
         if (k < k1) {
             j = col[k];
-            keep = j < i && dinv[j] > 0.0 && fsai_keep(vals[k], di, dinv[j], tau);
+            keep = fsai_before(cls, j, i) && dinv[j] > 0.0 && fsai_keep(vals[k], di, dinv[j], tau);
         }
         const unsigned bal = __ballot_sync(FULL, keep);
         if (keep) {
@@ -109,19 +122,25 @@ k_fsai_fill(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col,
     if (lane == 0) P[m - 1] = (int)i;
     for (int t = lane; t < m * (m + 1) / 2; t += 32) L[t] = 0.0;
     __syncwarp();
-    // 2. A[P, P], lower part: row P[a] of the CSR is scanned once, every entry looks its column up in P[0..a]
+    // 2. A[P, P], lower part: row P[a] of the CSR is scanned once, every entry looks its column up in P[0..a].  P[0..m-2]
+    //    ascend in equation number; the row's own equation i stands last whatever its number (elimination order above), so
+    //    its CSR row is scanned completely and the entries A[P[a], i] of the other rows are taken from it by symmetry.
     for (int a = 0; a < m; ++a) {
         const int r = P[a];
+        const bool own = a == m - 1;
         const int64_t r0 = rowptr[r], r1 = rowptr[r + 1];
         for (int64_t k = r0 + lane; k < r1; k += 32) {
             const int c = col[k];
-            if (c > r) break;                       // columns ascend: the rest of this lane's entries lie in the upper part
-            int lo = 0, hi = a + 1;
+            if (own) {
+                if (c == r) { L[tri(a, a)] = vals[k]; continue; }
+            } else if (c > r) break;                // columns ascend: the rest of this lane's entries lie in the upper part
+            int lo = 0, hi = own ? a : a + 1;
+            const int top = hi;
             while (lo < hi) {
                 const int mid = (lo + hi) >> 1;
                 if (P[mid] < c) lo = mid + 1; else hi = mid;
             }
-            if (lo <= a && P[lo] == c) L[tri(a, lo)] = vals[k];
+            if (lo < top && P[lo] == c) L[tri(a, lo)] = vals[k];
         }
     }
     __syncwarp();
@@ -164,12 +183,13 @@ k_fsai_fill(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col,
     for (int a = lane; a < m; a += 32) g_cv[g0 + a] = make_int2(P[a], __float_as_int((float)g[a]));
 }
 
-// G^T row j = { (i, g_ij) : i >= j, j in P_i }: walk the upper part of row j of A (structurally symmetric) in column order
-// and look j up in the row of G of every candidate.  FILL = false counts, FILL = true writes.
+// G^T row j = { (i, g_ij) : i = j or j before i, j in P_i }: walk the later part of row j of A (structurally symmetric) in
+// column order and look j up in the row of G of every candidate (ascending columns, then the diagonal).  FILL = false
+// counts, FILL = true writes.
 template <bool FILL>
 __global__ void __launch_bounds__(32 * FSAI_WARPS)
-k_fsai_transpose(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col, int64_t n, const int64_t* __restrict__ g_rowptr,
-                 const int2* __restrict__ g_cv, int64_t* __restrict__ cnt, const int64_t* __restrict__ t_rowptr,
+k_fsai_transpose(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col, const unsigned char* __restrict__ cls, int64_t n,
+                 const int64_t* __restrict__ g_rowptr, const int2* __restrict__ g_cv, int64_t* __restrict__ cnt, const int64_t* __restrict__ t_rowptr,
                  int2* __restrict__ t_cv, int* __restrict__ max_row) {
     const int lane = threadIdx.x & 31;
     const int64_t j = (int64_t)blockIdx.x * FSAI_WARPS + (threadIdx.x >> 5);
@@ -183,8 +203,11 @@ k_fsai_transpose(const int64_t* __restrict__ rowptr, const int32_t* __restrict__
         int i = 0, v = 0;
         if (k < k1) {
             i = col[k];
-            if (i >= j) {
-                int64_t lo = g_rowptr[i], hi = g_rowptr[i + 1];
+            if (i == j) {
+                const int64_t g1 = g_rowptr[i + 1];
+                if (g1 > g_rowptr[i]) { hit = true; v = g_cv[g1 - 1].y; }      // the diagonal stands last in its row
+            } else if (fsai_before(cls, (int)j, i)) {
+                int64_t lo = g_rowptr[i], hi = g_rowptr[i + 1] - 1;            // off-diagonal part, ascending
                 const int64_t end = hi;
                 while (lo < hi) {
                     const int64_t mid = (lo + hi) >> 1;
@@ -462,6 +485,21 @@ __global__ void k_perm_gather(const double* __restrict__ xp, const int32_t* __re
     if (i < n) x[i] = xp[perm[i]];
 }
 
+// elimination class of every equation: 1 for the equations of mid-side nodes (local nodes >= n_vertex of any element)
+__global__ void k_mark_midside(const int32_t* __restrict__ conn, int64_t n_elem, int nne, int n_vertex, unsigned char* __restrict__ node_cls) {
+    const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const int nm = nne - n_vertex;
+    if (t >= n_elem * nm) return;
+    node_cls[conn[(t / nm) * nne + n_vertex + t % nm]] = 1;           // every writer stores the same value
+}
+__global__ void k_cls_of_eq(const int32_t* __restrict__ eq, const unsigned char* __restrict__ node_cls, int64_t n_nodes, int dim,
+                            unsigned char* __restrict__ cls) {
+    const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (t >= n_nodes * dim) return;
+    const int e = eq[t];
+    if (e >= 0) cls[e] = node_cls[t / dim];
+}
+
 // largest number of entries in a tile of rt consecutive rows (ring stage size of k_csr32_tma)
 __global__ void k_tile_max(const int64_t* __restrict__ rowptr, int64_t n, int rt, int* __restrict__ out) {
     int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
@@ -554,6 +592,7 @@ int fsai_build(sc_ctx* ctx, sc_fsai* f, const double* vals) {
     int64_t* cnt = nullptr;
     double* row_tau = nullptr;
     int* n_fail = nullptr;
+    unsigned char *cls = nullptr, *node_cls = nullptr;
     int rc = SC_OK;
     auto body = [&]() -> int {
         SC_TRY(sc_alloc(ctx, &dinv, (size_t)n));
@@ -564,16 +603,29 @@ int fsai_build(sc_ctx* ctx, sc_fsai* f, const double* vals) {
         SC_CUDA(ctx, cudaMemsetAsync(cnt + n, 0, sizeof(int64_t), st));
         SC_TRY(la_extract_diag(ctx, vals, dinv, true));
         const unsigned nb = nblk(n, FSAI_WARPS);
-        k_fsai_count<<<nb, 32 * FSAI_WARPS, 0, st>>>(ctx->d_rowptr, ctx->d_col, vals, dinv, ctx->fsai_tau, n, cnt, row_tau, n_fail + 2);
+        // vertex equations before mid-side equations (fsai_before); linear elements and caller-supplied matrices: one class
+        const int n_vertex = ctx->elem_type == SC_TRI6 ? 3 : ctx->elem_type == SC_QUAD8 ? 4 : ctx->elem_type == SC_TETRA10 ? 4
+                             : ctx->elem_type == SC_HEXA20 ? 8 : 0;
+        if (n_vertex && ctx->d_eq && ctx->d_conn && !ctx->csr_only && !ctx->fsai_no_vertex_first) {
+            SC_TRY(sc_alloc(ctx, &cls, (size_t)n));
+            SC_TRY(sc_alloc(ctx, &node_cls, (size_t)ctx->n_nodes));
+            SC_CUDA(ctx, cudaMemsetAsync(cls, 0, (size_t)n, st));
+            SC_CUDA(ctx, cudaMemsetAsync(node_cls, 0, (size_t)ctx->n_nodes, st));
+            k_mark_midside<<<nblk(ctx->n_elem * (ctx->nne - n_vertex), 256), 256, 0, st>>>(ctx->d_conn, ctx->n_elem, ctx->nne, n_vertex, node_cls);
+            SC_CHECK_LAUNCH(ctx);
+            k_cls_of_eq<<<nblk(ctx->n_nodes * ctx->dim, 256), 256, 0, st>>>(ctx->d_eq, node_cls, ctx->n_nodes, ctx->dim, cls);
+            SC_CHECK_LAUNCH(ctx);
+        }
+        k_fsai_count<<<nb, 32 * FSAI_WARPS, 0, st>>>(ctx->d_rowptr, ctx->d_col, vals, dinv, cls, ctx->fsai_tau, n, cnt, row_tau, n_fail + 2);
         SC_CHECK_LAUNCH(ctx);
         SC_TRY(sc_alloc(ctx, &f->rowptr, (size_t)n + 1));
         SC_TRY(scan_counts(ctx, cnt, f->rowptr, n, &f->nnz));
         SC_TRY(sc_alloc(ctx, &f->cv, (size_t)f->nnz));
-        k_fsai_fill<<<nb, 32 * FSAI_WARPS, 0, st>>>(ctx->d_rowptr, ctx->d_col, vals, dinv, n, f->rowptr, row_tau, f->cv, n_fail);
+        k_fsai_fill<<<nb, 32 * FSAI_WARPS, 0, st>>>(ctx->d_rowptr, ctx->d_col, vals, dinv, cls, n, f->rowptr, row_tau, f->cv, n_fail);
         SC_CHECK_LAUNCH(ctx);
         // transpose (same number of entries)
         SC_CUDA(ctx, cudaMemsetAsync(cnt + n, 0, sizeof(int64_t), st));
-        k_fsai_transpose<false><<<nb, 32 * FSAI_WARPS, 0, st>>>(ctx->d_rowptr, ctx->d_col, n, f->rowptr, f->cv, cnt, nullptr, nullptr, n_fail + 1);
+        k_fsai_transpose<false><<<nb, 32 * FSAI_WARPS, 0, st>>>(ctx->d_rowptr, ctx->d_col, cls, n, f->rowptr, f->cv, cnt, nullptr, nullptr, n_fail + 1);
         SC_CHECK_LAUNCH(ctx);
         SC_TRY(sc_alloc(ctx, &f->t_rowptr, (size_t)n + 1));
         int64_t tn = 0;
@@ -581,7 +633,7 @@ int fsai_build(sc_ctx* ctx, sc_fsai* f, const double* vals) {
         if (tn != f->nnz) return sc_fail(ctx, SC_ERR_STATE, "FSAI transpose found %lld of %lld entries: the CSR pattern is not "
                                          "structurally symmetric", (long long)tn, (long long)f->nnz);
         SC_TRY(sc_alloc(ctx, &f->t_cv, (size_t)f->nnz));
-        k_fsai_transpose<true><<<nb, 32 * FSAI_WARPS, 0, st>>>(ctx->d_rowptr, ctx->d_col, n, f->rowptr, f->cv, nullptr, f->t_rowptr,
+        k_fsai_transpose<true><<<nb, 32 * FSAI_WARPS, 0, st>>>(ctx->d_rowptr, ctx->d_col, cls, n, f->rowptr, f->cv, nullptr, f->t_rowptr,
                                                                f->t_cv, nullptr);
         SC_CHECK_LAUNCH(ctx);
         int h[3] = {0, 0, 0};
@@ -642,7 +694,7 @@ int fsai_build(sc_ctx* ctx, sc_fsai* f, const double* vals) {
     rc = body();
     timer.stop();
     if (rc == SC_OK && cudaStreamSynchronize(st) != cudaSuccess) rc = sc_fail(ctx, SC_ERR_CUDA, "FSAI set-up failed: %s", cudaGetErrorString(cudaGetLastError()));
-    sc_free(&dinv); sc_free(&cnt); sc_free(&row_tau); sc_free(&n_fail);
+    sc_free(&dinv); sc_free(&cnt); sc_free(&row_tau); sc_free(&n_fail); sc_free(&cls); sc_free(&node_cls);
     if (rc != SC_OK) { fsai_free(f); return rc; }
     f->seconds = timer.ms() * 1e-3;
     const double avg = n > 0 ? (double)f->nnz / (double)n : 1.0;

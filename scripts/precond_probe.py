@@ -33,12 +33,12 @@ def setup(model, E, opts):
 if os.environ.get("PARITY", "1") == "1":
     import fem_np as oracle
     sp_, nst = int(os.environ.get("PSIZE", "12")), int(os.environ.get("PSTEPS", "60"))
-    pm = boxmesh.box_model(sp_, sp_, sp_, bench.H, et); pm.connectivities()
+    pm = boxmesh.box_model(sp_, sp_, sp_, bench.H, et, hexa20_order=os.environ.get("ORDER20", "grouped")); pm.connectivities()
     pne, pn = len(pm.elem), pm.number_eq
     pE = boxmesh.lognormal_young(pne, bench.E_MEAN, bench.E_STD, seed=20)
     Ko, Mo = oracle.assemble_global(oracle.model_from_readmesh(pm), pE, np.full(pne, bench.NU), np.full(pne, bench.RHO), 2)
     c0, c1 = oracle.rayleigh_coefficients(bench.DAMPING)
-    pd = int(pm.eq_nb_dof[boxmesh.top_centre_node(sp_, sp_, sp_) - 1, 1])
+    pd = int(pm.eq_nb_dof[boxmesh.top_centre_node(sp_, sp_, sp_, model=pm, h=bench.H) - 1, 1])
 
     def force(t):
         f = np.zeros(pn); f[pd] = -1000.0 * min(1.0, t / 4.0)
@@ -54,13 +54,14 @@ if os.environ.get("PARITY", "1") == "1":
               f"precond {ctx.precond_info()}", flush=True)
         ctx.close()
 
-model = boxmesh.box_model(s, s, s, bench.H, et)
+order20 = os.environ.get("ORDER20", "grouped")
+model = boxmesh.box_model(s, s, s, bench.H, et, hexa20_order=order20)
 ne = len(model.elem)
 E = boxmesh.lognormal_young(ne, bench.E_MEAN, bench.E_STD)
 for v in variants:
     mx, ctx = setup(model, E, v)
     total = nsteps + 12
-    d = int(model.eq_nb_dof[boxmesh.top_centre_node(s, s, s) - 1, 1])
+    d = int(model.eq_nb_dof[boxmesh.top_centre_node(s, s, s, model=model, h=bench.H) - 1, 1])
     ramp = np.ones(total); ramp[:5] = np.linspace(0, 1, 5)
     ctx.set_load_schedule(np.arange(total + 1, dtype=np.int64), np.full(total, d, dtype=np.int64), -1000.0 * ramp)
     ctx.set_state(None, None)
@@ -71,7 +72,8 @@ for v in variants:
     its = st["pcg_iterations"] / nsteps
     print(f"{et} {s}^3 [{v or 'default'}] {model.number_eq} dof: {its:.1f} it/step, {1e3 * st['seconds_device'] / nsteps:.1f} ms/step, "
           f"{1e3 * st['seconds_device'] / max(st['pcg_iterations'], 1):.3f} ms/iteration, first call {t_first:.2f} s "
-          f"(fsai set-up {st0['fsai_setup_seconds']:.3f} s), precond {ctx.precond_info()}, last residual {st['last_residual']:.2e}", flush=True)
+          f"(fsai set-up {st0['fsai_setup_seconds']:.3f} s), precond {ctx.precond_info()}, last residual {st['last_residual']:.2e}, "
+          f"numbering {order20}, dict patterns {ctx.pattern_stats().get('dict_patterns')}", flush=True)
     u = ctx.get_state()[0]
     print("   checksum |u|", float(np.abs(u).sum()), flush=True)
     ctx.close()

@@ -303,6 +303,49 @@ def test_box_mesh_random_field(oracle, tmp_path):
         assert np.abs(mx.ctx.get_values(1) - Mo.data).max() <= TOL_MAT * np.abs(Mo.data).max()
 
 
+def test_mid_size_box_vs_oracle(oracle):
+    """32^3 hexa8 box (105 k dofs) of the benchmark generator: big enough for interior column-dictionary nodes, z-face tiles
+    with explicit lists, several tiles per CTA and both consumer groups of the node-blocked SpMV.  Pattern bit for bit, K and
+    M against the oracle, and a fused central-difference history (lagged stiffness-proportional damping) against the
+    oracle's (a sparse LU of 100 k 3-D equations for the Newmark oracle takes > 10 min: the implicit solver is checked on
+    smaller boxes)."""
+    from scatter_b200 import _lib, boxmesh, system_matrix
+    s, h = 32, 0.5
+    model = boxmesh.box_model(s, s, s, h, "hexa8"); model.connectivities()
+    ne, n = len(model.elem), model.number_eq
+    E = boxmesh.lognormal_young(ne, 30e6, 1e6, seed=11); nu = np.full(ne, 0.2); rho = np.full(ne, 1500.0)
+    Ko, Mo = oracle.assemble_global(oracle.model_from_readmesh(model), E, nu, rho, 2)
+    Ko = sp.csr_matrix(Ko); Mo = sp.csr_matrix(Mo)
+    mx = system_matrix.GenerateMatrix(n, 2)
+    ctx = mx.ctx
+    ctx.set_mesh("hexa8", model.nodes[:, 1:], model.node_rows(), model.equation_table_int(), n, None)
+    ctx.set_materials(E, nu, rho)
+    ctx.build_pattern()
+    ctx.assemble(2, _lib.ASM_K | _lib.ASM_M_FULL | _lib.ASM_M_LUMPED)
+    rowptr, col = ctx.get_pattern()
+    assert np.array_equal(rowptr, Ko.indptr) and np.array_equal(col, Ko.indices)
+    assert np.abs(ctx.get_values(_lib.MAT_K) - Ko.data).max() <= TOL_MAT * np.abs(Ko.data).max()
+    assert np.abs(ctx.get_values(_lib.MAT_M) - Mo.data).max() <= TOL_MAT * np.abs(Mo.data).max()
+    assert ctx.pattern_stats()["dict_patterns"] > 0
+    damping = [1, 0.01, 30, 0.01]
+    mx.damping_Rayleigh(damping)
+    c0, c1 = oracle.rayleigh_coefficients(damping)
+    d = int(model.eq_nb_dof[boxmesh.top_centre_node(s, s, s) - 1, 1])
+    nt = 42
+
+    def force(t):
+        f = np.zeros(n); f[d] = -1000.0 * min(1.0, t / 4.0)
+        return f
+    ctx.set_load_schedule(np.arange(nt + 1, dtype=np.int64), np.full(nt, d, dtype=np.int64), -1000.0 * np.minimum(1.0, np.arange(nt) / 4.0))
+    # explicit: dt at 0.3 of the CFL estimate of the stiffest element
+    dt = 0.3 * h / np.sqrt(E.max() * (1 - 0.2) / ((1 + 0.2) * (1 - 0.4)) / 1500.0)
+    Uc, Vc, _, _ = oracle.central_difference(Mo, Mo * c0 + Ko * c1, Ko, force, np.arange(41) * dt, 10, c1=c1)
+    ctx.set_state(None, None)
+    u, v, _, _ = ctx.run_central_difference(dt, 0, 40, 10)
+    assert rel_l2(u, Uc) <= TOL_HIST and rel_l2(v, Vc) <= TOL_HIST
+    ctx.close()
+
+
 @pytest.mark.parametrize("case", ["cube", "cube_abs", "rose_2D_side", "column_3D_tetra4", "box"])
 def test_column_dictionary_is_bitwise_neutral(case, golden_meshes, monkeypatch, tmp_path):
     """node_dict.cu replaces the explicit column lists of nodes with a frequent relative list by a dictionary id: SpMV, the

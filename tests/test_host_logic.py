@@ -357,6 +357,40 @@ def test_box_generator_matches_file_reader(tmp_path, oracle):
     assert np.array_equal(e1, e2) and np.allclose(n1[:, 3], n2[:, 3] + 1.0) and np.array_equal(n1[:, 1:3], n2[:, 1:3])
 
 
+def test_interleaved_hexa20_numbering_is_the_same_mesh(oracle):
+    """`hexa20_order="interleaved"` only renumbers the nodes: every element keeps its 20 coordinates in gmsh order, the
+    equation count is unchanged, and the interior of the numbering is translation invariant (few distinct relative column
+    lists, small bandwidth) -- what the column dictionary of the node-blocked SpMV needs."""
+    from scatter_b200 import boxmesh
+    s = 8
+    a = boxmesh.box_model(s, s, s, 0.5, "hexa20"); a.connectivities()
+    b = boxmesh.box_model(s, s, s, 0.5, "hexa20", hexa20_order="interleaved"); b.connectivities()
+    assert a.number_eq == b.number_eq and len(a.nodes) == len(b.nodes)
+    assert np.array_equal(b.nodes[:, 0], np.arange(1, len(b.nodes) + 1))
+    assert np.allclose(a.nodes[:, 1:][a.node_rows()], b.nodes[:, 1:][b.node_rows()])
+    ta, tb = boxmesh.top_centre_node(s, s, s), boxmesh.top_centre_node(s, s, s, model=b)
+    assert np.allclose(a.nodes[ta - 1, 1:], b.nodes[tb - 1, 1:])
+    assert boxmesh.top_centre_node(s, s, s, model=a) == ta
+
+    def stats(m):
+        eq_elem = np.nan_to_num(m.eq_nb_dof, nan=-1).astype(int)[np.asarray(m.node_rows())].reshape(len(m.elem), -1)
+        P = oracle.structural_pattern(eq_elem, m.number_eq)
+        bw = int(np.abs(P.indices - np.repeat(np.arange(P.shape[0]), np.diff(P.indptr))).max())
+        pats = {}
+        for row in m.eq_nb_dof:
+            rows = row[~np.isnan(row)].astype(int)
+            if len(rows):
+                key = tuple(P.indices[P.indptr[rows[0]]:P.indptr[rows[0] + 1]] - rows[0])
+                pats[key] = pats.get(key, 0) + 1
+        return bw, sorted(pats.values(), reverse=True)
+    bw_a, top_a = stats(a)
+    bw_b, top_b = stats(b)
+    assert bw_b * 4 < bw_a
+    assert sum(top_b[:4]) > 10 * sum(top_a[:4])          # the four interior node types dominate
+    with pytest.raises(ValueError):
+        boxmesh.box_arrays(2, 2, 2, 0.5, "hexa20", hexa20_order="random")
+
+
 def test_exporter_at_a_million_nodes(tmp_path):
     """the result dictionary, a node-subset pickle and one binary VTK frame of a 10^6-node mesh within a time
     budget (the reference's per-node Python loops, export_results.py:68-103,143-213, take minutes there), with the
