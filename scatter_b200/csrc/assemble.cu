@@ -20,6 +20,7 @@
 #include <algorithm>
 #include <cstdlib>
 #include "common.h"
+#include "tma.h"
 
 #ifndef SC_BLK_UG
 #define SC_BLK_UG 2
@@ -552,6 +553,399 @@ __global__ void __launch_bounds__(TPB, MINB) k_assemble_blk(AsmParams p, int npb
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Record-fed generation (default).  ncu of k_assemble_blk: 35 % of the samples in the index prologue and the element
+// de-duplication, every element's Jacobians evaluated in the ~4.5 blocks that see it, six barrier-separated phases.  Here
+//   1. k_elem_records evaluates every element ONCE: J^-1 and detJ*w per Gauss point plus lambda, mu, rho -> one record of
+//      REC doubles per element in HBM (hexa8, 2x2x2 points: 688 B, written coalesced through shared memory);
+//   2. the distinct elements of every node block and each pair's index into that list are structure, not values: they
+//      are listed once with the pattern (k_blk_desc), first-seen order, no atomics;
+//   3. k_assemble_rec fetches the records of its block with one bulk copy (TMA, cp.async.bulk) per element straight into
+//      shared memory, completion counted on an mbarrier, while the pair lanes load their own indices; the pair lanes
+//      then run all Gauss points without a barrier, reading each point's ten numbers with 16-byte shared loads (the
+//      record stride is = 2 mod 4 doubles, so the eight lanes of a quarter warp never share a bank).
+// The arithmetic per pair and the summation order are those of k_assemble_blk: both kernels give the same bits.
+__host__ __device__ constexpr int rec_point_stride(int dim) { return (dim * dim + 1 + 1) & ~1; }            // J^-1, detJ*w (+ pad): even
+__host__ __device__ constexpr int rec_stride(int dim, int ngp) {                                            // + lambda, mu, rho; = 2 (mod 4)
+    int r = ngp * rec_point_stride(dim) + 3;
+    while (r % 4 != 2) ++r;
+    return r;
+}
+
+template <int NNE, int DIM, int NGP>
+__global__ void __launch_bounds__(128)
+k_elem_records(const double* __restrict__ xyz, const int32_t* __restrict__ conn, const double* __restrict__ E,
+               const double* __restrict__ nu, const double* __restrict__ rho, const double* __restrict__ tabdN,
+               const double* __restrict__ tabw, int64_t n_elem, double* __restrict__ out) {
+    constexpr int DD = DIM * DIM, ND = NNE * DIM;
+    constexpr int ISTP = rec_point_stride(DIM), REC = rec_stride(DIM, NGP);
+    constexpr int EPB = 128 / NGP;                       // elements per block, one thread per (element, Gauss point)
+    __shared__ double s_rec[EPB * REC];
+    __shared__ double sdN[NGP * NNE * DIM];
+    const int tid = threadIdx.x;
+    for (int t = tid; t < NGP * NNE * DIM; t += 128) sdN[t] = tabdN[t];
+    for (int t = tid; t < EPB * REC; t += 128) s_rec[t] = 0.0;
+    __syncthreads();
+    const int el = tid / NGP, g = tid % NGP;
+    const int64_t e0 = (int64_t)blockIdx.x * EPB, e = e0 + el;
+    if (el < EPB && e < n_elem) {
+        double xe[ND];
+#pragma unroll
+        for (int b = 0; b < NNE; ++b) {
+            const int c = conn[e * NNE + b];
+#pragma unroll
+            for (int d = 0; d < DIM; ++d) xe[b * DIM + d] = xyz[(int64_t)c * 3 + d];
+        }
+        double J[DD], inv[DD], det;
+#pragma unroll
+        for (int r = 0; r < DD; ++r) J[r] = 0.0;
+#pragma unroll
+        for (int b = 0; b < NNE; ++b)
+#pragma unroll
+            for (int d = 0; d < DIM; ++d) {
+                const double dn = sdN[(g * NNE + b) * DIM + d];
+#pragma unroll
+                for (int kk = 0; kk < DIM; ++kk) J[d * DIM + kk] += dn * xe[b * DIM + kk];
+            }
+        invert<DIM>(J, inv, det);
+        double* o = s_rec + el * REC + g * ISTP;
+#pragma unroll
+        for (int r = 0; r < DD; ++r) o[r] = inv[r];
+        o[DD] = det * tabw[g];
+        if (g == 0) {
+            const double Ee = E[e], ne = nu[e];
+            double* m = s_rec + el * REC + NGP * ISTP;
+            m[0] = Ee * ne / ((1.0 + ne) * (1.0 - 2.0 * ne));
+            m[1] = Ee / (2.0 * (1.0 + ne));
+            m[2] = rho[e];
+        }
+    }
+    __syncthreads();
+    const int64_t left = n_elem - e0;
+    const int cnt = (int)(left < EPB ? left : EPB) * REC;
+    double* dst = out + e0 * REC;
+    for (int t = tid; t < cnt; t += 128) dst[t] = s_rec[t];
+}
+
+// distinct elements of the pairs of every block of npb consecutive nodes, in the order of their first pair; one thread per pair
+__global__ void k_blk_desc(const int64_t* __restrict__ n2e_ptr, const int32_t* __restrict__ n2e, const int32_t* __restrict__ node_rl,
+                           int64_t n_nodes, int npb, int ppb, int32_t* __restrict__ blk_elem, int32_t* __restrict__ blk_U,
+                           uint8_t* __restrict__ pair_ui, int* __restrict__ umax) {
+    extern __shared__ int s_desc[];
+    int* s_e = s_desc;                                   // [ppb] element of the pair (-1: none / node without rows)
+    int* s_f = s_desc + ppb;                             // [ppb] 1: first pair of its element in the block
+    const int k = threadIdx.x;
+    const int64_t a0 = (int64_t)blockIdx.x * npb, a1 = min(a0 + npb, n_nodes);
+    const int64_t P0 = n2e_ptr[a0];
+    const int npairs = (int)(n2e_ptr[a1] - P0);
+    int e = -1;
+    if (k < npairs) {
+        e = n2e[P0 + k];
+        int64_t a = a0;
+        while (a + 1 < a1 && n2e_ptr[a + 1] - P0 <= k) ++a;
+        if (node_rl[a] <= 0) e = -1;
+    }
+    s_e[k] = e;
+    __syncthreads();
+    int first_at = k;
+    if (e >= 0)
+        for (int j = 0; j < k; ++j)
+            if (s_e[j] == e) { first_at = j; break; }
+    s_f[k] = (e >= 0 && first_at == k) ? 1 : 0;
+    __syncthreads();
+    if (k < npairs) {
+        int u = 255;
+        if (e >= 0) {
+            u = 0;
+            for (int j = 0; j < first_at; ++j) u += s_f[j];
+            if (first_at == k) blk_elem[(int64_t)blockIdx.x * ppb + u] = e;
+        }
+        pair_ui[P0 + k] = (uint8_t)u;
+    }
+    if (k == 0) {
+        int U = 0;
+        for (int j = 0; j < ppb; ++j) U += s_f[j];
+        blk_U[blockIdx.x] = U;
+        atomicMax(umax, U);
+    }
+}
+
+struct RecParams {
+    const double* rec;
+    const int32_t* blk_elem; const int32_t* blk_U; const uint8_t* pair_ui;
+    int ppb, umax;
+};
+
+template <int NNE, int DIM, int NGP, int TPB, int LPP, int MINB>
+__global__ void __launch_bounds__(TPB, MINB) k_assemble_rec(AsmParams p, RecParams rp, int npb) {
+    constexpr int DD = DIM * DIM, ND = NNE * DIM;
+    constexpr int NBB = NNE / LPP;                       // node blocks per lane
+    constexpr int PPB = TPB / LPP;                       // pairs per block
+    constexpr int SST = DIM * ND + 1;                    // stride of one pair's row block in the staging area (odd)
+    constexpr int ISTP = rec_point_stride(DIM), REC = rec_stride(DIM, NGP);
+    constexpr int UGB = SC_BLK_UG;
+    constexpr int EPT = (PPB + 31) / 32;                 // record copies issued per lane of warp 0
+    static_assert(NNE % LPP == 0 && (TPB / 32) % LPP == 0 && PPB <= 255, "unsupported split");
+    extern __shared__ __align__(128) double smem[];
+    double* srec = smem;                                 // [umax][REC]  records of the block's elements   (phase 1)
+    double* stage = smem;                                // [PPB][SST]   row block of every pair           (phase 2)
+    double* stage_m = stage + (size_t)PPB * SST;         // [PPB][NNE]
+    const size_t sz_stage = (size_t)PPB * SST + (size_t)PPB * NNE, sz_rec = (size_t)rp.umax * REC;
+    const size_t region_a = ((sz_stage > sz_rec ? sz_stage : sz_rec) + 1) & ~(size_t)1;
+    double* sdN = smem + region_a;                       // [NGP*NNE*DIM] table copies for lane-dependent rows
+    double* sN = sdN + NGP * NNE * DIM;                  // [NGP*NNE]
+    double* s_mitem = sN + NGP * NNE;                    // [npb*max_nbr]
+    long long* s_rowbase = reinterpret_cast<long long*>(s_mitem + (size_t)npb * p.max_nbr);   // [npb*DIM]
+    uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_rowbase + (size_t)npb * DIM);            // [1]
+    int* s_ptr = reinterpret_cast<int*>(s_bar + 1);      // [npb+1]
+    int* s_nptr = s_ptr + npb + 1;                       // [npb+1]
+    int* s_rl = s_nptr + npb + 1;                        // [npb]
+    unsigned char* s_inv = reinterpret_cast<unsigned char*>(s_rl + npb + (npb & 1) + 2);     // [PPB][max_nbr] (4-byte aligned)
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int k = (warp / LPP) * 32 + lane, half = warp % LPP;
+    const int64_t a0 = (int64_t)blockIdx.x * npb;
+    const int64_t a1 = min(a0 + npb, p.n_nodes);
+    const int nbn = (int)(a1 - a0);
+    const int64_t P0 = p.n2e_ptr[a0];
+    const int64_t nbr0 = p.nbr_ptr[a0];
+    const int npairs = (int)(p.n2e_ptr[a1] - P0);
+    // everything a thread needs from global memory is requested before the first barrier
+    const int U = rp.blk_U[blockIdx.x];
+    int e_copy[EPT];
+#pragma unroll
+    for (int c = 0; c < EPT; ++c) e_copy[c] = (warp == 0 && lane + 32 * c < U) ? rp.blk_elem[(int64_t)blockIdx.x * rp.ppb + lane + 32 * c] : -1;
+    int ui = 255, al = 0;
+    unsigned char pos[NNE];
+    if (k < npairs) {
+        ui = rp.pair_ui[P0 + k];
+        al = p.pair_al[P0 + k];
+        if (half == 0) {
+#pragma unroll
+            for (int b = 0; b < NNE; ++b) pos[b] = p.pair_pos[(P0 + k) * NNE + b];
+        }
+    }
+    for (int t = tid; t <= nbn; t += TPB) {
+        s_ptr[t] = (int)(p.n2e_ptr[a0 + t] - P0);
+        s_nptr[t] = (int)(p.nbr_ptr[a0 + t] - nbr0);
+        if (t < nbn) s_rl[t] = p.node_rl[a0 + t];
+    }
+    for (int t = tid; t < NGP * NNE * DIM; t += TPB) sdN[t] = p.tabdN[t];
+    for (int t = tid; t < NGP * NNE; t += TPB) sN[t] = p.tabN[t];
+    for (int t = tid; t < (PPB * p.max_nbr + 3) / 4; t += TPB) reinterpret_cast<unsigned*>(s_inv)[t] = 0xffffffffu;
+    if (tid == 0) { tma_mbar_init(s_bar, 1); tma_mbar_fence_init(); }
+    long long rb_reg[DIM];
+#pragma unroll
+    for (int c = 0; c < DIM; ++c) {
+        const int t = tid + c * TPB;
+        rb_reg[c] = -1;
+        if (t < nbn * DIM) {
+            const int rr = p.eq[a0 * DIM + t];
+            if (rr >= 0 && p.node_rl[a0 + t / DIM] > 0) rb_reg[c] = (long long)p.rowptr[rr];
+        }
+    }
+    __syncthreads();
+    if (warp == 0) {                                     // the block's records: one bulk copy per element
+        if (lane == 0) tma_mbar_expect_tx(s_bar, (uint32_t)(U * REC * sizeof(double)));
+        __syncwarp();
+#pragma unroll
+        for (int c = 0; c < EPT; ++c)
+            if (e_copy[c] >= 0) tma_bulk_load(srec + (size_t)(lane + 32 * c) * REC, rp.rec + (int64_t)e_copy[c] * REC, (uint32_t)(REC * sizeof(double)), s_bar);
+    }
+#pragma unroll
+    for (int c = 0; c < DIM; ++c)
+        if (tid + c * TPB < nbn * DIM) s_rowbase[tid + c * TPB] = rb_reg[c];
+    const int n_items = s_nptr[nbn];
+    const bool valid = ui != 255;
+    if (valid && half == 0) {
+#pragma unroll
+        for (int b = 0; b < NNE; ++b) s_inv[k * p.max_nbr + pos[b]] = (unsigned char)b;
+    }
+
+    // ---- phase 1: gradient products of every pair over all Gauss points --------------------------------------------
+    double acc[DIM][NBB * DIM];
+    double mab[NBB];
+#pragma unroll
+    for (int i = 0; i < DIM; ++i)
+#pragma unroll
+        for (int c = 0; c < NBB * DIM; ++c) acc[i][c] = 0.0;
+#pragma unroll
+    for (int b = 0; b < NBB; ++b) mab[b] = 0.0;
+    tma_mbar_wait(s_bar, 0);
+    double lam = 0.0, mu = 0.0, rho = 0.0;
+    if (valid) {
+        const double* sr = srec + (size_t)ui * REC;
+#pragma unroll UGB
+        for (int g = 0; g < NGP; ++g) {
+            const double2* si2 = reinterpret_cast<const double2*>(sr + g * ISTP);
+            double rv[ISTP];
+#pragma unroll
+            for (int r = 0; r < ISTP / 2; ++r) { const double2 v = si2[r]; rv[2 * r] = v.x; rv[2 * r + 1] = v.y; }
+            const double wj = rv[DD];
+            double wga[DIM];
+#pragma unroll
+            for (int kk = 0; kk < DIM; ++kk) {
+                double s = 0.0;
+#pragma unroll
+                for (int d = 0; d < DIM; ++d) s += sdN[(g * NNE + al) * DIM + d] * rv[kk * DIM + d];
+                wga[kk] = wj * s;
+            }
+            const double wna = wj * sN[g * NNE + al];
+#pragma unroll
+            for (int bb = 0; bb < NBB; ++bb) {
+                const double* dnb = c_tabdN + (g * NNE + half * NBB + bb) * DIM;
+                double gb[DIM];
+#pragma unroll
+                for (int kk = 0; kk < DIM; ++kk) {
+                    double s = 0.0;
+#pragma unroll
+                    for (int d = 0; d < DIM; ++d) s += dnb[d] * rv[kk * DIM + d];
+                    gb[kk] = s;
+                }
+#pragma unroll
+                for (int i = 0; i < DIM; ++i)
+#pragma unroll
+                    for (int j = 0; j < DIM; ++j) acc[i][bb * DIM + j] += wga[i] * gb[j];
+                mab[bb] += wna * c_tabN[g * NNE + half * NBB + bb];
+            }
+        }
+        lam = sr[NGP * ISTP + 0]; mu = sr[NGP * ISTP + 1]; rho = sr[NGP * ISTP + 2];
+    }
+    __syncthreads();                                     // the records are dead: region A becomes the staging area
+    if (valid) {
+#pragma unroll
+        for (int bb = 0; bb < NBB; ++bb) {
+            double tr = 0.0;
+#pragma unroll
+            for (int d = 0; d < DIM; ++d) tr += acc[d][bb * DIM + d];
+            tr *= mu;
+#pragma unroll
+            for (int i = 0; i < DIM; ++i)
+#pragma unroll
+                for (int j = 0; j < DIM; ++j) {
+                    double t = lam * acc[i][bb * DIM + j] + mu * acc[j][bb * DIM + i];
+                    if (i == j) t += tr;
+                    stage[(size_t)k * SST + i * ND + (half * NBB + bb) * DIM + j] = t;
+                }
+            stage_m[k * NNE + half * NBB + bb] = rho * mab[bb];
+        }
+    }
+    __syncthreads();
+
+    // ---- phase 2: one thread per (node, neighbour) item adds the staged contributions of the node's elements in
+    //      ascending element id (the reference's summation order) ------------------------------------------------------
+    for (int q = tid; q < n_items; q += TPB) {
+        int lo = 0, hi = nbn;
+        while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if (s_nptr[mid] <= q) lo = mid; else hi = mid;
+        }
+        const int n = lo, pidx = q - s_nptr[n];
+        const int off = p.nbr_off[nbr0 + q];
+        const int fmask = p.nbr_free[nbr0 + q];
+        double blk[DIM][DIM];
+#pragma unroll
+        for (int i = 0; i < DIM; ++i)
+#pragma unroll
+            for (int j = 0; j < DIM; ++j) blk[i][j] = 0.0;
+        double m = 0.0;
+        const int pr1 = s_ptr[n + 1];
+        if (s_rl[n] > 0)
+        for (int pr0 = s_ptr[n]; pr0 < pr1; pr0 += 8) {
+            int bs[8];
+#pragma unroll
+            for (int c = 0; c < 8; ++c) bs[c] = (pr0 + c < pr1) ? s_inv[(pr0 + c) * p.max_nbr + pidx] : 0xff;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                const int b = bs[c];
+                if (b == 0xff) continue;
+                const double* sp = stage + (size_t)(pr0 + c) * SST + b * DIM;
+#pragma unroll
+                for (int i = 0; i < DIM; ++i)
+#pragma unroll
+                    for (int j = 0; j < DIM; ++j) blk[i][j] += sp[i * ND + j];
+                m += stage_m[(pr0 + c) * NNE + b];
+            }
+        }
+        s_mitem[q] = m;
+#pragma unroll
+        for (int i = 0; i < DIM; ++i) {
+            const long long rb = s_rowbase[n * DIM + i];
+            if (rb < 0) continue;
+            int64_t o = rb + off;
+#pragma unroll
+            for (int j = 0; j < DIM; ++j) {
+                if (!(fmask & (1 << j))) continue;
+                if (p.K) p.K[o] = blk[i][j];
+                if (p.M) p.M[o] = (i == j) ? m : 0.0;
+                ++o;
+            }
+        }
+    }
+    if (p.Ml) {
+        __syncthreads();
+        for (int t = tid; t < nbn * DIM; t += TPB) {
+            const int n = t / DIM, i = t % DIM;
+            if (s_rowbase[t] < 0) continue;
+            double s = 0.0;
+            for (int q = s_nptr[n]; q < s_nptr[n + 1]; ++q)
+                if (p.nbr_free[nbr0 + q] & (1 << i)) s += s_mitem[q];
+            p.Ml[p.eq[(a0 + n) * DIM + i]] = s;
+        }
+    }
+}
+
+// records + record-fed kernel; *handled stays false when the path does not apply (no descriptors, not enough memory for
+// the records or the shared-memory image): the caller falls back to k_assemble_blk
+template <int NNE, int DIM, int NGP, int TPB, int LPP, int MINB>
+int launch_rec_cfg(sc_ctx* ctx, const AsmParams& p, const ShapeTable& t, bool* handled) {
+    constexpr int PPB = TPB / LPP;
+    constexpr int ND = NNE * DIM, SST = DIM * ND + 1;
+    constexpr int REC = rec_stride(DIM, NGP);
+    *handled = false;
+    if (ctx->no_asm_records || !ctx->d_blk_elem || !p.pair_pos || ctx->blk_ppb != PPB || ctx->max_valence <= 0 || ctx->max_valence > PPB ||
+        p.max_nbr > 255)
+        return SC_OK;
+    const int npb = std::max(1, PPB / ctx->max_valence);
+    if (npb != ctx->blk_npb) return SC_OK;
+    const size_t region_a = (std::max((size_t)PPB * SST + (size_t)PPB * NNE, (size_t)ctx->blk_umax * REC) + 1) & ~(size_t)1;
+    const size_t bytes = (region_a + (size_t)NGP * NNE * DIM + (size_t)NGP * NNE + (size_t)npb * p.max_nbr + (size_t)npb * DIM + 1) * sizeof(double) +
+                         (3 * (size_t)(npb + 1) + 4) * sizeof(int) + (size_t)PPB * p.max_nbr + 16;
+    if (bytes > 72 * 1024) return SC_OK;
+    // record scratch: kept by the context between assemblies (allocating and releasing 11 GB costs more than the kernels),
+    // released by asm_release_scratch when a time loop starts or the pattern goes
+    const size_t rec_doubles = (size_t)ctx->n_elem * REC;
+    if (ctx->asm_rec_cap < rec_doubles) {
+        sc_free(&ctx->d_asm_rec); ctx->asm_rec_cap = 0;
+        size_t free_b = 0, total_b = 0;
+        if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess || free_b < rec_doubles * sizeof(double) + (size_t(2) << 30)) return SC_OK;
+        if (cudaMalloc((void**)&ctx->d_asm_rec, rec_doubles * sizeof(double) + 64) != cudaSuccess) { cudaGetLastError(); ctx->d_asm_rec = nullptr; return SC_OK; }
+        ctx->asm_rec_cap = rec_doubles;
+    }
+    double* rec = ctx->d_asm_rec;
+    int rc = SC_OK;
+    auto body = [&]() -> int {
+        SC_CUDA(ctx, cudaMemcpyToSymbolAsync(c_tabN, t.N.data(), t.N.size() * sizeof(double), 0, cudaMemcpyHostToDevice, ctx->stream));
+        SC_CUDA(ctx, cudaMemcpyToSymbolAsync(c_tabdN, t.dN.data(), t.dN.size() * sizeof(double), 0, cudaMemcpyHostToDevice, ctx->stream));
+        constexpr int EPB = 128 / NGP;
+        k_elem_records<NNE, DIM, NGP><<<(unsigned)((ctx->n_elem + EPB - 1) / EPB), 128, 0, ctx->stream>>>(
+            p.xyz, p.conn, p.E, p.nu, p.rho, p.tabdN, p.tabw, ctx->n_elem, rec);
+        SC_CHECK_LAUNCH(ctx);
+        RecParams rp;
+        rp.rec = rec; rp.blk_elem = ctx->d_blk_elem; rp.blk_U = ctx->d_blk_U; rp.pair_ui = ctx->d_pair_ui;
+        rp.ppb = ctx->blk_ppb; rp.umax = ctx->blk_umax;
+        const unsigned grid = (unsigned)((p.n_nodes + npb - 1) / npb);
+        auto kern = k_assemble_rec<NNE, DIM, NGP, TPB, LPP, MINB>;
+        SC_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+        kern<<<grid, TPB, bytes, ctx->stream>>>(p, rp, npb);
+        SC_CHECK_LAUNCH(ctx);
+        return SC_OK;
+    };
+    rc = body();
+    if (rc == SC_OK) *handled = true;
+    return rc;
+}
+
 template <int NNE, int DIM, int NGP, int TPB, int LPP, int MINB>
 int launch_blk_cfg(sc_ctx* ctx, const AsmParams& p, const ShapeTable& t, bool* handled) {
     constexpr int PPB = TPB / LPP;
@@ -583,10 +977,16 @@ int launch_blk(sc_ctx* ctx, const AsmParams& p, const ShapeTable& t, bool* handl
     // per set-up task instead of held in registers 7.9 ms
     if constexpr (DIM * NNE * DIM > 72 && NNE % 5 == 0) {
         // tetra10 / hexa20: five lanes per pair (2 / 4 node blocks each), 160-thread blocks of 32 pairs
+        SC_TRY((launch_rec_cfg<NNE, DIM, NGP, 160, 5, 3>(ctx, p, t, handled)));
+        if (*handled) return SC_OK;
         return launch_blk_cfg<NNE, DIM, NGP, 160, 5, 3>(ctx, p, t, handled);
     } else if constexpr (DIM * NNE * DIM > 36 && NNE % 2 == 0) {
+        SC_TRY((launch_rec_cfg<NNE, DIM, NGP, 128, 2, 4>(ctx, p, t, handled)));
+        if (*handled) return SC_OK;
         return launch_blk_cfg<NNE, DIM, NGP, 128, 2, 4>(ctx, p, t, handled);
     } else {
+        SC_TRY((launch_rec_cfg<NNE, DIM, NGP, 128, 1, 2>(ctx, p, t, handled)));
+        if (*handled) return SC_OK;
         return launch_blk_cfg<NNE, DIM, NGP, 128, 1, 2>(ctx, p, t, handled);
     }
 }
@@ -612,6 +1012,43 @@ int launch(sc_ctx* ctx, const AsmParams& p) {
 }
 
 }  // namespace
+
+void asm_release_scratch(sc_ctx* ctx) {
+    sc_free(&ctx->d_asm_rec);
+    ctx->asm_rec_cap = 0;
+}
+
+int asm_build_block_desc(sc_ctx* ctx) {
+    sc_free(&ctx->d_blk_elem); sc_free(&ctx->d_blk_U); sc_free(&ctx->d_pair_ui);
+    ctx->blk_npb = ctx->blk_ppb = ctx->blk_umax = 0;
+    if (!ctx->d_pair_pos || ctx->max_valence <= 0 || ctx->n_nodes <= 0) return SC_OK;
+    int tpb = 0, lpp = 1;
+    asm_blk_shape(ctx->nne, ctx->dim, &tpb, &lpp);
+    const int ppb = tpb / lpp;
+    if (ctx->max_valence > ppb) return SC_OK;
+    const int npb = std::max(1, ppb / ctx->max_valence);
+    const int64_t n_blocks = (ctx->n_nodes + npb - 1) / npb;
+    const int64_t n_pairs = ctx->n_elem * ctx->nne;
+    int* d_umax = nullptr;
+    SC_TRY(sc_alloc(ctx, &ctx->d_blk_elem, (size_t)n_blocks * ppb));
+    SC_TRY(sc_alloc(ctx, &ctx->d_blk_U, (size_t)n_blocks));
+    SC_TRY(sc_alloc(ctx, &ctx->d_pair_ui, (size_t)n_pairs));
+    SC_TRY(sc_alloc(ctx, &d_umax, 1));
+    cudaMemsetAsync(d_umax, 0, sizeof(int), ctx->stream);
+    cudaMemsetAsync(ctx->d_blk_elem, 0xff, (size_t)n_blocks * ppb * sizeof(int32_t), ctx->stream);
+    cudaMemsetAsync(ctx->d_pair_ui, 0xff, (size_t)n_pairs, ctx->stream);
+    k_blk_desc<<<(unsigned)n_blocks, ppb, 2 * ppb * sizeof(int), ctx->stream>>>(ctx->d_n2e_ptr, ctx->d_n2e, ctx->d_node_rl, ctx->n_nodes, npb, ppb,
+                                                                                 ctx->d_blk_elem, ctx->d_blk_U, ctx->d_pair_ui, d_umax);
+    ctx->launches++;
+    int umax = 0;
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaMemcpyAsync(&umax, d_umax, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    sc_free(&d_umax);
+    if (e != cudaSuccess) return sc_fail(ctx, SC_ERR_CUDA, "block descriptors of the assembly failed: %s", cudaGetErrorString(e));
+    ctx->blk_npb = npb; ctx->blk_ppb = ppb; ctx->blk_umax = std::max(umax, 1);
+    return SC_OK;
+}
 
 int sc_assemble_run(sc_ctx* ctx, int order, int flags, double* seconds) {
     ShapeTable t;

@@ -80,6 +80,14 @@ struct sc_ctx {
     int32_t* d_ncol = nullptr;      // [sum node_rl] column list per node
     uint8_t* d_pair_pos = nullptr;  // [n_pairs*nne] position of every element node in the pair's node neighbour list (or null)
     uint8_t* d_pair_al = nullptr;   // [n_pairs] local index of the pair's node in its element
+    // block descriptors of the record-fed assembly kernel (assemble.cu: asm_build_block_desc, built with the pattern)
+    int32_t* d_blk_elem = nullptr;  // [n_blocks][blk_ppb] distinct elements of every block of blk_npb consecutive nodes (first-seen order)
+    int32_t* d_blk_U = nullptr;     // [n_blocks] how many
+    uint8_t* d_pair_ui = nullptr;   // [n_pairs] index of the pair's element in its block's list (255: pair of a node without rows)
+    int blk_npb = 0, blk_ppb = 0, blk_umax = 0;
+    double* d_asm_rec = nullptr;    // [n_elem][REC] element records (scratch of the assembly, see asm_release_scratch)
+    size_t asm_rec_cap = 0;         // doubles allocated
+    bool no_asm_records = false;    // sc_set_option("assembly_records", 0): k_assemble_blk (Jacobian set-up inside every block)
     int64_t ncol_total = 0;
     int32_t* d_dict = nullptr;      // [n_dict*dict_stride] most frequent relative column lists (node_dict.cu); nodes with one of
     int n_dict = 0, dict_stride = 0;   // them carry its id in their descriptor and have no explicit list in d_ncol
@@ -252,6 +260,14 @@ void sc_free(T** p) {
 int sc_pattern_build(sc_ctx* ctx);
 // assemble.cu
 int sc_assemble_run(sc_ctx* ctx, int order, int flags, double* seconds);
+void asm_release_scratch(sc_ctx* ctx);                                  // drop the element-record scratch (time loops, pattern change)
+int asm_build_block_desc(sc_ctx* ctx);                                  // called at the end of sc_pattern_build
+// threads and lanes per (node, element) pair of the block assembly kernels for an element type
+inline void asm_blk_shape(int nne, int dim, int* tpb, int* lpp) {
+    if (dim * nne * dim > 72 && nne % 5 == 0) { *tpb = 160; *lpp = 5; }         // tetra10 / hexa20
+    else if (dim * nne * dim > 36 && nne % 2 == 0) { *tpb = 128; *lpp = 2; }    // hexa8, quad8
+    else { *tpb = 128; *lpp = 1; }
+}
 // linalg.cu
 int sc_work(sc_ctx* ctx, int idx, double** out);                       // work vector idx
 int la_spmv(sc_ctx* ctx, const double* vals, const double* x, double* y);                 // y = A x

@@ -358,6 +358,7 @@ int sc_pattern_build(sc_ctx* ctx) {
                                                   ctx->d_pair_pos, ctx->d_pair_al);
         SC_CHECK_LAUNCH(ctx);
     }
+    SC_TRY(asm_build_block_desc(ctx));
     // ---- node-blocked column lists + descriptors (time-loop kernels, spmv_node.cu) ------------------------------------
     {
         int64_t* d_ncol_ptr = nullptr;

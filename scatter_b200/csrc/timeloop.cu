@@ -689,6 +689,7 @@ int ensure_state(sc_ctx* ctx) {
 
 int tl_newmark(sc_ctx* ctx, double dt, int64_t t0, int64_t n_steps, int64_t oi, double beta, double gamma, double rtol,
                int maxit, int64_t n_out, double* u_out, double* v_out, double* a_out, sc_stats* stats) {
+    asm_release_scratch(ctx);                 // the assembly's element records are not needed while stepping
     auto wall0 = std::chrono::steady_clock::now();
     const int64_t n = ctx->n_eq;
     cudaStream_t st = ctx->stream;
@@ -802,6 +803,7 @@ int tl_newmark(sc_ctx* ctx, double dt, int64_t t0, int64_t n_steps, int64_t oi, 
 
 int tl_central_difference(sc_ctx* ctx, double dt, int64_t t0, int64_t n_steps, int64_t oi, int64_t n_out, double* u_out,
                           double* v_out, double* a_out, sc_stats* stats) {
+    asm_release_scratch(ctx);                 // the assembly's element records are not needed while stepping
     auto wall0 = std::chrono::steady_clock::now();
     const int64_t n = ctx->n_eq;
     cudaStream_t st = ctx->stream;
@@ -1004,6 +1006,7 @@ int tl_central_difference(sc_ctx* ctx, double dt, int64_t t0, int64_t n_steps, i
 // The half-step force is the mean of the two step forces (the load schedule is defined on whole steps).
 int tl_bathe(sc_ctx* ctx, double dt, int64_t t0, int64_t n_steps, int64_t oi, double rtol, int maxit, int64_t n_out, double* u_out,
              double* v_out, double* a_out, sc_stats* stats) {
+    asm_release_scratch(ctx);                 // the assembly's element records are not needed while stepping
     auto wall0 = std::chrono::steady_clock::now();
     const int64_t n = ctx->n_eq;
     cudaStream_t st = ctx->stream;
@@ -1097,6 +1100,7 @@ int tl_bathe(sc_ctx* ctx, double dt, int64_t t0, int64_t n_steps, int64_t oi, do
 
 // Static solver: K u(t) = F(t) for every step, solved incrementally (du = K^-1 (F(t) - K u)) with Jacobi-PCG.
 int tl_static(sc_ctx* ctx, int64_t t0, int64_t n_steps, int64_t oi, double rtol, int maxit, int64_t n_out, double* u_out, sc_stats* stats) {
+    asm_release_scratch(ctx);                 // the assembly's element records are not needed while stepping
     auto wall0 = std::chrono::steady_clock::now();
     const int64_t n = ctx->n_eq;
     cudaStream_t st = ctx->stream;

@@ -259,25 +259,28 @@ def test_assembly_is_bit_reproducible(golden_meshes):
 @pytest.mark.parametrize("case", ["cube", "column_3D_tetra4", "column_2D", "column_2D_tri6", "column_high_order", "column_3D_tetra10",
                                   "rose_2D_side"])
 def test_assembly_kernel_generations_agree(case, golden_meshes, monkeypatch):
-    """k_assemble_blk (default) and the warp-per-node k_assemble sum the same contributions in the same order; they differ
-    only in how a single element contribution is rounded (material law per Gauss point vs once)."""
+    """The record-fed kernel (default: k_elem_records + k_assemble_rec), k_assemble_blk (Jacobian set-up inside every block)
+    and the warp-per-node k_assemble sum the same contributions in the same order.  The first two do the same arithmetic per
+    pair -- identical bits; the third differs in how a single element contribution is rounded (material law per Gauss
+    point vs once)."""
     if case not in cases.MATRIX_CASES:
         pytest.skip("case not in the fixture set")
     fn, bc = cases.MATRIX_CASES[case]
     vals = {}
     from scatter_b200 import _lib
-    for name, opt in (("blk", None), ("generic", "generic_assembly")):
+    for name, opt, value in (("rec", None, None), ("blk", "assembly_records", 0), ("generic", "generic_assembly", 1)):
         if opt:
-            monkeypatch.setitem(_lib.DEFAULT_OPTIONS, opt, 1)
+            monkeypatch.setitem(_lib.DEFAULT_OPTIONS, opt, value)
         _, mx = build(golden_meshes[fn], bc, cases.case_materials(case), cases.settings())
         vals[name] = (mx.ctx.get_values(0), mx.ctx.get_values(1), mx.ctx.get_lumped_mass())
         mx.ctx.close()
         if opt:
             monkeypatch.delitem(_lib.DEFAULT_OPTIONS, opt)
-    for other in ("generic",):
-        for a, b in zip(vals["blk"], vals[other]):
-            assert a.shape == b.shape
-            assert np.abs(a - b).max() <= 1e-13 * np.abs(b).max()
+    for a, b in zip(vals["rec"], vals["blk"]):
+        assert a.shape == b.shape and np.array_equal(a, b)
+    for a, b in zip(vals["rec"], vals["generic"]):
+        assert a.shape == b.shape
+        assert np.abs(a - b).max() <= 1e-13 * np.abs(b).max()
 
 
 def test_box_mesh_random_field(oracle, tmp_path):
