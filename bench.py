@@ -723,8 +723,9 @@ def run_ours(args):
                 "assembly": {"seconds": t_asm, "pattern_seconds": t_pattern, "gbs": asm_bytes / t_asm / 1e9,
                              "frac_hbm": asm_bytes / t_asm / 1e9 / peak, "elements_per_s": ne / t_asm, "algorithmic_bytes": asm_bytes,
                              "host_mesh_seconds": t_mesh, "h2d_seconds": t_h2d,
-                             # the kernel is FP64 bound, not HBM bound: modelled FMA count of
-                             # k_assemble_blk per hexa8 element against 64 FMA/clk/SM at the maximum SM clock
+                             # the kernels are FP64 / issue bound, not HBM bound: modelled FP64 operation count
+                             # of k_elem_records + k_assemble_tma per hexa8 element against 64 FMA/clk/SM at the maximum SM clock
+                             "kernels": "k_elem_records + k_assemble_tma (persistent, TMA-fed)",
                              "fma_per_element": ASM_FMA_PER_HEXA8,
                              "frac_fp64_peak": ne * ASM_FMA_PER_HEXA8 / t_asm / (64.0 * info["sm_count"] * sm_max_hz)},
                 "random_field": rf,
@@ -990,9 +991,10 @@ def run_secondary_newmark(args, local_rank):
     return out
 
 
-# FP64 FMAs k_assemble_blk spends per hexa8 element (order 2): per Gauss point 121 for J, J^-1, detJ evaluated ~4 times per
-# element (once per block that sees it) and 84 in each of the 16 pair lanes
-ASM_FMA_PER_HEXA8 = 8 * (4 * 121 + 16 * 84)
+# FP64 operations the assembly spends per hexa8 element (order 2): per Gauss point 121 for J, J^-1, detJ -- once per element
+# (k_elem_records; k_assemble_blk of round 1 repeated it in each of the ~4 blocks that see the element) -- and 84 in each
+# of the 16 pair lanes of k_assemble_tma, plus the 8 x 8 x 9 ordered additions of the row gather
+ASM_FMA_PER_HEXA8 = 8 * (121 + 16 * 84) + 576
 
 # dram__bytes_read.sum + dram__bytes_write.sum of one fused central-difference launch (k_spmv_node<2,..> with the column
 # dictionary) from the committed ncu capture, by box size

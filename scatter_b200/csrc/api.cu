@@ -44,7 +44,8 @@ void free_pattern(sc_ctx* c) {
     sc_free(&c->d_n2e_ptr); sc_free(&c->d_n2e); sc_free(&c->d_nbr_ptr); sc_free(&c->d_nbr); sc_free(&c->d_nbr_off); sc_free(&c->d_nbr_free);
     sc_free(&c->d_node_rl); sc_free(&c->d_node_row0); sc_free(&c->d_rowptr); sc_free(&c->d_col); sc_free(&c->d_nd); sc_free(&c->d_ncol); sc_free(&c->d_dict); c->n_dict = 0; sc_free(&c->d_pair_pos); sc_free(&c->d_pair_al);
     asm_release_scratch(c);
-    sc_free(&c->d_blk_elem); sc_free(&c->d_blk_U); sc_free(&c->d_pair_ui); c->blk_npb = c->blk_ppb = c->blk_umax = 0;
+    sc_free(&c->d_blk_elem); sc_free(&c->d_blk_U); sc_free(&c->d_pair_ui); sc_free(&c->d_blk_desc);
+    c->blk_npb = c->blk_ppb = c->blk_umax = c->blk_desc_stride = 0;
     sc_free(&c->d_K); sc_free(&c->d_M); sc_free(&c->d_Ml); sc_free(&c->d_Khat); sc_free(&c->d_Khat2); sc_free(&c->d_C); c->csr_only = false;
     sc_free(&c->d_cabs_rowid); sc_free(&c->d_cabs_rptr); sc_free(&c->d_cabs_col); sc_free(&c->d_cabs_slot); sc_free(&c->d_cabs_val);
     c->cabs_n = c->cabs_rows = 0;
@@ -196,6 +197,7 @@ int sc_set_option(sc_ctx* ctx, const char* name, int64_t value) {
     }
     else if (k == "halo_overlap") { ctx->no_overlap = !on; ctx->ov_planned = false; }   // interior tiles step beside the halo exchange (default off: measured, no gain -- DESIGN.md 3.5)
     else if (k == "assembly_records") ctx->no_asm_records = !on;          // element records + TMA-fed row-gather kernel (default on)
+    else if (k == "assembly_persistent") ctx->no_asm_persistent = !on;    // persistent TMA-fed assembly kernel (default on)
     else if (k == "generic_assembly") ctx->force_generic_assembly = on;   // warp-per-node assembly for every element type (default off)
     else return sc_fail(ctx, SC_ERR_ARG, "unknown option '%s'", name);
     pcg_graph_drop(ctx);

@@ -627,7 +627,7 @@ k_elem_records(const double* __restrict__ xyz, const int32_t* __restrict__ conn,
     for (int t = tid; t < cnt; t += 128) dst[t] = s_rec[t];
 }
 
-// distinct elements of the pairs of every block of npb consecutive nodes, in the order of their first pair; one thread per pair
+// distinct elements of the pairs of every block of npb consecutive nodes, ascending; one thread per pair
 __global__ void k_blk_desc(const int64_t* __restrict__ n2e_ptr, const int32_t* __restrict__ n2e, const int32_t* __restrict__ node_rl,
                            int64_t n_nodes, int npb, int ppb, int32_t* __restrict__ blk_elem, int32_t* __restrict__ blk_U,
                            uint8_t* __restrict__ pair_ui, int* __restrict__ umax) {
@@ -647,18 +647,18 @@ __global__ void k_blk_desc(const int64_t* __restrict__ n2e_ptr, const int32_t* _
     }
     s_e[k] = e;
     __syncthreads();
-    int first_at = k;
+    bool first = e >= 0;
     if (e >= 0)
         for (int j = 0; j < k; ++j)
-            if (s_e[j] == e) { first_at = j; break; }
-    s_f[k] = (e >= 0 && first_at == k) ? 1 : 0;
+            if (s_e[j] == e) { first = false; break; }
+    s_f[k] = first ? 1 : 0;
     __syncthreads();
     if (k < npairs) {
         int u = 255;
-        if (e >= 0) {
+        if (e >= 0) {                                    // rank of the element among the block's distinct elements (ascending id)
             u = 0;
-            for (int j = 0; j < first_at; ++j) u += s_f[j];
-            if (first_at == k) blk_elem[(int64_t)blockIdx.x * ppb + u] = e;
+            for (int j = 0; j < ppb; ++j) u += (s_f[j] && s_e[j] < e) ? 1 : 0;
+            if (first) blk_elem[(int64_t)blockIdx.x * ppb + u] = e;
         }
         pair_ui[P0 + k] = (uint8_t)u;
     }
@@ -895,6 +895,380 @@ __global__ void __launch_bounds__(TPB, MINB) k_assemble_rec(AsmParams p, RecPara
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Persistent, fully TMA-fed generation.  ncu of k_assemble_rec (profiles/r2_k_assemble_rec_128cube.txt): the FP64 phases are
+// 25 % of the samples; 17 % sit in the index prologue (two dependent levels of global loads), 16 % wait for the records,
+// 12 % at barriers -- every block pays its whole load latency, and only four blocks per SM overlap.  Here every index a
+// block needs is packed at pattern time into ONE contiguous descriptor (k_blk_pack: pointers, row bases, element list,
+// pair -> element / local node / slot map, item offsets and masks), and a persistent CTA runs its blocks through a
+// pipeline: the descriptor of block i+2 and the records of block i+1 are in flight (bulk copies counted on mbarriers)
+// while block i integrates, stages and gathers.  The compute warps never wait for global memory; their only global
+// accesses are the stores of K / M.  Same arithmetic and summation order as the two kernels above (same bits).
+struct DescLayout {                                      // byte offsets inside one block descriptor
+    int stride;                                          // multiple of 16
+    int o_ptr, o_nptr, o_rl, o_eq, o_runs, o_rowbase, o_off, o_ui, o_al, o_pos, o_fmask;
+};
+inline DescLayout make_desc_layout(int npb, int ppb, int nne, int dim, int max_nbr, int umax) {
+    DescLayout L;
+    int o = 16;                                          // header: npairs, nbn, n_items, U | runs << 16
+    L.o_ptr = o; o += 4 * (npb + 1);
+    L.o_nptr = o; o += 4 * (npb + 1);
+    L.o_rl = o; o += 4 * npb;
+    L.o_eq = o; o += 4 * npb * dim;
+    L.o_runs = o; o += 8 * umax;                         // runs of consecutive element ids: first element, first slot | count << 16
+    o = (o + 7) & ~7;
+    L.o_rowbase = o; o += 8 * npb * dim;
+    L.o_off = o; o += 2 * npb * max_nbr;
+    L.o_ui = o; o += ppb;
+    L.o_al = o; o += ppb;
+    L.o_pos = o; o += ppb * nne;
+    L.o_fmask = o; o += npb * max_nbr;
+    L.stride = (o + 15) & ~15;
+    return L;
+}
+
+__global__ void __launch_bounds__(128)
+k_blk_pack(const int64_t* __restrict__ n2e_ptr, const int64_t* __restrict__ nbr_ptr, const int32_t* __restrict__ node_rl,
+           const int32_t* __restrict__ eq, const int64_t* __restrict__ rowptr, const uint16_t* __restrict__ nbr_off,
+           const uint8_t* __restrict__ nbr_free, const uint8_t* __restrict__ pair_al, const uint8_t* __restrict__ pair_pos,
+           const int32_t* __restrict__ blk_elem, const int32_t* __restrict__ blk_U, const uint8_t* __restrict__ pair_ui,
+           int64_t n_nodes, int npb, int ppb, int nne, int dim, int max_nbr, int umax, DescLayout L, unsigned char* __restrict__ out) {
+    unsigned char* D = out + (size_t)blockIdx.x * L.stride;
+    const int tid = threadIdx.x;
+    const int64_t a0 = (int64_t)blockIdx.x * npb, a1 = min(a0 + npb, n_nodes);
+    const int nbn = (int)(a1 - a0);
+    const int64_t P0 = n2e_ptr[a0], nbr0 = nbr_ptr[a0];
+    const int npairs = (int)(n2e_ptr[a1] - P0), n_items = (int)(nbr_ptr[a1] - nbr0);
+    const int U = blk_U[blockIdx.x];
+    if (tid == 0) {                                      // consecutive element ids are consecutive records: one bulk copy per run
+        int* runs = reinterpret_cast<int*>(D + L.o_runs);
+        const int32_t* el = blk_elem + (int64_t)blockIdx.x * ppb;
+        int nr = 0;
+        for (int t = 0; t < U;) {
+            int c = 1;
+            while (t + c < U && el[t + c] == el[t] + c) ++c;
+            runs[2 * nr] = el[t]; runs[2 * nr + 1] = t | (c << 16);
+            ++nr; t += c;
+        }
+        int* h = reinterpret_cast<int*>(D);
+        h[0] = npairs; h[1] = nbn; h[2] = n_items; h[3] = U | (nr << 16);
+    }
+    for (int t = tid; t <= npb; t += 128) {
+        const int64_t a = min(a0 + t, a1);
+        reinterpret_cast<int*>(D + L.o_ptr)[t] = (int)(n2e_ptr[a] - P0);
+        reinterpret_cast<int*>(D + L.o_nptr)[t] = (int)(nbr_ptr[a] - nbr0);
+        if (t < npb) reinterpret_cast<int*>(D + L.o_rl)[t] = t < nbn ? node_rl[a0 + t] : 0;
+    }
+    for (int t = tid; t < npb * dim; t += 128) {
+        int e = -1;
+        long long rb = -1;
+        if (t < nbn * dim) {
+            e = eq[a0 * dim + t];
+            if (e >= 0 && node_rl[a0 + t / dim] > 0) rb = (long long)rowptr[e];
+        }
+        reinterpret_cast<int*>(D + L.o_eq)[t] = e;
+        reinterpret_cast<long long*>(D + L.o_rowbase)[t] = rb;
+    }
+    for (int t = tid; t < ppb; t += 128) {
+        D[L.o_ui + t] = t < npairs ? pair_ui[P0 + t] : (unsigned char)255;
+        D[L.o_al + t] = t < npairs ? pair_al[P0 + t] : (unsigned char)0;
+    }
+    for (int t = tid; t < ppb * nne; t += 128) D[L.o_pos + t] = t < npairs * nne ? pair_pos[P0 * nne + t] : (unsigned char)0;
+    for (int t = tid; t < npb * max_nbr; t += 128) {
+        reinterpret_cast<uint16_t*>(D + L.o_off)[t] = t < n_items ? nbr_off[nbr0 + t] : (uint16_t)0;
+        D[L.o_fmask + t] = t < n_items ? nbr_free[nbr0 + t] : (unsigned char)0;
+    }
+}
+
+struct TmaSmem { size_t srec, stage, stage_m, sdN, sN, mitem, bars, desc, inv, total; };
+__host__ __device__ inline TmaSmem tma_smem_layout(int rec, int umax, int ppb, int sst, int nne, int dim, int ngp, int npb, int max_nbr, int desc_stride) {
+    TmaSmem m;
+    size_t o = 0;
+    m.srec = o; o += (size_t)umax * rec * 8;
+    m.stage = o; o += (size_t)ppb * sst * 8;
+    m.stage_m = o; o += (size_t)ppb * nne * 8;
+    m.sdN = o; o += (size_t)ngp * nne * dim * 8;
+    m.sN = o; o += (size_t)ngp * nne * 8;
+    m.mitem = o; o += (size_t)npb * max_nbr * 8;
+    m.bars = o; o += 4 * 8;
+    o = (o + 15) & ~(size_t)15;
+    m.desc = o; o += 2 * (size_t)desc_stride;
+    m.inv = o; o += (size_t)ppb * ((max_nbr + 3) & ~3);
+    m.total = (o + 15) & ~(size_t)15;
+    return m;
+}
+
+template <int NNE, int DIM, int NGP, int TPB, int LPP, int MINB>
+__global__ void __launch_bounds__(TPB, MINB)
+k_assemble_tma(AsmParams p, const double* __restrict__ rec, const unsigned char* __restrict__ desc, DescLayout L, int64_t n_blocks,
+               int npb, int umax) {
+    constexpr int DD = DIM * DIM, ND = NNE * DIM;
+    constexpr int NBB = NNE / LPP;
+    constexpr int PPB = TPB / LPP;
+    constexpr int SST = DIM * ND + 1;
+    constexpr int ISTP = rec_point_stride(DIM), REC = rec_stride(DIM, NGP);
+    constexpr int UGB = SC_BLK_UG;
+    static_assert(NNE % LPP == 0 && (TPB / 32) % LPP == 0 && PPB <= 255, "unsupported split");
+    extern __shared__ __align__(128) unsigned char smem_b[];
+    const TmaSmem sm = tma_smem_layout(REC, umax, PPB, SST, NNE, DIM, NGP, npb, p.max_nbr, L.stride);
+    double* srec = reinterpret_cast<double*>(smem_b + sm.srec);
+    double* stage = reinterpret_cast<double*>(smem_b + sm.stage);
+    double* stage_m = reinterpret_cast<double*>(smem_b + sm.stage_m);
+    double* sdN = reinterpret_cast<double*>(smem_b + sm.sdN);
+    double* sN = reinterpret_cast<double*>(smem_b + sm.sN);
+    double* s_mitem = reinterpret_cast<double*>(smem_b + sm.mitem);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_b + sm.bars);      // [0], [1]: descriptor slots, [2]: records
+    unsigned char* sdesc = smem_b + sm.desc;
+    unsigned char* s_inv = smem_b + sm.inv;
+    const int irow = (p.max_nbr + 3) & ~3;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int k = (warp / LPP) * 32 + lane, half = warp % LPP;
+    const int64_t G = gridDim.x;
+    int64_t b = blockIdx.x;
+    if (b >= n_blocks) return;
+    if (tid == 0) {
+        tma_mbar_init(&bars[0], 1); tma_mbar_init(&bars[1], 1); tma_mbar_init(&bars[2], 1);
+        tma_mbar_fence_init();
+    }
+    for (int t = tid; t < NGP * NNE * DIM; t += TPB) sdN[t] = p.tabdN[t];
+    for (int t = tid; t < NGP * NNE; t += TPB) sN[t] = p.tabN[t];
+    __syncthreads();
+    // records of the block whose descriptor sits in `D` (warp 0, after the descriptor arrived)
+    auto issue_records = [&](const unsigned char* D) {
+        const int hu = reinterpret_cast<const int*>(D)[3];
+        const int U = hu & 0xffff, nr = hu >> 16;
+        if (lane == 0) tma_mbar_expect_tx(&bars[2], (uint32_t)(U * REC * sizeof(double)));
+        __syncwarp();
+        const int* runs = reinterpret_cast<const int*>(D + L.o_runs);
+        for (int r = lane; r < nr; r += 32) {
+            const int e0 = runs[2 * r], sc = runs[2 * r + 1];
+            tma_bulk_load(srec + (size_t)(sc & 0xffff) * REC, rec + (int64_t)e0 * REC, (uint32_t)((sc >> 16) * REC * sizeof(double)), &bars[2]);
+        }
+    };
+    if (warp == 0) {
+        if (lane == 0) {
+            tma_mbar_expect_tx(&bars[0], (uint32_t)L.stride);
+            tma_bulk_load(sdesc, desc + (size_t)b * L.stride, (uint32_t)L.stride, &bars[0]);
+            if (b + G < n_blocks) {
+                tma_mbar_expect_tx(&bars[1], (uint32_t)L.stride);
+                tma_bulk_load(sdesc + L.stride, desc + (size_t)(b + G) * L.stride, (uint32_t)L.stride, &bars[1]);
+            }
+        }
+        __syncwarp();
+        tma_mbar_wait(&bars[0], 0);
+        issue_records(sdesc);
+    }
+
+    for (int it = 0; b < n_blocks; b += G, ++it) {
+        const int slot = it & 1;
+        const unsigned char* D = sdesc + (size_t)slot * L.stride;
+        tma_mbar_wait(&bars[slot], (uint32_t)((it >> 1) & 1));
+        const int nbn = reinterpret_cast<const int*>(D)[1], n_items = reinterpret_cast<const int*>(D)[2];
+        const int* s_ptr = reinterpret_cast<const int*>(D + L.o_ptr);
+        const int* s_nptr = reinterpret_cast<const int*>(D + L.o_nptr);
+        const int* s_rl = reinterpret_cast<const int*>(D + L.o_rl);
+        const long long* s_rowbase = reinterpret_cast<const long long*>(D + L.o_rowbase);
+        const int ui = D[L.o_ui + k], al = D[L.o_al + k];
+        const bool valid = ui != 255;
+        if (half == 0) {                                 // this pair's row of the slot -> local node map (only its owner writes it)
+            unsigned* row = reinterpret_cast<unsigned*>(s_inv + (size_t)k * irow);
+            for (int t = 0; t < irow / 4; ++t) row[t] = 0xffffffffu;
+            if (valid) {
+#pragma unroll
+                for (int bb = 0; bb < NNE; ++bb) s_inv[(size_t)k * irow + D[L.o_pos + k * NNE + bb]] = (unsigned char)bb;
+            }
+        }
+        // ---- phase 1: gradient products of every pair over all Gauss points ----------------------------------------
+        double acc[DIM][NBB * DIM];
+        double mab[NBB];
+#pragma unroll
+        for (int i = 0; i < DIM; ++i)
+#pragma unroll
+            for (int c = 0; c < NBB * DIM; ++c) acc[i][c] = 0.0;
+#pragma unroll
+        for (int bb = 0; bb < NBB; ++bb) mab[bb] = 0.0;
+        tma_mbar_wait(&bars[2], (uint32_t)(it & 1));
+        double lam = 0.0, mu = 0.0, rho = 0.0;
+        if (valid) {
+            const double* sr = srec + (size_t)ui * REC;
+#pragma unroll UGB
+            for (int g = 0; g < NGP; ++g) {
+                const double2* si2 = reinterpret_cast<const double2*>(sr + g * ISTP);
+                double rv[ISTP];
+#pragma unroll
+                for (int r = 0; r < ISTP / 2; ++r) { const double2 v = si2[r]; rv[2 * r] = v.x; rv[2 * r + 1] = v.y; }
+                const double wj = rv[DD];
+                double wga[DIM];
+#pragma unroll
+                for (int kk = 0; kk < DIM; ++kk) {
+                    double s = 0.0;
+#pragma unroll
+                    for (int d = 0; d < DIM; ++d) s += sdN[(g * NNE + al) * DIM + d] * rv[kk * DIM + d];
+                    wga[kk] = wj * s;
+                }
+                const double wna = wj * sN[g * NNE + al];
+#pragma unroll
+                for (int bb = 0; bb < NBB; ++bb) {
+                    const double* dnb = c_tabdN + (g * NNE + half * NBB + bb) * DIM;
+                    double gb[DIM];
+#pragma unroll
+                    for (int kk = 0; kk < DIM; ++kk) {
+                        double s = 0.0;
+#pragma unroll
+                        for (int d = 0; d < DIM; ++d) s += dnb[d] * rv[kk * DIM + d];
+                        gb[kk] = s;
+                    }
+#pragma unroll
+                    for (int i = 0; i < DIM; ++i)
+#pragma unroll
+                        for (int j = 0; j < DIM; ++j) acc[i][bb * DIM + j] += wga[i] * gb[j];
+                    mab[bb] += wna * c_tabN[g * NNE + half * NBB + bb];
+                }
+            }
+            lam = sr[NGP * ISTP + 0]; mu = sr[NGP * ISTP + 1]; rho = sr[NGP * ISTP + 2];
+        }
+        __syncthreads();                                 // A: the records are dead -> fetch the next block's
+        if (warp == 0 && b + G < n_blocks) {
+            tma_mbar_wait(&bars[slot ^ 1], (uint32_t)(((it + 1) >> 1) & 1));
+            issue_records(sdesc + (size_t)(slot ^ 1) * L.stride);
+        }
+        if (valid) {
+#pragma unroll
+            for (int bb = 0; bb < NBB; ++bb) {
+                double tr = 0.0;
+#pragma unroll
+                for (int d = 0; d < DIM; ++d) tr += acc[d][bb * DIM + d];
+                tr *= mu;
+#pragma unroll
+                for (int i = 0; i < DIM; ++i)
+#pragma unroll
+                    for (int j = 0; j < DIM; ++j) {
+                        double t = lam * acc[i][bb * DIM + j] + mu * acc[j][bb * DIM + i];
+                        if (i == j) t += tr;
+                        stage[(size_t)k * SST + i * ND + (half * NBB + bb) * DIM + j] = t;
+                    }
+                stage_m[k * NNE + half * NBB + bb] = rho * mab[bb];
+            }
+        }
+        __syncthreads();                                 // B
+        // ---- phase 2: ordered gather, one thread per (node, neighbour) item -----------------------------------------
+        const uint16_t* s_off = reinterpret_cast<const uint16_t*>(D + L.o_off);
+        const unsigned char* s_fm = D + L.o_fmask;
+        for (int q = tid; q < n_items; q += TPB) {
+            int lo = 0, hi = nbn;
+            while (hi - lo > 1) {
+                const int mid = (lo + hi) >> 1;
+                if (s_nptr[mid] <= q) lo = mid; else hi = mid;
+            }
+            const int n = lo, pidx = q - s_nptr[n];
+            const int off = s_off[q];
+            const int fmask = s_fm[q];
+            double blk[DIM][DIM];
+#pragma unroll
+            for (int i = 0; i < DIM; ++i)
+#pragma unroll
+                for (int j = 0; j < DIM; ++j) blk[i][j] = 0.0;
+            double m = 0.0;
+            const int pr1 = s_ptr[n + 1];
+            if (s_rl[n] > 0)
+            for (int pr0 = s_ptr[n]; pr0 < pr1; pr0 += 8) {
+                int bs[8];
+#pragma unroll
+                for (int c = 0; c < 8; ++c) bs[c] = (pr0 + c < pr1) ? s_inv[(size_t)(pr0 + c) * irow + pidx] : 0xff;
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    const int bl = bs[c];
+                    if (bl == 0xff) continue;
+                    const double* sp = stage + (size_t)(pr0 + c) * SST + bl * DIM;
+#pragma unroll
+                    for (int i = 0; i < DIM; ++i)
+#pragma unroll
+                        for (int j = 0; j < DIM; ++j) blk[i][j] += sp[i * ND + j];
+                    m += stage_m[(pr0 + c) * NNE + bl];
+                }
+            }
+            s_mitem[q] = m;
+#pragma unroll
+            for (int i = 0; i < DIM; ++i) {
+                const long long rb = s_rowbase[n * DIM + i];
+                if (rb < 0) continue;
+                int64_t o = rb + off;
+#pragma unroll
+                for (int j = 0; j < DIM; ++j) {
+                    if (!(fmask & (1 << j))) continue;
+                    if (p.K) p.K[o] = blk[i][j];
+                    if (p.M) p.M[o] = (i == j) ? m : 0.0;
+                    ++o;
+                }
+            }
+        }
+        __syncthreads();                                 // C: staging area and slot map are free again
+        if (warp == 0) {
+            // lumped mass = ordered row sums of the items' mass blocks (s_mitem is not written again before barrier B of the
+            // next block); then the descriptor slot is free: fetch the one of the block after the next
+            if (p.Ml) {
+                const int* s_eq = reinterpret_cast<const int*>(D + L.o_eq);
+                for (int t = lane; t < nbn * DIM; t += 32) {
+                    const int n = t / DIM, i = t % DIM;
+                    if (s_rowbase[t] < 0) continue;
+                    double s = 0.0;
+                    for (int q = s_nptr[n]; q < s_nptr[n + 1]; ++q)
+                        if (s_fm[q] & (1 << i)) s += s_mitem[q];
+                    p.Ml[s_eq[t]] = s;
+                }
+            }
+            __syncwarp();
+            if (lane == 0 && b + 2 * G < n_blocks) {
+                tma_mbar_expect_tx(&bars[slot], (uint32_t)L.stride);
+                tma_bulk_load(sdesc + (size_t)slot * L.stride, desc + (size_t)(b + 2 * G) * L.stride, (uint32_t)L.stride, &bars[slot]);
+            }
+        }
+    }
+}
+
+template <int NNE, int DIM, int NGP, int TPB, int LPP, int MINB>
+int launch_tma_cfg(sc_ctx* ctx, const AsmParams& p, const ShapeTable& t, bool* handled) {
+    constexpr int PPB = TPB / LPP;
+    constexpr int ND = NNE * DIM, SST = DIM * ND + 1;
+    constexpr int REC = rec_stride(DIM, NGP);
+    *handled = false;
+    if (ctx->no_asm_records || ctx->no_asm_persistent || !ctx->d_blk_desc || !p.pair_pos || ctx->blk_ppb != PPB || ctx->max_valence <= 0 ||
+        ctx->max_valence > PPB || p.max_nbr > 255)
+        return SC_OK;
+    const int npb = std::max(1, PPB / ctx->max_valence);
+    if (npb != ctx->blk_npb) return SC_OK;
+    const DescLayout L = make_desc_layout(npb, PPB, NNE, DIM, p.max_nbr, ctx->blk_umax);
+    if (L.stride != ctx->blk_desc_stride) return SC_OK;
+    const TmaSmem sm = tma_smem_layout(REC, ctx->blk_umax, PPB, SST, NNE, DIM, NGP, npb, p.max_nbr, L.stride);
+    if (sm.total > 112 * 1024) return SC_OK;
+    const size_t rec_doubles = (size_t)ctx->n_elem * REC;
+    if (ctx->asm_rec_cap < rec_doubles) {
+        sc_free(&ctx->d_asm_rec); ctx->asm_rec_cap = 0;
+        size_t free_b = 0, total_b = 0;
+        if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess || free_b < rec_doubles * sizeof(double) + (size_t(2) << 30)) return SC_OK;
+        if (cudaMalloc((void**)&ctx->d_asm_rec, rec_doubles * sizeof(double) + 64) != cudaSuccess) { cudaGetLastError(); ctx->d_asm_rec = nullptr; return SC_OK; }
+        ctx->asm_rec_cap = rec_doubles;
+    }
+    auto kern = k_assemble_tma<NNE, DIM, NGP, TPB, LPP, MINB>;
+    SC_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm.total));
+    int occ = 0;
+    SC_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, TPB, sm.total));
+    if (occ < 1) return SC_OK;
+    SC_CUDA(ctx, cudaMemcpyToSymbolAsync(c_tabN, t.N.data(), t.N.size() * sizeof(double), 0, cudaMemcpyHostToDevice, ctx->stream));
+    SC_CUDA(ctx, cudaMemcpyToSymbolAsync(c_tabdN, t.dN.data(), t.dN.size() * sizeof(double), 0, cudaMemcpyHostToDevice, ctx->stream));
+    constexpr int EPB = 128 / NGP;
+    k_elem_records<NNE, DIM, NGP><<<(unsigned)((ctx->n_elem + EPB - 1) / EPB), 128, 0, ctx->stream>>>(
+        p.xyz, p.conn, p.E, p.nu, p.rho, p.tabdN, p.tabw, ctx->n_elem, ctx->d_asm_rec);
+    SC_CHECK_LAUNCH(ctx);
+    const int64_t n_blocks = (p.n_nodes + npb - 1) / npb;
+    const unsigned grid = (unsigned)std::min<int64_t>(n_blocks, (int64_t)ctx->sm_count * occ);
+    kern<<<grid, TPB, sm.total, ctx->stream>>>(p, ctx->d_asm_rec, ctx->d_blk_desc, L, n_blocks, npb, ctx->blk_umax);
+    SC_CHECK_LAUNCH(ctx);
+    *handled = true;
+    return SC_OK;
+}
+
 // records + record-fed kernel; *handled stays false when the path does not apply (no descriptors, not enough memory for
 // the records or the shared-memory image): the caller falls back to k_assemble_blk
 template <int NNE, int DIM, int NGP, int TPB, int LPP, int MINB>
@@ -977,14 +1351,20 @@ int launch_blk(sc_ctx* ctx, const AsmParams& p, const ShapeTable& t, bool* handl
     // per set-up task instead of held in registers 7.9 ms
     if constexpr (DIM * NNE * DIM > 72 && NNE % 5 == 0) {
         // tetra10 / hexa20: five lanes per pair (2 / 4 node blocks each), 160-thread blocks of 32 pairs
+        SC_TRY((launch_tma_cfg<NNE, DIM, NGP, 160, 5, 2>(ctx, p, t, handled)));
+        if (*handled) return SC_OK;
         SC_TRY((launch_rec_cfg<NNE, DIM, NGP, 160, 5, 3>(ctx, p, t, handled)));
         if (*handled) return SC_OK;
         return launch_blk_cfg<NNE, DIM, NGP, 160, 5, 3>(ctx, p, t, handled);
     } else if constexpr (DIM * NNE * DIM > 36 && NNE % 2 == 0) {
+        SC_TRY((launch_tma_cfg<NNE, DIM, NGP, 128, 2, 3>(ctx, p, t, handled)));
+        if (*handled) return SC_OK;
         SC_TRY((launch_rec_cfg<NNE, DIM, NGP, 128, 2, 4>(ctx, p, t, handled)));
         if (*handled) return SC_OK;
         return launch_blk_cfg<NNE, DIM, NGP, 128, 2, 4>(ctx, p, t, handled);
     } else {
+        SC_TRY((launch_tma_cfg<NNE, DIM, NGP, 128, 1, 2>(ctx, p, t, handled)));
+        if (*handled) return SC_OK;
         SC_TRY((launch_rec_cfg<NNE, DIM, NGP, 128, 1, 2>(ctx, p, t, handled)));
         if (*handled) return SC_OK;
         return launch_blk_cfg<NNE, DIM, NGP, 128, 1, 2>(ctx, p, t, handled);
@@ -1019,8 +1399,8 @@ void asm_release_scratch(sc_ctx* ctx) {
 }
 
 int asm_build_block_desc(sc_ctx* ctx) {
-    sc_free(&ctx->d_blk_elem); sc_free(&ctx->d_blk_U); sc_free(&ctx->d_pair_ui);
-    ctx->blk_npb = ctx->blk_ppb = ctx->blk_umax = 0;
+    sc_free(&ctx->d_blk_elem); sc_free(&ctx->d_blk_U); sc_free(&ctx->d_pair_ui); sc_free(&ctx->d_blk_desc);
+    ctx->blk_npb = ctx->blk_ppb = ctx->blk_umax = ctx->blk_desc_stride = 0;
     if (!ctx->d_pair_pos || ctx->max_valence <= 0 || ctx->n_nodes <= 0) return SC_OK;
     int tpb = 0, lpp = 1;
     asm_blk_shape(ctx->nne, ctx->dim, &tpb, &lpp);
@@ -1047,6 +1427,22 @@ int asm_build_block_desc(sc_ctx* ctx) {
     sc_free(&d_umax);
     if (e != cudaSuccess) return sc_fail(ctx, SC_ERR_CUDA, "block descriptors of the assembly failed: %s", cudaGetErrorString(e));
     ctx->blk_npb = npb; ctx->blk_ppb = ppb; ctx->blk_umax = std::max(umax, 1);
+    // packed per-block descriptors of the persistent kernel
+    const DescLayout L = make_desc_layout(npb, ppb, ctx->nne, ctx->dim, ctx->max_nbr, ctx->blk_umax);
+    size_t free_b = 0, total_b = 0;
+    const size_t desc_bytes = (size_t)n_blocks * L.stride;
+    if (ctx->max_nbr > 255 || cudaMemGetInfo(&free_b, &total_b) != cudaSuccess || free_b < desc_bytes + (size_t(4) << 30)) return SC_OK;
+    SC_TRY(sc_alloc(ctx, &ctx->d_blk_desc, desc_bytes));
+    cudaMemsetAsync(ctx->d_blk_desc, 0, desc_bytes, ctx->stream);
+    k_blk_pack<<<(unsigned)n_blocks, 128, 0, ctx->stream>>>(ctx->d_n2e_ptr, ctx->d_nbr_ptr, ctx->d_node_rl, ctx->d_eq, ctx->d_rowptr, ctx->d_nbr_off,
+                                                            ctx->d_nbr_free, ctx->d_pair_al, ctx->d_pair_pos, ctx->d_blk_elem, ctx->d_blk_U,
+                                                            ctx->d_pair_ui, ctx->n_nodes, npb, ppb, ctx->nne, ctx->dim, ctx->max_nbr, ctx->blk_umax, L,
+                                                            ctx->d_blk_desc);
+    ctx->launches++;
+    e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) return sc_fail(ctx, SC_ERR_CUDA, "packing the block descriptors of the assembly failed: %s", cudaGetErrorString(e));
+    ctx->blk_desc_stride = L.stride;
     return SC_OK;
 }
 

@@ -85,6 +85,9 @@ struct sc_ctx {
     int32_t* d_blk_U = nullptr;     // [n_blocks] how many
     uint8_t* d_pair_ui = nullptr;   // [n_pairs] index of the pair's element in its block's list (255: pair of a node without rows)
     int blk_npb = 0, blk_ppb = 0, blk_umax = 0;
+    unsigned char* d_blk_desc = nullptr;   // [n_blocks][blk_desc_stride] packed block descriptors of the persistent kernel (k_blk_pack)
+    int blk_desc_stride = 0;
+    bool no_asm_persistent = false; // sc_set_option("assembly_persistent", 0): one CTA per node block (k_assemble_rec)
     double* d_asm_rec = nullptr;    // [n_elem][REC] element records (scratch of the assembly, see asm_release_scratch)
     size_t asm_rec_cap = 0;         // doubles allocated
     bool no_asm_records = false;    // sc_set_option("assembly_records", 0): k_assemble_blk (Jacobian set-up inside every block)
