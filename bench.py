@@ -1026,7 +1026,7 @@ def main():
     ap.add_argument("--order20", default="interleaved", choices=["interleaved", "grouped"],
                     help="node numbering of the synthetic hexa20 box: cell by cell (translation invariant, like the hexa8 lattice) or "
                          "corner lattice followed by the three edge lattices (round 1)")
-    ap.add_argument("--rtol20", type=float, default=1e-12, help="PCG tolerance of the hexa20 workload (the product default)")
+    ap.add_argument("--rtol20", type=float, default=1e-12, help="PCG tolerance of the hexa20 workload (history error 4.7e-10 after 1000 steps on the 12^3 probe, profiles/r2_hexa20_rtol_probe_12cube_1000steps.txt; the solver classes default to 1e-14)")
     ap.add_argument("--option", action="append", default=[], metavar="NAME=VALUE",
                     help="library option for A/B runs (sc_set_option), e.g. halo_overlap=0; the defaults are the product path")
     args = ap.parse_args()

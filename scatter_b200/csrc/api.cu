@@ -196,8 +196,7 @@ int sc_set_option(sc_ctx* ctx, const char* name, int64_t value) {
         ctx->ov_spare_sms = (int)value;
     }
     else if (k == "halo_overlap") { ctx->no_overlap = !on; ctx->ov_planned = false; }   // interior tiles step beside the halo exchange (default off: measured, no gain -- DESIGN.md 3.5)
-    else if (k == "assembly_records") ctx->no_asm_records = !on;          // element records + TMA-fed row-gather kernel (default on)
-    else if (k == "assembly_persistent") ctx->no_asm_persistent = !on;    // persistent TMA-fed assembly kernel (default on)
+    else if (k == "assembly_records") ctx->no_asm_records = !on;          // element records + persistent TMA-fed row-gather kernel (default on)
     else if (k == "generic_assembly") ctx->force_generic_assembly = on;   // warp-per-node assembly for every element type (default off)
     else return sc_fail(ctx, SC_ERR_ARG, "unknown option '%s'", name);
     pcg_graph_drop(ctx);

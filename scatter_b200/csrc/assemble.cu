@@ -554,16 +554,18 @@ __global__ void __launch_bounds__(TPB, MINB) k_assemble_blk(AsmParams p, int npb
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
-// Record-fed generation (default).  ncu of k_assemble_blk: 35 % of the samples in the index prologue and the element
-// de-duplication, every element's Jacobians evaluated in the ~4.5 blocks that see it, six barrier-separated phases.  Here
+// Record-fed generations (round 2; default: k_assemble_tma below).  ncu of k_assemble_blk: 35 % of the samples in the index
+// prologue and the element de-duplication, every element's Jacobians evaluated in the ~4.5 blocks that see it, six
+// barrier-separated phases.  Now
 //   1. k_elem_records evaluates every element ONCE: J^-1 and detJ*w per Gauss point plus lambda, mu, rho -> one record of
 //      REC doubles per element in HBM (hexa8, 2x2x2 points: 688 B, written coalesced through shared memory);
 //   2. the distinct elements of every node block and each pair's index into that list are structure, not values: they
-//      are listed once with the pattern (k_blk_desc), first-seen order, no atomics;
-//   3. k_assemble_rec fetches the records of its block with one bulk copy (TMA, cp.async.bulk) per element straight into
-//      shared memory, completion counted on an mbarrier, while the pair lanes load their own indices; the pair lanes
-//      then run all Gauss points without a barrier, reading each point's ten numbers with 16-byte shared loads (the
-//      record stride is = 2 mod 4 doubles, so the eight lanes of a quarter warp never share a bank).
+//      are listed once with the pattern (k_blk_desc: ascending element id, no atomics) and packed with every other index
+//      of the block into one contiguous descriptor (k_blk_pack);
+//   3. the row-gather kernel fetches descriptor and records with bulk copies (TMA, cp.async.bulk) straight into shared
+//      memory, completion counted on mbarriers; the pair lanes run all Gauss points without a barrier, reading each
+//      point's ten numbers with 16-byte shared loads (the record stride is = 2 mod 4 doubles, so the eight lanes of a
+//      quarter warp never share a bank).
 // The arithmetic per pair and the summation order are those of k_assemble_blk: both kernels give the same bits.
 __host__ __device__ constexpr int rec_point_stride(int dim) { return (dim * dim + 1 + 1) & ~1; }            // J^-1, detJ*w (+ pad): even
 __host__ __device__ constexpr int rec_stride(int dim, int ngp) {                                            // + lambda, mu, rho; = 2 (mod 4)
@@ -670,235 +672,11 @@ __global__ void k_blk_desc(const int64_t* __restrict__ n2e_ptr, const int32_t* _
     }
 }
 
-struct RecParams {
-    const double* rec;
-    const int32_t* blk_elem; const int32_t* blk_U; const uint8_t* pair_ui;
-    int ppb, umax;
-};
-
-template <int NNE, int DIM, int NGP, int TPB, int LPP, int MINB>
-__global__ void __launch_bounds__(TPB, MINB) k_assemble_rec(AsmParams p, RecParams rp, int npb) {
-    constexpr int DD = DIM * DIM, ND = NNE * DIM;
-    constexpr int NBB = NNE / LPP;                       // node blocks per lane
-    constexpr int PPB = TPB / LPP;                       // pairs per block
-    constexpr int SST = DIM * ND + 1;                    // stride of one pair's row block in the staging area (odd)
-    constexpr int ISTP = rec_point_stride(DIM), REC = rec_stride(DIM, NGP);
-    constexpr int UGB = SC_BLK_UG;
-    constexpr int EPT = (PPB + 31) / 32;                 // record copies issued per lane of warp 0
-    static_assert(NNE % LPP == 0 && (TPB / 32) % LPP == 0 && PPB <= 255, "unsupported split");
-    extern __shared__ __align__(128) double smem[];
-    double* srec = smem;                                 // [umax][REC]  records of the block's elements   (phase 1)
-    double* stage = smem;                                // [PPB][SST]   row block of every pair           (phase 2)
-    double* stage_m = stage + (size_t)PPB * SST;         // [PPB][NNE]
-    const size_t sz_stage = (size_t)PPB * SST + (size_t)PPB * NNE, sz_rec = (size_t)rp.umax * REC;
-    const size_t region_a = ((sz_stage > sz_rec ? sz_stage : sz_rec) + 1) & ~(size_t)1;
-    double* sdN = smem + region_a;                       // [NGP*NNE*DIM] table copies for lane-dependent rows
-    double* sN = sdN + NGP * NNE * DIM;                  // [NGP*NNE]
-    double* s_mitem = sN + NGP * NNE;                    // [npb*max_nbr]
-    long long* s_rowbase = reinterpret_cast<long long*>(s_mitem + (size_t)npb * p.max_nbr);   // [npb*DIM]
-    uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_rowbase + (size_t)npb * DIM);            // [1]
-    int* s_ptr = reinterpret_cast<int*>(s_bar + 1);      // [npb+1]
-    int* s_nptr = s_ptr + npb + 1;                       // [npb+1]
-    int* s_rl = s_nptr + npb + 1;                        // [npb]
-    unsigned char* s_inv = reinterpret_cast<unsigned char*>(s_rl + npb + (npb & 1) + 2);     // [PPB][max_nbr] (4-byte aligned)
-
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int k = (warp / LPP) * 32 + lane, half = warp % LPP;
-    const int64_t a0 = (int64_t)blockIdx.x * npb;
-    const int64_t a1 = min(a0 + npb, p.n_nodes);
-    const int nbn = (int)(a1 - a0);
-    const int64_t P0 = p.n2e_ptr[a0];
-    const int64_t nbr0 = p.nbr_ptr[a0];
-    const int npairs = (int)(p.n2e_ptr[a1] - P0);
-    // everything a thread needs from global memory is requested before the first barrier
-    const int U = rp.blk_U[blockIdx.x];
-    int e_copy[EPT];
-#pragma unroll
-    for (int c = 0; c < EPT; ++c) e_copy[c] = (warp == 0 && lane + 32 * c < U) ? rp.blk_elem[(int64_t)blockIdx.x * rp.ppb + lane + 32 * c] : -1;
-    int ui = 255, al = 0;
-    unsigned char pos[NNE];
-    if (k < npairs) {
-        ui = rp.pair_ui[P0 + k];
-        al = p.pair_al[P0 + k];
-        if (half == 0) {
-#pragma unroll
-            for (int b = 0; b < NNE; ++b) pos[b] = p.pair_pos[(P0 + k) * NNE + b];
-        }
-    }
-    for (int t = tid; t <= nbn; t += TPB) {
-        s_ptr[t] = (int)(p.n2e_ptr[a0 + t] - P0);
-        s_nptr[t] = (int)(p.nbr_ptr[a0 + t] - nbr0);
-        if (t < nbn) s_rl[t] = p.node_rl[a0 + t];
-    }
-    for (int t = tid; t < NGP * NNE * DIM; t += TPB) sdN[t] = p.tabdN[t];
-    for (int t = tid; t < NGP * NNE; t += TPB) sN[t] = p.tabN[t];
-    for (int t = tid; t < (PPB * p.max_nbr + 3) / 4; t += TPB) reinterpret_cast<unsigned*>(s_inv)[t] = 0xffffffffu;
-    if (tid == 0) { tma_mbar_init(s_bar, 1); tma_mbar_fence_init(); }
-    long long rb_reg[DIM];
-#pragma unroll
-    for (int c = 0; c < DIM; ++c) {
-        const int t = tid + c * TPB;
-        rb_reg[c] = -1;
-        if (t < nbn * DIM) {
-            const int rr = p.eq[a0 * DIM + t];
-            if (rr >= 0 && p.node_rl[a0 + t / DIM] > 0) rb_reg[c] = (long long)p.rowptr[rr];
-        }
-    }
-    __syncthreads();
-    if (warp == 0) {                                     // the block's records: one bulk copy per element
-        if (lane == 0) tma_mbar_expect_tx(s_bar, (uint32_t)(U * REC * sizeof(double)));
-        __syncwarp();
-#pragma unroll
-        for (int c = 0; c < EPT; ++c)
-            if (e_copy[c] >= 0) tma_bulk_load(srec + (size_t)(lane + 32 * c) * REC, rp.rec + (int64_t)e_copy[c] * REC, (uint32_t)(REC * sizeof(double)), s_bar);
-    }
-#pragma unroll
-    for (int c = 0; c < DIM; ++c)
-        if (tid + c * TPB < nbn * DIM) s_rowbase[tid + c * TPB] = rb_reg[c];
-    const int n_items = s_nptr[nbn];
-    const bool valid = ui != 255;
-    if (valid && half == 0) {
-#pragma unroll
-        for (int b = 0; b < NNE; ++b) s_inv[k * p.max_nbr + pos[b]] = (unsigned char)b;
-    }
-
-    // ---- phase 1: gradient products of every pair over all Gauss points --------------------------------------------
-    double acc[DIM][NBB * DIM];
-    double mab[NBB];
-#pragma unroll
-    for (int i = 0; i < DIM; ++i)
-#pragma unroll
-        for (int c = 0; c < NBB * DIM; ++c) acc[i][c] = 0.0;
-#pragma unroll
-    for (int b = 0; b < NBB; ++b) mab[b] = 0.0;
-    tma_mbar_wait(s_bar, 0);
-    double lam = 0.0, mu = 0.0, rho = 0.0;
-    if (valid) {
-        const double* sr = srec + (size_t)ui * REC;
-#pragma unroll UGB
-        for (int g = 0; g < NGP; ++g) {
-            const double2* si2 = reinterpret_cast<const double2*>(sr + g * ISTP);
-            double rv[ISTP];
-#pragma unroll
-            for (int r = 0; r < ISTP / 2; ++r) { const double2 v = si2[r]; rv[2 * r] = v.x; rv[2 * r + 1] = v.y; }
-            const double wj = rv[DD];
-            double wga[DIM];
-#pragma unroll
-            for (int kk = 0; kk < DIM; ++kk) {
-                double s = 0.0;
-#pragma unroll
-                for (int d = 0; d < DIM; ++d) s += sdN[(g * NNE + al) * DIM + d] * rv[kk * DIM + d];
-                wga[kk] = wj * s;
-            }
-            const double wna = wj * sN[g * NNE + al];
-#pragma unroll
-            for (int bb = 0; bb < NBB; ++bb) {
-                const double* dnb = c_tabdN + (g * NNE + half * NBB + bb) * DIM;
-                double gb[DIM];
-#pragma unroll
-                for (int kk = 0; kk < DIM; ++kk) {
-                    double s = 0.0;
-#pragma unroll
-                    for (int d = 0; d < DIM; ++d) s += dnb[d] * rv[kk * DIM + d];
-                    gb[kk] = s;
-                }
-#pragma unroll
-                for (int i = 0; i < DIM; ++i)
-#pragma unroll
-                    for (int j = 0; j < DIM; ++j) acc[i][bb * DIM + j] += wga[i] * gb[j];
-                mab[bb] += wna * c_tabN[g * NNE + half * NBB + bb];
-            }
-        }
-        lam = sr[NGP * ISTP + 0]; mu = sr[NGP * ISTP + 1]; rho = sr[NGP * ISTP + 2];
-    }
-    __syncthreads();                                     // the records are dead: region A becomes the staging area
-    if (valid) {
-#pragma unroll
-        for (int bb = 0; bb < NBB; ++bb) {
-            double tr = 0.0;
-#pragma unroll
-            for (int d = 0; d < DIM; ++d) tr += acc[d][bb * DIM + d];
-            tr *= mu;
-#pragma unroll
-            for (int i = 0; i < DIM; ++i)
-#pragma unroll
-                for (int j = 0; j < DIM; ++j) {
-                    double t = lam * acc[i][bb * DIM + j] + mu * acc[j][bb * DIM + i];
-                    if (i == j) t += tr;
-                    stage[(size_t)k * SST + i * ND + (half * NBB + bb) * DIM + j] = t;
-                }
-            stage_m[k * NNE + half * NBB + bb] = rho * mab[bb];
-        }
-    }
-    __syncthreads();
-
-    // ---- phase 2: one thread per (node, neighbour) item adds the staged contributions of the node's elements in
-    //      ascending element id (the reference's summation order) ------------------------------------------------------
-    for (int q = tid; q < n_items; q += TPB) {
-        int lo = 0, hi = nbn;
-        while (hi - lo > 1) {
-            const int mid = (lo + hi) >> 1;
-            if (s_nptr[mid] <= q) lo = mid; else hi = mid;
-        }
-        const int n = lo, pidx = q - s_nptr[n];
-        const int off = p.nbr_off[nbr0 + q];
-        const int fmask = p.nbr_free[nbr0 + q];
-        double blk[DIM][DIM];
-#pragma unroll
-        for (int i = 0; i < DIM; ++i)
-#pragma unroll
-            for (int j = 0; j < DIM; ++j) blk[i][j] = 0.0;
-        double m = 0.0;
-        const int pr1 = s_ptr[n + 1];
-        if (s_rl[n] > 0)
-        for (int pr0 = s_ptr[n]; pr0 < pr1; pr0 += 8) {
-            int bs[8];
-#pragma unroll
-            for (int c = 0; c < 8; ++c) bs[c] = (pr0 + c < pr1) ? s_inv[(pr0 + c) * p.max_nbr + pidx] : 0xff;
-#pragma unroll
-            for (int c = 0; c < 8; ++c) {
-                const int b = bs[c];
-                if (b == 0xff) continue;
-                const double* sp = stage + (size_t)(pr0 + c) * SST + b * DIM;
-#pragma unroll
-                for (int i = 0; i < DIM; ++i)
-#pragma unroll
-                    for (int j = 0; j < DIM; ++j) blk[i][j] += sp[i * ND + j];
-                m += stage_m[(pr0 + c) * NNE + b];
-            }
-        }
-        s_mitem[q] = m;
-#pragma unroll
-        for (int i = 0; i < DIM; ++i) {
-            const long long rb = s_rowbase[n * DIM + i];
-            if (rb < 0) continue;
-            int64_t o = rb + off;
-#pragma unroll
-            for (int j = 0; j < DIM; ++j) {
-                if (!(fmask & (1 << j))) continue;
-                if (p.K) p.K[o] = blk[i][j];
-                if (p.M) p.M[o] = (i == j) ? m : 0.0;
-                ++o;
-            }
-        }
-    }
-    if (p.Ml) {
-        __syncthreads();
-        for (int t = tid; t < nbn * DIM; t += TPB) {
-            const int n = t / DIM, i = t % DIM;
-            if (s_rowbase[t] < 0) continue;
-            double s = 0.0;
-            for (int q = s_nptr[n]; q < s_nptr[n + 1]; ++q)
-                if (p.nbr_free[nbr0 + q] & (1 << i)) s += s_mitem[q];
-            p.Ml[p.eq[(a0 + n) * DIM + i]] = s;
-        }
-    }
-}
-
 // ---------------------------------------------------------------------------------------------------------------------
-// Persistent, fully TMA-fed generation.  ncu of k_assemble_rec (profiles/r2_k_assemble_rec_128cube.txt): the FP64 phases are
-// 25 % of the samples; 17 % sit in the index prologue (two dependent levels of global loads), 16 % wait for the records,
-// 12 % at barriers -- every block pays its whole load latency, and only four blocks per SM overlap.  Here every index a
+// Persistent, fully TMA-fed kernel.  A first record-fed kernel with one CTA per node block (50.9 ms at 255^3, since removed;
+// profiles/r2_k_assemble_rec_128cube.txt) spent 25 % of its samples in the FP64 phases, 17 % in the index prologue (two
+// dependent levels of global loads), 16 % waiting for the records, 12 % at barriers -- every block paid its whole load
+// latency, and only four blocks per SM overlapped.  Here every index a
 // block needs is packed at pattern time into ONE contiguous descriptor (k_blk_pack: pointers, row bases, element list,
 // pair -> element / local node / slot map, item offsets and masks), and a persistent CTA runs its blocks through a
 // pipeline: the descriptor of block i+2 and the records of block i+1 are in flight (bulk copies counted on mbarriers)
@@ -1233,7 +1011,7 @@ int launch_tma_cfg(sc_ctx* ctx, const AsmParams& p, const ShapeTable& t, bool* h
     constexpr int ND = NNE * DIM, SST = DIM * ND + 1;
     constexpr int REC = rec_stride(DIM, NGP);
     *handled = false;
-    if (ctx->no_asm_records || ctx->no_asm_persistent || !ctx->d_blk_desc || !p.pair_pos || ctx->blk_ppb != PPB || ctx->max_valence <= 0 ||
+    if (ctx->no_asm_records || !ctx->d_blk_desc || !p.pair_pos || ctx->blk_ppb != PPB || ctx->max_valence <= 0 ||
         ctx->max_valence > PPB || p.max_nbr > 255)
         return SC_OK;
     const int npb = std::max(1, PPB / ctx->max_valence);
@@ -1269,57 +1047,6 @@ int launch_tma_cfg(sc_ctx* ctx, const AsmParams& p, const ShapeTable& t, bool* h
     return SC_OK;
 }
 
-// records + record-fed kernel; *handled stays false when the path does not apply (no descriptors, not enough memory for
-// the records or the shared-memory image): the caller falls back to k_assemble_blk
-template <int NNE, int DIM, int NGP, int TPB, int LPP, int MINB>
-int launch_rec_cfg(sc_ctx* ctx, const AsmParams& p, const ShapeTable& t, bool* handled) {
-    constexpr int PPB = TPB / LPP;
-    constexpr int ND = NNE * DIM, SST = DIM * ND + 1;
-    constexpr int REC = rec_stride(DIM, NGP);
-    *handled = false;
-    if (ctx->no_asm_records || !ctx->d_blk_elem || !p.pair_pos || ctx->blk_ppb != PPB || ctx->max_valence <= 0 || ctx->max_valence > PPB ||
-        p.max_nbr > 255)
-        return SC_OK;
-    const int npb = std::max(1, PPB / ctx->max_valence);
-    if (npb != ctx->blk_npb) return SC_OK;
-    const size_t region_a = (std::max((size_t)PPB * SST + (size_t)PPB * NNE, (size_t)ctx->blk_umax * REC) + 1) & ~(size_t)1;
-    const size_t bytes = (region_a + (size_t)NGP * NNE * DIM + (size_t)NGP * NNE + (size_t)npb * p.max_nbr + (size_t)npb * DIM + 1) * sizeof(double) +
-                         (3 * (size_t)(npb + 1) + 4) * sizeof(int) + (size_t)PPB * p.max_nbr + 16;
-    if (bytes > 72 * 1024) return SC_OK;
-    // record scratch: kept by the context between assemblies (allocating and releasing 11 GB costs more than the kernels),
-    // released by asm_release_scratch when a time loop starts or the pattern goes
-    const size_t rec_doubles = (size_t)ctx->n_elem * REC;
-    if (ctx->asm_rec_cap < rec_doubles) {
-        sc_free(&ctx->d_asm_rec); ctx->asm_rec_cap = 0;
-        size_t free_b = 0, total_b = 0;
-        if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess || free_b < rec_doubles * sizeof(double) + (size_t(2) << 30)) return SC_OK;
-        if (cudaMalloc((void**)&ctx->d_asm_rec, rec_doubles * sizeof(double) + 64) != cudaSuccess) { cudaGetLastError(); ctx->d_asm_rec = nullptr; return SC_OK; }
-        ctx->asm_rec_cap = rec_doubles;
-    }
-    double* rec = ctx->d_asm_rec;
-    int rc = SC_OK;
-    auto body = [&]() -> int {
-        SC_CUDA(ctx, cudaMemcpyToSymbolAsync(c_tabN, t.N.data(), t.N.size() * sizeof(double), 0, cudaMemcpyHostToDevice, ctx->stream));
-        SC_CUDA(ctx, cudaMemcpyToSymbolAsync(c_tabdN, t.dN.data(), t.dN.size() * sizeof(double), 0, cudaMemcpyHostToDevice, ctx->stream));
-        constexpr int EPB = 128 / NGP;
-        k_elem_records<NNE, DIM, NGP><<<(unsigned)((ctx->n_elem + EPB - 1) / EPB), 128, 0, ctx->stream>>>(
-            p.xyz, p.conn, p.E, p.nu, p.rho, p.tabdN, p.tabw, ctx->n_elem, rec);
-        SC_CHECK_LAUNCH(ctx);
-        RecParams rp;
-        rp.rec = rec; rp.blk_elem = ctx->d_blk_elem; rp.blk_U = ctx->d_blk_U; rp.pair_ui = ctx->d_pair_ui;
-        rp.ppb = ctx->blk_ppb; rp.umax = ctx->blk_umax;
-        const unsigned grid = (unsigned)((p.n_nodes + npb - 1) / npb);
-        auto kern = k_assemble_rec<NNE, DIM, NGP, TPB, LPP, MINB>;
-        SC_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
-        kern<<<grid, TPB, bytes, ctx->stream>>>(p, rp, npb);
-        SC_CHECK_LAUNCH(ctx);
-        return SC_OK;
-    };
-    rc = body();
-    if (rc == SC_OK) *handled = true;
-    return rc;
-}
-
 template <int NNE, int DIM, int NGP, int TPB, int LPP, int MINB>
 int launch_blk_cfg(sc_ctx* ctx, const AsmParams& p, const ShapeTable& t, bool* handled) {
     constexpr int PPB = TPB / LPP;
@@ -1353,19 +1080,13 @@ int launch_blk(sc_ctx* ctx, const AsmParams& p, const ShapeTable& t, bool* handl
         // tetra10 / hexa20: five lanes per pair (2 / 4 node blocks each), 160-thread blocks of 32 pairs
         SC_TRY((launch_tma_cfg<NNE, DIM, NGP, 160, 5, 2>(ctx, p, t, handled)));
         if (*handled) return SC_OK;
-        SC_TRY((launch_rec_cfg<NNE, DIM, NGP, 160, 5, 3>(ctx, p, t, handled)));
-        if (*handled) return SC_OK;
         return launch_blk_cfg<NNE, DIM, NGP, 160, 5, 3>(ctx, p, t, handled);
     } else if constexpr (DIM * NNE * DIM > 36 && NNE % 2 == 0) {
         SC_TRY((launch_tma_cfg<NNE, DIM, NGP, 128, 2, 3>(ctx, p, t, handled)));
         if (*handled) return SC_OK;
-        SC_TRY((launch_rec_cfg<NNE, DIM, NGP, 128, 2, 4>(ctx, p, t, handled)));
-        if (*handled) return SC_OK;
         return launch_blk_cfg<NNE, DIM, NGP, 128, 2, 4>(ctx, p, t, handled);
     } else {
         SC_TRY((launch_tma_cfg<NNE, DIM, NGP, 128, 1, 2>(ctx, p, t, handled)));
-        if (*handled) return SC_OK;
-        SC_TRY((launch_rec_cfg<NNE, DIM, NGP, 128, 1, 2>(ctx, p, t, handled)));
         if (*handled) return SC_OK;
         return launch_blk_cfg<NNE, DIM, NGP, 128, 1, 2>(ctx, p, t, handled);
     }
@@ -1443,6 +1164,7 @@ int asm_build_block_desc(sc_ctx* ctx) {
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
     if (e != cudaSuccess) return sc_fail(ctx, SC_ERR_CUDA, "packing the block descriptors of the assembly failed: %s", cudaGetErrorString(e));
     ctx->blk_desc_stride = L.stride;
+    sc_free(&ctx->d_blk_elem); sc_free(&ctx->d_blk_U); sc_free(&ctx->d_pair_ui);      // packed into the descriptors
     return SC_OK;
 }
 

@@ -81,16 +81,15 @@ struct sc_ctx {
     uint8_t* d_pair_pos = nullptr;  // [n_pairs*nne] position of every element node in the pair's node neighbour list (or null)
     uint8_t* d_pair_al = nullptr;   // [n_pairs] local index of the pair's node in its element
     // block descriptors of the record-fed assembly kernel (assemble.cu: asm_build_block_desc, built with the pattern)
-    int32_t* d_blk_elem = nullptr;  // [n_blocks][blk_ppb] distinct elements of every block of blk_npb consecutive nodes (first-seen order)
-    int32_t* d_blk_U = nullptr;     // [n_blocks] how many
-    uint8_t* d_pair_ui = nullptr;   // [n_pairs] index of the pair's element in its block's list (255: pair of a node without rows)
+    int32_t* d_blk_elem = nullptr;  // [n_blocks][blk_ppb] distinct elements of every block of blk_npb consecutive nodes, ascending
+    int32_t* d_blk_U = nullptr;     // [n_blocks] how many                      (these three only live until k_blk_pack has
+    uint8_t* d_pair_ui = nullptr;   // [n_pairs] index of the pair's element in its block's list (255: none)    packed them)
     int blk_npb = 0, blk_ppb = 0, blk_umax = 0;
     unsigned char* d_blk_desc = nullptr;   // [n_blocks][blk_desc_stride] packed block descriptors of the persistent kernel (k_blk_pack)
     int blk_desc_stride = 0;
-    bool no_asm_persistent = false; // sc_set_option("assembly_persistent", 0): one CTA per node block (k_assemble_rec)
     double* d_asm_rec = nullptr;    // [n_elem][REC] element records (scratch of the assembly, see asm_release_scratch)
     size_t asm_rec_cap = 0;         // doubles allocated
-    bool no_asm_records = false;    // sc_set_option("assembly_records", 0): k_assemble_blk (Jacobian set-up inside every block)
+    bool no_asm_records = false;    // sc_set_option("assembly_records", 0): k_assemble_blk (Jacobian set-up inside every block, no scratch)
     int64_t ncol_total = 0;
     int32_t* d_dict = nullptr;      // [n_dict*dict_stride] most frequent relative column lists (node_dict.cu); nodes with one of
     int n_dict = 0, dict_stride = 0;   // them carry its id in their descriptor and have no explicit list in d_ncol

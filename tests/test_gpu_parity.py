@@ -259,17 +259,16 @@ def test_assembly_is_bit_reproducible(golden_meshes):
 @pytest.mark.parametrize("case", ["cube", "column_3D_tetra4", "column_2D", "column_2D_tri6", "column_high_order", "column_3D_tetra10",
                                   "rose_2D_side"])
 def test_assembly_kernel_generations_agree(case, golden_meshes, monkeypatch):
-    """The persistent TMA-fed kernel (default: k_elem_records + k_assemble_tma), its one-CTA-per-block form k_assemble_rec,
-    k_assemble_blk (Jacobian set-up inside every block) and the warp-per-node k_assemble sum the same contributions in the
-    same order.  The first three do the same arithmetic per pair -- identical bits; the last differs in how a single element
-    contribution is rounded (material law per Gauss point vs once)."""
+    """The persistent TMA-fed kernel (default: k_elem_records + k_assemble_tma), k_assemble_blk (Jacobian set-up inside every
+    block) and the warp-per-node k_assemble sum the same contributions in the same order.  The first two do the same
+    arithmetic per pair -- identical bits; the last differs in how a single element contribution is rounded (material law
+    per Gauss point vs once)."""
     if case not in cases.MATRIX_CASES:
         pytest.skip("case not in the fixture set")
     fn, bc = cases.MATRIX_CASES[case]
     vals = {}
     from scatter_b200 import _lib
-    for name, opt, value in (("tma", None, None), ("rec", "assembly_persistent", 0), ("blk", "assembly_records", 0),
-                             ("generic", "generic_assembly", 1)):
+    for name, opt, value in (("tma", None, None), ("blk", "assembly_records", 0), ("generic", "generic_assembly", 1)):
         if opt:
             monkeypatch.setitem(_lib.DEFAULT_OPTIONS, opt, value)
         _, mx = build(golden_meshes[fn], bc, cases.case_materials(case), cases.settings())
@@ -277,7 +276,7 @@ def test_assembly_kernel_generations_agree(case, golden_meshes, monkeypatch):
         mx.ctx.close()
         if opt:
             monkeypatch.delitem(_lib.DEFAULT_OPTIONS, opt)
-    for other in ("rec", "blk"):
+    for other in ("blk",):
         for a, b in zip(vals["tma"], vals[other]):
             assert a.shape == b.shape and np.array_equal(a, b), other
     for a, b in zip(vals["tma"], vals["generic"]):
