@@ -69,10 +69,12 @@ int64_t     sc_kernel_launches(sc_ctx* ctx);     /* running count of kernels lau
  * sub-step 2): entries of the FSAI factor G (0: none, Jacobi in use), its set-up time, vectors in the projection basis */
 int         sc_precond_info(sc_ctx* ctx, int slot, int64_t* fsai_nnz, double* fsai_seconds, int* projection_vectors);
 /* kernel-selection switches for tests and A/B measurements (the defaults are the product path; nothing reads the
- * environment): "node_spmv", "tma_spmv", "column_dictionary", "small_pcg", "pcg_graph" (default 1), "generic_assembly"
+ * environment): "node_spmv", "tma_spmv", "column_dictionary", "small_pcg", "pcg_graph", "assembly_records" (default 1:
+ * element records + persistent TMA-fed assembly; 0: block kernel without scratch, same bits), "generic_assembly"
  * (default 0), "spmv_groups" (consumer groups per CTA of the node-blocked SpMV: 2, or 1 for the two-CTA layout);
  * solver options of the implicit integrators: "fsai" (default 1: factorised sparse approximate inverse preconditioner
- * for systems beyond the cooperative small-system kernel; 0: Jacobi), "fsai_tau_permille" (pattern filter, default 50),
+ * for systems beyond the cooperative small-system kernel; 0: Jacobi), "fsai_tau_permille" (pattern filter, default 50), "fsai_vertex_first"
+ * (default 1: vertex equations of quadratic meshes precede mid-side equations in the factor's elimination order),
  * "pcg_projection" (previous solutions the right-hand side is projected on before PCG, default 16, 0: off) */
 int         sc_set_option(sc_ctx* ctx, const char* name, int64_t value);
 

@@ -770,6 +770,22 @@ def test_hexa20_box_stream_pcg_vs_oracle(oracle, monkeypatch):
     ctx.close()
 
 
+def test_scatter_newmark_implicit_equals_explicit(golden_meshes, tmp_path):
+    """`Solver.NEWMARK_IMPLICIT` (scatter.py:118-121 picks NewmarkImplicitForce) is the total-force form of the same
+    recurrence: for the linear systems of this path it must give the history of the default solver, through the whole
+    `scatter(...)` call."""
+    from scatter_b200 import scatter, Solver
+    c = cases.history_case("quad4_heaviside")
+    res = {}
+    for name, sv in (("explicit", Solver.NEWMARK_EXPLICIT), ("implicit", Solver.NEWMARK_IMPLICIT)):
+        out = os.path.join(tmp_path, name)
+        res[name] = scatter(golden_meshes[c["mesh"]], out, c["materials"], c["bc"], dict(c["settings"]), dict(c["loading"]),
+                            time_step=c["time_step"], solver=sv)
+    assert np.abs(res["explicit"].dis).max() > 0
+    for f in ("dis", "vel", "acc"):
+        assert np.array_equal(getattr(res["explicit"], f), getattr(res["implicit"], f)), f
+
+
 def test_scatter_entry_point_writes_reference_layout(golden_meshes, golden_histories, tmp_path):
     from scatter_b200 import scatter
     c = cases.history_case("quad4_heaviside")
