@@ -45,7 +45,7 @@ void free_pattern(sc_ctx* c) {
     sc_free(&c->d_node_rl); sc_free(&c->d_node_row0); sc_free(&c->d_rowptr); sc_free(&c->d_col); sc_free(&c->d_nd); sc_free(&c->d_ncol); sc_free(&c->d_dict); c->n_dict = 0; sc_free(&c->d_pair_pos); sc_free(&c->d_pair_al);
     asm_release_scratch(c);
     sc_free(&c->d_blk_elem); sc_free(&c->d_blk_U); sc_free(&c->d_pair_ui); sc_free(&c->d_blk_desc);
-    c->blk_npb = c->blk_ppb = c->blk_umax = c->blk_desc_stride = 0;
+    c->blk_npb = c->blk_imax = c->blk_ppb = c->blk_umax = c->blk_desc_stride = 0; c->blk_count = 0;
     sc_free(&c->d_K); sc_free(&c->d_M); sc_free(&c->d_Ml); sc_free(&c->d_Khat); sc_free(&c->d_Khat2); sc_free(&c->d_C); c->csr_only = false;
     sc_free(&c->d_cabs_rowid); sc_free(&c->d_cabs_rptr); sc_free(&c->d_cabs_col); sc_free(&c->d_cabs_slot); sc_free(&c->d_cabs_val);
     c->cabs_n = c->cabs_rows = 0;

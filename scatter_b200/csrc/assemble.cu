@@ -19,6 +19,7 @@
 // which equals B^T D B with the reference's Voigt ordering; detJ is used signed (discretisation.py:126).
 #include <algorithm>
 #include <cstdlib>
+#include <cub/device/device_scan.cuh>
 #include "common.h"
 #include "tma.h"
 
@@ -629,15 +630,48 @@ k_elem_records(const double* __restrict__ xyz, const int32_t* __restrict__ conn,
     for (int t = tid; t < cnt; t += 128) dst[t] = s_rec[t];
 }
 
-// distinct elements of the pairs of every block of npb consecutive nodes, ascending; one thread per pair
+// Node blocks of the record-fed kernel: as many consecutive nodes as fit into the ppb pair lanes of a CTA (greedy, restarted
+// at every chunk of BLK_CHUNK nodes so that the chunks pack in parallel).  A fixed count of ppb / max_valence nodes leaves
+// lanes idle wherever valences differ (hexa20: vertex nodes 8, mid-side nodes 4 elements; unstructured meshes).  Node and
+// item caps bound the per-block arrays (shared memory of the kernel): see asm_build_block_desc.
+// FILL = false: blocks per chunk; FILL = true: first node of every block (blocks of chunk c start at chunk_ptr[c]).
+constexpr int BLK_CHUNK = 128;
+template <bool FILL>
+__global__ void k_blk_chunks(const int64_t* __restrict__ n2e_ptr, const int64_t* __restrict__ nbr_ptr, int64_t n_nodes, int ppb,
+                             int node_cap, int item_cap, int64_t* __restrict__ cnt, const int64_t* __restrict__ chunk_ptr, int64_t* __restrict__ blk_first,
+                             int* __restrict__ maxima) {
+    const int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const int64_t a0 = c * BLK_CHUNK;
+    if (a0 >= n_nodes) return;
+    const int64_t a1 = min(a0 + BLK_CHUNK, n_nodes);
+    int64_t nb = 0, out = FILL ? chunk_ptr[c] : 0;
+    int pairs = 0, nodes = 0, items = 0, max_nodes = 0, max_items = 0;
+    for (int64_t a = a0; a < a1; ++a) {
+        const int v = (int)(n2e_ptr[a + 1] - n2e_ptr[a]);
+        const int ni = (int)(nbr_ptr[a + 1] - nbr_ptr[a]);
+        if (nodes > 0 && (pairs + v > ppb || nodes >= node_cap || items + ni > item_cap)) {   // close the block
+            max_nodes = max(max_nodes, nodes); max_items = max(max_items, items);
+            pairs = 0; nodes = 0; items = 0;
+        }
+        if (nodes == 0) {
+            if (FILL) blk_first[out + nb] = a;
+            ++nb;
+        }
+        pairs += v; ++nodes; items += ni;
+    }
+    max_nodes = max(max_nodes, nodes); max_items = max(max_items, items);
+    if (!FILL) { cnt[c] = nb; atomicMax(&maxima[0], max_nodes); atomicMax(&maxima[1], max_items); }
+}
+
+// distinct elements of the pairs of every node block, ascending; one thread per pair
 __global__ void k_blk_desc(const int64_t* __restrict__ n2e_ptr, const int32_t* __restrict__ n2e, const int32_t* __restrict__ node_rl,
-                           int64_t n_nodes, int npb, int ppb, int32_t* __restrict__ blk_elem, int32_t* __restrict__ blk_U,
+                           const int64_t* __restrict__ blk_first, int ppb, int32_t* __restrict__ blk_elem, int32_t* __restrict__ blk_U,
                            uint8_t* __restrict__ pair_ui, int* __restrict__ umax) {
     extern __shared__ int s_desc[];
     int* s_e = s_desc;                                   // [ppb] element of the pair (-1: none / node without rows)
     int* s_f = s_desc + ppb;                             // [ppb] 1: first pair of its element in the block
     const int k = threadIdx.x;
-    const int64_t a0 = (int64_t)blockIdx.x * npb, a1 = min(a0 + npb, n_nodes);
+    const int64_t a0 = blk_first[blockIdx.x], a1 = blk_first[blockIdx.x + 1];
     const int64_t P0 = n2e_ptr[a0];
     const int npairs = (int)(n2e_ptr[a1] - P0);
     int e = -1;
@@ -686,7 +720,7 @@ struct DescLayout {                                      // byte offsets inside 
     int stride;                                          // multiple of 16
     int o_ptr, o_nptr, o_rl, o_eq, o_runs, o_rowbase, o_off, o_ui, o_al, o_pos, o_fmask;
 };
-inline DescLayout make_desc_layout(int npb, int ppb, int nne, int dim, int max_nbr, int umax) {
+inline DescLayout make_desc_layout(int npb, int imax, int ppb, int nne, int dim, int umax) {   // npb / imax: most nodes / items of a block
     DescLayout L;
     int o = 16;                                          // header: npairs, nbn, n_items, U | runs << 16
     L.o_ptr = o; o += 4 * (npb + 1);
@@ -696,11 +730,11 @@ inline DescLayout make_desc_layout(int npb, int ppb, int nne, int dim, int max_n
     L.o_runs = o; o += 8 * umax;                         // runs of consecutive element ids: first element, first slot | count << 16
     o = (o + 7) & ~7;
     L.o_rowbase = o; o += 8 * npb * dim;
-    L.o_off = o; o += 2 * npb * max_nbr;
+    L.o_off = o; o += 2 * imax;
     L.o_ui = o; o += ppb;
     L.o_al = o; o += ppb;
     L.o_pos = o; o += ppb * nne;
-    L.o_fmask = o; o += npb * max_nbr;
+    L.o_fmask = o; o += imax;
     L.stride = (o + 15) & ~15;
     return L;
 }
@@ -710,10 +744,11 @@ k_blk_pack(const int64_t* __restrict__ n2e_ptr, const int64_t* __restrict__ nbr_
            const int32_t* __restrict__ eq, const int64_t* __restrict__ rowptr, const uint16_t* __restrict__ nbr_off,
            const uint8_t* __restrict__ nbr_free, const uint8_t* __restrict__ pair_al, const uint8_t* __restrict__ pair_pos,
            const int32_t* __restrict__ blk_elem, const int32_t* __restrict__ blk_U, const uint8_t* __restrict__ pair_ui,
-           int64_t n_nodes, int npb, int ppb, int nne, int dim, int max_nbr, int umax, DescLayout L, unsigned char* __restrict__ out) {
+           const int64_t* __restrict__ blk_first, int npb, int imax, int ppb, int nne, int dim, int umax, DescLayout L,
+           unsigned char* __restrict__ out) {
     unsigned char* D = out + (size_t)blockIdx.x * L.stride;
     const int tid = threadIdx.x;
-    const int64_t a0 = (int64_t)blockIdx.x * npb, a1 = min(a0 + npb, n_nodes);
+    const int64_t a0 = blk_first[blockIdx.x], a1 = blk_first[blockIdx.x + 1];
     const int nbn = (int)(a1 - a0);
     const int64_t P0 = n2e_ptr[a0], nbr0 = nbr_ptr[a0];
     const int npairs = (int)(n2e_ptr[a1] - P0), n_items = (int)(nbr_ptr[a1] - nbr0);
@@ -752,14 +787,14 @@ k_blk_pack(const int64_t* __restrict__ n2e_ptr, const int64_t* __restrict__ nbr_
         D[L.o_al + t] = t < npairs ? pair_al[P0 + t] : (unsigned char)0;
     }
     for (int t = tid; t < ppb * nne; t += 128) D[L.o_pos + t] = t < npairs * nne ? pair_pos[P0 * nne + t] : (unsigned char)0;
-    for (int t = tid; t < npb * max_nbr; t += 128) {
+    for (int t = tid; t < imax; t += 128) {
         reinterpret_cast<uint16_t*>(D + L.o_off)[t] = t < n_items ? nbr_off[nbr0 + t] : (uint16_t)0;
         D[L.o_fmask + t] = t < n_items ? nbr_free[nbr0 + t] : (unsigned char)0;
     }
 }
 
 struct TmaSmem { size_t srec, stage, stage_m, sdN, sN, mitem, bars, desc, inv, total; };
-__host__ __device__ inline TmaSmem tma_smem_layout(int rec, int umax, int ppb, int sst, int nne, int dim, int ngp, int npb, int max_nbr, int desc_stride) {
+__host__ __device__ inline TmaSmem tma_smem_layout(int rec, int umax, int ppb, int sst, int nne, int dim, int ngp, int imax, int max_nbr, int desc_stride) {
     TmaSmem m;
     size_t o = 0;
     m.srec = o; o += (size_t)umax * rec * 8;
@@ -767,7 +802,7 @@ __host__ __device__ inline TmaSmem tma_smem_layout(int rec, int umax, int ppb, i
     m.stage_m = o; o += (size_t)ppb * nne * 8;
     m.sdN = o; o += (size_t)ngp * nne * dim * 8;
     m.sN = o; o += (size_t)ngp * nne * 8;
-    m.mitem = o; o += (size_t)npb * max_nbr * 8;
+    m.mitem = o; o += (size_t)imax * 8;
     m.bars = o; o += 4 * 8;
     o = (o + 15) & ~(size_t)15;
     m.desc = o; o += 2 * (size_t)desc_stride;
@@ -779,7 +814,7 @@ __host__ __device__ inline TmaSmem tma_smem_layout(int rec, int umax, int ppb, i
 template <int NNE, int DIM, int NGP, int TPB, int LPP, int MINB>
 __global__ void __launch_bounds__(TPB, MINB)
 k_assemble_tma(AsmParams p, const double* __restrict__ rec, const unsigned char* __restrict__ desc, DescLayout L, int64_t n_blocks,
-               int npb, int umax) {
+               int imax, int umax) {
     constexpr int DD = DIM * DIM, ND = NNE * DIM;
     constexpr int NBB = NNE / LPP;
     constexpr int PPB = TPB / LPP;
@@ -788,7 +823,7 @@ k_assemble_tma(AsmParams p, const double* __restrict__ rec, const unsigned char*
     constexpr int UGB = SC_BLK_UG;
     static_assert(NNE % LPP == 0 && (TPB / 32) % LPP == 0 && PPB <= 255, "unsupported split");
     extern __shared__ __align__(128) unsigned char smem_b[];
-    const TmaSmem sm = tma_smem_layout(REC, umax, PPB, SST, NNE, DIM, NGP, npb, p.max_nbr, L.stride);
+    const TmaSmem sm = tma_smem_layout(REC, umax, PPB, SST, NNE, DIM, NGP, imax, p.max_nbr, L.stride);
     double* srec = reinterpret_cast<double*>(smem_b + sm.srec);
     double* stage = reinterpret_cast<double*>(smem_b + sm.stage);
     double* stage_m = reinterpret_cast<double*>(smem_b + sm.stage_m);
@@ -1014,11 +1049,9 @@ int launch_tma_cfg(sc_ctx* ctx, const AsmParams& p, const ShapeTable& t, bool* h
     if (ctx->no_asm_records || !ctx->d_blk_desc || !p.pair_pos || ctx->blk_ppb != PPB || ctx->max_valence <= 0 ||
         ctx->max_valence > PPB || p.max_nbr > 255)
         return SC_OK;
-    const int npb = std::max(1, PPB / ctx->max_valence);
-    if (npb != ctx->blk_npb) return SC_OK;
-    const DescLayout L = make_desc_layout(npb, PPB, NNE, DIM, p.max_nbr, ctx->blk_umax);
+    const DescLayout L = make_desc_layout(ctx->blk_npb, ctx->blk_imax, PPB, NNE, DIM, ctx->blk_umax);
     if (L.stride != ctx->blk_desc_stride) return SC_OK;
-    const TmaSmem sm = tma_smem_layout(REC, ctx->blk_umax, PPB, SST, NNE, DIM, NGP, npb, p.max_nbr, L.stride);
+    const TmaSmem sm = tma_smem_layout(REC, ctx->blk_umax, PPB, SST, NNE, DIM, NGP, ctx->blk_imax, p.max_nbr, L.stride);
     if (sm.total > 112 * 1024) return SC_OK;
     const size_t rec_doubles = (size_t)ctx->n_elem * REC;
     if (ctx->asm_rec_cap < rec_doubles) {
@@ -1039,9 +1072,9 @@ int launch_tma_cfg(sc_ctx* ctx, const AsmParams& p, const ShapeTable& t, bool* h
     k_elem_records<NNE, DIM, NGP><<<(unsigned)((ctx->n_elem + EPB - 1) / EPB), 128, 0, ctx->stream>>>(
         p.xyz, p.conn, p.E, p.nu, p.rho, p.tabdN, p.tabw, ctx->n_elem, ctx->d_asm_rec);
     SC_CHECK_LAUNCH(ctx);
-    const int64_t n_blocks = (p.n_nodes + npb - 1) / npb;
+    const int64_t n_blocks = ctx->blk_count;
     const unsigned grid = (unsigned)std::min<int64_t>(n_blocks, (int64_t)ctx->sm_count * occ);
-    kern<<<grid, TPB, sm.total, ctx->stream>>>(p, ctx->d_asm_rec, ctx->d_blk_desc, L, n_blocks, npb, ctx->blk_umax);
+    kern<<<grid, TPB, sm.total, ctx->stream>>>(p, ctx->d_asm_rec, ctx->d_blk_desc, L, n_blocks, ctx->blk_imax, ctx->blk_umax);
     SC_CHECK_LAUNCH(ctx);
     *handled = true;
     return SC_OK;
@@ -1121,51 +1154,88 @@ void asm_release_scratch(sc_ctx* ctx) {
 
 int asm_build_block_desc(sc_ctx* ctx) {
     sc_free(&ctx->d_blk_elem); sc_free(&ctx->d_blk_U); sc_free(&ctx->d_pair_ui); sc_free(&ctx->d_blk_desc);
-    ctx->blk_npb = ctx->blk_ppb = ctx->blk_umax = ctx->blk_desc_stride = 0;
-    if (!ctx->d_pair_pos || ctx->max_valence <= 0 || ctx->n_nodes <= 0) return SC_OK;
+    ctx->blk_npb = ctx->blk_imax = ctx->blk_ppb = ctx->blk_umax = ctx->blk_desc_stride = 0;
+    ctx->blk_count = 0;
+    if (!ctx->d_pair_pos || ctx->max_valence <= 0 || ctx->n_nodes <= 0 || ctx->max_nbr > 255) return SC_OK;
     int tpb = 0, lpp = 1;
     asm_blk_shape(ctx->nne, ctx->dim, &tpb, &lpp);
     const int ppb = tpb / lpp;
     if (ctx->max_valence > ppb) return SC_OK;
-    const int npb = std::max(1, ppb / ctx->max_valence);
-    const int64_t n_blocks = (ctx->n_nodes + npb - 1) / npb;
+    cudaStream_t st = ctx->stream;
+    const int64_t n_chunks = (ctx->n_nodes + BLK_CHUNK - 1) / BLK_CHUNK;
     const int64_t n_pairs = ctx->n_elem * ctx->nne;
-    int* d_umax = nullptr;
-    SC_TRY(sc_alloc(ctx, &ctx->d_blk_elem, (size_t)n_blocks * ppb));
-    SC_TRY(sc_alloc(ctx, &ctx->d_blk_U, (size_t)n_blocks));
-    SC_TRY(sc_alloc(ctx, &ctx->d_pair_ui, (size_t)n_pairs));
-    SC_TRY(sc_alloc(ctx, &d_umax, 1));
-    cudaMemsetAsync(d_umax, 0, sizeof(int), ctx->stream);
-    cudaMemsetAsync(ctx->d_blk_elem, 0xff, (size_t)n_blocks * ppb * sizeof(int32_t), ctx->stream);
-    cudaMemsetAsync(ctx->d_pair_ui, 0xff, (size_t)n_pairs, ctx->stream);
-    k_blk_desc<<<(unsigned)n_blocks, ppb, 2 * ppb * sizeof(int), ctx->stream>>>(ctx->d_n2e_ptr, ctx->d_n2e, ctx->d_node_rl, ctx->n_nodes, npb, ppb,
-                                                                                 ctx->d_blk_elem, ctx->d_blk_U, ctx->d_pair_ui, d_umax);
-    ctx->launches++;
-    int umax = 0;
-    cudaError_t e = cudaGetLastError();
-    if (e == cudaSuccess) e = cudaMemcpyAsync(&umax, d_umax, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-    sc_free(&d_umax);
-    if (e != cudaSuccess) return sc_fail(ctx, SC_ERR_CUDA, "block descriptors of the assembly failed: %s", cudaGetErrorString(e));
-    ctx->blk_npb = npb; ctx->blk_ppb = ppb; ctx->blk_umax = std::max(umax, 1);
-    // packed per-block descriptors of the persistent kernel
-    const DescLayout L = make_desc_layout(npb, ppb, ctx->nne, ctx->dim, ctx->max_nbr, ctx->blk_umax);
-    size_t free_b = 0, total_b = 0;
-    const size_t desc_bytes = (size_t)n_blocks * L.stride;
-    if (ctx->max_nbr > 255 || cudaMemGetInfo(&free_b, &total_b) != cudaSuccess || free_b < desc_bytes + (size_t(4) << 30)) return SC_OK;
-    SC_TRY(sc_alloc(ctx, &ctx->d_blk_desc, desc_bytes));
-    cudaMemsetAsync(ctx->d_blk_desc, 0, desc_bytes, ctx->stream);
-    k_blk_pack<<<(unsigned)n_blocks, 128, 0, ctx->stream>>>(ctx->d_n2e_ptr, ctx->d_nbr_ptr, ctx->d_node_rl, ctx->d_eq, ctx->d_rowptr, ctx->d_nbr_off,
-                                                            ctx->d_nbr_free, ctx->d_pair_al, ctx->d_pair_pos, ctx->d_blk_elem, ctx->d_blk_U,
-                                                            ctx->d_pair_ui, ctx->n_nodes, npb, ppb, ctx->nne, ctx->dim, ctx->max_nbr, ctx->blk_umax, L,
-                                                            ctx->d_blk_desc);
-    ctx->launches++;
-    e = cudaGetLastError();
-    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-    if (e != cudaSuccess) return sc_fail(ctx, SC_ERR_CUDA, "packing the block descriptors of the assembly failed: %s", cudaGetErrorString(e));
-    ctx->blk_desc_stride = L.stride;
+    int64_t *d_cnt = nullptr, *d_cptr = nullptr, *d_first = nullptr;
+    int* d_max = nullptr;
+    int rc = SC_OK;
+    auto body = [&]() -> int {
+        // 1. node blocks: greedy packing by pair count, chunk by chunk
+        SC_TRY(sc_alloc(ctx, &d_cnt, (size_t)n_chunks + 1));
+        SC_TRY(sc_alloc(ctx, &d_cptr, (size_t)n_chunks + 1));
+        SC_TRY(sc_alloc(ctx, &d_max, 3));
+        SC_CUDA(ctx, cudaMemsetAsync(d_max, 0, 3 * sizeof(int), st));
+        SC_CUDA(ctx, cudaMemsetAsync(d_cnt + n_chunks, 0, sizeof(int64_t), st));
+        const unsigned cg = (unsigned)((n_chunks + 127) / 128);
+        // caps relative to the uniform packing ppb / max_valence: twice the nodes; the same number of (node, neighbour) items
+        // for linear elements (valences only differ at boundaries; the hexa8 kernel sits 1.3 kB below the shared memory of
+        // three CTAs per SM), a third more for quadratic ones, whose mid-side nodes have half the valence of the vertices
+        const int npb0 = std::max(1, ppb / ctx->max_valence);
+        const bool quadratic = ctx->elem_type == SC_TRI6 || ctx->elem_type == SC_QUAD8 || ctx->elem_type == SC_TETRA10 || ctx->elem_type == SC_HEXA20;
+        const int node_cap = 2 * npb0, item_cap = std::max(npb0 * ctx->max_nbr * (quadratic ? 4 : 3) / 3, ctx->max_nbr);
+        k_blk_chunks<false><<<cg, 128, 0, st>>>(ctx->d_n2e_ptr, ctx->d_nbr_ptr, ctx->n_nodes, ppb, node_cap, item_cap, d_cnt, nullptr, nullptr, d_max);
+        SC_CHECK_LAUNCH(ctx);
+        size_t tmp_bytes = 0;
+        SC_CUDA(ctx, cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, d_cnt, d_cptr, n_chunks + 1, st));
+        void* tmp = nullptr;
+        SC_CUDA(ctx, cudaMalloc(&tmp, tmp_bytes ? tmp_bytes : 1));
+        const cudaError_t se = cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, d_cnt, d_cptr, n_chunks + 1, st);
+        ctx->launches += 2;
+        int64_t n_blocks = 0;
+        cudaError_t ce = cudaMemcpyAsync(&n_blocks, d_cptr + n_chunks, sizeof(int64_t), cudaMemcpyDeviceToHost, st);
+        int h_max[3] = {0, 0, 0};
+        if (ce == cudaSuccess) ce = cudaMemcpyAsync(h_max, d_max, 2 * sizeof(int), cudaMemcpyDeviceToHost, st);
+        if (ce == cudaSuccess) ce = cudaStreamSynchronize(st);
+        cudaFree(tmp);
+        if (se != cudaSuccess || ce != cudaSuccess)
+            return sc_fail(ctx, SC_ERR_CUDA, "node blocks of the assembly failed: %s", cudaGetErrorString(se != cudaSuccess ? se : ce));
+        SC_TRY(sc_alloc(ctx, &d_first, (size_t)n_blocks + 1));
+        k_blk_chunks<true><<<cg, 128, 0, st>>>(ctx->d_n2e_ptr, ctx->d_nbr_ptr, ctx->n_nodes, ppb, node_cap, item_cap, nullptr, d_cptr, d_first, nullptr);
+        SC_CHECK_LAUNCH(ctx);
+        SC_CUDA(ctx, cudaMemcpyAsync(d_first + n_blocks, &ctx->n_nodes, sizeof(int64_t), cudaMemcpyHostToDevice, st));
+        // 2. distinct elements per block, each pair's index into that list
+        SC_TRY(sc_alloc(ctx, &ctx->d_blk_elem, (size_t)n_blocks * ppb));
+        SC_TRY(sc_alloc(ctx, &ctx->d_blk_U, (size_t)n_blocks));
+        SC_TRY(sc_alloc(ctx, &ctx->d_pair_ui, (size_t)n_pairs));
+        SC_CUDA(ctx, cudaMemsetAsync(ctx->d_blk_elem, 0xff, (size_t)n_blocks * ppb * sizeof(int32_t), st));
+        SC_CUDA(ctx, cudaMemsetAsync(ctx->d_pair_ui, 0xff, (size_t)n_pairs, st));
+        k_blk_desc<<<(unsigned)n_blocks, ppb, 2 * ppb * sizeof(int), st>>>(ctx->d_n2e_ptr, ctx->d_n2e, ctx->d_node_rl, d_first, ppb, ctx->d_blk_elem,
+                                                                          ctx->d_blk_U, ctx->d_pair_ui, d_max + 2);
+        SC_CHECK_LAUNCH(ctx);
+        int umax = 0;
+        SC_CUDA(ctx, cudaMemcpyAsync(&umax, d_max + 2, sizeof(int), cudaMemcpyDeviceToHost, st));
+        SC_CUDA(ctx, cudaStreamSynchronize(st));
+        const int npb = std::max(h_max[0], 1), imax = std::max(h_max[1], 1);
+        umax = std::max(umax, 1);
+        // 3. packed per-block descriptors of the persistent kernel
+        const DescLayout L = make_desc_layout(npb, imax, ppb, ctx->nne, ctx->dim, umax);
+        size_t free_b = 0, total_b = 0;
+        const size_t desc_bytes = (size_t)n_blocks * L.stride;
+        if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess || free_b < desc_bytes + (size_t(4) << 30)) return SC_OK;
+        SC_TRY(sc_alloc(ctx, &ctx->d_blk_desc, desc_bytes));
+        SC_CUDA(ctx, cudaMemsetAsync(ctx->d_blk_desc, 0, desc_bytes, st));
+        k_blk_pack<<<(unsigned)n_blocks, 128, 0, st>>>(ctx->d_n2e_ptr, ctx->d_nbr_ptr, ctx->d_node_rl, ctx->d_eq, ctx->d_rowptr, ctx->d_nbr_off,
+                                                        ctx->d_nbr_free, ctx->d_pair_al, ctx->d_pair_pos, ctx->d_blk_elem, ctx->d_blk_U,
+                                                        ctx->d_pair_ui, d_first, npb, imax, ppb, ctx->nne, ctx->dim, umax, L, ctx->d_blk_desc);
+        SC_CHECK_LAUNCH(ctx);
+        SC_CUDA(ctx, cudaStreamSynchronize(st));
+        ctx->blk_npb = npb; ctx->blk_imax = imax; ctx->blk_ppb = ppb; ctx->blk_umax = umax;
+        ctx->blk_count = n_blocks; ctx->blk_desc_stride = L.stride;
+        return SC_OK;
+    };
+    rc = body();
+    sc_free(&d_cnt); sc_free(&d_cptr); sc_free(&d_first); sc_free(&d_max);
     sc_free(&ctx->d_blk_elem); sc_free(&ctx->d_blk_U); sc_free(&ctx->d_pair_ui);      // packed into the descriptors
-    return SC_OK;
+    if (rc != SC_OK) { sc_free(&ctx->d_blk_desc); ctx->blk_desc_stride = 0; }
+    return rc;
 }
 
 int sc_assemble_run(sc_ctx* ctx, int order, int flags, double* seconds) {

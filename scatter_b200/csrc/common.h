@@ -84,7 +84,8 @@ struct sc_ctx {
     int32_t* d_blk_elem = nullptr;  // [n_blocks][blk_ppb] distinct elements of every block of blk_npb consecutive nodes, ascending
     int32_t* d_blk_U = nullptr;     // [n_blocks] how many                      (these three only live until k_blk_pack has
     uint8_t* d_pair_ui = nullptr;   // [n_pairs] index of the pair's element in its block's list (255: none)    packed them)
-    int blk_npb = 0, blk_ppb = 0, blk_umax = 0;
+    int blk_npb = 0, blk_imax = 0, blk_ppb = 0, blk_umax = 0;   // most nodes / (node, neighbour) items / pair lanes / distinct elements of a block
+    int64_t blk_count = 0;          // node blocks (consecutive nodes packed greedily into the pair lanes of a CTA)
     unsigned char* d_blk_desc = nullptr;   // [n_blocks][blk_desc_stride] packed block descriptors of the persistent kernel (k_blk_pack)
     int blk_desc_stride = 0;
     double* d_asm_rec = nullptr;    // [n_elem][REC] element records (scratch of the assembly, see asm_release_scratch)

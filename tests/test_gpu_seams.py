@@ -250,3 +250,43 @@ def test_layered_box_with_moving_plane_load(oracle, tmp_path):
     # the load really travels: the loaded dofs at the first and last loaded step differ
     f0, f1 = force(12), force(len(time) - 1)
     assert set(np.nonzero(f0)[0]) != set(np.nonzero(f1)[0])
+
+
+@pytest.mark.parametrize("order20,vertex_first", [("grouped", 1), ("interleaved", 1), ("interleaved", 0)])
+def test_hexa20_box_implicit_vs_oracle(order20, vertex_first, oracle, monkeypatch):
+    """BASELINE config 4 at a size the oracle's direct solve finishes in seconds: hexa20 box of the benchmark generator in both
+    node numberings (lattice by lattice / cell by cell), pattern bit-exact, K and consistent M <= 1e-12, and a Newmark history
+    through the driver large systems use (FSAI with either elimination order + projection + true-residual check, rtol 1e-12)
+    <= 1e-8 against the oracle's `splu` recurrence."""
+    from scatter_b200 import _lib, boxmesh, system_matrix
+    monkeypatch.setitem(_lib.DEFAULT_OPTIONS, "small_pcg", 0)
+    monkeypatch.setitem(_lib.DEFAULT_OPTIONS, "fsai_vertex_first", vertex_first)
+    s, h = 8, 0.5
+    model = boxmesh.box_model(s, s, s, h, "hexa20", hexa20_order=order20)
+    model.connectivities()
+    ne, n = len(model.elem), model.number_eq
+    E = boxmesh.lognormal_young(ne, 30e6, 1e6, seed=5); nu = np.full(ne, 0.2); rho = np.full(ne, 1500.0)
+    Ko, Mo = oracle.assemble_global(oracle.model_from_readmesh(model), E, nu, rho, 2)
+    Ko = sp.csr_matrix(Ko); Mo = sp.csr_matrix(Mo)
+    mx = system_matrix.GenerateMatrix(n, 2)
+    mx.generate_stiffness_and_mass(model, None, elem_props=(E, nu, rho))
+    damping = [1, 0.01, 30, 0.01]
+    mx.damping_Rayleigh(damping)
+    ctx = mx.ctx
+    rowptr, col = mx.pattern()
+    assert np.array_equal(rowptr, Ko.indptr) and np.array_equal(col, Ko.indices)
+    assert np.abs(ctx.get_values(_lib.MAT_K) - Ko.data).max() <= 1e-12 * np.abs(Ko.data).max()
+    assert np.abs(ctx.get_values(_lib.MAT_M) - Mo.data).max() <= 1e-12 * np.abs(Mo.data).max()
+    c0, c1 = oracle.rayleigh_coefficients(damping)
+    nt = 21
+    dof = int(model.eq_nb_dof[boxmesh.top_centre_node(s, s, s, model=model, h=h) - 1, 1])
+    force, sched = _point_load(n, dof, nt)
+    dt = 5e-4
+    U, V, A, _ = oracle.newmark(Mo, Mo * c0 + Ko * c1, Ko, force, np.arange(nt) * dt, 5)
+    ctx.set_load_schedule(*sched)
+    ctx.set_state(None, None)
+    u, v, a, st = ctx.run_newmark(dt, 0, nt - 1, 5, rtol=1e-12)
+    assert np.abs(U).max() > 0 and rel_l2(u, U) <= TOL_HIST and rel_l2(v, V) <= TOL_HIST
+    info = ctx.precond_info()
+    assert info["fsai_nnz"] > n and st["pcg_iterations"] > 0
+    ctx.close()
