@@ -9,8 +9,10 @@
 // the elements touching its node.  A block of consecutive nodes therefore produces its CSR rows alone: it walks the
 // elements of each node in ascending element id -- the order in which the reference adds them to a slot -- evaluates
 // only the DIM x (NNE*DIM) row block of Ke that belongs to the node, and sums per slot in that order.  Nobody else
-// writes those rows, so the result is reproducible bit for bit.  Two kernels implement it: `k_assemble_blk` (default:
-// row block in registers, one, two or five lanes per (node, element) pair, Jacobian set-up shared by the pairs of a
+// writes those rows, so the result is reproducible bit for bit.  Three kernels implement it: `k_elem_records` +
+// `k_assemble_tma` (default: Jacobians once per element into HBM records; persistent CTAs fed by TMA bulk copies of
+// packed block descriptors and records; row block in registers, one, two or five lanes per (node, element) pair),
+// `k_assemble_blk` (round 1, same arithmetic and bits without any scratch: Jacobian set-up shared by the pairs of a
 // block) and `k_assemble` (one warp per node, shared-memory staging; very high node valences).
 //
 // Isotropic elasticity lets the row block be formed without B or D:
@@ -241,9 +243,8 @@ __global__ void k_assemble(AsmParams p, int warps) {
 // order of the reference (system_matrix.py:98-103) and needs no atomics.
 __constant__ double c_tabN[SC_MAX_GP * SC_MAX_NNE];
 __constant__ double c_tabdN[SC_MAX_GP * SC_MAX_NNE * 3];
-__constant__ double c_tabw[SC_MAX_GP];
 
-// Block-level element sharing (default for every element type).  Repeating the Jacobian set-up in every lane of every
+// Block-level element sharing (round 1; now the fallback that needs no scratch memory).  Repeating the Jacobian set-up in every lane of every
 // (node, element) pair costs 16 evaluations per hexa8 element and Gauss point inside one block alone (the previous
 // generation of this kernel did).  Here a block first lists the *distinct* elements of its pairs (consecutive nodes share most of theirs),
 // evaluates J^-1 and detJ*w once per (element, Gauss point) -- a few threads per element, coordinates in registers --
