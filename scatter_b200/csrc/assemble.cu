@@ -689,25 +689,33 @@ __global__ void k_blk_chunks(const int64_t* __restrict__ n2e_ptr, const int64_t*
     if (!FILL) { cnt[c] = nb; atomicMax(&maxima[0], max_nodes); atomicMax(&maxima[1], max_items); }
 }
 
-// distinct elements of the pairs of every node block, ascending; one thread per pair
+// distinct elements of the pairs of every node block and their record slots; one thread per pair
 __global__ void k_blk_desc(const int64_t* __restrict__ n2e_ptr, const int32_t* __restrict__ n2e, const int32_t* __restrict__ node_rl,
                            const int64_t* __restrict__ blk_first, int ppb, int32_t* __restrict__ blk_elem, int32_t* __restrict__ blk_U,
                            uint8_t* __restrict__ pair_ui, int* __restrict__ umax) {
     extern __shared__ int s_desc[];
     int* s_e = s_desc;                                   // [ppb] element of the pair (-1: none / node without rows)
-    int* s_f = s_desc + ppb;                             // [ppb] 1: first pair of its element in the block
+    int* s_f = s_e + ppb;                                // [ppb] 1: first pair of its element in the block
+    int* s_u = s_f + ppb;                                // [ppb] rank of the pair's element among the block's distinct elements
+    int* s_g0 = s_u + ppb;                               // [ppb] first pair of the pair's node
+    int* s_g1 = s_g0 + ppb;                              // [ppb] one past its last pair
+    int* s_slot = s_g1 + ppb;                            // [ppb] record slot of the element of rank u
+    int* s_used = s_slot + ppb;                          // [ppb] slot taken
     const int k = threadIdx.x;
     const int64_t a0 = blk_first[blockIdx.x], a1 = blk_first[blockIdx.x + 1];
     const int64_t P0 = n2e_ptr[a0];
     const int npairs = (int)(n2e_ptr[a1] - P0);
     int e = -1;
+    s_g0[k] = s_g1[k] = 0;
     if (k < npairs) {
         e = n2e[P0 + k];
         int64_t a = a0;
         while (a + 1 < a1 && n2e_ptr[a + 1] - P0 <= k) ++a;
         if (node_rl[a] <= 0) e = -1;
+        s_g0[k] = (int)(n2e_ptr[a] - P0); s_g1[k] = (int)(n2e_ptr[a + 1] - P0);
     }
     s_e[k] = e;
+    s_slot[k] = -1; s_used[k] = 0;
     __syncthreads();
     bool first = e >= 0;
     if (e >= 0)
@@ -715,20 +723,53 @@ __global__ void k_blk_desc(const int64_t* __restrict__ n2e_ptr, const int32_t* _
             if (s_e[j] == e) { first = false; break; }
     s_f[k] = first ? 1 : 0;
     __syncthreads();
-    if (k < npairs) {
-        int u = 255;
-        if (e >= 0) {                                    // rank of the element among the block's distinct elements (ascending id)
-            u = 0;
-            for (int j = 0; j < ppb; ++j) u += (s_f[j] && s_e[j] < e) ? 1 : 0;
-            if (first) blk_elem[(int64_t)blockIdx.x * ppb + u] = e;
-        }
-        pair_ui[P0 + k] = (uint8_t)u;
+    int u = 255;
+    if (e >= 0) {                                        // rank of the element among the block's distinct elements (ascending id)
+        u = 0;
+        for (int j = 0; j < ppb; ++j) u += (s_f[j] && s_e[j] < e) ? 1 : 0;
     }
+    s_u[k] = u;
+    __syncthreads();
+    // Record slots.  The pair lanes of a quarter warp -- the pairs of one node -- read their records with 16-byte shared
+    // loads at the same offset, so two of them meet in a bank iff their slots are equal mod 8 (the record stride is odd in
+    // 16-byte units).  With slot = rank the eight elements of a hexa8 node (ranks x, x+1, x+9, x+10, ...) collide pairwise:
+    // 2.1 wavefronts per access instead of 1 (ncu).  Greedy colouring, node by node: every element takes the lowest free
+    // slot whose residue mod 8 is not used by an element it shares a node with (else the lowest free slot) -- 1.1
+    // wavefronts on the interior blocks of a structured hexa8 mesh (ascending element id instead of node order: 1.5).
     if (k == 0) {
         int U = 0;
         for (int j = 0; j < ppb; ++j) U += s_f[j];
+        for (int jr = 0; jr < npairs; ++jr) {
+            const int r = s_u[jr];
+            if (r == 255 || s_slot[r] >= 0) continue;
+            unsigned forbid = 0;
+            for (int j = 0; j < npairs; ++j) {
+                if (s_u[j] != r) continue;
+                for (int jj = s_g0[j]; jj < s_g1[j]; ++jj) {
+                    const int uu = s_u[jj];
+                    if (uu != 255 && uu != r && s_slot[uu] >= 0) forbid |= 1u << (s_slot[uu] & 7);
+                }
+            }
+            int pick = -1, fallback = -1;
+            for (int t = 0; t < U; ++t) {
+                if (s_used[t]) continue;
+                if (fallback < 0) fallback = t;
+                if (!((forbid >> (t & 7)) & 1u)) { pick = t; break; }
+            }
+            if (pick < 0) pick = fallback;
+            s_slot[r] = pick; s_used[pick] = 1;
+        }
         blk_U[blockIdx.x] = U;
         atomicMax(umax, U);
+    }
+    __syncthreads();
+    if (k < npairs) {
+        int slot = 255;
+        if (e >= 0) {
+            slot = s_slot[u];
+            if (first) blk_elem[(int64_t)blockIdx.x * ppb + slot] = e;
+        }
+        pair_ui[P0 + k] = (uint8_t)slot;
     }
 }
 
@@ -819,13 +860,15 @@ k_blk_pack(const int64_t* __restrict__ n2e_ptr, const int64_t* __restrict__ nbr_
     }
 }
 
-struct TmaSmem { size_t srec, stage, stage_m, sdN, sN, mitem, bars, desc, inv, total; };
+struct TmaSmem { size_t srec, stage, sdN, sN, mitem, bars, desc, inv, total; };
+// staging row of one pair: its DIM x (NNE*DIM) row block followed by the NNE mass entries; odd stride, so the pair lanes
+// of a half warp (consecutive pairs) and the (node, neighbour) lanes of the gather spread over the banks
+__host__ __device__ constexpr int tma_stage_stride(int nne, int dim) { return (dim * nne * dim + nne) | 1; }
 __host__ __device__ inline TmaSmem tma_smem_layout(int rec, int umax, int ppb, int sst, int nne, int dim, int ngp, int imax, int max_nbr, int desc_stride) {
     TmaSmem m;
     size_t o = 0;
     m.srec = o; o += (size_t)umax * rec * 8;
     m.stage = o; o += (size_t)ppb * sst * 8;
-    m.stage_m = o; o += (size_t)ppb * nne * 8;
     m.sdN = o; o += (size_t)ngp * nne * dim * 8;
     m.sN = o; o += (size_t)ngp * nne * 8;
     m.mitem = o; o += (size_t)imax * 8;
@@ -844,7 +887,7 @@ k_assemble_tma(AsmParams p, const double* __restrict__ rec, const unsigned char*
     constexpr int DD = DIM * DIM, ND = NNE * DIM;
     constexpr int NBB = NNE / LPP;
     constexpr int PPB = TPB / LPP;
-    constexpr int SST = DIM * ND + 1;
+    constexpr int SST = tma_stage_stride(NNE, DIM), SMO = DIM * ND;   // row stride and offset of the mass entries in a row
     constexpr int ISTP = rec_point_stride(DIM), REC = rec_stride(DIM, NGP);
     constexpr int UGB = SC_BLK_UG;
     static_assert(NNE % LPP == 0 && (TPB / 32) % LPP == 0 && PPB <= 255, "unsupported split");
@@ -852,7 +895,6 @@ k_assemble_tma(AsmParams p, const double* __restrict__ rec, const unsigned char*
     const TmaSmem sm = tma_smem_layout(REC, umax, PPB, SST, NNE, DIM, NGP, imax, p.max_nbr, L.stride);
     double* srec = reinterpret_cast<double*>(smem_b + sm.srec);
     double* stage = reinterpret_cast<double*>(smem_b + sm.stage);
-    double* stage_m = reinterpret_cast<double*>(smem_b + sm.stage_m);
     double* sdN = reinterpret_cast<double*>(smem_b + sm.sdN);
     double* sN = reinterpret_cast<double*>(smem_b + sm.sN);
     double* s_mitem = reinterpret_cast<double*>(smem_b + sm.mitem);
@@ -987,7 +1029,7 @@ k_assemble_tma(AsmParams p, const double* __restrict__ rec, const unsigned char*
                         if (i == j) t += tr;
                         stage[(size_t)k * SST + i * ND + (half * NBB + bb) * DIM + j] = t;
                     }
-                stage_m[k * NNE + half * NBB + bb] = rho * mab[bb];
+                stage[(size_t)k * SST + SMO + half * NBB + bb] = rho * mab[bb];
             }
         }
         __syncthreads();                                 // B
@@ -1024,7 +1066,7 @@ k_assemble_tma(AsmParams p, const double* __restrict__ rec, const unsigned char*
                     for (int i = 0; i < DIM; ++i)
 #pragma unroll
                         for (int j = 0; j < DIM; ++j) blk[i][j] += sp[i * ND + j];
-                    m += stage_m[(pr0 + c) * NNE + bl];
+                    m += stage[(size_t)(pr0 + c) * SST + SMO + bl];
                 }
             }
             s_mitem[q] = m;
@@ -1069,7 +1111,7 @@ k_assemble_tma(AsmParams p, const double* __restrict__ rec, const unsigned char*
 template <int NNE, int DIM, int NGP, int TPB, int LPP, int MINB>
 int launch_tma_cfg(sc_ctx* ctx, const AsmParams& p, const ShapeTable& t, bool* handled) {
     constexpr int PPB = TPB / LPP;
-    constexpr int ND = NNE * DIM, SST = DIM * ND + 1;
+    constexpr int SST = tma_stage_stride(NNE, DIM);
     constexpr int REC = rec_stride(DIM, NGP);
     *handled = false;
     if (ctx->no_asm_records || !ctx->d_blk_desc || !p.pair_pos || ctx->blk_ppb != PPB || ctx->max_valence <= 0 ||
@@ -1233,7 +1275,7 @@ int asm_build_block_desc(sc_ctx* ctx) {
         SC_TRY(sc_alloc(ctx, &ctx->d_pair_ui, (size_t)n_pairs));
         SC_CUDA(ctx, cudaMemsetAsync(ctx->d_blk_elem, 0xff, (size_t)n_blocks * ppb * sizeof(int32_t), st));
         SC_CUDA(ctx, cudaMemsetAsync(ctx->d_pair_ui, 0xff, (size_t)n_pairs, st));
-        k_blk_desc<<<(unsigned)n_blocks, ppb, 2 * ppb * sizeof(int), st>>>(ctx->d_n2e_ptr, ctx->d_n2e, ctx->d_node_rl, d_first, ppb, ctx->d_blk_elem,
+        k_blk_desc<<<(unsigned)n_blocks, ppb, 7 * ppb * sizeof(int), st>>>(ctx->d_n2e_ptr, ctx->d_n2e, ctx->d_node_rl, d_first, ppb, ctx->d_blk_elem,
                                                                           ctx->d_blk_U, ctx->d_pair_ui, d_max + 2);
         SC_CHECK_LAUNCH(ctx);
         int umax = 0;
