@@ -689,33 +689,25 @@ __global__ void k_blk_chunks(const int64_t* __restrict__ n2e_ptr, const int64_t*
     if (!FILL) { cnt[c] = nb; atomicMax(&maxima[0], max_nodes); atomicMax(&maxima[1], max_items); }
 }
 
-// distinct elements of the pairs of every node block and their record slots; one thread per pair
+// distinct elements of the pairs of every node block, ascending; one thread per pair
 __global__ void k_blk_desc(const int64_t* __restrict__ n2e_ptr, const int32_t* __restrict__ n2e, const int32_t* __restrict__ node_rl,
                            const int64_t* __restrict__ blk_first, int ppb, int32_t* __restrict__ blk_elem, int32_t* __restrict__ blk_U,
                            uint8_t* __restrict__ pair_ui, int* __restrict__ umax) {
     extern __shared__ int s_desc[];
     int* s_e = s_desc;                                   // [ppb] element of the pair (-1: none / node without rows)
-    int* s_f = s_e + ppb;                                // [ppb] 1: first pair of its element in the block
-    int* s_u = s_f + ppb;                                // [ppb] rank of the pair's element among the block's distinct elements
-    int* s_g0 = s_u + ppb;                               // [ppb] first pair of the pair's node
-    int* s_g1 = s_g0 + ppb;                              // [ppb] one past its last pair
-    int* s_slot = s_g1 + ppb;                            // [ppb] record slot of the element of rank u
-    int* s_used = s_slot + ppb;                          // [ppb] slot taken
+    int* s_f = s_desc + ppb;                             // [ppb] 1: first pair of its element in the block
     const int k = threadIdx.x;
     const int64_t a0 = blk_first[blockIdx.x], a1 = blk_first[blockIdx.x + 1];
     const int64_t P0 = n2e_ptr[a0];
     const int npairs = (int)(n2e_ptr[a1] - P0);
     int e = -1;
-    s_g0[k] = s_g1[k] = 0;
     if (k < npairs) {
         e = n2e[P0 + k];
         int64_t a = a0;
         while (a + 1 < a1 && n2e_ptr[a + 1] - P0 <= k) ++a;
         if (node_rl[a] <= 0) e = -1;
-        s_g0[k] = (int)(n2e_ptr[a] - P0); s_g1[k] = (int)(n2e_ptr[a + 1] - P0);
     }
     s_e[k] = e;
-    s_slot[k] = -1; s_used[k] = 0;
     __syncthreads();
     bool first = e >= 0;
     if (e >= 0)
@@ -723,53 +715,25 @@ __global__ void k_blk_desc(const int64_t* __restrict__ n2e_ptr, const int32_t* _
             if (s_e[j] == e) { first = false; break; }
     s_f[k] = first ? 1 : 0;
     __syncthreads();
-    int u = 255;
-    if (e >= 0) {                                        // rank of the element among the block's distinct elements (ascending id)
-        u = 0;
-        for (int j = 0; j < ppb; ++j) u += (s_f[j] && s_e[j] < e) ? 1 : 0;
+    // record slot of an element = its rank among the block's distinct elements (ascending id): consecutive elements sit in
+    // consecutive slots and are fetched as one bulk copy.  (Measured and dropped: colouring the slots so that the eight
+    // elements of a node fall into different shared-memory banks -- their ranks x, x+1, x+9, x+10, ... collide pairwise
+    // on the 16-byte record reads, 2.1 wavefronts instead of 1 -- saved 1.3 ms per assembly of the 255^3 box and cost
+    // 31 ms in this kernel, once per pattern.)
+    if (k < npairs) {
+        int u = 255;
+        if (e >= 0) {
+            u = 0;
+            for (int j = 0; j < ppb; ++j) u += (s_f[j] && s_e[j] < e) ? 1 : 0;
+            if (first) blk_elem[(int64_t)blockIdx.x * ppb + u] = e;
+        }
+        pair_ui[P0 + k] = (uint8_t)u;
     }
-    s_u[k] = u;
-    __syncthreads();
-    // Record slots.  The pair lanes of a quarter warp -- the pairs of one node -- read their records with 16-byte shared
-    // loads at the same offset, so two of them meet in a bank iff their slots are equal mod 8 (the record stride is odd in
-    // 16-byte units).  With slot = rank the eight elements of a hexa8 node (ranks x, x+1, x+9, x+10, ...) collide pairwise:
-    // 2.1 wavefronts per access instead of 1 (ncu).  Greedy colouring, node by node: every element takes the lowest free
-    // slot whose residue mod 8 is not used by an element it shares a node with (else the lowest free slot) -- 1.1
-    // wavefronts on the interior blocks of a structured hexa8 mesh (ascending element id instead of node order: 1.5).
     if (k == 0) {
         int U = 0;
         for (int j = 0; j < ppb; ++j) U += s_f[j];
-        for (int jr = 0; jr < npairs; ++jr) {
-            const int r = s_u[jr];
-            if (r == 255 || s_slot[r] >= 0) continue;
-            unsigned forbid = 0;
-            for (int j = 0; j < npairs; ++j) {
-                if (s_u[j] != r) continue;
-                for (int jj = s_g0[j]; jj < s_g1[j]; ++jj) {
-                    const int uu = s_u[jj];
-                    if (uu != 255 && uu != r && s_slot[uu] >= 0) forbid |= 1u << (s_slot[uu] & 7);
-                }
-            }
-            int pick = -1, fallback = -1;
-            for (int t = 0; t < U; ++t) {
-                if (s_used[t]) continue;
-                if (fallback < 0) fallback = t;
-                if (!((forbid >> (t & 7)) & 1u)) { pick = t; break; }
-            }
-            if (pick < 0) pick = fallback;
-            s_slot[r] = pick; s_used[pick] = 1;
-        }
         blk_U[blockIdx.x] = U;
         atomicMax(umax, U);
-    }
-    __syncthreads();
-    if (k < npairs) {
-        int slot = 255;
-        if (e >= 0) {
-            slot = s_slot[u];
-            if (first) blk_elem[(int64_t)blockIdx.x * ppb + slot] = e;
-        }
-        pair_ui[P0 + k] = (uint8_t)slot;
     }
 }
 
@@ -1248,7 +1212,7 @@ int asm_build_block_desc(sc_ctx* ctx) {
         // three CTAs per SM), a third more for quadratic ones, whose mid-side nodes have half the valence of the vertices
         const int npb0 = std::max(1, ppb / ctx->max_valence);
         const bool quadratic = ctx->elem_type == SC_TRI6 || ctx->elem_type == SC_QUAD8 || ctx->elem_type == SC_TETRA10 || ctx->elem_type == SC_HEXA20;
-        const int node_cap = 2 * npb0, item_cap = std::max(npb0 * ctx->max_nbr * (quadratic ? 4 : 3) / 3, ctx->max_nbr);
+        const int node_cap = std::min(2 * npb0, 64), item_cap = std::max(npb0 * ctx->max_nbr * (quadratic ? 4 : 3) / 3, ctx->max_nbr);
         k_blk_chunks<false><<<cg, 128, 0, st>>>(ctx->d_n2e_ptr, ctx->d_nbr_ptr, ctx->n_nodes, ppb, node_cap, item_cap, d_cnt, nullptr, nullptr, d_max);
         SC_CHECK_LAUNCH(ctx);
         size_t tmp_bytes = 0;
@@ -1275,7 +1239,7 @@ int asm_build_block_desc(sc_ctx* ctx) {
         SC_TRY(sc_alloc(ctx, &ctx->d_pair_ui, (size_t)n_pairs));
         SC_CUDA(ctx, cudaMemsetAsync(ctx->d_blk_elem, 0xff, (size_t)n_blocks * ppb * sizeof(int32_t), st));
         SC_CUDA(ctx, cudaMemsetAsync(ctx->d_pair_ui, 0xff, (size_t)n_pairs, st));
-        k_blk_desc<<<(unsigned)n_blocks, ppb, 7 * ppb * sizeof(int), st>>>(ctx->d_n2e_ptr, ctx->d_n2e, ctx->d_node_rl, d_first, ppb, ctx->d_blk_elem,
+        k_blk_desc<<<(unsigned)n_blocks, ppb, 2 * ppb * sizeof(int), st>>>(ctx->d_n2e_ptr, ctx->d_n2e, ctx->d_node_rl, d_first, ppb, ctx->d_blk_elem,
                                                                           ctx->d_blk_U, ctx->d_pair_ui, d_max + 2);
         SC_CHECK_LAUNCH(ctx);
         int umax = 0;
