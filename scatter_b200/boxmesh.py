@@ -40,19 +40,27 @@ def box_arrays(nx: int, ny: int, nz: int, h: float = 0.5, element_type: str = "h
         return out.reshape(-1, 3)
 
     n_corner = NX * NY * NZ
-    # element (ek, ej, ei) in id order; its first corner on the node lattice
-    ek, ej, ei = (a.ravel() for a in np.meshgrid(np.arange(nzl), np.arange(ny), np.arange(nx), indexing="ij"))
     ne = nx * ny * nzl
-    first = (ek * NY + ej) * NX + ei
     off8 = np.array([(dk * NY + dj) * NX + di for di, dj, dk in _CORNER_OFF], dtype=np.int64)
-    corner = first[:, None] + off8[None, :]              # one contiguous pass (column-wise fills are strided)
     if element_type == "hexa8":
+        # first corner of element (ek, ej, ei), in id order, by broadcasting (no index grids), and the 1-based ids in the
+        # same pass; coordinates written straight into the node table
+        first = ((np.arange(nzl, dtype=np.int64) * NY)[:, None, None] + np.arange(ny, dtype=np.int64)[None, :, None]) * NX \
+            + np.arange(nx, dtype=np.int64)[None, None, :]
+        elem = first.reshape(-1, 1) + (off8 + 1)[None, :]
         nodes = np.empty((n_corner, 4))
         nodes[:, 0] = np.arange(1, n_corner + 1)
-        nodes[:, 1:] = lattice(NZ, NY, NX)
-        return nodes, corner + 1
+        grid = nodes.reshape(NZ, NY, NX, 4)
+        grid[..., 1] = np.arange(NX) * h
+        grid[..., 2] = (np.arange(NY) * h)[:, None]
+        grid[..., 3] = ((np.arange(NZ) + k0) * h)[:, None, None]
+        return nodes, elem
     if element_type != "hexa20":
         raise ValueError("box meshes are hexa8 or hexa20")
+    # element (ek, ej, ei) in id order; its first corner on the node lattice
+    ek, ej, ei = (a.ravel() for a in np.meshgrid(np.arange(nzl), np.arange(ny), np.arange(nx), indexing="ij"))
+    first = (ek * NY + ej) * NX + ei
+    corner = first[:, None] + off8[None, :]              # one contiguous pass (column-wise fills are strided)
     # mid-edge nodes: x-edges, then y-edges, then z-edges, each group x fastest
     nxe, nye = nx * NY * NZ, NX * ny * NZ
     base = {0: n_corner, 1: n_corner + nxe, 2: n_corner + nxe + nye}
